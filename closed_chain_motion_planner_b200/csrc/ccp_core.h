@@ -1,0 +1,659 @@
+// ccp_core.h — the engine arithmetic of the closed-chain projection, written once as
+// __host__ __device__ code.  The CUDA kernels (ccp_kernels.cu) are the product; the SAME header
+// compiled by g++ (oracle/oracle_b.cpp, test infrastructure only) reproduces the device results
+// bit for bit, because
+//   * every fused multiply-add is an explicit fma() and nothing else may be contracted
+//     (nvcc --fmad=false, g++ -ffp-contract=off),
+//   * sqrt and division are IEEE-754 correctly rounded on both sides,
+//   * sin/cos/atan2 are our own polynomial kernels (glibc and CUDA libm differ by >= 1 ulp).
+//
+// What it computes (reference: jkw0701/closed_chain_motion_planner)
+//   function()  ConstraintFunction.h:84-102     relative pose of arm a's EE against arm 0's EE
+//   jacobian()  called at ConstraintFunction.h:70 (OMPL finite differences there; analytic here)
+//   project()   ConstraintFunction.h:57-82      fixed-step min-norm Newton iteration
+//   FK          panda_rbdl.cpp:24-42,73-161     modified-DH chain, flange 0.107, Rz(-pi/4)
+//
+// Formulation (one thread owns one sample; all state is a handful of 3-vectors/quaternions):
+//   rotation    world quaternion of each arm's EE by right-multiplying the link quaternions
+//               q_Rx(alpha_i) (x) q_Rz(theta_i/2): half-angle sincos, no rot->quat conversion.
+//   position    the EE-0 origin is pushed DOWN arm 0 (tip -> base), through the world, and UP
+//               arm a (base -> tip): 3-vector recursions only, no 3x3 products.
+//   residual    f0 = |t_c - t_0|,  f1 = 2 atan2(|vec d|, |d_w|),  d = q_c (x) conj(q_0).
+//   jacobian    with u = (t_c - t_0)/f0 and n = sign(d_w) vec(d)/|vec d| (both in EE-a's frame):
+//               carry (r, w, m) = (lever arm to EE-0, u, n) down each arm; at joint i
+//               df0/dq_i = -+ (r x w)_z, df1/dq_i = -+ m_z (+ on arm 0, - on arm a).
+//   step        x -= step * J^T (J J^T)^-1 f, (J J^T) factored as L D L^T in registers; rows that
+//               vanish or make D_k <= 0 are dropped (what JacobiSVD's rank threshold does).
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define CCP_HD __host__ __device__ __forceinline__
+#else
+#define CCP_HD inline __attribute__((always_inline))
+#endif
+
+#define CCP_FMA(a, b, c) fma((a), (b), (c))
+
+#define CCPC_DOF 7
+#define CCPC_MAX_ARMS 3
+
+// ------------------------------------------------------------------------------------------
+// Packed model (device constant / shared memory image).  Built by ccp_pack_model() on the host.
+// ------------------------------------------------------------------------------------------
+struct ccp_link {
+  double tx, ty, tz;  // link translation (a, -sin(alpha) d, cos(alpha) d), panda_rbdl.cpp:159
+  double sa, ca;      // sin/cos alpha
+  double sha, cha;    // sin/cos alpha/2
+  double qoff;        // theta offset (calibration dh.col(2))
+};
+
+struct ccp_arm {
+  ccp_link link[CCPC_DOF];
+  double qwb[4];  // base orientation in world, (w,x,y,z)
+  double Rwb[9];  // same, row-major
+  double pwb[3];
+  double fl;            // flange offset along z7
+  double sphi, cphi;    // sin/cos of the EE yaw (-pi/4)
+  double shphi, chphi;  // half angle
+};
+
+struct ccp_pair_ref {
+  double t0[3];  // init_chain_ translation           (ConstraintFunction.h:39)
+  double q0[4];  // init_chain_ rotation, (w,x,y,z)
+};
+
+struct ccp_model {
+  int32_t n_arms;
+  int32_t max_iter;
+  double tol_p, tol_r;  // tolerance1_, tolerance2_
+  double step;          // 0.30
+  double margin;        // 1e-3
+  double lb[CCPC_DOF], ub[CCPC_DOF];
+  ccp_arm arm[CCPC_MAX_ARMS];
+  ccp_pair_ref ref[CCPC_MAX_ARMS - 1];
+};
+
+// ------------------------------------------------------------------------------------------
+// Elementary functions
+// ------------------------------------------------------------------------------------------
+CCP_HD int32_t ccp_lo32(double t) {
+#if defined(__CUDA_ARCH__)
+  return __double2loint(t);
+#else
+  uint64_t u;
+  memcpy(&u, &t, sizeof u);
+  return (int32_t)(uint32_t)u;
+#endif
+}
+
+// sin and cos of x.  Cody-Waite reduction by pi/2 in three pieces (33+33+53 bits), then the
+// classic degree-13/14 minimax kernels on [-pi/4, pi/4] (coefficients: Sun fdlibm k_sin/k_cos).
+// < 1 ulp for |x| < ~1e6, degrades gracefully (and identically on host and device) beyond.
+CCP_HD void ccp_sincos(double x, double* s_out, double* c_out) {
+  const double TWO_OVER_PI = 0x1.45f306dc9c883p-1;
+  const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: round-to-nearest-integer trick
+  const double PIO2_1 = 0x1.921fb54400000p+0;
+  const double PIO2_2 = 0x1.0b4611a600000p-34;
+  const double PIO2_3 = 0x1.3198a2e037073p-69;
+  double t = CCP_FMA(x, TWO_OVER_PI, MAGIC);
+  int32_t q = ccp_lo32(t);
+  double k = t - MAGIC;
+  double r = CCP_FMA(-k, PIO2_1, x);
+  r = CCP_FMA(-k, PIO2_2, r);
+  r = CCP_FMA(-k, PIO2_3, r);
+  double z = r * r;
+  double ps = CCP_FMA(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+  ps = CCP_FMA(z, ps, 2.75573137070700676789e-06);
+  ps = CCP_FMA(z, ps, -1.98412698298579493134e-04);
+  ps = CCP_FMA(z, ps, 8.33333333332248946124e-03);
+  ps = CCP_FMA(z, ps, -1.66666666666666324348e-01);
+  double pc = CCP_FMA(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  pc = CCP_FMA(z, pc, -2.75573143513906633035e-07);
+  pc = CCP_FMA(z, pc, 2.48015872894767294178e-05);
+  pc = CCP_FMA(z, pc, -1.38888888888741095749e-03);
+  pc = CCP_FMA(z, pc, 4.16666666666666019037e-02);
+  double sr = CCP_FMA(r * z, ps, r);
+  double cr = CCP_FMA(z * z, pc, CCP_FMA(z, -0.5, 1.0));
+  double s = (q & 1) ? cr : sr;
+  double c = (q & 1) ? sr : cr;
+  *s_out = (q & 2) ? -s : s;
+  *c_out = ((q + 1) & 2) ? -c : c;
+}
+
+// atan2(y, x) for y >= 0, x >= 0 (the only case angularDistance needs).  Result in [0, pi/2].
+// min/max -> t in [0,1]; shift by atan(0), pi/8 or pi/4 so |t'| <= tan(pi/16); 12-term series.
+CCP_HD double ccp_atan2_pos(double y, double x) {
+  const bool inv = y > x;
+  const double num = inv ? x : y;
+  const double den = inv ? y : x;
+  double t = (den > 0.0) ? num / den : 0.0;
+  const bool hi = t > 0x1.561b82ab7f990p-1;   // tan(3 pi/16)
+  const bool mid = t > 0x1.975f5e0553158p-3;  // tan(pi/16)
+  const double t0 = hi ? 1.0 : (mid ? 0x1.a827999fcef32p-2 : 0.0);   // 1, tan(pi/8), 0
+  const double off = hi ? 0x1.921fb54442d18p-1 : (mid ? 0x1.921fb54442d18p-2 : 0.0);  // pi/4, pi/8, 0
+  double tr = (t - t0) / CCP_FMA(t, t0, 1.0);
+  double z = tr * tr;
+  double p = CCP_FMA(z, -0x1.642c8590b2164p-5, 0x1.8618618618618p-5);  // -1/23, 1/21
+  p = CCP_FMA(z, p, -0x1.af286bca1af28p-5);                            // -1/19
+  p = CCP_FMA(z, p, 0x1.e1e1e1e1e1e1ep-5);                             // 1/17
+  p = CCP_FMA(z, p, -0x1.1111111111111p-4);                            // -1/15
+  p = CCP_FMA(z, p, 0x1.3b13b13b13b14p-4);                             // 1/13
+  p = CCP_FMA(z, p, -0x1.745d1745d1746p-4);                            // -1/11
+  p = CCP_FMA(z, p, 0x1.c71c71c71c71cp-4);                             // 1/9
+  p = CCP_FMA(z, p, -0x1.2492492492492p-3);                            // -1/7
+  p = CCP_FMA(z, p, 0x1.999999999999ap-3);                             // 1/5
+  p = CCP_FMA(z, p, -0x1.5555555555555p-2);                            // -1/3
+  double a = off + CCP_FMA(tr * z, p, tr);
+  return inv ? (0x1.921fb54442d18p+0 - a) : a;
+}
+
+// ------------------------------------------------------------------------------------------
+// Small vector / quaternion helpers (operation order is part of the definition)
+// ------------------------------------------------------------------------------------------
+// (x,y) <- Rz(theta) (x,y)
+CCP_HD void ccp_rot2(double c, double s, double& x, double& y) {
+  double nx = CCP_FMA(c, x, -(s * y));
+  double ny = CCP_FMA(s, x, c * y);
+  x = nx;
+  y = ny;
+}
+// (x,y) <- Rz(theta)^T (x,y)
+CCP_HD void ccp_rot2t(double c, double s, double& x, double& y) {
+  double nx = CCP_FMA(c, x, s * y);
+  double ny = CCP_FMA(c, y, -(s * x));
+  x = nx;
+  y = ny;
+}
+
+// q <- q (x) (a, b, 0, 0)   rotation about x
+CCP_HD void ccp_qmul_rx(double* q, double a, double b) {
+  double w = CCP_FMA(q[0], a, -(q[1] * b));
+  double x = CCP_FMA(q[1], a, q[0] * b);
+  double y = CCP_FMA(q[2], a, q[3] * b);
+  double z = CCP_FMA(q[3], a, -(q[2] * b));
+  q[0] = w; q[1] = x; q[2] = y; q[3] = z;
+}
+// q <- q (x) (c, 0, 0, s)   rotation about z
+CCP_HD void ccp_qmul_rz(double* q, double c, double s) {
+  double w = CCP_FMA(q[0], c, -(q[3] * s));
+  double x = CCP_FMA(q[1], c, q[2] * s);
+  double y = CCP_FMA(q[2], c, -(q[1] * s));
+  double z = CCP_FMA(q[3], c, q[0] * s);
+  q[0] = w; q[1] = x; q[2] = y; q[3] = z;
+}
+// r = conj(a) (x) b
+CCP_HD void ccp_qmul_conj_left(const double* a, const double* b, double* r) {
+  const double w1 = a[0], x1 = -a[1], y1 = -a[2], z1 = -a[3];
+  r[0] = CCP_FMA(w1, b[0], -CCP_FMA(x1, b[1], CCP_FMA(y1, b[2], z1 * b[3])));
+  r[1] = CCP_FMA(w1, b[1], CCP_FMA(x1, b[0], CCP_FMA(y1, b[3], -(z1 * b[2]))));
+  r[2] = CCP_FMA(w1, b[2], CCP_FMA(y1, b[0], CCP_FMA(z1, b[1], -(x1 * b[3]))));
+  r[3] = CCP_FMA(w1, b[3], CCP_FMA(z1, b[0], CCP_FMA(x1, b[2], -(y1 * b[1]))));
+}
+// r = a (x) conj(b)
+CCP_HD void ccp_qmul_conj_right(const double* a, const double* b, double* r) {
+  const double w2 = b[0], x2 = -b[1], y2 = -b[2], z2 = -b[3];
+  r[0] = CCP_FMA(a[0], w2, -CCP_FMA(a[1], x2, CCP_FMA(a[2], y2, a[3] * z2)));
+  r[1] = CCP_FMA(a[0], x2, CCP_FMA(a[1], w2, CCP_FMA(a[2], z2, -(a[3] * y2))));
+  r[2] = CCP_FMA(a[0], y2, CCP_FMA(a[2], w2, CCP_FMA(a[3], x2, -(a[1] * z2))));
+  r[3] = CCP_FMA(a[0], z2, CCP_FMA(a[3], w2, CCP_FMA(a[1], y2, -(a[2] * x2))));
+}
+// v <- R(q)^T v  (rotate by the conjugate of unit quaternion q)
+CCP_HD void ccp_qrot_inv(const double* q, double* v) {
+  // a = -vec(q);  t = 2 (a x v);  v' = v + w t + a x t
+  const double ax = -q[1], ay = -q[2], az = -q[3];
+  double tx = CCP_FMA(ay, v[2], -(az * v[1]));
+  double ty = CCP_FMA(az, v[0], -(ax * v[2]));
+  double tz = CCP_FMA(ax, v[1], -(ay * v[0]));
+  tx = tx + tx; ty = ty + ty; tz = tz + tz;
+  double cx = CCP_FMA(ay, tz, -(az * ty));
+  double cy = CCP_FMA(az, tx, -(ax * tz));
+  double cz = CCP_FMA(ax, ty, -(ay * tx));
+  v[0] = CCP_FMA(q[0], tx, v[0]) + cx;
+  v[1] = CCP_FMA(q[0], ty, v[1]) + cy;
+  v[2] = CCP_FMA(q[0], tz, v[2]) + cz;
+}
+
+// One link going DOWN the chain (frame i -> frame i-1): v <- Rx(alpha) Rz(theta) v (+ t)
+CCP_HD void ccp_down_vec(const ccp_link& L, double s, double c, double* v) {
+  ccp_rot2(c, s, v[0], v[1]);
+  ccp_rot2(L.ca, L.sa, v[1], v[2]);
+}
+CCP_HD void ccp_down_pt(const ccp_link& L, double s, double c, double* r) {
+  ccp_down_vec(L, s, c, r);
+  r[0] += L.tx; r[1] += L.ty; r[2] += L.tz;
+}
+// One link going UP the chain (frame i-1 -> frame i): r <- Rz(theta)^T Rx(alpha)^T (r - t)
+CCP_HD void ccp_up_pt(const ccp_link& L, double s, double c, double* r) {
+  r[0] -= L.tx; r[1] -= L.ty; r[2] -= L.tz;
+  ccp_rot2t(L.ca, L.sa, r[1], r[2]);
+  ccp_rot2t(c, s, r[0], r[1]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Forward evaluation: residual f(x) and everything the Jacobian pass needs.
+// ------------------------------------------------------------------------------------------
+template <int K>
+struct ccp_fwd {
+  double sc[K][CCPC_DOF][2];  // full-angle (sin, cos) of every joint
+  double tc[K - 1][3];        // translation of chain a:  R_a^T (p_0 - p_a)
+  double qc[K - 1][4];        // rotation of chain a:     conj(q_a) (x) q_0
+  double d[K - 1][4];         // qc (x) conj(q_ref)
+  double f[2 * (K - 1)];      // (f0, f1) per pair
+  double sv[K - 1];           // |vec d|
+};
+
+template <int K>
+CCP_HD void ccp_forward(const ccp_model& M, const double* x, ccp_fwd<K>& F) {
+  double q[K][4];
+#pragma unroll
+  for (int a = 0; a < K; ++a) {
+    const ccp_arm& A = M.arm[a];
+    q[a][0] = A.qwb[0]; q[a][1] = A.qwb[1]; q[a][2] = A.qwb[2]; q[a][3] = A.qwb[3];
+#pragma unroll
+    for (int i = 0; i < CCPC_DOF; ++i) {
+      const ccp_link& L = A.link[i];
+      double h = 0.5 * (x[a * CCPC_DOF + i] + L.qoff);
+      double sh, ch;
+      ccp_sincos(h, &sh, &ch);
+      ccp_qmul_rx(q[a], L.cha, L.sha);
+      ccp_qmul_rz(q[a], ch, sh);
+      double sh2 = sh + sh;
+      F.sc[a][i][0] = sh2 * ch;                // sin(theta)
+      F.sc[a][i][1] = CCP_FMA(-sh2, sh, 1.0);  // cos(theta)
+    }
+    ccp_qmul_rz(q[a], A.chphi, A.shphi);
+  }
+  // EE-0 origin: frame 7 of arm 0 -> base 0 -> world
+  double r[3] = {0.0, 0.0, M.arm[0].fl};
+#pragma unroll
+  for (int i = CCPC_DOF - 1; i >= 0; --i) ccp_down_pt(M.arm[0].link[i], F.sc[0][i][0], F.sc[0][i][1], r);
+  double p0[3];
+  {
+    const ccp_arm& A = M.arm[0];
+    p0[0] = CCP_FMA(A.Rwb[0], r[0], CCP_FMA(A.Rwb[1], r[1], CCP_FMA(A.Rwb[2], r[2], A.pwb[0])));
+    p0[1] = CCP_FMA(A.Rwb[3], r[0], CCP_FMA(A.Rwb[4], r[1], CCP_FMA(A.Rwb[5], r[2], A.pwb[1])));
+    p0[2] = CCP_FMA(A.Rwb[6], r[0], CCP_FMA(A.Rwb[7], r[1], CCP_FMA(A.Rwb[8], r[2], A.pwb[2])));
+  }
+#pragma unroll
+  for (int a = 1; a < K; ++a) {
+    const ccp_arm& A = M.arm[a];
+    double e0 = p0[0] - A.pwb[0], e1 = p0[1] - A.pwb[1], e2 = p0[2] - A.pwb[2];
+    double v[3];
+    v[0] = CCP_FMA(A.Rwb[0], e0, CCP_FMA(A.Rwb[3], e1, A.Rwb[6] * e2));
+    v[1] = CCP_FMA(A.Rwb[1], e0, CCP_FMA(A.Rwb[4], e1, A.Rwb[7] * e2));
+    v[2] = CCP_FMA(A.Rwb[2], e0, CCP_FMA(A.Rwb[5], e1, A.Rwb[8] * e2));
+#pragma unroll
+    for (int i = 0; i < CCPC_DOF; ++i) ccp_up_pt(A.link[i], F.sc[a][i][0], F.sc[a][i][1], v);
+    v[2] -= A.fl;
+    ccp_rot2t(A.cphi, A.sphi, v[0], v[1]);
+    double* tc = F.tc[a - 1];
+    tc[0] = v[0]; tc[1] = v[1]; tc[2] = v[2];
+    ccp_qmul_conj_left(q[a], q[0], F.qc[a - 1]);
+    ccp_qmul_conj_right(F.qc[a - 1], M.ref[a - 1].q0, F.d[a - 1]);
+    const double* d = F.d[a - 1];
+    const double* t0 = M.ref[a - 1].t0;
+    double ex = tc[0] - t0[0], ey = tc[1] - t0[1], ez = tc[2] - t0[2];
+    F.f[2 * (a - 1)] = sqrt(CCP_FMA(ex, ex, CCP_FMA(ey, ey, ez * ez)));
+    double sv = sqrt(CCP_FMA(d[1], d[1], CCP_FMA(d[2], d[2], d[3] * d[3])));
+    F.sv[a - 1] = sv;
+    double atn = ccp_atan2_pos(sv, fabs(d[0]));
+    F.f[2 * (a - 1) + 1] = atn + atn;
+  }
+}
+
+// Loop test of project(): `(f0 > tol1) || (f1 > tol2)` for any pair (ConstraintFunction.h:68).
+template <int K>
+CCP_HD bool ccp_needs_step(const ccp_model& M, const double* f) {
+  bool any = false;
+#pragma unroll
+  for (int a = 0; a < K - 1; ++a) any = any || (f[2 * a] > M.tol_p) || (f[2 * a + 1] > M.tol_r);
+  return any;
+}
+// Success test of project() (ConstraintFunction.h:75): norm1 is the 0/1 flag `f0 > tol1`, so
+// `norm1 < tol1` means f0 <= tol1; norm2 = f1 must be STRICTLY below tol2.  NaNs fail.
+template <int K>
+CCP_HD bool ccp_converged(const ccp_model& M, const double* f) {
+  bool all = true;
+#pragma unroll
+  for (int a = 0; a < K - 1; ++a) all = all && (f[2 * a] <= M.tol_p) && (f[2 * a + 1] < M.tol_r);
+  return all;
+}
+// isSatisfied (ConstraintFunction.h:114-120): finite, f0 <= tol1, f1 <= tol2.
+template <int K>
+CCP_HD bool ccp_is_satisfied(const ccp_model& M, const double* f) {
+  bool all = true;
+#pragma unroll
+  for (int a = 0; a < K - 1; ++a) {
+    double f0 = f[2 * a], f1 = f[2 * a + 1];
+    all = all && (f0 - f0 == 0.0) && (f1 - f1 == 0.0) && (f0 <= M.tol_p) && (f1 <= M.tol_r);
+  }
+  return all;
+}
+// jointValid (ConstraintFunction.h:43-55)
+template <int K>
+CCP_HD bool ccp_joint_valid(const ccp_model& M, const double* x) {
+  bool ok = true;
+#pragma unroll
+  for (int a = 0; a < K; ++a)
+#pragma unroll
+    for (int i = 0; i < CCPC_DOF; ++i) {
+      double v = x[a * CCPC_DOF + i];
+      ok = ok && !(v < M.lb[i] + M.margin) && !(v > M.ub[i] - M.margin);
+    }
+  return ok;
+}
+
+// ------------------------------------------------------------------------------------------
+// Jacobian pass.  Ja[p][row][i]: d f_{2p+row} / d q(arm p+1, joint i);
+//                 J0[p][row][i]: d f_{2p+row} / d q(arm 0,   joint i).
+// ------------------------------------------------------------------------------------------
+template <int K>
+struct ccp_jac {
+  double Ja[K - 1][2][CCPC_DOF];
+  double J0[K - 1][2][CCPC_DOF];
+};
+
+template <int K>
+CCP_HD void ccp_jacobian(const ccp_model& M, const ccp_fwd<K>& F, ccp_jac<K>& J) {
+#pragma unroll
+  for (int p = 0; p < K - 1; ++p) {
+    const int a = p + 1;
+    const double* tc = F.tc[p];
+    const double* t0 = M.ref[p].t0;
+    const double* d = F.d[p];
+    const double f0 = F.f[2 * p];
+    const double sv = F.sv[p];
+    const double inv_f0 = (f0 > 0.0) ? 1.0 / f0 : 0.0;
+    double inv_sv = (sv > 0.0) ? 1.0 / sv : 0.0;
+    inv_sv = (d[0] < 0.0) ? -inv_sv : inv_sv;
+    double u[3] = {(tc[0] - t0[0]) * inv_f0, (tc[1] - t0[1]) * inv_f0, (tc[2] - t0[2]) * inv_f0};
+    double n[3] = {d[1] * inv_sv, d[2] * inv_sv, d[3] * inv_sv};
+    // arm a: frame EE_a -> frame 7 -> ... -> frame 1
+    {
+      const ccp_arm& A = M.arm[a];
+      double r[3] = {tc[0], tc[1], tc[2]};
+      double w[3] = {u[0], u[1], u[2]};
+      double m[3] = {n[0], n[1], n[2]};
+      ccp_rot2(A.cphi, A.sphi, r[0], r[1]);
+      r[2] += A.fl;
+      ccp_rot2(A.cphi, A.sphi, w[0], w[1]);
+      ccp_rot2(A.cphi, A.sphi, m[0], m[1]);
+#pragma unroll
+      for (int i = CCPC_DOF - 1; i >= 0; --i) {
+        J.Ja[p][0][i] = -CCP_FMA(r[0], w[1], -(r[1] * w[0]));
+        J.Ja[p][1][i] = -m[2];
+        if (i > 0) {
+          const double s = F.sc[a][i][0], c = F.sc[a][i][1];
+          ccp_down_pt(A.link[i], s, c, r);
+          ccp_down_vec(A.link[i], s, c, w);
+          ccp_down_vec(A.link[i], s, c, m);
+        }
+      }
+    }
+    // arm 0: u, n rotated into EE_0's frame by R_c^T, lever arm starts at the EE-0 origin
+    {
+      const ccp_arm& A = M.arm[0];
+      double r[3] = {0.0, 0.0, A.fl};
+      double w[3] = {u[0], u[1], u[2]};
+      double m[3] = {n[0], n[1], n[2]};
+      ccp_qrot_inv(F.qc[p], w);
+      ccp_qrot_inv(F.qc[p], m);
+      ccp_rot2(A.cphi, A.sphi, w[0], w[1]);
+      ccp_rot2(A.cphi, A.sphi, m[0], m[1]);
+#pragma unroll
+      for (int i = CCPC_DOF - 1; i >= 0; --i) {
+        J.J0[p][0][i] = CCP_FMA(r[0], w[1], -(r[1] * w[0]));
+        J.J0[p][1][i] = m[2];
+        if (i > 0) {
+          const double s = F.sc[0][i][0], c = F.sc[0][i][1];
+          ccp_down_pt(A.link[i], s, c, r);
+          ccp_down_vec(A.link[i], s, c, w);
+          ccp_down_vec(A.link[i], s, c, m);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Newton step: x <- x - step * J^T (J J^T)^-1 f         (ConstraintFunction.h:71)
+// ------------------------------------------------------------------------------------------
+template <int K>
+CCP_HD void ccp_newton_step(const ccp_model& M, const ccp_fwd<K>& F, const ccp_jac<K>& J, double* x) {
+  constexpr int m = 2 * (K - 1);
+  double G[m][m];
+  // Gram matrix, lower triangle.  Rows of the same pair share both arms' columns; rows of
+  // different pairs only share arm 0's columns.
+#pragma unroll
+  for (int p = 0; p < K - 1; ++p)
+#pragma unroll
+    for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+      for (int pp = 0; pp <= p; ++pp)
+#pragma unroll
+        for (int rj = 0; rj < 2; ++rj) {
+          const int I = 2 * p + ri, Jx = 2 * pp + rj;
+          if (Jx > I) continue;
+          double acc = 0.0;
+#pragma unroll
+          for (int i = 0; i < CCPC_DOF; ++i) acc = CCP_FMA(J.J0[p][ri][i], J.J0[pp][rj][i], acc);
+          if (pp == p) {
+#pragma unroll
+            for (int i = 0; i < CCPC_DOF; ++i) acc = CCP_FMA(J.Ja[p][ri][i], J.Ja[p][rj][i], acc);
+          }
+          G[I][Jx] = acc;
+        }
+  // L D L^T with row dropping.  Lm is unit lower triangular, D the pivots.
+  double D[m], invD[m], y[m];
+  double Lm[m][m];
+#pragma unroll
+  for (int k = 0; k < m; ++k) {
+    double dk = G[k][k];
+#pragma unroll
+    for (int j = 0; j < k; ++j) dk = CCP_FMA(-(Lm[k][j] * D[j]), Lm[k][j], dk);
+    const bool keep = dk > 0.0;
+    D[k] = keep ? dk : 0.0;
+    invD[k] = keep ? 1.0 / dk : 0.0;
+#pragma unroll
+    for (int i = k + 1; i < m; ++i) {
+      double v = G[i][k];
+#pragma unroll
+      for (int j = 0; j < k; ++j) v = CCP_FMA(-(Lm[i][j] * D[j]), Lm[k][j], v);
+      Lm[i][k] = v * invD[k];
+    }
+  }
+  // forward substitution L z = f, scale by D^-1, back substitution L^T y = z
+#pragma unroll
+  for (int k = 0; k < m; ++k) {
+    double v = F.f[k];
+#pragma unroll
+    for (int j = 0; j < k; ++j) v = CCP_FMA(-Lm[k][j], y[j], v);
+    y[k] = v;
+  }
+#pragma unroll
+  for (int k = 0; k < m; ++k) y[k] = y[k] * invD[k];
+#pragma unroll
+  for (int k = m - 1; k >= 0; --k) {
+    double v = y[k];
+#pragma unroll
+    for (int j = k + 1; j < m; ++j) v = CCP_FMA(-Lm[j][k], y[j], v);
+    y[k] = (invD[k] != 0.0) ? v : 0.0;
+  }
+  // x -= step * J^T y
+#pragma unroll
+  for (int i = 0; i < CCPC_DOF; ++i) {
+    double dx = 0.0;
+#pragma unroll
+    for (int p = 0; p < K - 1; ++p) {
+      dx = CCP_FMA(J.J0[p][0][i], y[2 * p], dx);
+      dx = CCP_FMA(J.J0[p][1][i], y[2 * p + 1], dx);
+    }
+    x[i] = CCP_FMA(-M.step, dx, x[i]);
+  }
+#pragma unroll
+  for (int p = 0; p < K - 1; ++p)
+#pragma unroll
+    for (int i = 0; i < CCPC_DOF; ++i) {
+      double dx = CCP_FMA(J.Ja[p][1][i], y[2 * p + 1], J.Ja[p][0][i] * y[2 * p]);
+      x[(p + 1) * CCPC_DOF + i] = CCP_FMA(-M.step, dx, x[(p + 1) * CCPC_DOF + i]);
+    }
+}
+
+// Dense m x n Jacobian (row-major) from the compact form: the layout jacobian() returns.
+template <int K>
+CCP_HD void ccp_jac_dense(const ccp_jac<K>& J, double* out) {
+  constexpr int m = 2 * (K - 1), n = CCPC_DOF * K;
+#pragma unroll
+  for (int i = 0; i < m * n; ++i) out[i] = 0.0;
+#pragma unroll
+  for (int p = 0; p < K - 1; ++p)
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int i = 0; i < CCPC_DOF; ++i) {
+        out[(2 * p + r) * n + i] = J.J0[p][r][i];
+        out[(2 * p + r) * n + (p + 1) * CCPC_DOF + i] = J.Ja[p][r][i];
+      }
+}
+
+// ------------------------------------------------------------------------------------------
+// project(): the whole Newton loop for ONE sample (ConstraintFunction.h:57-82).
+// Used as-is by the host build; the CUDA kernel runs the same three calls inside its
+// lane-refill loop.
+// ------------------------------------------------------------------------------------------
+template <int K>
+CCP_HD void ccp_project_one(const ccp_model& M, double* x, double* f_out, int32_t* iters, bool* converged,
+                            bool* ok) {
+  ccp_fwd<K> F;
+  ccp_jac<K> J;
+  int32_t it = 0;
+  ccp_forward<K>(M, x, F);
+  while (ccp_needs_step<K>(M, F.f) && it < M.max_iter) {
+    ++it;
+    ccp_jacobian<K>(M, F, J);
+    ccp_newton_step<K>(M, F, J, x);
+    ccp_forward<K>(M, x, F);
+  }
+  const bool conv = ccp_converged<K>(M, F.f);
+#pragma unroll
+  for (int k = 0; k < 2 * (K - 1); ++k) f_out[k] = F.f[k];
+  *iters = it;
+  *converged = conv;
+  *ok = conv && ccp_joint_valid<K>(M, x);
+}
+
+// setInitialPosition (ConstraintFunction.h:31-40): reference chain = chain at q_start with an
+// identity reference.
+template <int K>
+CCP_HD void ccp_reference_chain(ccp_model& M, const double* q_start) {
+#pragma unroll
+  for (int p = 0; p < K - 1; ++p) {
+    M.ref[p].t0[0] = M.ref[p].t0[1] = M.ref[p].t0[2] = 0.0;
+    M.ref[p].q0[0] = 1.0;
+    M.ref[p].q0[1] = M.ref[p].q0[2] = M.ref[p].q0[3] = 0.0;
+  }
+  ccp_fwd<K> F;
+  ccp_forward<K>(M, q_start, F);
+#pragma unroll
+  for (int p = 0; p < K - 1; ++p) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) M.ref[p].t0[k] = F.tc[p][k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) M.ref[p].q0[k] = F.qc[p][k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Single-arm kinematics in the arm's BASE frame (RobotModel API, panda_rbdl.cpp:9-42).
+// T: row-major 3x4 [R|p].  Jac: 6x7 row-major, rows [linear; angular] (panda_rbdl.cpp:16-19).
+// ------------------------------------------------------------------------------------------
+CCP_HD void ccp_arm_fk(const ccp_arm& A, const double* q, double* T, double* Jac) {
+  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  double o[3] = {0, 0, 0};
+  double zs[CCPC_DOF][3], os[CCPC_DOF][3];
+#pragma unroll
+  for (int i = 0; i < CCPC_DOF; ++i) {
+    const ccp_link& L = A.link[i];
+    double s, c;
+    ccp_sincos(q[i] + L.qoff, &s, &c);
+    // o += R t ;  R <- R Rx(alpha) Rz(theta)
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+      o[r] = CCP_FMA(R[3 * r], L.tx, CCP_FMA(R[3 * r + 1], L.ty, CCP_FMA(R[3 * r + 2], L.tz, o[r])));
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      double c0 = R[3 * r], c1 = R[3 * r + 1], c2 = R[3 * r + 2];
+      double n1 = CCP_FMA(c1, L.ca, c2 * L.sa);     // column 1 of R Rx
+      double n2 = CCP_FMA(c2, L.ca, -(c1 * L.sa));  // column 2 of R Rx
+      R[3 * r] = CCP_FMA(c0, c, n1 * s);
+      R[3 * r + 1] = CCP_FMA(n1, c, -(c0 * s));
+      R[3 * r + 2] = n2;
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      zs[i][r] = R[3 * r + 2];
+      os[i][r] = o[r];
+    }
+  }
+  double p[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) p[r] = CCP_FMA(R[3 * r + 2], A.fl, o[r]);
+  if (T) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      double c0 = R[3 * r], c1 = R[3 * r + 1];
+      T[4 * r] = CCP_FMA(c0, A.cphi, c1 * A.sphi);
+      T[4 * r + 1] = CCP_FMA(c1, A.cphi, -(c0 * A.sphi));
+      T[4 * r + 2] = R[3 * r + 2];
+      T[4 * r + 3] = p[r];
+    }
+  }
+  if (Jac) {
+#pragma unroll
+    for (int i = 0; i < CCPC_DOF; ++i) {
+      double lx = p[0] - os[i][0], ly = p[1] - os[i][1], lz = p[2] - os[i][2];
+      Jac[0 * 7 + i] = CCP_FMA(zs[i][1], lz, -(zs[i][2] * ly));
+      Jac[1 * 7 + i] = CCP_FMA(zs[i][2], lx, -(zs[i][0] * lz));
+      Jac[2 * 7 + i] = CCP_FMA(zs[i][0], ly, -(zs[i][1] * lx));
+      Jac[3 * 7 + i] = zs[i][0];
+      Jac[4 * 7 + i] = zs[i][1];
+      Jac[5 * 7 + i] = zs[i][2];
+    }
+  }
+}
+
+// KinematicChainSpace::enforceBounds (KinematicChain.h:118-130): fmod wrap into [-pi, pi).
+// fmod is exact in IEEE arithmetic, so host and device agree bit for bit.
+CCP_HD double ccp_wrap_pi(double v) {
+  const double PI = 3.14159265358979323846, TWO_PI = 2.0 * 3.14159265358979323846;
+  double w = fmod(v, TWO_PI);
+  if (w < -PI) w += TWO_PI;
+  else if (w >= PI) w -= TWO_PI;
+  return w;
+}
+
+// ------------------------------------------------------------------------------------------
+// Counter-based seed stream: 53-bit uniforms from splitmix64 of (seed, sample, joint).
+// ------------------------------------------------------------------------------------------
+CCP_HD uint64_t ccp_mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+CCP_HD double ccp_uniform01(uint64_t seed, uint64_t sample, uint32_t lane) {
+  uint64_t h = ccp_mix64(seed ^ 0xD1B54A32D192ED03ull);
+  h = ccp_mix64(h + sample * 0x9E3779B97F4A7C15ull);
+  h = ccp_mix64(h + (uint64_t)lane);
+  return (double)(h >> 11) * 0x1.0p-53;
+}
+// sampleUniform: x_j = lb_j + u (ub_j - lb_j)   (OMPL RealVectorStateSampler over
+// KinematicChain.h:77-99 bounds)
+CCP_HD double ccp_seed_uniform(const ccp_model& M, uint64_t seed, uint64_t sample, int j) {
+  const int i = j % CCPC_DOF;
+  return CCP_FMA(ccp_uniform01(seed, sample, (uint32_t)j), M.ub[i] - M.lb[i], M.lb[i]);
+}

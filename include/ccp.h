@@ -1,0 +1,204 @@
+/*
+ * ccp.h — C ABI of the B200-native batched closed-chain constraint-projection engine.
+ *
+ * This is the drop-in boundary for ONE hot path of jkw0701/closed_chain_motion_planner:
+ * KinematicChainConstraint::{function, jacobian, project, isSatisfied, jointValid,
+ * setInitialPosition, setTolerance, setArmModels} and the PandaModel kinematics it calls.
+ * Every entry point cites the reference interface it replaces (paths relative to the
+ * reference root).  Plain pointers and sizes only; no C++/torch types; no exceptions.
+ *
+ * Conventions
+ *   - K = number of arms (2 or 3), n = 7*K joints per state, m = 2*(K-1) residual rows.
+ *   - "dev" pointers are CUDA device pointers on the handle's device; "host" pointers are
+ *     ordinary host memory (pinned or pageable).  `stream` is a cudaStream_t passed as void*
+ *     (NULL = the legacy default stream).  Device-pointer calls are asynchronous on `stream`;
+ *     host-pointer calls (`*_host`) return after the results are in the caller's buffers.
+ *   - layout: CCP_LAYOUT_AOS = states stored state-major, double[count][n] (what the reference's
+ *     OMPL RealVectorStateSpace::StateType::values look like when gathered);
+ *     CCP_LAYOUT_SOA = joint-major, double[n][count] (coalesced, the engine's native layout).
+ *   - All functions return CCP_OK (0) or a negative ccp_status; ccp_last_error() gives text.
+ *   - There is no CPU fallback: without a CUDA device ccp_create fails with CCP_ERR_CUDA.
+ */
+#ifndef CCP_H_
+#define CCP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CCP_MAX_ARMS 3
+#define CCP_DOF 7
+
+typedef enum ccp_status {
+  CCP_OK = 0,
+  CCP_ERR_INVALID = -1,   /* bad argument (null pointer, n_arms not 2/3, tolerance <= 0 ...) */
+  CCP_ERR_CUDA = -2,      /* CUDA runtime error, or no CUDA device */
+  CCP_ERR_STATE = -3,     /* call order (e.g. project before set_reference) */
+  CCP_ERR_NCCL = -4
+} ccp_status;
+
+typedef enum ccp_layout { CCP_LAYOUT_AOS = 0, CCP_LAYOUT_SOA = 1 } ccp_layout;
+
+/* One arm.  Replaces ArmModel{rbdl_model, t_wb} (kinematics/panda_model.h:7-23) and
+ * PandaModel::initModel(dh) (src/kinematics/panda_rbdl.cpp:73-148): modified (Craig) DH rows
+ * plus the optional 7x4 calibration offsets already ADDED in (a, d, theta, alpha).            */
+typedef struct ccp_arm_desc {
+  double dh_a[CCP_DOF];            /* panda_rbdl.cpp:98  (+ dh.col(0)) */
+  double dh_d[CCP_DOF];            /* panda_rbdl.cpp:99  (+ dh.col(1)) */
+  double dh_alpha[CCP_DOF];        /* panda_rbdl.cpp:97  (+ dh.col(3)) */
+  double dh_theta_offset[CCP_DOF]; /* dh.col(2), panda_rbdl.cpp:94,119 */
+  double t_wb[12];                 /* base frame in world, row-major 3x4 [R|p]; grasping_point.cpp:11-16 */
+  double flange;                   /* 0.107 m, panda_rbdl.cpp:125 */
+  double ee_yaw;                   /* -pi/4,   panda_rbdl.cpp:31  */
+} ccp_arm_desc;
+
+/* The whole closed chain: arm[0] is the constraint's first arm (arm_models_[0]),
+ * arm[a>=1] closes the chain against arm[0] (ConstraintFunction.h:89-92).          */
+typedef struct ccp_model_desc {
+  int32_t n_arms;                  /* 2 (reference) or 3 (21-DoF extension) */
+  int32_t reserved;
+  ccp_arm_desc arm[CCP_MAX_ARMS];
+  double lb[CCP_DOF];              /* ConstraintFunction.h:27 */
+  double ub[CCP_DOF];              /* ConstraintFunction.h:28 */
+} ccp_model_desc;
+
+typedef struct ccp_options {
+  double step;          /* 0.30  ConstraintFunction.h:71 */
+  int32_t max_iter;     /* 250   ConstraintFunction.h:26,68 */
+  int32_t reserved;
+  double joint_margin;  /* 1e-3  ConstraintFunction.h:45 */
+} ccp_options;
+
+typedef struct ccp_handle ccp_handle;
+
+/* Fill `d` with the stock Panda constants of the reference (panda_rbdl.cpp:97-99,125,31;
+ * ConstraintFunction.h:27-28) for `n_arms` arms whose base frames are
+ * grasping_point::t_wb[arm_index[i]] (grasping_point.cpp:11-20: 0=left, 1=right, 2=top). */
+int ccp_default_model(int32_t n_arms, const int32_t* arm_index, ccp_model_desc* d);
+
+/* ≙ constructing KinematicChainConstraint(links) + setArmModels (ConstraintFunction.h:24-29,122-126)
+ * with PandaModel::initModel for every arm.  Tolerances start at the reference's 1e-3 / 5e-3
+ * (ConstrainedPlanningCommon.cpp:120-121), options at step 0.30 / 250 / 1e-3.             */
+int ccp_create(const ccp_model_desc* model, int32_t device, ccp_handle** out);
+void ccp_destroy(ccp_handle* h);
+const char* ccp_last_error(const ccp_handle* h); /* h may be NULL: error of the last failed ccp_create */
+int ccp_n_arms(const ccp_handle* h);
+int ccp_device(const ccp_handle* h);
+
+/* ≙ setInitialPosition (ConstraintFunction.h:31-40): q_start is a HOST array of 7*K doubles.
+ * Computes, on the device, the grasp-closure reference pose(s) init_chain_.                */
+int ccp_set_reference(ccp_handle* h, const double* q_start_host);
+/* Reads back init_chain_ for pair a (arm a+1 against arm 0): t0[3] translation and
+ * q0[4] = (w,x,y,z) unit quaternion of the rotation.                                        */
+int ccp_get_reference(const ccp_handle* h, int32_t pair, double* t0_host, double* q0_host);
+/* ≙ setTolerance (ConstraintFunction.h:104-112); CCP_ERR_INVALID when either is <= 0
+ * (the reference throws ompl::Exception).                                                   */
+int ccp_set_tolerance(ccp_handle* h, double tol_position, double tol_rotation);
+int ccp_set_options(ccp_handle* h, const ccp_options* opt);
+int ccp_get_options(const ccp_handle* h, ccp_options* opt, double* tol_position, double* tol_rotation);
+
+/* ---- batched constraint API, device pointers ------------------------------------------- */
+
+/* ≙ function(x, out) (ConstraintFunction.h:84-102) for `count` states.
+ * f_dev: double[m][count] when layout is SOA, double[count][m] when AOS.                    */
+int ccp_function_batch(ccp_handle* h, const double* x_dev, int64_t count, int32_t layout,
+                       double* f_dev, void* stream);
+
+/* ≙ jacobian(x, out) (inherited OMPL default, called at ConstraintFunction.h:70), computed
+ * analytically.  J_dev: AOS double[count][m][n] (row-major m x n per state);
+ * SOA double[m][n][count].                                                                  */
+int ccp_jacobian_batch(ccp_handle* h, const double* x_dev, int64_t count, int32_t layout,
+                       double* J_dev, void* stream);
+
+/* ≙ project(x) (ConstraintFunction.h:57-82) for `count` seeds: the Newton loop with the
+ * reference's loop/exit semantics.  x_out may alias seeds (in-place, like the reference).
+ * Any of ok/converged/iters/resid may be NULL.
+ *   ok[i]        = project()'s return value (converged AND jointValid)
+ *   converged[i] = residual under tolerance at exit (f0 <= tol1 and f1 < tol2 for every pair)
+ *   iters[i]     = Newton steps taken (0..max_iter)
+ *   resid        = final function(x): SOA double[m][count] / AOS double[count][m]
+ * The last iterate is written to x_out even on failure (reference semantics).               */
+int ccp_project_batch(ccp_handle* h, const double* seeds_dev, int64_t count, int32_t layout,
+                      double* x_out_dev, uint8_t* ok_dev, uint8_t* converged_dev,
+                      int32_t* iters_dev, double* resid_dev, void* stream);
+
+/* ≙ isSatisfied (ConstraintFunction.h:114-120): finite and f0 <= tol1 and f1 <= tol2.       */
+int ccp_is_satisfied_batch(ccp_handle* h, const double* x_dev, int64_t count, int32_t layout,
+                           uint8_t* out_dev, void* stream);
+/* ≙ jointValid (ConstraintFunction.h:43-55).                                                */
+int ccp_joint_valid_batch(ccp_handle* h, const double* x_dev, int64_t count, int32_t layout,
+                          uint8_t* out_dev, void* stream);
+
+/* ---- batched kinematics API (RobotModel virtuals, kinematics/panda_rbdl.h:13-23) -------- */
+
+/* ≙ PandaModel::getTransform (panda_rbdl.cpp:35-42) of arm `arm` in its BASE frame for `count`
+ * 7-vectors q (AOS double[count][7] or SOA double[7][count]).
+ * T_dev: AOS double[count][12] row-major 3x4 [R|p]; SOA double[12][count].                  */
+int ccp_fk_batch(ccp_handle* h, int32_t arm, const double* q_dev, int64_t count, int32_t layout,
+                 double* T_dev, void* stream);
+/* ≙ PandaModel::getJacobianMatrix (panda_rbdl.cpp:9-22): 6x7, rows [linear(3); angular(3)],
+ * base frame.  J_dev: AOS double[count][6][7]; SOA double[6][7][count].                     */
+int ccp_arm_jacobian_batch(ccp_handle* h, int32_t arm, const double* q_dev, int64_t count,
+                           int32_t layout, double* J_dev, void* stream);
+
+/* ---- batched projected-state sampler (jy_ProjectedStateSampler, jy_ProjectedStateSpace.cpp:10-29)
+ * Seeds come from a counter-based generator: seed i depends only on (rng_seed, first_index+i),
+ * so any rank/GPU can generate any slice.  mode 0 = uniform in [lb,ub] (sampleUniform),
+ * mode 1 = uniform in the box near +- distance, clipped to [lb,ub] (sampleUniformNear),
+ * mode 2 = gaussian(mean = near, stddev = distance), clipped to [lb,ub] (sampleGaussian).
+ * Each seed is projected; if wrap_bounds != 0 the result is wrapped to [-pi,pi)
+ * (KinematicChainSpace::enforceBounds, KinematicChain.h:118-130).
+ * Outputs (any may be NULL except n_ok_dev when compact_dev != NULL):
+ *   x_out_dev/ok_dev/iters_dev : per-seed results as in ccp_project_batch (AOS/SOA by layout)
+ *   compact_dev : double[<=count][n] AOS, the states with ok==1 densely packed (order unspecified)
+ *   n_ok_dev    : int64 counter (device), ADDED to (caller zeroes it)                        */
+typedef struct ccp_sampler_args {
+  uint64_t rng_seed;
+  int64_t first_index;
+  int32_t mode;
+  int32_t wrap_bounds;
+  double distance;
+  const double* near_host; /* 7*K doubles, host; modes 1,2 */
+} ccp_sampler_args;
+
+int ccp_generate_seeds(ccp_handle* h, const ccp_sampler_args* a, int64_t count, int32_t layout,
+                       double* seeds_dev, void* stream);
+int ccp_sample_project_batch(ccp_handle* h, const ccp_sampler_args* a, int64_t count, int32_t layout,
+                             double* x_out_dev, uint8_t* ok_dev, int32_t* iters_dev,
+                             double* compact_dev, int64_t* n_ok_dev, void* stream);
+/* ≙ KinematicChainSpace::enforceBounds (KinematicChain.h:118-130), in place.                */
+int ccp_enforce_bounds_batch(ccp_handle* h, double* x_dev, int64_t count, int32_t layout, void* stream);
+
+/* ---- host-buffer entry points (what a planner that owns host states calls) -------------- */
+/* Same as ccp_project_batch but all pointers are HOST memory, AOS double[count][n]
+ * (the gathered OMPL states).  Copies in, projects, copies out; synchronous.                */
+int ccp_project_batch_host(ccp_handle* h, const double* seeds_host, int64_t count,
+                           double* x_out_host, uint8_t* ok_host, uint8_t* converged_host,
+                           int32_t* iters_host, double* resid_host);
+int ccp_function_batch_host(ccp_handle* h, const double* x_host, int64_t count, double* f_host);
+int ccp_jacobian_batch_host(ccp_handle* h, const double* x_host, int64_t count, double* J_host);
+
+/* ---- measurement helpers ---------------------------------------------------------------- */
+/* Register-only DFMA chains on every SM: returns achieved FP64 FLOP/s (FMA = 2) and the
+ * kernel time in ms.  Used as the MEASURED FP64 peak of the box (MEASURED_PEAKS.json has none). */
+int ccp_fp64_peak_probe(ccp_handle* h, int32_t repeats, double* flops_per_s, double* ms);
+/* Number of engine kernels launched through this handle since creation. */
+int64_t ccp_launch_count(const ccp_handle* h);
+/* Time (ms, CUDA events on the launching stream) of the last projection kernel launched by a
+ * *_host call or by ccp_project_batch_timed.                                                */
+int ccp_project_batch_timed(ccp_handle* h, const double* seeds_dev, int64_t count, int32_t layout,
+                            double* x_out_dev, uint8_t* ok_dev, uint8_t* converged_dev,
+                            int32_t* iters_dev, double* resid_dev, void* stream, float* kernel_ms);
+
+/* Algorithmic FLOPs per Newton iteration / per final evaluation for this handle's K
+ * (frozen in csrc/ccp_flops.h).                                                 */
+int ccp_algorithmic_flops(const ccp_handle* h, double* per_iteration, double* per_tail);
+
+const char* ccp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CCP_H_ */

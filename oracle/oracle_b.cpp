@@ -1,0 +1,150 @@
+// oracle_b.cpp — ORACLE-B: the ENGINE arithmetic (csrc/ccp_core.h) compiled for the host.
+//
+// TEST INFRASTRUCTURE ONLY.  The product never links this file.  Its one job is the bitwise
+// host/device reproducibility check: the CUDA kernels and this file include the same
+// __host__ __device__ header, are built with FP contraction off (nvcc --fmad=false,
+// g++ -ffp-contract=off) and explicit fma(), so projections must agree BIT FOR BIT
+// (tests/test_parity_gpu.py).  Correctness of the algorithm itself is pinned by ORACLE-A
+// (oracle_a.c), which shares no code with the engine.
+//
+// Follows: ConstraintFunction.h:31-40 (setInitialPosition), :43-55 (jointValid), :57-82 (project),
+// :84-102 (function), :114-120 (isSatisfied); panda_rbdl.cpp:9-42 (arm FK / Jacobian).
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "ccp.h"
+#include "ccp_core.h"
+#include "ccp_pack.h"
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+template <int K>
+static void function_batch(const ccp_model* M, const double* x, int64_t count, double* f) {
+  constexpr int n = 7 * K, m = 2 * (K - 1);
+#pragma omp parallel for schedule(static)
+  for (int64_t s = 0; s < count; ++s) {
+    ccp_fwd<K> F;
+    ccp_forward<K>(*M, x + s * n, F);
+    for (int k = 0; k < m; ++k) f[s * m + k] = F.f[k];
+  }
+}
+
+template <int K>
+static void jacobian_batch(const ccp_model* M, const double* x, int64_t count, double* Jout) {
+  constexpr int n = 7 * K, m = 2 * (K - 1);
+#pragma omp parallel for schedule(static)
+  for (int64_t s = 0; s < count; ++s) {
+    ccp_fwd<K> F;
+    ccp_jac<K> J;
+    ccp_forward<K>(*M, x + s * n, F);
+    ccp_jacobian<K>(*M, F, J);
+    ccp_jac_dense<K>(J, Jout + s * m * n);
+  }
+}
+
+template <int K>
+static void project_batch(const ccp_model* M, double* x, int64_t count, uint8_t* ok, uint8_t* conv,
+                          int32_t* iters, double* resid, int nthreads) {
+  constexpr int n = 7 * K, m = 2 * (K - 1);
+  (void)nthreads;
+#pragma omp parallel for schedule(dynamic, 64) num_threads(nthreads > 0 ? nthreads : 1)
+  for (int64_t s = 0; s < count; ++s) {
+    double f[m];
+    int32_t it;
+    bool c, o;
+    ccp_project_one<K>(*M, x + s * n, f, &it, &c, &o);
+    if (ok) ok[s] = o;
+    if (conv) conv[s] = c;
+    if (iters) iters[s] = it;
+    if (resid) for (int k = 0; k < m; ++k) resid[s * m + k] = f[k];
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int ob_model_size(void) { return (int)sizeof(ccp_model); }
+
+int ob_create(const ccp_model_desc* d, ccp_model* M) { return ccp_pack_model(d, M); }
+
+int ob_default_desc(int32_t n_arms, const int32_t* arm_index, ccp_model_desc* d) {
+  return ccp_fill_default_model(n_arms, arm_index, d);
+}
+
+void ob_set_reference(ccp_model* M, const double* q_start) {
+  if (M->n_arms == 2) ccp_reference_chain<2>(*M, q_start);
+  else ccp_reference_chain<3>(*M, q_start);
+}
+void ob_get_reference(const ccp_model* M, int pair, double* t0, double* q0) {
+  memcpy(t0, M->ref[pair].t0, 3 * sizeof(double));
+  memcpy(q0, M->ref[pair].q0, 4 * sizeof(double));
+}
+void ob_set_tolerance(ccp_model* M, double t1, double t2) { M->tol_p = t1; M->tol_r = t2; }
+void ob_set_options(ccp_model* M, double step, int max_iter, double margin) {
+  M->step = step; M->max_iter = max_iter; M->margin = margin;
+}
+
+void ob_function_batch(const ccp_model* M, const double* x, int64_t count, double* f) {
+  if (M->n_arms == 2) function_batch<2>(M, x, count, f);
+  else function_batch<3>(M, x, count, f);
+}
+
+void ob_jacobian_batch(const ccp_model* M, const double* x, int64_t count, double* J) {
+  if (M->n_arms == 2) jacobian_batch<2>(M, x, count, J);
+  else jacobian_batch<3>(M, x, count, J);
+}
+
+// x: AOS count x n, updated in place
+void ob_project_batch(const ccp_model* M, double* x, int64_t count, uint8_t* ok, uint8_t* conv,
+                      int32_t* iters, double* resid, int nthreads) {
+  if (M->n_arms == 2) project_batch<2>(M, x, count, ok, conv, iters, resid, nthreads);
+  else project_batch<3>(M, x, count, ok, conv, iters, resid, nthreads);
+}
+
+void ob_joint_valid_batch(const ccp_model* M, const double* x, int64_t count, uint8_t* out) {
+  const int n = 7 * M->n_arms;
+  for (int64_t s = 0; s < count; ++s)
+    out[s] = M->n_arms == 2 ? ccp_joint_valid<2>(*M, x + s * n) : ccp_joint_valid<3>(*M, x + s * n);
+}
+void ob_is_satisfied_batch(const ccp_model* M, const double* x, int64_t count, uint8_t* out) {
+  const int n = 7 * M->n_arms;
+  for (int64_t s = 0; s < count; ++s) {
+    if (M->n_arms == 2) {
+      ccp_fwd<2> F;
+      ccp_forward<2>(*M, x + s * n, F);
+      out[s] = ccp_is_satisfied<2>(*M, F.f);
+    } else {
+      ccp_fwd<3> F;
+      ccp_forward<3>(*M, x + s * n, F);
+      out[s] = ccp_is_satisfied<3>(*M, F.f);
+    }
+  }
+}
+
+void ob_arm_fk_batch(const ccp_model* M, int arm, const double* q, int64_t count, double* T, double* J) {
+  for (int64_t s = 0; s < count; ++s)
+    ccp_arm_fk(M->arm[arm], q + 7 * s, T ? T + 12 * s : nullptr, J ? J + 42 * s : nullptr);
+}
+
+void ob_seeds_uniform(const ccp_model* M, uint64_t seed, int64_t first, int64_t count, double* x) {
+  const int n = 7 * M->n_arms;
+  for (int64_t s = 0; s < count; ++s)
+    for (int j = 0; j < n; ++j) x[s * n + j] = ccp_seed_uniform(*M, seed, (uint64_t)(first + s), j);
+}
+
+void ob_enforce_bounds(double* x, int64_t n) {
+  for (int64_t i = 0; i < n; ++i) x[i] = ccp_wrap_pi(x[i]);
+}
+
+void ob_sincos(const double* x, int64_t n, double* s, double* c) {
+  for (int64_t i = 0; i < n; ++i) ccp_sincos(x[i], s + i, c + i);
+}
+void ob_atan2_pos(const double* y, const double* x, int64_t n, double* out) {
+  for (int64_t i = 0; i < n; ++i) out[i] = ccp_atan2_pos(y[i], x[i]);
+}
+
+}  // extern "C"
