@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py — converged closed-chain projections/s (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--count C] [--config NAME]
+
+A "step" is one pass of the hot path — KinematicChainConstraint::project (ConstraintFunction.h:57-82)
+batched over C synthetic Seeds-U (uniform in the joint bounds, counter-based stream) — on
+every rank.  Workload at N=1: BASELINE configs[1], dumbbell, 1M seeds (fits one GPU).  N>1: weak scaling,
+every rank projects its own C seeds from a disjoint counter range, then the ranks all-gather the converged
+counts and the compacted converged states over NCCL (the path's one exchange step).
+
+Printed JSON (rank 0, one line): see the keys built in main().  Definitions:
+  value        converged (project()==true) projections per second, whole job, seeds resident in HBM
+  e2e          same metric through the host-buffer C-ABI call (pinned host seeds in, results out)
+  roofline     FP64 pipe: algorithmic FLOPs (csrc/ccp_flops.h x the kernel's own per-sample iteration
+               counters) / CUDA-event time of the projection kernel, against the DFMA peak MEASURED in
+               this run by ccp_fp64_peak_probe (MEASURED_PEAKS.json has no FP64 entry)
+  cpu_baseline the reference-faithful CPU restatement (oracle A: FD Jacobian + SVD solve, = the
+               reference's arithmetic without RBDL/OMPL overhead) on all host cores, bounded sample
+--impl reference times that CPU restatement alone (the reference itself cannot be built here: OMPL,
+RBDL, Eigen, ROS are absent — DESIGN.md).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "converged closed-chain projections/sec"
+UNIT = "converged projections/s"
+
+
+def _env_int(k, d):
+    try:
+        return int(os.environ.get(k, d))
+    except ValueError:
+        return d
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [t.strip() for t in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+                pw.append(float(p[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def cpu_baseline(config: str, sample: int, threads: int):
+    """Oracle A (reference-faithful restatement) on the first `sample` Seeds-U of the workload."""
+    import numpy as np
+
+    from closed_chain_motion_planner_b200 import grasping_point
+    from oracle.oracle import OracleA
+
+    cfg = grasping_point().loadConfig(config)
+    A = OracleA(cfg.arm_indices)
+    A.set_initial_position(cfg.start)
+    seeds = A.seeds_uniform(0, 0, sample)
+    t0 = time.perf_counter()
+    r = A.project(seeds, fd=True, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return {"seconds": dt, "projections_per_s": sample / dt, "converged_per_s": float(r["ok"].sum()) / dt,
+            "ok_fraction": float(np.mean(r["ok"])), "mean_iters": float(np.mean(r["iters"]))}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path = oracle A on all host cores."""
+    rank = _env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    per_step = args.ref_sample
+    times = []
+    res = None
+    for i in range(args.warmup + args.steps):
+        res = cpu_baseline(args.config, per_step, threads)
+        if i >= args.warmup:
+            times.append(res["seconds"])
+    tot = sum(times)
+    value = res["ok_fraction"] * per_step * len(times) / tot
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.config} closed-chain projection, Seeds-U (bounded sample of the 1M-seed workload)",
+                   "seeds_per_step": per_step, "arms": 2},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"first {per_step} Seeds-U of {args.config} per step, oracle A (FD Jacobian + SVD solve, "
+                                   "OpenMP over all host cores); the reference itself is not buildable here"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "projections_per_s": per_step * len(times) / tot, "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="dumbbell")
+    ap.add_argument("--count", type=int, default=1_000_000, help="seeds per rank per step")
+    ap.add_argument("--cpu-sample", type=int, default=6000, help="seeds of the cpu_baseline leg")
+    ap.add_argument("--ref-sample", type=int, default=4000, help="seeds per step of --impl reference")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--layout", default="aos", choices=["aos", "soa"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import closed_chain_motion_planner_b200 as pkg
+    from closed_chain_motion_planner_b200 import _capi
+    import ctypes as C
+
+    rank, world, local = _env_int("RANK", 0), _env_int("WORLD_SIZE", 1), _env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    c = pkg.KinematicChainConstraint.from_config(args.config, device=local)
+    lib, h = c._lib, c._h
+    n, m = c.getAmbientDimension(), c.getCoDimension()
+    count = args.count
+    layout = pkg.CCP_LAYOUT_AOS if args.layout == "aos" else pkg.CCP_LAYOUT_SOA
+    shape = (count, n) if layout == pkg.CCP_LAYOUT_AOS else (n, count)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # measured FP64 peak of this GPU (register-only DFMA chains), before the timed region
+    peak_flops, _ = c.fp64PeakProbe(5)
+
+    # synthetic seeds, resident in HBM: a different slice of the counter stream per step and per rank
+    n_batches = min(args.warmup + args.steps, 8)
+    batches = []
+    for b in range(n_batches):
+        t = torch.empty(shape, dtype=torch.float64, device=dev)
+        a = _capi.SamplerArgs(rng_seed=0, first_index=(rank * 64 + b) * count, mode=0, wrap_bounds=0, distance=0.0,
+                              near_host=None)
+        assert lib.ccp_generate_seeds(h, C.byref(a), count, layout, t.data_ptr(), stream) == 0
+        batches.append(t)
+    x_out = torch.empty(shape, dtype=torch.float64, device=dev)
+    ok = torch.empty(count, dtype=torch.uint8, device=dev)
+    cv = torch.empty(count, dtype=torch.uint8, device=dev)
+    iters = torch.empty(count, dtype=torch.int32, device=dev)
+    compact = torch.empty((count, n), dtype=torch.float64, device=dev)
+    n_ok = torch.zeros(1, dtype=torch.int64, device=dev)
+    from closed_chain_motion_planner_b200.dist import gather_capacity, gather_converged
+
+    cap = gather_capacity(count)
+    pool = torch.empty((world, cap, n), dtype=torch.float64, device=dev) if world > 1 else None
+    counts_all = torch.zeros(world, dtype=torch.int64, device=dev)
+    max_count_seen = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def step(i, ev0=None, ev1=None):
+        n_ok.zero_()
+        if ev0 is not None:
+            ev0.record()
+        rc = lib.ccp_project_batch(h, batches[i % n_batches].data_ptr(), count, layout, x_out.data_ptr(), ok.data_ptr(),
+                                   cv.data_ptr(), iters.data_ptr(), None, compact.data_ptr(), n_ok.data_ptr(), stream)
+        assert rc == 0, lib.ccp_last_error(h)
+        if ev1 is not None:
+            ev1.record()
+        if world > 1:
+            # the path's one exchange step: converged counts + compacted converged states (fixed capacity,
+            # no host sync), NCCL all-gather over NVLink
+            gather_converged(compact, n_ok, cap, None, pool, counts_all)
+            torch.maximum(max_count_seen, counts_all.max().view(1), out=max_count_seen)
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = c.launchCount()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    total_ok = 0
+    total_flops = 0.0
+    total_iters = 0
+    fl_iter, fl_tail = c.algorithmicFlops()
+    t_begin.record()
+    per_step_stats = []
+    for s in range(args.steps):
+        step(args.warmup + s, *evs[s])
+        # per-step result read: the converged count (8 bytes) — keeps the kernel honest, stays on device
+        per_step_stats.append((n_ok.clone(), iters.sum(dtype=torch.int64)))
+    t_end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches = c.launchCount() - launches0
+    assert int(max_count_seen.item()) <= cap, "gather capacity overflow"
+    clocks = sampler.stop() if rank == 0 else None
+
+    ms_total = t_begin.elapsed_time(t_end)
+    kernel_ms = [a.elapsed_time(b) for a, b in evs]
+    for nk, its in per_step_stats:
+        total_ok += int(nk.item())
+        total_iters += int(its.item())
+    total_flops = total_iters * fl_iter + args.steps * count * fl_tail
+
+    # max over ranks of the timed region; sums over ranks of the work
+    tt = torch.tensor([ms_total, sum(kernel_ms)], dtype=torch.float64, device=dev)
+    ww = torch.tensor([float(total_ok), float(total_flops), float(total_iters)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ww, op=dist.ReduceOp.SUM)
+    ms_total_max, kernel_ms_sum_max = tt.tolist()
+    ok_all, flops_all, iters_all = ww.tolist()
+
+    # ---- e2e: the host-buffer C-ABI call, pinned host seeds, copies inside the timed region -------------
+    e2e = None
+    if not args.no_e2e:
+        hs = torch.empty((count, n), dtype=torch.float64).pin_memory()
+        src = batches[0] if layout == pkg.CCP_LAYOUT_AOS else batches[0].T.contiguous()
+        hs.copy_(src)
+        hx = torch.empty((count, n), dtype=torch.float64).pin_memory()
+        hok = torch.empty(count, dtype=torch.uint8).pin_memory()
+        hit = torch.empty(count, dtype=torch.int32).pin_memory()
+        torch.cuda.synchronize()
+        e_steps = max(3, min(args.steps, 5))
+        for _ in range(2):
+            assert lib.ccp_project_batch_host(h, hs.data_ptr(), count, hx.data_ptr(), hok.data_ptr(), None, hit.data_ptr(), None) == 0
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        ok_e2e = 0
+        for _ in range(e_steps):
+            assert lib.ccp_project_batch_host(h, hs.data_ptr(), count, hx.data_ptr(), hok.data_ptr(), None, hit.data_ptr(), None) == 0
+            ok_e2e += int(hok.sum().item())
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], dtype=torch.float64, device=dev)
+        oe = torch.tensor([float(ok_e2e)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            dist.all_reduce(oe, op=dist.ReduceOp.SUM)
+        e2e = {"value": oe.item() / te.item(), "unit": UNIT, "h2d_bytes_per_step": count * n * 8,
+               "d2h_bytes_per_step": count * (n * 8 + 1 + 4), "steps": e_steps,
+               "projections_per_s": world * count * e_steps / te.item(),
+               "api": "ccp_project_batch_host (pinned host AOS states in, states + ok + iters out)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    secs = ms_total_max * 1e-3
+    value = ok_all / secs
+    ksecs = kernel_ms_sum_max * 1e-3
+    achieved = (flops_all / world) / ksecs  # per-GPU FLOP/s of the projection kernel
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    alg_bytes = (2 * n * 8 + 1 + 1 + 4) * count  # seeds in, states out, ok, converged, iters
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.config} (configs/{args.config}.yaml) closed-chain projection, {count} uniform seeds per GPU per step",
+                   "seeds_per_gpu_per_step": count, "arms": c.k_, "layout": args.layout,
+                   "tolerances": [1e-3, 5e-3], "step": 0.30, "max_iter": 250,
+                   "l2": f"inputs+outputs {2 * count * n * 8 / 1e6:.0f} MB per step exceed the 126 MB L2; seed batches rotate over {n_batches} buffers",
+                   "exchange": "none" if world == 1 else "NCCL all_gather of counts + padded compacted converged states per step"},
+        "projections_per_s": world * count * args.steps / secs,
+        "ok_fraction": ok_all / (world * count * args.steps),
+        "mean_iters": iters_all / (world * count * args.steps),
+        "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": peak_flops / 1e12, "unit": "TFLOP/s",
+                     "frac": achieved / peak_flops, "traffic": None,
+                     "peak_source": "measured in this run: ccp_fp64_peak_probe (register-only DFMA chains, best of 5)",
+                     "flops_per_iteration": fl_iter, "flops_per_tail": fl_tail,
+                     "kernel_ms_per_launch": kernel_ms_sum_max / args.steps,
+                     "hbm": {"achieved_gbs": alg_bytes / (ksecs / args.steps) / 1e9, "peak_gbs": hbm_peak,
+                             "frac": alg_bytes / (ksecs / args.steps) / 1e9 / hbm_peak,
+                             "algorithmic_bytes_per_projection": 2 * n * 8 + 6,
+                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        cb = cpu_baseline(args.config, args.cpu_sample, threads)
+        line["cpu_baseline"] = {"value": cb["converged_per_s"], "unit": UNIT, "cores": threads, "kind": "port",
+                                "projections_per_s": cb["projections_per_s"], "mean_iters": cb["mean_iters"],
+                                "sample": f"first {args.cpu_sample} Seeds-U of {args.config}, oracle A (reference-faithful FD "
+                                          f"Jacobian + SVD solve) on {threads} threads, {cb['seconds']:.1f} s"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -78,7 +78,7 @@ SYMBOLS = {
     "ccp_get_options": (C.c_int, [_H, C.POINTER(Options), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ccp_function_batch": (C.c_int, [_H, _P, _I64, _I32, _P, _P]),
     "ccp_jacobian_batch": (C.c_int, [_H, _P, _I64, _I32, _P, _P]),
-    "ccp_project_batch": (C.c_int, [_H, _P, _I64, _I32, _P, _P, _P, _P, _P, _P]),
+    "ccp_project_batch": (C.c_int, [_H, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ccp_is_satisfied_batch": (C.c_int, [_H, _P, _I64, _I32, _P, _P]),
     "ccp_joint_valid_batch": (C.c_int, [_H, _P, _I64, _I32, _P, _P]),
     "ccp_fk_batch": (C.c_int, [_H, _I32, _P, _I64, _I32, _P, _P]),
@@ -91,7 +91,7 @@ SYMBOLS = {
     "ccp_jacobian_batch_host": (C.c_int, [_H, _P, _I64, _P]),
     "ccp_fp64_peak_probe": (C.c_int, [_H, _I32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ccp_launch_count": (C.c_int64, [_H]),
-    "ccp_project_batch_timed": (C.c_int, [_H, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_float)]),
+    "ccp_project_batch_timed": (C.c_int, [_H, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_float)]),
     "ccp_algorithmic_flops": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ccp_version": (C.c_char_p, []),
 }

@@ -1,0 +1,904 @@
+// ccp_kernels.cu — sm_100a kernels and the C ABI (include/ccp.h) of the batched closed-chain
+// constraint-projection engine.
+//
+// Kernel design (DESIGN.md has the long form):
+//   * one THREAD owns one sample: the matrices are 3-vectors and quaternions, nothing is a dense
+//     contraction, so every lane does useful FP64 work and no shuffles sit on the critical path;
+//   * the Newton loop is a persistent LANE-REFILL loop: the moment a lane's sample converges (or hits
+//     the 250-iteration cap) the lane writes its result and claims the next seed from a global
+//     counter, so the 18..250-iteration spread does not idle the warp;
+//   * the model (DH constants, frames, tolerances; 2.1 KB) is a __grid_constant__ kernel parameter:
+//     every use is an immediate constant-bank operand of the DFMA, no loads, no registers;
+//   * all arithmetic is the shared header ccp_core.h (explicit fma, --fmad=false).
+//
+// Reference behaviour replaced: KinematicChainConstraint::{function,jacobian,project,isSatisfied,
+// jointValid,setInitialPosition} (include/.../base/constraints/ConstraintFunction.h:31-120) and
+// PandaModel FK/Jacobian (src/kinematics/panda_rbdl.cpp:9-42).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <new>
+
+#include "ccp.h"
+#include "ccp_core.h"
+#include "ccp_flops.h"
+#include "ccp_pack.h"
+
+#define CCP_VERSION_STRING "ccp-b200 0.1 (sm_100a)"
+
+// ------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------
+#define CCP_NUM_COUNTERS 64
+
+struct ccp_handle {
+  int device;
+  int sm_count;
+  bool has_ref;
+  ccp_model model;  // host image; passed BY VALUE to every kernel
+  long long launches;
+  unsigned long long* d_counters;  // CCP_NUM_COUNTERS work counters (one per in-flight launch)
+  unsigned launch_seq;
+  // grow-only device staging for the *_host entry points
+  void* d_stage;
+  size_t d_stage_bytes;
+  cudaStream_t hstream[3];
+  cudaEvent_t ev0, ev1;
+  std::mutex mu;
+  char err[512];
+};
+
+static thread_local char g_create_err[512] = "";
+
+static int set_err(ccp_handle* h, int code, const char* fmt, const char* a = "", const char* b = "") {
+  char* dst = h ? h->err : g_create_err;
+  snprintf(dst, 512, fmt, a, b);
+  return code;
+}
+#define CCP_CUDA(call)                                                                             \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return set_err(h, CCP_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// state access (AOS: [count][n], SOA: [n][count])
+// ------------------------------------------------------------------------------------------
+template <bool SOA>
+__device__ __forceinline__ double ld_elem(const double* __restrict__ base, long long idx, int j, long long count,
+                                          int n) {
+  return SOA ? __ldg(base + (long long)j * count + idx) : __ldg(base + idx * n + j);
+}
+template <bool SOA>
+__device__ __forceinline__ void st_elem(double* __restrict__ base, long long idx, int j, long long count, int n,
+                                        double v) {
+  if (SOA) base[(long long)j * count + idx] = v;
+  else base[idx * n + j] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// projection kernel
+// ------------------------------------------------------------------------------------------
+struct ccp_project_args {
+  const double* seeds;  // nullptr when gen_mode >= 0
+  double* x_out;
+  uint8_t* ok;
+  uint8_t* conv;
+  int32_t* iters;
+  double* resid;
+  double* compact;             // AOS [<=count][n] of ok states, or nullptr
+  unsigned long long* n_ok;    // appended-to counter for `compact`
+  unsigned long long* counter; // work counter (zeroed before launch)
+  long long count;
+  int gen_mode;  // -1 load seeds; 0 uniform; 1 uniform-near; 2 gaussian
+  int wrap;
+  unsigned long long rng_seed;
+  long long first_index;
+  double distance;
+  double near[CCPC_DOF * CCPC_MAX_ARMS];
+};
+
+// warp-aggregated claim of the next sample index by the lanes currently finishing
+__device__ __forceinline__ long long claim_next(unsigned long long* counter) {
+  const unsigned mask = __activemask();
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(mask) - 1;
+  unsigned long long base = 0;
+  if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(mask));
+  base = __shfl_sync(mask, base, leader);
+  return (long long)(base + __popc(mask & ((1u << lane) - 1u)));
+}
+
+// Box-Muller pair member from two uniforms (mode 2).  log() is CUDA libm: the gaussian stream is
+// engine-defined; parity tests read the generated seeds back instead of regenerating them.
+__device__ __forceinline__ double gauss01(unsigned long long seed, unsigned long long sample, unsigned j) {
+  double u1 = ccp_uniform01(seed, sample, 2u * j + 64u);
+  double u2 = ccp_uniform01(seed, sample, 2u * j + 65u);
+  u1 = (u1 <= 0.0) ? 0x1.0p-53 : u1;
+  double s, c;
+  ccp_sincos(6.283185307179586476925 * u2, &s, &c);
+  return sqrt(-2.0 * log(u1)) * c;
+}
+
+template <int K>
+__device__ __forceinline__ double make_seed(const ccp_model& M, const ccp_project_args& A, long long idx, int j) {
+  const unsigned long long sample = (unsigned long long)(A.first_index + idx);
+  const int i = j % CCPC_DOF;
+  if (A.gen_mode == 0) return ccp_seed_uniform(M, A.rng_seed, sample, j);
+  if (A.gen_mode == 1) {
+    // RealVectorStateSampler::sampleUniformNear: U[max(lb, near-d), min(ub, near+d)]
+    double lo = A.near[j] - A.distance, hi = A.near[j] + A.distance;
+    lo = (lo < M.lb[i]) ? M.lb[i] : lo;
+    hi = (hi > M.ub[i]) ? M.ub[i] : hi;
+    return CCP_FMA(ccp_uniform01(A.rng_seed, sample, (unsigned)j), hi - lo, lo);
+  }
+  // RealVectorStateSampler::sampleGaussian: N(mean, stddev) clipped to the bounds
+  double v = CCP_FMA(gauss01(A.rng_seed, sample, (unsigned)j), A.distance, A.near[j]);
+  v = (v < M.lb[i]) ? M.lb[i] : v;
+  v = (v > M.ub[i]) ? M.ub[i] : v;
+  return v;
+}
+
+// GEN = false: seeds are read from memory (project).  GEN = true: seeds come from the counter-based
+// generator and the sampler epilogue (wrap, compaction) is compiled in (sample_project).
+template <int K, bool SOA, bool GEN, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
+ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ ccp_project_args A) {
+  constexpr int n = CCPC_DOF * K, m = 2 * (K - 1);
+  double x[n];
+  int it = 0;
+  long long idx = claim_next(A.counter);
+  if (idx < A.count) {
+    if (!GEN) {
+#pragma unroll
+      for (int j = 0; j < n; ++j) x[j] = ld_elem<SOA>(A.seeds, idx, j, A.count, n);
+    } else {
+#pragma unroll
+      for (int j = 0; j < n; ++j) x[j] = make_seed<K>(M, A, idx, j);
+    }
+  }
+  while (idx < A.count) {
+    ccp_fwd<K> F;
+    ccp_forward<K>(M, x, F);
+    const bool cont = ccp_needs_step<K>(M, F.f) && it < M.max_iter;
+    if (cont) {
+      ++it;
+      ccp_jac<K> J;
+      ccp_jacobian<K>(M, F, J);
+      ccp_newton_step<K>(M, F, J, x);
+    } else {
+      // ---- epilogue of this sample (ConstraintFunction.h:75-81), then refill the lane ----
+      const bool cv = ccp_converged<K>(M, F.f);
+      const bool okk = cv && ccp_joint_valid<K>(M, x);
+      if (GEN && A.wrap) {
+#pragma unroll
+        for (int j = 0; j < n; ++j) x[j] = ccp_wrap_pi(x[j]);
+      }
+      if (A.x_out) {
+#pragma unroll
+        for (int j = 0; j < n; ++j) st_elem<SOA>(A.x_out, idx, j, A.count, n, x[j]);
+      }
+      if (A.ok) A.ok[idx] = okk;
+      if (A.conv) A.conv[idx] = cv;
+      if (A.iters) A.iters[idx] = it;
+      if (A.resid) {
+#pragma unroll
+        for (int k = 0; k < m; ++k) st_elem<SOA>(A.resid, idx, k, A.count, m, F.f[k]);
+      }
+      if (A.n_ok && okk) {
+        const unsigned long long slot = atomicAdd(A.n_ok, 1ULL);
+        if (A.compact) {
+#pragma unroll
+          for (int j = 0; j < n; ++j) A.compact[slot * n + j] = x[j];
+        }
+      }
+      idx = claim_next(A.counter);
+      it = 0;
+      if (idx < A.count) {
+        if (!GEN) {
+#pragma unroll
+          for (int j = 0; j < n; ++j) x[j] = ld_elem<SOA>(A.seeds, idx, j, A.count, n);
+        } else {
+#pragma unroll
+          for (int j = 0; j < n; ++j) x[j] = make_seed<K>(M, A, idx, j);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// small batched kernels (thread per state, grid-stride)
+// ------------------------------------------------------------------------------------------
+template <int K, bool SOA>
+__global__ void __launch_bounds__(128)
+ccp_function_kernel(const __grid_constant__ ccp_model M, const double* __restrict__ xin, long long count,
+                    double* __restrict__ f, uint8_t* __restrict__ satisfied) {
+  constexpr int n = CCPC_DOF * K, m = 2 * (K - 1);
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < count;
+       idx += (long long)gridDim.x * blockDim.x) {
+    double x[n];
+#pragma unroll
+    for (int j = 0; j < n; ++j) x[j] = ld_elem<SOA>(xin, idx, j, count, n);
+    ccp_fwd<K> F;
+    ccp_forward<K>(M, x, F);
+    if (f) {
+#pragma unroll
+      for (int k = 0; k < m; ++k) st_elem<SOA>(f, idx, k, count, m, F.f[k]);
+    }
+    if (satisfied) satisfied[idx] = ccp_is_satisfied<K>(M, F.f);
+  }
+}
+
+template <int K, bool SOA>
+__global__ void __launch_bounds__(128)
+ccp_jacobian_kernel(const __grid_constant__ ccp_model M, const double* __restrict__ xin, long long count,
+                    double* __restrict__ Jout) {
+  constexpr int n = CCPC_DOF * K, m = 2 * (K - 1);
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < count;
+       idx += (long long)gridDim.x * blockDim.x) {
+    double x[n];
+#pragma unroll
+    for (int j = 0; j < n; ++j) x[j] = ld_elem<SOA>(xin, idx, j, count, n);
+    ccp_fwd<K> F;
+    ccp_jac<K> J;
+    ccp_forward<K>(M, x, F);
+    ccp_jacobian<K>(M, F, J);
+    double D[m * n];
+    ccp_jac_dense<K>(J, D);
+#pragma unroll
+    for (int k = 0; k < m * n; ++k) st_elem<SOA>(Jout, idx, k, count, m * n, D[k]);
+  }
+}
+
+template <int K, bool SOA>
+__global__ void __launch_bounds__(128)
+ccp_joint_valid_kernel(const __grid_constant__ ccp_model M, const double* __restrict__ xin, long long count,
+                       uint8_t* __restrict__ out) {
+  constexpr int n = CCPC_DOF * K;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < count;
+       idx += (long long)gridDim.x * blockDim.x) {
+    double x[n];
+#pragma unroll
+    for (int j = 0; j < n; ++j) x[j] = ld_elem<SOA>(xin, idx, j, count, n);
+    out[idx] = ccp_joint_valid<K>(M, x);
+  }
+}
+
+template <bool SOA>
+__global__ void __launch_bounds__(128)
+ccp_arm_fk_kernel(const __grid_constant__ ccp_model M, int arm, const double* __restrict__ qin, long long count,
+                  double* __restrict__ T, double* __restrict__ Jac) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < count;
+       idx += (long long)gridDim.x * blockDim.x) {
+    double q[CCPC_DOF];
+#pragma unroll
+    for (int j = 0; j < CCPC_DOF; ++j) q[j] = ld_elem<SOA>(qin, idx, j, count, CCPC_DOF);
+    double Tl[12], Jl[42];
+    // `arm` is uniform; select the arm with a switch so the model stays in the constant bank
+    switch (arm) {
+      case 0: ccp_arm_fk(M.arm[0], q, Tl, Jl); break;
+      case 1: ccp_arm_fk(M.arm[1], q, Tl, Jl); break;
+      default: ccp_arm_fk(M.arm[2], q, Tl, Jl); break;
+    }
+    if (T) {
+#pragma unroll
+      for (int k = 0; k < 12; ++k) st_elem<SOA>(T, idx, k, count, 12, Tl[k]);
+    }
+    if (Jac) {
+#pragma unroll
+      for (int k = 0; k < 42; ++k) st_elem<SOA>(Jac, idx, k, count, 42, Jl[k]);
+    }
+  }
+}
+
+template <int K, bool SOA>
+__global__ void __launch_bounds__(128)
+ccp_seed_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ ccp_project_args A,
+                double* __restrict__ out) {
+  constexpr int n = CCPC_DOF * K;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < A.count;
+       idx += (long long)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int j = 0; j < n; ++j) st_elem<SOA>(out, idx, j, A.count, n, make_seed<K>(M, A, idx, j));
+  }
+}
+
+__global__ void __launch_bounds__(256) ccp_wrap_kernel(double* __restrict__ x, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x)
+    x[i] = ccp_wrap_pi(x[i]);
+}
+
+template <int K>
+__global__ void ccp_reference_kernel(const __grid_constant__ ccp_model M, const double* __restrict__ q_start,
+                                     ccp_pair_ref* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  ccp_model L = M;
+  double q[CCPC_DOF * K];
+  for (int j = 0; j < CCPC_DOF * K; ++j) q[j] = q_start[j];
+  ccp_reference_chain<K>(L, q);
+  for (int p = 0; p < K - 1; ++p) out[p] = L.ref[p];
+}
+
+// Register-only DFMA chains: 8 independent accumulators per thread, `inner` x 8 x 2 FLOP per thread.
+__global__ void __launch_bounds__(256) ccp_dfma_probe_kernel(double* __restrict__ sink, int inner, double a, double b) {
+  double r0 = threadIdx.x * 1e-3, r1 = r0 + 1, r2 = r0 + 2, r3 = r0 + 3, r4 = r0 + 4, r5 = r0 + 5, r6 = r0 + 6,
+         r7 = r0 + 7;
+#pragma unroll 1
+  for (int i = 0; i < inner; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      r0 = fma(r0, a, b); r1 = fma(r1, a, b); r2 = fma(r2, a, b); r3 = fma(r3, a, b);
+      r4 = fma(r4, a, b); r5 = fma(r5, a, b); r6 = fma(r6, a, b); r7 = fma(r7, a, b);
+    }
+  }
+  double s = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+  if (s == 123.456) sink[0] = s;  // never true; keeps the chain alive
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static inline int grid_for(const ccp_handle* h, long long count, int block, int per_sm) {
+  long long need = (count + block - 1) / block;
+  long long cap = (long long)h->sm_count * per_sm;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+struct device_guard {
+  int prev;
+  bool ok;
+  explicit device_guard(int dev) : prev(-1), ok(false) {
+    if (cudaGetDevice(&prev) != cudaSuccess) return;
+    ok = (prev == dev) || (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~device_guard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+// projection launch configuration: BLOCK threads, MINB blocks per SM (persistent grid)
+#define CCP_PROJ_BLOCK 128
+#define CCP_PROJ_MINB_K2 3
+#define CCP_PROJ_MINB_K3 2
+
+template <int K, bool SOA>
+static cudaError_t launch_project_t(const ccp_handle* h, const ccp_project_args& A, cudaStream_t st) {
+  constexpr int MINB = (K == 2) ? CCP_PROJ_MINB_K2 : CCP_PROJ_MINB_K3;
+  long long need = (A.count + CCP_PROJ_BLOCK - 1) / CCP_PROJ_BLOCK;
+  long long cap = (long long)h->sm_count * MINB;
+  int grid = (int)(need < cap ? need : cap);
+  if (grid < 1) grid = 1;
+  if (A.gen_mode < 0) ccp_project_kernel<K, SOA, false, CCP_PROJ_BLOCK, MINB><<<grid, CCP_PROJ_BLOCK, 0, st>>>(h->model, A);
+  else ccp_project_kernel<K, SOA, true, CCP_PROJ_BLOCK, MINB><<<grid, CCP_PROJ_BLOCK, 0, st>>>(h->model, A);
+  return cudaGetLastError();
+}
+
+static int launch_project(ccp_handle* h, ccp_project_args& A, int layout, cudaStream_t st) {
+  if (!h->has_ref) return set_err(h, CCP_ERR_STATE, "%s", "project before ccp_set_reference (setInitialPosition)");
+  if (A.count == 0) return CCP_OK;
+  unsigned slot;
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    slot = h->launch_seq++ % CCP_NUM_COUNTERS;
+    h->launches++;
+  }
+  A.counter = h->d_counters + slot;
+  CCP_CUDA(cudaMemsetAsync(A.counter, 0, sizeof(unsigned long long), st));
+  cudaError_t e;
+  const bool soa = layout == CCP_LAYOUT_SOA;
+  if (h->model.n_arms == 2) e = soa ? launch_project_t<2, true>(h, A, st) : launch_project_t<2, false>(h, A, st);
+  else e = soa ? launch_project_t<3, true>(h, A, st) : launch_project_t<3, false>(h, A, st);
+  if (e != cudaSuccess) return set_err(h, CCP_ERR_CUDA, "project kernel launch: %s", cudaGetErrorString(e));
+  return CCP_OK;
+}
+
+static int check_common(ccp_handle* h, const void* p, int64_t count, int32_t layout) {
+  if (!h) return CCP_ERR_INVALID;
+  if (count < 0) return set_err(h, CCP_ERR_INVALID, "%s", "negative count");
+  if (count > 0 && !p) return set_err(h, CCP_ERR_INVALID, "%s", "null state pointer");
+  if (layout != CCP_LAYOUT_AOS && layout != CCP_LAYOUT_SOA) return set_err(h, CCP_ERR_INVALID, "%s", "bad layout");
+  return CCP_OK;
+}
+
+static int ensure_stage(ccp_handle* h, size_t bytes) {
+  if (bytes <= h->d_stage_bytes) return CCP_OK;
+  if (h->d_stage) cudaFree(h->d_stage);
+  h->d_stage = nullptr;
+  h->d_stage_bytes = 0;
+  size_t want = bytes + bytes / 4;
+  CCP_CUDA(cudaMalloc(&h->d_stage, want));
+  h->d_stage_bytes = want;
+  return CCP_OK;
+}
+
+extern "C" {
+
+const char* ccp_version(void) { return CCP_VERSION_STRING; }
+
+int ccp_default_model(int32_t n_arms, const int32_t* arm_index, ccp_model_desc* d) {
+  return ccp_fill_default_model(n_arms, arm_index, d) == 0 ? CCP_OK : CCP_ERR_INVALID;
+}
+
+int ccp_create(const ccp_model_desc* model, int32_t device, ccp_handle** out) {
+  ccp_handle* h = nullptr;
+  if (!model || !out) return set_err(nullptr, CCP_ERR_INVALID, "%s", "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return set_err(nullptr, CCP_ERR_CUDA, "%s", "no CUDA device: this engine has no CPU fallback");
+  if (device < 0 || device >= ndev) return set_err(nullptr, CCP_ERR_INVALID, "%s", "device index out of range");
+  ccp_model M;
+  if (ccp_pack_model(model, &M) != 0) return set_err(nullptr, CCP_ERR_INVALID, "%s", "invalid model (n_arms must be 2 or 3)");
+  ccp_handle* nh = new (std::nothrow) ccp_handle();
+  if (!nh) return set_err(nullptr, CCP_ERR_INVALID, "%s", "out of memory");
+  nh->device = device;
+  nh->model = M;
+  nh->has_ref = false;
+  nh->launches = 0;
+  nh->launch_seq = 0;
+  nh->d_stage = nullptr;
+  nh->d_stage_bytes = 0;
+  nh->err[0] = 0;
+  device_guard g(device);
+  cudaError_t e = g.ok ? cudaSuccess : cudaErrorInvalidDevice;
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&nh->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (e == cudaSuccess) e = cudaMalloc(&nh->d_counters, CCP_NUM_COUNTERS * sizeof(unsigned long long));
+  for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&nh->hstream[i], cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&nh->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&nh->ev1);
+  if (e != cudaSuccess) {
+    set_err(nullptr, CCP_ERR_CUDA, "ccp_create: %s", cudaGetErrorString(e));
+    delete nh;
+    return CCP_ERR_CUDA;
+  }
+  *out = nh;
+  return CCP_OK;
+}
+
+void ccp_destroy(ccp_handle* h) {
+  if (!h) return;
+  device_guard g(h->device);
+  cudaDeviceSynchronize();
+  if (h->d_counters) cudaFree(h->d_counters);
+  if (h->d_stage) cudaFree(h->d_stage);
+  for (int i = 0; i < 3; ++i) cudaStreamDestroy(h->hstream[i]);
+  cudaEventDestroy(h->ev0);
+  cudaEventDestroy(h->ev1);
+  delete h;
+}
+
+const char* ccp_last_error(const ccp_handle* h) { return h ? h->err : g_create_err; }
+int ccp_n_arms(const ccp_handle* h) { return h ? h->model.n_arms : CCP_ERR_INVALID; }
+int ccp_device(const ccp_handle* h) { return h ? h->device : CCP_ERR_INVALID; }
+int64_t ccp_launch_count(const ccp_handle* h) { return h ? h->launches : 0; }
+
+int ccp_set_reference(ccp_handle* h, const double* q_start_host) {
+  if (!h || !q_start_host) return h ? set_err(h, CCP_ERR_INVALID, "%s", "null q_start") : CCP_ERR_INVALID;
+  device_guard g(h->device);
+  const int n = CCPC_DOF * h->model.n_arms;
+  double* dq = nullptr;
+  ccp_pair_ref* dref = nullptr;
+  CCP_CUDA(cudaMalloc(&dq, sizeof(double) * n));
+  cudaError_t e = cudaMalloc(&dref, sizeof(ccp_pair_ref) * (CCPC_MAX_ARMS - 1));
+  if (e == cudaSuccess) e = cudaMemcpy(dq, q_start_host, sizeof(double) * n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    if (h->model.n_arms == 2) ccp_reference_kernel<2><<<1, 32>>>(h->model, dq, dref);
+    else ccp_reference_kernel<3><<<1, 32>>>(h->model, dq, dref);
+    e = cudaGetLastError();
+    h->launches++;
+  }
+  ccp_pair_ref ref[CCPC_MAX_ARMS - 1];
+  if (e == cudaSuccess)
+    e = cudaMemcpy(ref, dref, sizeof(ccp_pair_ref) * (h->model.n_arms - 1), cudaMemcpyDeviceToHost);
+  cudaFree(dq);
+  if (dref) cudaFree(dref);
+  if (e != cudaSuccess) return set_err(h, CCP_ERR_CUDA, "ccp_set_reference: %s", cudaGetErrorString(e));
+  for (int p = 0; p < h->model.n_arms - 1; ++p) h->model.ref[p] = ref[p];
+  h->has_ref = true;
+  return CCP_OK;
+}
+
+int ccp_get_reference(const ccp_handle* h, int32_t pair, double* t0_host, double* q0_host) {
+  if (!h || pair < 0 || pair >= h->model.n_arms - 1 || !h->has_ref) return CCP_ERR_INVALID;
+  if (t0_host) memcpy(t0_host, h->model.ref[pair].t0, 3 * sizeof(double));
+  if (q0_host) memcpy(q0_host, h->model.ref[pair].q0, 4 * sizeof(double));
+  return CCP_OK;
+}
+
+int ccp_set_tolerance(ccp_handle* h, double tol_position, double tol_rotation) {
+  if (!h) return CCP_ERR_INVALID;
+  if (!(tol_position > 0) || !(tol_rotation > 0))
+    return set_err(h, CCP_ERR_INVALID, "%s", "setTolerance: tolerance must be positive.");
+  h->model.tol_p = tol_position;
+  h->model.tol_r = tol_rotation;
+  return CCP_OK;
+}
+
+int ccp_set_options(ccp_handle* h, const ccp_options* opt) {
+  if (!h || !opt) return CCP_ERR_INVALID;
+  if (!(opt->step > 0) || opt->max_iter < 0 || !(opt->joint_margin >= 0))
+    return set_err(h, CCP_ERR_INVALID, "%s", "bad options");
+  h->model.step = opt->step;
+  h->model.max_iter = opt->max_iter;
+  h->model.margin = opt->joint_margin;
+  return CCP_OK;
+}
+
+int ccp_get_options(const ccp_handle* h, ccp_options* opt, double* tol_position, double* tol_rotation) {
+  if (!h) return CCP_ERR_INVALID;
+  if (opt) {
+    opt->step = h->model.step;
+    opt->max_iter = h->model.max_iter;
+    opt->reserved = 0;
+    opt->joint_margin = h->model.margin;
+  }
+  if (tol_position) *tol_position = h->model.tol_p;
+  if (tol_rotation) *tol_rotation = h->model.tol_r;
+  return CCP_OK;
+}
+
+int ccp_algorithmic_flops(const ccp_handle* h, double* per_iteration, double* per_tail) {
+  if (!h) return CCP_ERR_INVALID;
+  const bool k2 = h->model.n_arms == 2;
+  if (per_iteration) *per_iteration = k2 ? CCP_FLOPS_ITER_K2 : CCP_FLOPS_ITER_K3;
+  if (per_tail) *per_tail = k2 ? CCP_FLOPS_TAIL_K2 : CCP_FLOPS_TAIL_K3;
+  return CCP_OK;
+}
+
+static int function_impl(ccp_handle* h, const double* x_dev, int64_t count, int32_t layout, double* f_dev,
+                         uint8_t* sat_dev, void* stream) {
+  int rc = check_common(h, x_dev, count, layout);
+  if (rc) return rc;
+  if (!h->has_ref) return set_err(h, CCP_ERR_STATE, "%s", "function before ccp_set_reference (setInitialPosition)");
+  if (count == 0) return CCP_OK;
+  device_guard g(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for(h, count, 128, 8);
+  const bool soa = layout == CCP_LAYOUT_SOA;
+  if (h->model.n_arms == 2) {
+    if (soa) ccp_function_kernel<2, true><<<grid, 128, 0, st>>>(h->model, x_dev, count, f_dev, sat_dev);
+    else ccp_function_kernel<2, false><<<grid, 128, 0, st>>>(h->model, x_dev, count, f_dev, sat_dev);
+  } else {
+    if (soa) ccp_function_kernel<3, true><<<grid, 128, 0, st>>>(h->model, x_dev, count, f_dev, sat_dev);
+    else ccp_function_kernel<3, false><<<grid, 128, 0, st>>>(h->model, x_dev, count, f_dev, sat_dev);
+  }
+  h->launches++;
+  CCP_CUDA(cudaGetLastError());
+  return CCP_OK;
+}
+
+int ccp_function_batch(ccp_handle* h, const double* x_dev, int64_t count, int32_t layout, double* f_dev,
+                       void* stream) {
+  if (h && count > 0 && !f_dev) return set_err(h, CCP_ERR_INVALID, "%s", "null output");
+  return function_impl(h, x_dev, count, layout, f_dev, nullptr, stream);
+}
+
+int ccp_is_satisfied_batch(ccp_handle* h, const double* x_dev, int64_t count, int32_t layout, uint8_t* out_dev,
+                           void* stream) {
+  if (h && count > 0 && !out_dev) return set_err(h, CCP_ERR_INVALID, "%s", "null output");
+  return function_impl(h, x_dev, count, layout, nullptr, out_dev, stream);
+}
+
+int ccp_jacobian_batch(ccp_handle* h, const double* x_dev, int64_t count, int32_t layout, double* J_dev,
+                       void* stream) {
+  int rc = check_common(h, x_dev, count, layout);
+  if (rc) return rc;
+  if (count > 0 && !J_dev) return set_err(h, CCP_ERR_INVALID, "%s", "null output");
+  if (!h->has_ref) return set_err(h, CCP_ERR_STATE, "%s", "jacobian before ccp_set_reference (setInitialPosition)");
+  if (count == 0) return CCP_OK;
+  device_guard g(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for(h, count, 128, 4);
+  const bool soa = layout == CCP_LAYOUT_SOA;
+  if (h->model.n_arms == 2) {
+    if (soa) ccp_jacobian_kernel<2, true><<<grid, 128, 0, st>>>(h->model, x_dev, count, J_dev);
+    else ccp_jacobian_kernel<2, false><<<grid, 128, 0, st>>>(h->model, x_dev, count, J_dev);
+  } else {
+    if (soa) ccp_jacobian_kernel<3, true><<<grid, 128, 0, st>>>(h->model, x_dev, count, J_dev);
+    else ccp_jacobian_kernel<3, false><<<grid, 128, 0, st>>>(h->model, x_dev, count, J_dev);
+  }
+  h->launches++;
+  CCP_CUDA(cudaGetLastError());
+  return CCP_OK;
+}
+
+int ccp_joint_valid_batch(ccp_handle* h, const double* x_dev, int64_t count, int32_t layout, uint8_t* out_dev,
+                          void* stream) {
+  int rc = check_common(h, x_dev, count, layout);
+  if (rc) return rc;
+  if (count > 0 && !out_dev) return set_err(h, CCP_ERR_INVALID, "%s", "null output");
+  if (count == 0) return CCP_OK;
+  device_guard g(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for(h, count, 128, 8);
+  const bool soa = layout == CCP_LAYOUT_SOA;
+  if (h->model.n_arms == 2) {
+    if (soa) ccp_joint_valid_kernel<2, true><<<grid, 128, 0, st>>>(h->model, x_dev, count, out_dev);
+    else ccp_joint_valid_kernel<2, false><<<grid, 128, 0, st>>>(h->model, x_dev, count, out_dev);
+  } else {
+    if (soa) ccp_joint_valid_kernel<3, true><<<grid, 128, 0, st>>>(h->model, x_dev, count, out_dev);
+    else ccp_joint_valid_kernel<3, false><<<grid, 128, 0, st>>>(h->model, x_dev, count, out_dev);
+  }
+  h->launches++;
+  CCP_CUDA(cudaGetLastError());
+  return CCP_OK;
+}
+
+static int arm_fk_impl(ccp_handle* h, int32_t arm, const double* q_dev, int64_t count, int32_t layout, double* T_dev,
+                       double* J_dev, void* stream) {
+  int rc = check_common(h, q_dev, count, layout);
+  if (rc) return rc;
+  if (arm < 0 || arm >= h->model.n_arms) return set_err(h, CCP_ERR_INVALID, "%s", "arm index out of range");
+  if (count == 0) return CCP_OK;
+  device_guard g(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for(h, count, 128, 4);
+  if (layout == CCP_LAYOUT_SOA) ccp_arm_fk_kernel<true><<<grid, 128, 0, st>>>(h->model, arm, q_dev, count, T_dev, J_dev);
+  else ccp_arm_fk_kernel<false><<<grid, 128, 0, st>>>(h->model, arm, q_dev, count, T_dev, J_dev);
+  h->launches++;
+  CCP_CUDA(cudaGetLastError());
+  return CCP_OK;
+}
+
+int ccp_fk_batch(ccp_handle* h, int32_t arm, const double* q_dev, int64_t count, int32_t layout, double* T_dev,
+                 void* stream) {
+  if (h && count > 0 && !T_dev) return set_err(h, CCP_ERR_INVALID, "%s", "null output");
+  return arm_fk_impl(h, arm, q_dev, count, layout, T_dev, nullptr, stream);
+}
+
+int ccp_arm_jacobian_batch(ccp_handle* h, int32_t arm, const double* q_dev, int64_t count, int32_t layout,
+                           double* J_dev, void* stream) {
+  if (h && count > 0 && !J_dev) return set_err(h, CCP_ERR_INVALID, "%s", "null output");
+  return arm_fk_impl(h, arm, q_dev, count, layout, nullptr, J_dev, stream);
+}
+
+int ccp_project_batch(ccp_handle* h, const double* seeds_dev, int64_t count, int32_t layout, double* x_out_dev,
+                      uint8_t* ok_dev, uint8_t* converged_dev, int32_t* iters_dev, double* resid_dev,
+                      double* compact_dev, int64_t* n_ok_dev, void* stream) {
+  int rc = check_common(h, seeds_dev, count, layout);
+  if (rc) return rc;
+  if (compact_dev && !n_ok_dev) return set_err(h, CCP_ERR_INVALID, "%s", "compact output needs n_ok");
+  device_guard g(h->device);
+  ccp_project_args A;
+  memset(&A, 0, sizeof A);
+  A.seeds = seeds_dev;
+  A.x_out = x_out_dev;
+  A.ok = ok_dev;
+  A.conv = converged_dev;
+  A.iters = iters_dev;
+  A.resid = resid_dev;
+  A.compact = compact_dev;
+  A.n_ok = (unsigned long long*)n_ok_dev;
+  A.count = count;
+  A.gen_mode = -1;
+  return launch_project(h, A, layout, (cudaStream_t)stream);
+}
+
+int ccp_project_batch_timed(ccp_handle* h, const double* seeds_dev, int64_t count, int32_t layout, double* x_out_dev,
+                            uint8_t* ok_dev, uint8_t* converged_dev, int32_t* iters_dev, double* resid_dev,
+                            double* compact_dev, int64_t* n_ok_dev, void* stream, float* kernel_ms) {
+  if (!h) return CCP_ERR_INVALID;
+  device_guard g(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  CCP_CUDA(cudaEventRecord(h->ev0, st));
+  int rc = ccp_project_batch(h, seeds_dev, count, layout, x_out_dev, ok_dev, converged_dev, iters_dev, resid_dev,
+                             compact_dev, n_ok_dev, stream);
+  if (rc) return rc;
+  CCP_CUDA(cudaEventRecord(h->ev1, st));
+  CCP_CUDA(cudaEventSynchronize(h->ev1));
+  float ms = 0.f;
+  CCP_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  if (kernel_ms) *kernel_ms = ms;
+  return CCP_OK;
+}
+
+static int fill_sampler_args(ccp_handle* h, const ccp_sampler_args* a, int64_t count, ccp_project_args* A) {
+  if (!a) return set_err(h, CCP_ERR_INVALID, "%s", "null sampler args");
+  if (a->mode < 0 || a->mode > 2) return set_err(h, CCP_ERR_INVALID, "%s", "sampler mode must be 0, 1 or 2");
+  if (a->mode != 0 && !a->near_host) return set_err(h, CCP_ERR_INVALID, "%s", "near state required for modes 1, 2");
+  memset(A, 0, sizeof *A);
+  A->count = count;
+  A->gen_mode = a->mode;
+  A->wrap = a->wrap_bounds;
+  A->rng_seed = a->rng_seed;
+  A->first_index = a->first_index;
+  A->distance = a->distance;
+  if (a->near_host)
+    for (int j = 0; j < CCPC_DOF * h->model.n_arms; ++j) A->near[j] = a->near_host[j];
+  return CCP_OK;
+}
+
+int ccp_generate_seeds(ccp_handle* h, const ccp_sampler_args* a, int64_t count, int32_t layout, double* seeds_dev,
+                       void* stream) {
+  int rc = check_common(h, seeds_dev, count, layout);
+  if (rc) return rc;
+  ccp_project_args A;
+  rc = fill_sampler_args(h, a, count, &A);
+  if (rc) return rc;
+  if (count == 0) return CCP_OK;
+  device_guard g(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for(h, count, 128, 8);
+  const bool soa = layout == CCP_LAYOUT_SOA;
+  if (h->model.n_arms == 2) {
+    if (soa) ccp_seed_kernel<2, true><<<grid, 128, 0, st>>>(h->model, A, seeds_dev);
+    else ccp_seed_kernel<2, false><<<grid, 128, 0, st>>>(h->model, A, seeds_dev);
+  } else {
+    if (soa) ccp_seed_kernel<3, true><<<grid, 128, 0, st>>>(h->model, A, seeds_dev);
+    else ccp_seed_kernel<3, false><<<grid, 128, 0, st>>>(h->model, A, seeds_dev);
+  }
+  h->launches++;
+  CCP_CUDA(cudaGetLastError());
+  return CCP_OK;
+}
+
+int ccp_sample_project_batch(ccp_handle* h, const ccp_sampler_args* a, int64_t count, int32_t layout,
+                             double* x_out_dev, uint8_t* ok_dev, int32_t* iters_dev, double* compact_dev,
+                             int64_t* n_ok_dev, void* stream) {
+  if (!h) return CCP_ERR_INVALID;
+  if (count < 0) return set_err(h, CCP_ERR_INVALID, "%s", "negative count");
+  if (layout != CCP_LAYOUT_AOS && layout != CCP_LAYOUT_SOA) return set_err(h, CCP_ERR_INVALID, "%s", "bad layout");
+  if (compact_dev && !n_ok_dev) return set_err(h, CCP_ERR_INVALID, "%s", "compact output needs n_ok");
+  ccp_project_args A;
+  int rc = fill_sampler_args(h, a, count, &A);
+  if (rc) return rc;
+  A.x_out = x_out_dev;
+  A.ok = ok_dev;
+  A.iters = iters_dev;
+  A.compact = compact_dev;
+  A.n_ok = (unsigned long long*)n_ok_dev;
+  device_guard g(h->device);
+  return launch_project(h, A, layout, (cudaStream_t)stream);
+}
+
+int ccp_enforce_bounds_batch(ccp_handle* h, double* x_dev, int64_t count, int32_t layout, void* stream) {
+  int rc = check_common(h, x_dev, count, layout);
+  if (rc) return rc;
+  if (count == 0) return CCP_OK;
+  device_guard g(h->device);
+  const long long total = (long long)count * CCPC_DOF * h->model.n_arms;
+  ccp_wrap_kernel<<<grid_for(h, total, 256, 8), 256, 0, (cudaStream_t)stream>>>(x_dev, total);
+  h->launches++;
+  CCP_CUDA(cudaGetLastError());
+  return CCP_OK;
+}
+
+// ---- host-buffer entry points ------------------------------------------------------------
+// Chunked 3-stage pipeline over the handle's private streams: H2D(i) | project(i) | D2H(i).
+// With pinned caller buffers the copies overlap the kernels; with pageable buffers CUDA stages
+// them internally and the call is still correct.
+int ccp_project_batch_host(ccp_handle* h, const double* seeds_host, int64_t count, double* x_out_host,
+                           uint8_t* ok_host, uint8_t* converged_host, int32_t* iters_host, double* resid_host) {
+  int rc = check_common(h, seeds_host, count, CCP_LAYOUT_AOS);
+  if (rc) return rc;
+  if (!h->has_ref) return set_err(h, CCP_ERR_STATE, "%s", "project before ccp_set_reference (setInitialPosition)");
+  if (count == 0) return CCP_OK;
+  device_guard g(h->device);
+  const int n = CCPC_DOF * h->model.n_arms, m = 2 * (h->model.n_arms - 1);
+  const size_t per = sizeof(double) * n + sizeof(double) * m + 8 /* ok, conv, pad */ + sizeof(int32_t) + 4;
+  rc = ensure_stage(h, per * (size_t)count + 1024);
+  if (rc) return rc;
+  // carve the stage: x [count][n] | resid [count][m] | iters | ok | conv
+  char* base = (char*)h->d_stage;
+  double* dx = (double*)base;
+  double* dres = (double*)(base + sizeof(double) * n * (size_t)count);
+  int32_t* dit = (int32_t*)((char*)dres + sizeof(double) * m * (size_t)count);
+  uint8_t* dok = (uint8_t*)((char*)dit + sizeof(int32_t) * (size_t)count);
+  uint8_t* dcv = dok + (size_t)count;
+  // chunking: big enough to fill the persistent grid several times over, small enough to overlap
+  int64_t chunk = count;
+  const int64_t min_chunk = (int64_t)h->sm_count * CCP_PROJ_BLOCK * 3 * 4;
+  if (count >= 4 * min_chunk) {
+    int64_t parts = count / min_chunk;
+    if (parts > 16) parts = 16;
+    chunk = (count + parts - 1) / parts;
+  }
+  int ci = 0;
+  for (int64_t off = 0; off < count; off += chunk, ++ci) {
+    const int64_t c = (count - off < chunk) ? (count - off) : chunk;
+    cudaStream_t st = h->hstream[ci % 3];
+    CCP_CUDA(cudaMemcpyAsync(dx + off * n, seeds_host + off * n, sizeof(double) * n * c, cudaMemcpyHostToDevice, st));
+    ccp_project_args A;
+    memset(&A, 0, sizeof A);
+    A.seeds = dx + off * n;
+    A.x_out = dx + off * n;
+    A.ok = dok + off;
+    A.conv = dcv + off;
+    A.iters = dit + off;
+    A.resid = dres + off * m;
+    A.count = c;
+    A.gen_mode = -1;
+    rc = launch_project(h, A, CCP_LAYOUT_AOS, st);
+    if (rc) return rc;
+    if (x_out_host)
+      CCP_CUDA(cudaMemcpyAsync(x_out_host + off * n, dx + off * n, sizeof(double) * n * c, cudaMemcpyDeviceToHost, st));
+    if (ok_host) CCP_CUDA(cudaMemcpyAsync(ok_host + off, dok + off, (size_t)c, cudaMemcpyDeviceToHost, st));
+    if (converged_host) CCP_CUDA(cudaMemcpyAsync(converged_host + off, dcv + off, (size_t)c, cudaMemcpyDeviceToHost, st));
+    if (iters_host) CCP_CUDA(cudaMemcpyAsync(iters_host + off, dit + off, sizeof(int32_t) * c, cudaMemcpyDeviceToHost, st));
+    if (resid_host)
+      CCP_CUDA(cudaMemcpyAsync(resid_host + off * m, dres + off * m, sizeof(double) * m * c, cudaMemcpyDeviceToHost, st));
+  }
+  for (int i = 0; i < 3; ++i) CCP_CUDA(cudaStreamSynchronize(h->hstream[i]));
+  return CCP_OK;
+}
+
+int ccp_function_batch_host(ccp_handle* h, const double* x_host, int64_t count, double* f_host) {
+  int rc = check_common(h, x_host, count, CCP_LAYOUT_AOS);
+  if (rc) return rc;
+  if (count > 0 && !f_host) return set_err(h, CCP_ERR_INVALID, "%s", "null output");
+  if (count == 0) return CCP_OK;
+  device_guard g(h->device);
+  const int n = CCPC_DOF * h->model.n_arms, m = 2 * (h->model.n_arms - 1);
+  rc = ensure_stage(h, sizeof(double) * (n + m) * (size_t)count);
+  if (rc) return rc;
+  double* dx = (double*)h->d_stage;
+  double* df = dx + (size_t)n * count;
+  cudaStream_t st = h->hstream[0];
+  CCP_CUDA(cudaMemcpyAsync(dx, x_host, sizeof(double) * n * count, cudaMemcpyHostToDevice, st));
+  rc = ccp_function_batch(h, dx, count, CCP_LAYOUT_AOS, df, st);
+  if (rc) return rc;
+  CCP_CUDA(cudaMemcpyAsync(f_host, df, sizeof(double) * m * count, cudaMemcpyDeviceToHost, st));
+  CCP_CUDA(cudaStreamSynchronize(st));
+  return CCP_OK;
+}
+
+int ccp_jacobian_batch_host(ccp_handle* h, const double* x_host, int64_t count, double* J_host) {
+  int rc = check_common(h, x_host, count, CCP_LAYOUT_AOS);
+  if (rc) return rc;
+  if (count > 0 && !J_host) return set_err(h, CCP_ERR_INVALID, "%s", "null output");
+  if (count == 0) return CCP_OK;
+  device_guard g(h->device);
+  const int n = CCPC_DOF * h->model.n_arms, m = 2 * (h->model.n_arms - 1);
+  rc = ensure_stage(h, sizeof(double) * (n + (size_t)m * n) * (size_t)count);
+  if (rc) return rc;
+  double* dx = (double*)h->d_stage;
+  double* dJ = dx + (size_t)n * count;
+  cudaStream_t st = h->hstream[0];
+  CCP_CUDA(cudaMemcpyAsync(dx, x_host, sizeof(double) * n * count, cudaMemcpyHostToDevice, st));
+  rc = ccp_jacobian_batch(h, dx, count, CCP_LAYOUT_AOS, dJ, st);
+  if (rc) return rc;
+  CCP_CUDA(cudaMemcpyAsync(J_host, dJ, sizeof(double) * m * n * count, cudaMemcpyDeviceToHost, st));
+  CCP_CUDA(cudaStreamSynchronize(st));
+  return CCP_OK;
+}
+
+int ccp_fp64_peak_probe(ccp_handle* h, int32_t repeats, double* flops_per_s, double* ms_out) {
+  if (!h) return CCP_ERR_INVALID;
+  device_guard g(h->device);
+  if (repeats < 1) repeats = 1;
+  const int inner = 4096;
+  const int grid = h->sm_count * 8, block = 256;
+  double* sink = nullptr;
+  CCP_CUDA(cudaMalloc(&sink, sizeof(double)));
+  cudaStream_t st = h->hstream[0];
+  ccp_dfma_probe_kernel<<<grid, block, 0, st>>>(sink, 64, 1.0000001, 1e-9);  // warm-up
+  float best = 1e30f;
+  for (int r = 0; r < repeats; ++r) {
+    cudaEventRecord(h->ev0, st);
+    ccp_dfma_probe_kernel<<<grid, block, 0, st>>>(sink, inner, 1.0000001, 1e-9);
+    cudaEventRecord(h->ev1, st);
+    cudaError_t e = cudaEventSynchronize(h->ev1);
+    if (e != cudaSuccess) {
+      cudaFree(sink);
+      return set_err(h, CCP_ERR_CUDA, "fp64 probe: %s", cudaGetErrorString(e));
+    }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    if (ms < best) best = ms;
+    h->launches++;
+  }
+  cudaFree(sink);
+  const double flops = (double)grid * block * (double)inner * 16.0 * 8.0 * 2.0;
+  if (flops_per_s) *flops_per_s = flops / (best * 1e-3);
+  if (ms_out) *ms_out = best;
+  return CCP_OK;
+}
+
+}  // extern "C"

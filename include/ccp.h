@@ -119,10 +119,15 @@ int ccp_jacobian_batch(ccp_handle* h, const double* x_dev, int64_t count, int32_
  *   converged[i] = residual under tolerance at exit (f0 <= tol1 and f1 < tol2 for every pair)
  *   iters[i]     = Newton steps taken (0..max_iter)
  *   resid        = final function(x): SOA double[m][count] / AOS double[count][m]
+ *   compact_dev  = AOS double[<=count][n]: the states with ok==1 densely packed by the kernel's
+ *                  epilogue (order unspecified), ready for the multi-GPU all-gather;
+ *   n_ok_dev     = int64 device counter the kernel ADDS the number of ok states to (caller zeroes
+ *                  it); required when compact_dev != NULL, optional otherwise.
  * The last iterate is written to x_out even on failure (reference semantics).               */
 int ccp_project_batch(ccp_handle* h, const double* seeds_dev, int64_t count, int32_t layout,
                       double* x_out_dev, uint8_t* ok_dev, uint8_t* converged_dev,
-                      int32_t* iters_dev, double* resid_dev, void* stream);
+                      int32_t* iters_dev, double* resid_dev, double* compact_dev,
+                      int64_t* n_ok_dev, void* stream);
 
 /* ≙ isSatisfied (ConstraintFunction.h:114-120): finite and f0 <= tol1 and f1 <= tol2.       */
 int ccp_is_satisfied_batch(ccp_handle* h, const double* x_dev, int64_t count, int32_t layout,
@@ -186,11 +191,11 @@ int ccp_jacobian_batch_host(ccp_handle* h, const double* x_host, int64_t count, 
 int ccp_fp64_peak_probe(ccp_handle* h, int32_t repeats, double* flops_per_s, double* ms);
 /* Number of engine kernels launched through this handle since creation. */
 int64_t ccp_launch_count(const ccp_handle* h);
-/* Time (ms, CUDA events on the launching stream) of the last projection kernel launched by a
- * *_host call or by ccp_project_batch_timed.                                                */
+/* ccp_project_batch bracketed by CUDA events on `stream`; synchronises and returns the kernel time. */
 int ccp_project_batch_timed(ccp_handle* h, const double* seeds_dev, int64_t count, int32_t layout,
                             double* x_out_dev, uint8_t* ok_dev, uint8_t* converged_dev,
-                            int32_t* iters_dev, double* resid_dev, void* stream, float* kernel_ms);
+                            int32_t* iters_dev, double* resid_dev, double* compact_dev,
+                            int64_t* n_ok_dev, void* stream, float* kernel_ms);
 
 /* Algorithmic FLOPs per Newton iteration / per final evaluation for this handle's K
  * (frozen in csrc/ccp_flops.h).                                                 */
