@@ -235,6 +235,7 @@ def main():
 
     for i in range(args.warmup):
         step(i)
+        _ = (n_ok.clone(), iters.sum(dtype=torch.int64))  # same (torch) bookkeeping ops as the timed loop: loads them once
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

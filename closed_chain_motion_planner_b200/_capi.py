@@ -89,6 +89,7 @@ SYMBOLS = {
     "ccp_project_batch_host": (C.c_int, [_H, _P, _I64, _P, _P, _P, _P, _P]),
     "ccp_function_batch_host": (C.c_int, [_H, _P, _I64, _P]),
     "ccp_jacobian_batch_host": (C.c_int, [_H, _P, _I64, _P]),
+    "ccp_arm_fk_batch_host": (C.c_int, [_H, _I32, _P, _I64, _P, _P]),
     "ccp_fp64_peak_probe": (C.c_int, [_H, _I32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ccp_launch_count": (C.c_int64, [_H]),
     "ccp_project_batch_timed": (C.c_int, [_H, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_float)]),

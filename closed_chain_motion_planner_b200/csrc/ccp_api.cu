@@ -1,4 +1,4 @@
-// ccp_kernels.cu — sm_100a kernels and the C ABI (include/ccp.h) of the batched closed-chain
+// ccp_api.cu — the small batched kernels and the C ABI (include/ccp.h) of the batched closed-chain
 // constraint-projection engine.
 //
 // Kernel design (DESIGN.md has the long form):
@@ -17,13 +17,17 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
 #include <new>
+#include <type_traits>
 
 #include "ccp.h"
 #include "ccp_core.h"
+#include "ccp_device.cuh"
+#include "ccp_internal.h"
 #include "ccp_flops.h"
 #include "ccp_pack.h"
 
@@ -65,155 +69,9 @@ static int set_err(ccp_handle* h, int code, const char* fmt, const char* a = "",
   } while (0)
 
 // ------------------------------------------------------------------------------------------
-// state access (AOS: [count][n], SOA: [n][count])
-// ------------------------------------------------------------------------------------------
-template <bool SOA>
-__device__ __forceinline__ double ld_elem(const double* __restrict__ base, long long idx, int j, long long count,
-                                          int n) {
-  return SOA ? __ldg(base + (long long)j * count + idx) : __ldg(base + idx * n + j);
-}
-template <bool SOA>
-__device__ __forceinline__ void st_elem(double* __restrict__ base, long long idx, int j, long long count, int n,
-                                        double v) {
-  if (SOA) base[(long long)j * count + idx] = v;
-  else base[idx * n + j] = v;
-}
-
-// ------------------------------------------------------------------------------------------
-// projection kernel
-// ------------------------------------------------------------------------------------------
-struct ccp_project_args {
-  const double* seeds;  // nullptr when gen_mode >= 0
-  double* x_out;
-  uint8_t* ok;
-  uint8_t* conv;
-  int32_t* iters;
-  double* resid;
-  double* compact;             // AOS [<=count][n] of ok states, or nullptr
-  unsigned long long* n_ok;    // appended-to counter for `compact`
-  unsigned long long* counter; // work counter (zeroed before launch)
-  long long count;
-  int gen_mode;  // -1 load seeds; 0 uniform; 1 uniform-near; 2 gaussian
-  int wrap;
-  unsigned long long rng_seed;
-  long long first_index;
-  double distance;
-  double near[CCPC_DOF * CCPC_MAX_ARMS];
-};
-
-// warp-aggregated claim of the next sample index by the lanes currently finishing
-__device__ __forceinline__ long long claim_next(unsigned long long* counter) {
-  const unsigned mask = __activemask();
-  const int lane = threadIdx.x & 31;
-  const int leader = __ffs(mask) - 1;
-  unsigned long long base = 0;
-  if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(mask));
-  base = __shfl_sync(mask, base, leader);
-  return (long long)(base + __popc(mask & ((1u << lane) - 1u)));
-}
-
-// Box-Muller pair member from two uniforms (mode 2).  log() is CUDA libm: the gaussian stream is
-// engine-defined; parity tests read the generated seeds back instead of regenerating them.
-__device__ __forceinline__ double gauss01(unsigned long long seed, unsigned long long sample, unsigned j) {
-  double u1 = ccp_uniform01(seed, sample, 2u * j + 64u);
-  double u2 = ccp_uniform01(seed, sample, 2u * j + 65u);
-  u1 = (u1 <= 0.0) ? 0x1.0p-53 : u1;
-  double s, c;
-  ccp_sincos(6.283185307179586476925 * u2, &s, &c);
-  return sqrt(-2.0 * log(u1)) * c;
-}
-
-template <int K>
-__device__ __forceinline__ double make_seed(const ccp_model& M, const ccp_project_args& A, long long idx, int j) {
-  const unsigned long long sample = (unsigned long long)(A.first_index + idx);
-  const int i = j % CCPC_DOF;
-  if (A.gen_mode == 0) return ccp_seed_uniform(M, A.rng_seed, sample, j);
-  if (A.gen_mode == 1) {
-    // RealVectorStateSampler::sampleUniformNear: U[max(lb, near-d), min(ub, near+d)]
-    double lo = A.near[j] - A.distance, hi = A.near[j] + A.distance;
-    lo = (lo < M.lb[i]) ? M.lb[i] : lo;
-    hi = (hi > M.ub[i]) ? M.ub[i] : hi;
-    return CCP_FMA(ccp_uniform01(A.rng_seed, sample, (unsigned)j), hi - lo, lo);
-  }
-  // RealVectorStateSampler::sampleGaussian: N(mean, stddev) clipped to the bounds
-  double v = CCP_FMA(gauss01(A.rng_seed, sample, (unsigned)j), A.distance, A.near[j]);
-  v = (v < M.lb[i]) ? M.lb[i] : v;
-  v = (v > M.ub[i]) ? M.ub[i] : v;
-  return v;
-}
-
-// GEN = false: seeds are read from memory (project).  GEN = true: seeds come from the counter-based
-// generator and the sampler epilogue (wrap, compaction) is compiled in (sample_project).
-template <int K, bool SOA, bool GEN, int BLOCK, int MINB>
-__global__ void __launch_bounds__(BLOCK, MINB)
-ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ ccp_project_args A) {
-  constexpr int n = CCPC_DOF * K, m = 2 * (K - 1);
-  double x[n];
-  int it = 0;
-  long long idx = claim_next(A.counter);
-  if (idx < A.count) {
-    if (!GEN) {
-#pragma unroll
-      for (int j = 0; j < n; ++j) x[j] = ld_elem<SOA>(A.seeds, idx, j, A.count, n);
-    } else {
-#pragma unroll
-      for (int j = 0; j < n; ++j) x[j] = make_seed<K>(M, A, idx, j);
-    }
-  }
-  while (idx < A.count) {
-    ccp_fwd<K> F;
-    ccp_forward<K>(M, x, F);
-    const bool cont = ccp_needs_step<K>(M, F.f) && it < M.max_iter;
-    if (cont) {
-      ++it;
-      ccp_jac<K> J;
-      ccp_jacobian<K>(M, F, J);
-      ccp_newton_step<K>(M, F, J, x);
-    } else {
-      // ---- epilogue of this sample (ConstraintFunction.h:75-81), then refill the lane ----
-      const bool cv = ccp_converged<K>(M, F.f);
-      const bool okk = cv && ccp_joint_valid<K>(M, x);
-      if (GEN && A.wrap) {
-#pragma unroll
-        for (int j = 0; j < n; ++j) x[j] = ccp_wrap_pi(x[j]);
-      }
-      if (A.x_out) {
-#pragma unroll
-        for (int j = 0; j < n; ++j) st_elem<SOA>(A.x_out, idx, j, A.count, n, x[j]);
-      }
-      if (A.ok) A.ok[idx] = okk;
-      if (A.conv) A.conv[idx] = cv;
-      if (A.iters) A.iters[idx] = it;
-      if (A.resid) {
-#pragma unroll
-        for (int k = 0; k < m; ++k) st_elem<SOA>(A.resid, idx, k, A.count, m, F.f[k]);
-      }
-      if (A.n_ok && okk) {
-        const unsigned long long slot = atomicAdd(A.n_ok, 1ULL);
-        if (A.compact) {
-#pragma unroll
-          for (int j = 0; j < n; ++j) A.compact[slot * n + j] = x[j];
-        }
-      }
-      idx = claim_next(A.counter);
-      it = 0;
-      if (idx < A.count) {
-        if (!GEN) {
-#pragma unroll
-          for (int j = 0; j < n; ++j) x[j] = ld_elem<SOA>(A.seeds, idx, j, A.count, n);
-        } else {
-#pragma unroll
-          for (int j = 0; j < n; ++j) x[j] = make_seed<K>(M, A, idx, j);
-        }
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
 // small batched kernels (thread per state, grid-stride)
 // ------------------------------------------------------------------------------------------
-template <int K, bool SOA>
+template <int K, bool PANDA, bool SOA>
 __global__ void __launch_bounds__(128)
 ccp_function_kernel(const __grid_constant__ ccp_model M, const double* __restrict__ xin, long long count,
                     double* __restrict__ f, uint8_t* __restrict__ satisfied) {
@@ -224,7 +82,8 @@ ccp_function_kernel(const __grid_constant__ ccp_model M, const double* __restric
 #pragma unroll
     for (int j = 0; j < n; ++j) x[j] = ld_elem<SOA>(xin, idx, j, count, n);
     ccp_fwd<K> F;
-    ccp_forward<K>(M, x, F);
+    ccp_sc_local<K> S;
+    ccp_forward<K, PANDA>(M, x, S, F);
     if (f) {
 #pragma unroll
       for (int k = 0; k < m; ++k) st_elem<SOA>(f, idx, k, count, m, F.f[k]);
@@ -233,7 +92,7 @@ ccp_function_kernel(const __grid_constant__ ccp_model M, const double* __restric
   }
 }
 
-template <int K, bool SOA>
+template <int K, bool PANDA, bool SOA>
 __global__ void __launch_bounds__(128)
 ccp_jacobian_kernel(const __grid_constant__ ccp_model M, const double* __restrict__ xin, long long count,
                     double* __restrict__ Jout) {
@@ -245,8 +104,9 @@ ccp_jacobian_kernel(const __grid_constant__ ccp_model M, const double* __restric
     for (int j = 0; j < n; ++j) x[j] = ld_elem<SOA>(xin, idx, j, count, n);
     ccp_fwd<K> F;
     ccp_jac<K> J;
-    ccp_forward<K>(M, x, F);
-    ccp_jacobian<K>(M, F, J);
+    ccp_sc_local<K> S;
+    ccp_forward<K, PANDA>(M, x, S, F);
+    ccp_jacobian<K, PANDA>(M, S, F, J);
     double D[m * n];
     ccp_jac_dense<K>(J, D);
 #pragma unroll
@@ -313,14 +173,14 @@ __global__ void __launch_bounds__(256) ccp_wrap_kernel(double* __restrict__ x, l
     x[i] = ccp_wrap_pi(x[i]);
 }
 
-template <int K>
+template <int K, bool PANDA>
 __global__ void ccp_reference_kernel(const __grid_constant__ ccp_model M, const double* __restrict__ q_start,
                                      ccp_pair_ref* __restrict__ out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   ccp_model L = M;
   double q[CCPC_DOF * K];
   for (int j = 0; j < CCPC_DOF * K; ++j) q[j] = q_start[j];
-  ccp_reference_chain<K>(L, q);
+  ccp_reference_chain<K, PANDA>(L, q);
   for (int p = 0; p < K - 1; ++p) out[p] = L.ref[p];
 }
 
@@ -339,6 +199,16 @@ __global__ void __launch_bounds__(256) ccp_dfma_probe_kernel(double* __restrict_
   double s = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
   if (s == 123.456) sink[0] = s;  // never true; keeps the chain alive
 }
+
+// dispatch helper: (arms, structured alpha) -> template arguments
+#define CCP_DISPATCH_KP(h, CALL)                                                  \
+  do {                                                                            \
+    if ((h)->model.n_arms == 2) {                                                 \
+      if ((h)->model.panda_alpha) { CALL(2, true); } else { CALL(2, false); }     \
+    } else {                                                                      \
+      if ((h)->model.panda_alpha) { CALL(3, true); } else { CALL(3, false); }     \
+    }                                                                             \
+  } while (0)
 
 // ------------------------------------------------------------------------------------------
 // host side
@@ -363,23 +233,6 @@ struct device_guard {
   }
 };
 
-// projection launch configuration: BLOCK threads, MINB blocks per SM (persistent grid)
-#define CCP_PROJ_BLOCK 128
-#define CCP_PROJ_MINB_K2 3
-#define CCP_PROJ_MINB_K3 2
-
-template <int K, bool SOA>
-static cudaError_t launch_project_t(const ccp_handle* h, const ccp_project_args& A, cudaStream_t st) {
-  constexpr int MINB = (K == 2) ? CCP_PROJ_MINB_K2 : CCP_PROJ_MINB_K3;
-  long long need = (A.count + CCP_PROJ_BLOCK - 1) / CCP_PROJ_BLOCK;
-  long long cap = (long long)h->sm_count * MINB;
-  int grid = (int)(need < cap ? need : cap);
-  if (grid < 1) grid = 1;
-  if (A.gen_mode < 0) ccp_project_kernel<K, SOA, false, CCP_PROJ_BLOCK, MINB><<<grid, CCP_PROJ_BLOCK, 0, st>>>(h->model, A);
-  else ccp_project_kernel<K, SOA, true, CCP_PROJ_BLOCK, MINB><<<grid, CCP_PROJ_BLOCK, 0, st>>>(h->model, A);
-  return cudaGetLastError();
-}
-
 static int launch_project(ccp_handle* h, ccp_project_args& A, int layout, cudaStream_t st) {
   if (!h->has_ref) return set_err(h, CCP_ERR_STATE, "%s", "project before ccp_set_reference (setInitialPosition)");
   if (A.count == 0) return CCP_OK;
@@ -391,10 +244,14 @@ static int launch_project(ccp_handle* h, ccp_project_args& A, int layout, cudaSt
   }
   A.counter = h->d_counters + slot;
   CCP_CUDA(cudaMemsetAsync(A.counter, 0, sizeof(unsigned long long), st));
-  cudaError_t e;
+  cudaError_t e = cudaSuccess;
   const bool soa = layout == CCP_LAYOUT_SOA;
-  if (h->model.n_arms == 2) e = soa ? launch_project_t<2, true>(h, A, st) : launch_project_t<2, false>(h, A, st);
-  else e = soa ? launch_project_t<3, true>(h, A, st) : launch_project_t<3, false>(h, A, st);
+  if (h->model.n_arms == 2)
+    e = h->model.panda_alpha ? ccp_launch_project_K2_P1(h->sm_count, h->model, A, soa, st)
+                             : ccp_launch_project_K2_P0(h->sm_count, h->model, A, soa, st);
+  else
+    e = h->model.panda_alpha ? ccp_launch_project_K3_P1(h->sm_count, h->model, A, soa, st)
+                             : ccp_launch_project_K3_P0(h->sm_count, h->model, A, soa, st);
   if (e != cudaSuccess) return set_err(h, CCP_ERR_CUDA, "project kernel launch: %s", cudaGetErrorString(e));
   return CCP_OK;
 }
@@ -489,8 +346,9 @@ int ccp_set_reference(ccp_handle* h, const double* q_start_host) {
   cudaError_t e = cudaMalloc(&dref, sizeof(ccp_pair_ref) * (CCPC_MAX_ARMS - 1));
   if (e == cudaSuccess) e = cudaMemcpy(dq, q_start_host, sizeof(double) * n, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
-    if (h->model.n_arms == 2) ccp_reference_kernel<2><<<1, 32>>>(h->model, dq, dref);
-    else ccp_reference_kernel<3><<<1, 32>>>(h->model, dq, dref);
+#define CCP_CALL(K, P) ccp_reference_kernel<K, P><<<1, 32>>>(h->model, dq, dref)
+    CCP_DISPATCH_KP(h, CCP_CALL);
+#undef CCP_CALL
     e = cudaGetLastError();
     h->launches++;
   }
@@ -562,13 +420,13 @@ static int function_impl(ccp_handle* h, const double* x_dev, int64_t count, int3
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = grid_for(h, count, 128, 8);
   const bool soa = layout == CCP_LAYOUT_SOA;
-  if (h->model.n_arms == 2) {
-    if (soa) ccp_function_kernel<2, true><<<grid, 128, 0, st>>>(h->model, x_dev, count, f_dev, sat_dev);
-    else ccp_function_kernel<2, false><<<grid, 128, 0, st>>>(h->model, x_dev, count, f_dev, sat_dev);
-  } else {
-    if (soa) ccp_function_kernel<3, true><<<grid, 128, 0, st>>>(h->model, x_dev, count, f_dev, sat_dev);
-    else ccp_function_kernel<3, false><<<grid, 128, 0, st>>>(h->model, x_dev, count, f_dev, sat_dev);
-  }
+#define CCP_CALL(K, P)                                                                                   \
+  do {                                                                                                   \
+    if (soa) ccp_function_kernel<K, P, true><<<grid, 128, 0, st>>>(h->model, x_dev, count, f_dev, sat_dev);   \
+    else ccp_function_kernel<K, P, false><<<grid, 128, 0, st>>>(h->model, x_dev, count, f_dev, sat_dev);      \
+  } while (0)
+  CCP_DISPATCH_KP(h, CCP_CALL);
+#undef CCP_CALL
   h->launches++;
   CCP_CUDA(cudaGetLastError());
   return CCP_OK;
@@ -597,13 +455,13 @@ int ccp_jacobian_batch(ccp_handle* h, const double* x_dev, int64_t count, int32_
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = grid_for(h, count, 128, 4);
   const bool soa = layout == CCP_LAYOUT_SOA;
-  if (h->model.n_arms == 2) {
-    if (soa) ccp_jacobian_kernel<2, true><<<grid, 128, 0, st>>>(h->model, x_dev, count, J_dev);
-    else ccp_jacobian_kernel<2, false><<<grid, 128, 0, st>>>(h->model, x_dev, count, J_dev);
-  } else {
-    if (soa) ccp_jacobian_kernel<3, true><<<grid, 128, 0, st>>>(h->model, x_dev, count, J_dev);
-    else ccp_jacobian_kernel<3, false><<<grid, 128, 0, st>>>(h->model, x_dev, count, J_dev);
-  }
+#define CCP_CALL(K, P)                                                                          \
+  do {                                                                                          \
+    if (soa) ccp_jacobian_kernel<K, P, true><<<grid, 128, 0, st>>>(h->model, x_dev, count, J_dev);   \
+    else ccp_jacobian_kernel<K, P, false><<<grid, 128, 0, st>>>(h->model, x_dev, count, J_dev);      \
+  } while (0)
+  CCP_DISPATCH_KP(h, CCP_CALL);
+#undef CCP_CALL
   h->launches++;
   CCP_CUDA(cudaGetLastError());
   return CCP_OK;
@@ -794,7 +652,7 @@ int ccp_project_batch_host(ccp_handle* h, const double* seeds_host, int64_t coun
   uint8_t* dcv = dok + (size_t)count;
   // chunking: big enough to fill the persistent grid several times over, small enough to overlap
   int64_t chunk = count;
-  const int64_t min_chunk = (int64_t)h->sm_count * CCP_PROJ_BLOCK * 3 * 4;
+  const int64_t min_chunk = (int64_t)h->sm_count * 512 * 4;
   if (count >= 4 * min_chunk) {
     int64_t parts = count / min_chunk;
     if (parts > 16) parts = 16;
@@ -865,6 +723,27 @@ int ccp_jacobian_batch_host(ccp_handle* h, const double* x_host, int64_t count, 
   rc = ccp_jacobian_batch(h, dx, count, CCP_LAYOUT_AOS, dJ, st);
   if (rc) return rc;
   CCP_CUDA(cudaMemcpyAsync(J_host, dJ, sizeof(double) * m * n * count, cudaMemcpyDeviceToHost, st));
+  CCP_CUDA(cudaStreamSynchronize(st));
+  return CCP_OK;
+}
+
+int ccp_arm_fk_batch_host(ccp_handle* h, int32_t arm, const double* q_host, int64_t count, double* T_host,
+                          double* J_host) {
+  int rc = check_common(h, q_host, count, CCP_LAYOUT_AOS);
+  if (rc) return rc;
+  if (count == 0) return CCP_OK;
+  device_guard g(h->device);
+  rc = ensure_stage(h, sizeof(double) * (7 + 12 + 42) * (size_t)count);
+  if (rc) return rc;
+  double* dq = (double*)h->d_stage;
+  double* dT = dq + 7 * (size_t)count;
+  double* dJ = dT + 12 * (size_t)count;
+  cudaStream_t st = h->hstream[0];
+  CCP_CUDA(cudaMemcpyAsync(dq, q_host, sizeof(double) * 7 * count, cudaMemcpyHostToDevice, st));
+  rc = arm_fk_impl(h, arm, dq, count, CCP_LAYOUT_AOS, T_host ? dT : nullptr, J_host ? dJ : nullptr, st);
+  if (rc) return rc;
+  if (T_host) CCP_CUDA(cudaMemcpyAsync(T_host, dT, sizeof(double) * 12 * count, cudaMemcpyDeviceToHost, st));
+  if (J_host) CCP_CUDA(cudaMemcpyAsync(J_host, dJ, sizeof(double) * 42 * count, cudaMemcpyDeviceToHost, st));
   CCP_CUDA(cudaStreamSynchronize(st));
   return CCP_OK;
 }

@@ -69,6 +69,9 @@ struct ccp_pair_ref {
 struct ccp_model {
   int32_t n_arms;
   int32_t max_iter;
+  int32_t panda_alpha;  // 1: every arm has the stock Panda alpha pattern (0,-pi/2,pi/2,pi/2,-pi/2,pi/2,pi/2)
+                        //    EXACTLY (no alpha calibration): the kernels use the structured link code
+  int32_t reserved;
   double tol_p, tol_r;  // tolerance1_, tolerance2_
   double step;          // 0.30
   double margin;        // 1e-3
@@ -217,60 +220,140 @@ CCP_HD void ccp_qrot_inv(const double* q, double* v) {
   v[2] = CCP_FMA(q[0], tz, v[2]) + cz;
 }
 
+// ------------------------------------------------------------------------------------------
+// Link code.  PANDA = true compiles the stock Panda alpha pattern in: alpha_i in {0, +-pi/2} exactly, so
+// Rx(alpha) is a signed permutation (no arithmetic), the structurally zero translation component is
+// skipped, and the link quaternion (1, +-1, 0, 0) is applied UNSCALED (4 adds); the accumulated factor
+// sqrt(2)^12 = 64 is removed from the chain quaternion with one exact scaling.
+// PANDA = false is the generic path (calibrated alpha offsets, panda_rbdl.cpp:92-95).
+// ------------------------------------------------------------------------------------------
+template <int I>
+struct ccp_panda_sgn {  // sign of alpha_I / (pi/2): link 0 has alpha = 0
+  static constexpr int value = (I == 0) ? 0 : ((I == 1 || I == 4) ? -1 : 1);
+};
+#define CCP_PANDA_QSCALE 0.015625  // 1/64 = (1/sqrt 2)^12: six quarter-turn links per arm, two arms
+
 // One link going DOWN the chain (frame i -> frame i-1): v <- Rx(alpha) Rz(theta) v (+ t)
+template <bool PANDA, int I>
 CCP_HD void ccp_down_vec(const ccp_link& L, double s, double c, double* v) {
   ccp_rot2(c, s, v[0], v[1]);
-  ccp_rot2(L.ca, L.sa, v[1], v[2]);
+  if (!PANDA) {
+    ccp_rot2(L.ca, L.sa, v[1], v[2]);
+  } else if (ccp_panda_sgn<I>::value > 0) {
+    const double y = v[1];
+    v[1] = -v[2];
+    v[2] = y;
+  } else if (ccp_panda_sgn<I>::value < 0) {
+    const double y = v[1];
+    v[1] = v[2];
+    v[2] = -y;
+  }
 }
+template <bool PANDA, int I>
 CCP_HD void ccp_down_pt(const ccp_link& L, double s, double c, double* r) {
-  ccp_down_vec(L, s, c, r);
-  r[0] += L.tx; r[1] += L.ty; r[2] += L.tz;
+  ccp_down_vec<PANDA, I>(L, s, c, r);
+  r[0] += L.tx;
+  if (!PANDA || ccp_panda_sgn<I>::value != 0) r[1] += L.ty;
+  if (!PANDA || ccp_panda_sgn<I>::value == 0) r[2] += L.tz;
 }
 // One link going UP the chain (frame i-1 -> frame i): r <- Rz(theta)^T Rx(alpha)^T (r - t)
+template <bool PANDA, int I>
 CCP_HD void ccp_up_pt(const ccp_link& L, double s, double c, double* r) {
-  r[0] -= L.tx; r[1] -= L.ty; r[2] -= L.tz;
-  ccp_rot2t(L.ca, L.sa, r[1], r[2]);
+  r[0] -= L.tx;
+  if (!PANDA || ccp_panda_sgn<I>::value != 0) r[1] -= L.ty;
+  if (!PANDA || ccp_panda_sgn<I>::value == 0) r[2] -= L.tz;
+  if (!PANDA) {
+    ccp_rot2t(L.ca, L.sa, r[1], r[2]);
+  } else if (ccp_panda_sgn<I>::value > 0) {
+    const double y = r[1];
+    r[1] = r[2];
+    r[2] = -y;
+  } else if (ccp_panda_sgn<I>::value < 0) {
+    const double y = r[1];
+    r[1] = -r[2];
+    r[2] = y;
+  }
   ccp_rot2t(c, s, r[0], r[1]);
 }
+// q <- q (x) q_Rx(alpha_I)   (unscaled in PANDA mode)
+template <bool PANDA, int I>
+CCP_HD void ccp_qmul_link_rx(const ccp_link& L, double* q) {
+  if (!PANDA) {
+    ccp_qmul_rx(q, L.cha, L.sha);
+  } else if (ccp_panda_sgn<I>::value > 0) {
+    const double w = q[0] - q[1], x = q[1] + q[0], y = q[2] + q[3], z = q[3] - q[2];
+    q[0] = w; q[1] = x; q[2] = y; q[3] = z;
+  } else if (ccp_panda_sgn<I>::value < 0) {
+    const double w = q[0] + q[1], x = q[1] - q[0], y = q[2] - q[3], z = q[3] + q[2];
+    q[0] = w; q[1] = x; q[2] = y; q[3] = z;
+  }
+}
+
+// Per-sample storage of the 7K (sin, cos) pairs between the passes.  The host build and the simple
+// kernels keep them in a local array; the projection kernel keeps them in shared memory
+// ([slot][thread], conflict-free) to free ~56 registers.
+template <int K>
+struct ccp_sc_local {
+  double v[K][CCPC_DOF][2];
+  CCP_HD double& s(int a, int i) { return v[a][i][0]; }
+  CCP_HD double& c(int a, int i) { return v[a][i][1]; }
+  CCP_HD double s(int a, int i) const { return v[a][i][0]; }
+  CCP_HD double c(int a, int i) const { return v[a][i][1]; }
+};
 
 // ------------------------------------------------------------------------------------------
 // Forward evaluation: residual f(x) and everything the Jacobian pass needs.
 // ------------------------------------------------------------------------------------------
 template <int K>
 struct ccp_fwd {
-  double sc[K][CCPC_DOF][2];  // full-angle (sin, cos) of every joint
   double tc[K - 1][3];        // translation of chain a:  R_a^T (p_0 - p_a)
-  double qc[K - 1][4];        // rotation of chain a:     conj(q_a) (x) q_0
+  double qc[K - 1][4];        // rotation of chain a:     conj(q_a) (x) q_0   (unit)
   double d[K - 1][4];         // qc (x) conj(q_ref)
   double f[2 * (K - 1)];      // (f0, f1) per pair
   double sv[K - 1];           // |vec d|
 };
 
-template <int K>
-CCP_HD void ccp_forward(const ccp_model& M, const double* x, ccp_fwd<K>& F) {
+template <bool PANDA, int I, class SC, class XT>
+CCP_HD void ccp_fwd_link_quat(const ccp_arm& A, int a, const XT& x, double* q, SC& S) {
+  const ccp_link& L = A.link[I];
+  double h = 0.5 * (x[a * CCPC_DOF + I] + L.qoff);
+  double sh, ch;
+  ccp_sincos(h, &sh, &ch);
+  ccp_qmul_link_rx<PANDA, I>(L, q);
+  ccp_qmul_rz(q, ch, sh);
+  double sh2 = sh + sh;
+  S.s(a, I) = sh2 * ch;                // sin(theta)
+  S.c(a, I) = CCP_FMA(-sh2, sh, 1.0);  // cos(theta)
+}
+
+template <int K, bool PANDA, class SC, class XT>
+CCP_HD void ccp_forward(const ccp_model& M, const XT& x, SC& S, ccp_fwd<K>& F) {
   double q[K][4];
 #pragma unroll
   for (int a = 0; a < K; ++a) {
     const ccp_arm& A = M.arm[a];
     q[a][0] = A.qwb[0]; q[a][1] = A.qwb[1]; q[a][2] = A.qwb[2]; q[a][3] = A.qwb[3];
-#pragma unroll
-    for (int i = 0; i < CCPC_DOF; ++i) {
-      const ccp_link& L = A.link[i];
-      double h = 0.5 * (x[a * CCPC_DOF + i] + L.qoff);
-      double sh, ch;
-      ccp_sincos(h, &sh, &ch);
-      ccp_qmul_rx(q[a], L.cha, L.sha);
-      ccp_qmul_rz(q[a], ch, sh);
-      double sh2 = sh + sh;
-      F.sc[a][i][0] = sh2 * ch;                // sin(theta)
-      F.sc[a][i][1] = CCP_FMA(-sh2, sh, 1.0);  // cos(theta)
-    }
+    ccp_fwd_link_quat<PANDA, 0>(A, a, x, q[a], S);
+    ccp_fwd_link_quat<PANDA, 1>(A, a, x, q[a], S);
+    ccp_fwd_link_quat<PANDA, 2>(A, a, x, q[a], S);
+    ccp_fwd_link_quat<PANDA, 3>(A, a, x, q[a], S);
+    ccp_fwd_link_quat<PANDA, 4>(A, a, x, q[a], S);
+    ccp_fwd_link_quat<PANDA, 5>(A, a, x, q[a], S);
+    ccp_fwd_link_quat<PANDA, 6>(A, a, x, q[a], S);
     ccp_qmul_rz(q[a], A.chphi, A.shphi);
   }
   // EE-0 origin: frame 7 of arm 0 -> base 0 -> world
   double r[3] = {0.0, 0.0, M.arm[0].fl};
-#pragma unroll
-  for (int i = CCPC_DOF - 1; i >= 0; --i) ccp_down_pt(M.arm[0].link[i], F.sc[0][i][0], F.sc[0][i][1], r);
+  {
+    const ccp_arm& A = M.arm[0];
+    ccp_down_pt<PANDA, 6>(A.link[6], S.s(0, 6), S.c(0, 6), r);
+    ccp_down_pt<PANDA, 5>(A.link[5], S.s(0, 5), S.c(0, 5), r);
+    ccp_down_pt<PANDA, 4>(A.link[4], S.s(0, 4), S.c(0, 4), r);
+    ccp_down_pt<PANDA, 3>(A.link[3], S.s(0, 3), S.c(0, 3), r);
+    ccp_down_pt<PANDA, 2>(A.link[2], S.s(0, 2), S.c(0, 2), r);
+    ccp_down_pt<PANDA, 1>(A.link[1], S.s(0, 1), S.c(0, 1), r);
+    ccp_down_pt<PANDA, 0>(A.link[0], S.s(0, 0), S.c(0, 0), r);
+  }
   double p0[3];
   {
     const ccp_arm& A = M.arm[0];
@@ -286,14 +369,23 @@ CCP_HD void ccp_forward(const ccp_model& M, const double* x, ccp_fwd<K>& F) {
     v[0] = CCP_FMA(A.Rwb[0], e0, CCP_FMA(A.Rwb[3], e1, A.Rwb[6] * e2));
     v[1] = CCP_FMA(A.Rwb[1], e0, CCP_FMA(A.Rwb[4], e1, A.Rwb[7] * e2));
     v[2] = CCP_FMA(A.Rwb[2], e0, CCP_FMA(A.Rwb[5], e1, A.Rwb[8] * e2));
-#pragma unroll
-    for (int i = 0; i < CCPC_DOF; ++i) ccp_up_pt(A.link[i], F.sc[a][i][0], F.sc[a][i][1], v);
+    ccp_up_pt<PANDA, 0>(A.link[0], S.s(a, 0), S.c(a, 0), v);
+    ccp_up_pt<PANDA, 1>(A.link[1], S.s(a, 1), S.c(a, 1), v);
+    ccp_up_pt<PANDA, 2>(A.link[2], S.s(a, 2), S.c(a, 2), v);
+    ccp_up_pt<PANDA, 3>(A.link[3], S.s(a, 3), S.c(a, 3), v);
+    ccp_up_pt<PANDA, 4>(A.link[4], S.s(a, 4), S.c(a, 4), v);
+    ccp_up_pt<PANDA, 5>(A.link[5], S.s(a, 5), S.c(a, 5), v);
+    ccp_up_pt<PANDA, 6>(A.link[6], S.s(a, 6), S.c(a, 6), v);
     v[2] -= A.fl;
     ccp_rot2t(A.cphi, A.sphi, v[0], v[1]);
     double* tc = F.tc[a - 1];
     tc[0] = v[0]; tc[1] = v[1]; tc[2] = v[2];
-    ccp_qmul_conj_left(q[a], q[0], F.qc[a - 1]);
-    ccp_qmul_conj_right(F.qc[a - 1], M.ref[a - 1].q0, F.d[a - 1]);
+    double* qc = F.qc[a - 1];
+    ccp_qmul_conj_left(q[a], q[0], qc);
+    if (PANDA) {
+      qc[0] *= CCP_PANDA_QSCALE; qc[1] *= CCP_PANDA_QSCALE; qc[2] *= CCP_PANDA_QSCALE; qc[3] *= CCP_PANDA_QSCALE;
+    }
+    ccp_qmul_conj_right(qc, M.ref[a - 1].q0, F.d[a - 1]);
     const double* d = F.d[a - 1];
     const double* t0 = M.ref[a - 1].t0;
     double ex = tc[0] - t0[0], ey = tc[1] - t0[1], ez = tc[2] - t0[2];
@@ -334,8 +426,8 @@ CCP_HD bool ccp_is_satisfied(const ccp_model& M, const double* f) {
   return all;
 }
 // jointValid (ConstraintFunction.h:43-55)
-template <int K>
-CCP_HD bool ccp_joint_valid(const ccp_model& M, const double* x) {
+template <int K, class XT>
+CCP_HD bool ccp_joint_valid(const ccp_model& M, const XT& x) {
   bool ok = true;
 #pragma unroll
   for (int a = 0; a < K; ++a)
@@ -355,10 +447,43 @@ template <int K>
 struct ccp_jac {
   double Ja[K - 1][2][CCPC_DOF];
   double J0[K - 1][2][CCPC_DOF];
+  CCP_HD double& a(int p, int r, int i) { return Ja[p][r][i]; }
+  CCP_HD double& z(int p, int r, int i) { return J0[p][r][i]; }
+  CCP_HD double a(int p, int r, int i) const { return Ja[p][r][i]; }
+  CCP_HD double z(int p, int r, int i) const { return J0[p][r][i]; }
 };
 
-template <int K>
-CCP_HD void ccp_jacobian(const ccp_model& M, const ccp_fwd<K>& F, ccp_jac<K>& J) {
+template <bool PANDA, int I, bool ARM0, class SC, class JT>
+CCP_HD void ccp_jac_link(const ccp_arm& A, int a, int p, const SC& S, double* r, double* w, double* m, JT& J) {
+  // joint I sees (r, w, m) in frame I:  d f0 / d q = +-(r x w)_z,  d f1 / d q = +-m_z  (+ on arm 0)
+  const double cz = CCP_FMA(r[0], w[1], -(r[1] * w[0]));
+  if (ARM0) {
+    J.z(p, 0, I) = cz;
+    J.z(p, 1, I) = m[2];
+  } else {
+    J.a(p, 0, I) = -cz;
+    J.a(p, 1, I) = -m[2];
+  }
+  if (I > 0) {
+    const double s = S.s(a, I), c = S.c(a, I);
+    ccp_down_pt<PANDA, I>(A.link[I], s, c, r);
+    ccp_down_vec<PANDA, I>(A.link[I], s, c, w);
+    ccp_down_vec<PANDA, I>(A.link[I], s, c, m);
+  }
+}
+template <bool PANDA, bool ARM0, class SC, class JT>
+CCP_HD void ccp_jac_arm(const ccp_arm& A, int a, int p, const SC& S, double* r, double* w, double* m, JT& J) {
+  ccp_jac_link<PANDA, 6, ARM0>(A, a, p, S, r, w, m, J);
+  ccp_jac_link<PANDA, 5, ARM0>(A, a, p, S, r, w, m, J);
+  ccp_jac_link<PANDA, 4, ARM0>(A, a, p, S, r, w, m, J);
+  ccp_jac_link<PANDA, 3, ARM0>(A, a, p, S, r, w, m, J);
+  ccp_jac_link<PANDA, 2, ARM0>(A, a, p, S, r, w, m, J);
+  ccp_jac_link<PANDA, 1, ARM0>(A, a, p, S, r, w, m, J);
+  ccp_jac_link<PANDA, 0, ARM0>(A, a, p, S, r, w, m, J);
+}
+
+template <int K, bool PANDA, class SC, class JT>
+CCP_HD void ccp_jacobian(const ccp_model& M, const SC& S, const ccp_fwd<K>& F, JT& J) {
 #pragma unroll
   for (int p = 0; p < K - 1; ++p) {
     const int a = p + 1;
@@ -382,17 +507,7 @@ CCP_HD void ccp_jacobian(const ccp_model& M, const ccp_fwd<K>& F, ccp_jac<K>& J)
       r[2] += A.fl;
       ccp_rot2(A.cphi, A.sphi, w[0], w[1]);
       ccp_rot2(A.cphi, A.sphi, m[0], m[1]);
-#pragma unroll
-      for (int i = CCPC_DOF - 1; i >= 0; --i) {
-        J.Ja[p][0][i] = -CCP_FMA(r[0], w[1], -(r[1] * w[0]));
-        J.Ja[p][1][i] = -m[2];
-        if (i > 0) {
-          const double s = F.sc[a][i][0], c = F.sc[a][i][1];
-          ccp_down_pt(A.link[i], s, c, r);
-          ccp_down_vec(A.link[i], s, c, w);
-          ccp_down_vec(A.link[i], s, c, m);
-        }
-      }
+      ccp_jac_arm<PANDA, false>(A, a, p, S, r, w, m, J);
     }
     // arm 0: u, n rotated into EE_0's frame by R_c^T, lever arm starts at the EE-0 origin
     {
@@ -404,17 +519,7 @@ CCP_HD void ccp_jacobian(const ccp_model& M, const ccp_fwd<K>& F, ccp_jac<K>& J)
       ccp_qrot_inv(F.qc[p], m);
       ccp_rot2(A.cphi, A.sphi, w[0], w[1]);
       ccp_rot2(A.cphi, A.sphi, m[0], m[1]);
-#pragma unroll
-      for (int i = CCPC_DOF - 1; i >= 0; --i) {
-        J.J0[p][0][i] = CCP_FMA(r[0], w[1], -(r[1] * w[0]));
-        J.J0[p][1][i] = m[2];
-        if (i > 0) {
-          const double s = F.sc[0][i][0], c = F.sc[0][i][1];
-          ccp_down_pt(A.link[i], s, c, r);
-          ccp_down_vec(A.link[i], s, c, w);
-          ccp_down_vec(A.link[i], s, c, m);
-        }
-      }
+      ccp_jac_arm<PANDA, true>(A, 0, p, S, r, w, m, J);
     }
   }
 }
@@ -422,8 +527,8 @@ CCP_HD void ccp_jacobian(const ccp_model& M, const ccp_fwd<K>& F, ccp_jac<K>& J)
 // ------------------------------------------------------------------------------------------
 // Newton step: x <- x - step * J^T (J J^T)^-1 f         (ConstraintFunction.h:71)
 // ------------------------------------------------------------------------------------------
-template <int K>
-CCP_HD void ccp_newton_step(const ccp_model& M, const ccp_fwd<K>& F, const ccp_jac<K>& J, double* x) {
+template <int K, class JT, class XT>
+CCP_HD void ccp_newton_step(const ccp_model& M, const ccp_fwd<K>& F, const JT& J, XT& x) {
   constexpr int m = 2 * (K - 1);
   double G[m][m];
   // Gram matrix, lower triangle.  Rows of the same pair share both arms' columns; rows of
@@ -440,10 +545,10 @@ CCP_HD void ccp_newton_step(const ccp_model& M, const ccp_fwd<K>& F, const ccp_j
           if (Jx > I) continue;
           double acc = 0.0;
 #pragma unroll
-          for (int i = 0; i < CCPC_DOF; ++i) acc = CCP_FMA(J.J0[p][ri][i], J.J0[pp][rj][i], acc);
+          for (int i = 0; i < CCPC_DOF; ++i) acc = CCP_FMA(J.z(p, ri, i), J.z(pp, rj, i), acc);
           if (pp == p) {
 #pragma unroll
-            for (int i = 0; i < CCPC_DOF; ++i) acc = CCP_FMA(J.Ja[p][ri][i], J.Ja[p][rj][i], acc);
+            for (int i = 0; i < CCPC_DOF; ++i) acc = CCP_FMA(J.a(p, ri, i), J.a(p, rj, i), acc);
           }
           G[I][Jx] = acc;
         }
@@ -489,8 +594,8 @@ CCP_HD void ccp_newton_step(const ccp_model& M, const ccp_fwd<K>& F, const ccp_j
     double dx = 0.0;
 #pragma unroll
     for (int p = 0; p < K - 1; ++p) {
-      dx = CCP_FMA(J.J0[p][0][i], y[2 * p], dx);
-      dx = CCP_FMA(J.J0[p][1][i], y[2 * p + 1], dx);
+      dx = CCP_FMA(J.z(p, 0, i), y[2 * p], dx);
+      dx = CCP_FMA(J.z(p, 1, i), y[2 * p + 1], dx);
     }
     x[i] = CCP_FMA(-M.step, dx, x[i]);
   }
@@ -498,7 +603,7 @@ CCP_HD void ccp_newton_step(const ccp_model& M, const ccp_fwd<K>& F, const ccp_j
   for (int p = 0; p < K - 1; ++p)
 #pragma unroll
     for (int i = 0; i < CCPC_DOF; ++i) {
-      double dx = CCP_FMA(J.Ja[p][1][i], y[2 * p + 1], J.Ja[p][0][i] * y[2 * p]);
+      double dx = CCP_FMA(J.a(p, 1, i), y[2 * p + 1], J.a(p, 0, i) * y[2 * p]);
       x[(p + 1) * CCPC_DOF + i] = CCP_FMA(-M.step, dx, x[(p + 1) * CCPC_DOF + i]);
     }
 }
@@ -525,18 +630,19 @@ CCP_HD void ccp_jac_dense(const ccp_jac<K>& J, double* out) {
 // Used as-is by the host build; the CUDA kernel runs the same three calls inside its
 // lane-refill loop.
 // ------------------------------------------------------------------------------------------
-template <int K>
+template <int K, bool PANDA>
 CCP_HD void ccp_project_one(const ccp_model& M, double* x, double* f_out, int32_t* iters, bool* converged,
                             bool* ok) {
   ccp_fwd<K> F;
   ccp_jac<K> J;
+  ccp_sc_local<K> S;
   int32_t it = 0;
-  ccp_forward<K>(M, x, F);
+  ccp_forward<K, PANDA>(M, x, S, F);
   while (ccp_needs_step<K>(M, F.f) && it < M.max_iter) {
     ++it;
-    ccp_jacobian<K>(M, F, J);
+    ccp_jacobian<K, PANDA>(M, S, F, J);
     ccp_newton_step<K>(M, F, J, x);
-    ccp_forward<K>(M, x, F);
+    ccp_forward<K, PANDA>(M, x, S, F);
   }
   const bool conv = ccp_converged<K>(M, F.f);
 #pragma unroll
@@ -548,7 +654,7 @@ CCP_HD void ccp_project_one(const ccp_model& M, double* x, double* f_out, int32_
 
 // setInitialPosition (ConstraintFunction.h:31-40): reference chain = chain at q_start with an
 // identity reference.
-template <int K>
+template <int K, bool PANDA>
 CCP_HD void ccp_reference_chain(ccp_model& M, const double* q_start) {
 #pragma unroll
   for (int p = 0; p < K - 1; ++p) {
@@ -557,7 +663,8 @@ CCP_HD void ccp_reference_chain(ccp_model& M, const double* q_start) {
     M.ref[p].q0[1] = M.ref[p].q0[2] = M.ref[p].q0[3] = 0.0;
   }
   ccp_fwd<K> F;
-  ccp_forward<K>(M, q_start, F);
+  ccp_sc_local<K> S;
+  ccp_forward<K, PANDA>(M, q_start, S, F);
 #pragma unroll
   for (int p = 0; p < K - 1; ++p) {
 #pragma unroll

@@ -1,0 +1,85 @@
+// ccp_device.cuh — device-side pieces shared by the translation units of libccp.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ccp_core.h"
+
+// ------------------------------------------------------------------------------------------
+// state access (AOS: [count][n], SOA: [n][count])
+// ------------------------------------------------------------------------------------------
+template <bool SOA>
+__device__ __forceinline__ double ld_elem(const double* __restrict__ base, long long idx, int j, long long count,
+                                          int n) {
+  return SOA ? __ldg(base + (long long)j * count + idx) : __ldg(base + idx * n + j);
+}
+template <bool SOA>
+__device__ __forceinline__ void st_elem(double* __restrict__ base, long long idx, int j, long long count, int n,
+                                        double v) {
+  if (SOA) base[(long long)j * count + idx] = v;
+  else base[idx * n + j] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// projection kernel
+// ------------------------------------------------------------------------------------------
+struct ccp_project_args {
+  const double* seeds;  // nullptr when gen_mode >= 0
+  double* x_out;
+  uint8_t* ok;
+  uint8_t* conv;
+  int32_t* iters;
+  double* resid;
+  double* compact;             // AOS [<=count][n] of ok states, or nullptr
+  unsigned long long* n_ok;    // appended-to counter for `compact`
+  unsigned long long* counter; // work counter (zeroed before launch)
+  long long count;
+  int gen_mode;  // -1 load seeds; 0 uniform; 1 uniform-near; 2 gaussian
+  int wrap;
+  unsigned long long rng_seed;
+  long long first_index;
+  double distance;
+  double near[CCPC_DOF * CCPC_MAX_ARMS];
+};
+
+// warp-aggregated claim of the next sample index by the lanes currently finishing
+__device__ __forceinline__ long long claim_next(unsigned long long* counter) {
+  const unsigned mask = __activemask();
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(mask) - 1;
+  unsigned long long base = 0;
+  if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(mask));
+  base = __shfl_sync(mask, base, leader);
+  return (long long)(base + __popc(mask & ((1u << lane) - 1u)));
+}
+
+// Box-Muller pair member from two uniforms (mode 2).  log() is CUDA libm: the gaussian stream is
+// engine-defined; parity tests read the generated seeds back instead of regenerating them.
+__device__ __forceinline__ double gauss01(unsigned long long seed, unsigned long long sample, unsigned j) {
+  double u1 = ccp_uniform01(seed, sample, 2u * j + 64u);
+  double u2 = ccp_uniform01(seed, sample, 2u * j + 65u);
+  u1 = (u1 <= 0.0) ? 0x1.0p-53 : u1;
+  double s, c;
+  ccp_sincos(6.283185307179586476925 * u2, &s, &c);
+  return sqrt(-2.0 * log(u1)) * c;
+}
+
+template <int K>
+__device__ __forceinline__ double make_seed(const ccp_model& M, const ccp_project_args& A, long long idx, int j) {
+  const unsigned long long sample = (unsigned long long)(A.first_index + idx);
+  const int i = j % CCPC_DOF;
+  if (A.gen_mode == 0) return ccp_seed_uniform(M, A.rng_seed, sample, j);
+  if (A.gen_mode == 1) {
+    // RealVectorStateSampler::sampleUniformNear: U[max(lb, near-d), min(ub, near+d)]
+    double lo = A.near[j] - A.distance, hi = A.near[j] + A.distance;
+    lo = (lo < M.lb[i]) ? M.lb[i] : lo;
+    hi = (hi > M.ub[i]) ? M.ub[i] : hi;
+    return CCP_FMA(ccp_uniform01(A.rng_seed, sample, (unsigned)j), hi - lo, lo);
+  }
+  // RealVectorStateSampler::sampleGaussian: N(mean, stddev) clipped to the bounds
+  double v = CCP_FMA(gauss01(A.rng_seed, sample, (unsigned)j), A.distance, A.near[j]);
+  v = (v < M.lb[i]) ? M.lb[i] : v;
+  v = (v > M.ub[i]) ? M.ub[i] : v;
+  return v;
+}
+

@@ -55,14 +55,28 @@ static inline int ccp_pack_model(const ccp_model_desc* d, ccp_model* M) {
     M->lb[i] = d->lb[i];
     M->ub[i] = d->ub[i];
   }
+  // Stock Panda alpha pattern on every arm (bitwise: no alpha calibration) -> structured link code.
+  static const double kPi2 = 1.57079632679489661923;
+  static const double kPandaAlpha[7] = {0.0, -1.0 * kPi2, kPi2, kPi2, -1.0 * kPi2, kPi2, kPi2};
+  int panda = 1;
+  for (int a = 0; a < d->n_arms; ++a)
+    for (int i = 0; i < CCP_DOF; ++i)
+      if (d->arm[a].dh_alpha[i] != kPandaAlpha[i]) panda = 0;
+  M->panda_alpha = panda;
   for (int a = 0; a < d->n_arms; ++a) {
     const ccp_arm_desc& s = d->arm[a];
     ccp_arm& A = M->arm[a];
     for (int i = 0; i < CCP_DOF; ++i) {
       ccp_link& L = A.link[i];
       const double al = s.dh_alpha[i];
-      L.sa = sin(al);
-      L.ca = cos(al);
+      if (panda) {
+        // exact quarter turns: sin = +-1, cos = 0 (the reference's cos(M_PI_2) = 6.1e-17 is rounding noise)
+        L.sa = (i == 0) ? 0.0 : ((al < 0.0) ? -1.0 : 1.0);
+        L.ca = (i == 0) ? 1.0 : 0.0;
+      } else {
+        L.sa = sin(al);
+        L.ca = cos(al);
+      }
       L.sha = sin(0.5 * al);
       L.cha = cos(0.5 * al);
       L.tx = s.dh_a[i];              // panda_rbdl.cpp:159: (a, -sin(alpha) d, cos(alpha) d)

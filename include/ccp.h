@@ -184,6 +184,10 @@ int ccp_project_batch_host(ccp_handle* h, const double* seeds_host, int64_t coun
                            int32_t* iters_host, double* resid_host);
 int ccp_function_batch_host(ccp_handle* h, const double* x_host, int64_t count, double* f_host);
 int ccp_jacobian_batch_host(ccp_handle* h, const double* x_host, int64_t count, double* J_host);
+/* ≙ PandaModel::getTransform / getJacobianMatrix for host 7-vectors (AOS): T_host double[count][12],
+ * J_host double[count][42]; either output may be NULL.                                          */
+int ccp_arm_fk_batch_host(ccp_handle* h, int32_t arm, const double* q_host, int64_t count,
+                          double* T_host, double* J_host);
 
 /* ---- measurement helpers ---------------------------------------------------------------- */
 /* Register-only DFMA chains on every SM: returns achieved FP64 FLOP/s (FMA = 2) and the

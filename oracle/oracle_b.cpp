@@ -22,31 +22,44 @@
 #endif
 
 namespace {
-template <int K>
-static void function_batch(const ccp_model* M, const double* x, int64_t count, double* f) {
+// dispatch on (arms, structured-alpha) exactly like the CUDA library does
+#define OB_DISPATCH(M, CALL)                                  \
+  do {                                                        \
+    if ((M)->n_arms == 2) {                                   \
+      if ((M)->panda_alpha) { CALL(2, true); } else { CALL(2, false); } \
+    } else {                                                  \
+      if ((M)->panda_alpha) { CALL(3, true); } else { CALL(3, false); } \
+    }                                                         \
+  } while (0)
+
+template <int K, bool P>
+static void function_batch(const ccp_model* M, const double* x, int64_t count, double* f, uint8_t* sat) {
   constexpr int n = 7 * K, m = 2 * (K - 1);
 #pragma omp parallel for schedule(static)
   for (int64_t s = 0; s < count; ++s) {
     ccp_fwd<K> F;
-    ccp_forward<K>(*M, x + s * n, F);
-    for (int k = 0; k < m; ++k) f[s * m + k] = F.f[k];
+    ccp_sc_local<K> S;
+    ccp_forward<K, P>(*M, x + s * n, S, F);
+    if (f) for (int k = 0; k < m; ++k) f[s * m + k] = F.f[k];
+    if (sat) sat[s] = ccp_is_satisfied<K>(*M, F.f);
   }
 }
 
-template <int K>
+template <int K, bool P>
 static void jacobian_batch(const ccp_model* M, const double* x, int64_t count, double* Jout) {
   constexpr int n = 7 * K, m = 2 * (K - 1);
 #pragma omp parallel for schedule(static)
   for (int64_t s = 0; s < count; ++s) {
     ccp_fwd<K> F;
     ccp_jac<K> J;
-    ccp_forward<K>(*M, x + s * n, F);
-    ccp_jacobian<K>(*M, F, J);
+    ccp_sc_local<K> S;
+    ccp_forward<K, P>(*M, x + s * n, S, F);
+    ccp_jacobian<K, P>(*M, S, F, J);
     ccp_jac_dense<K>(J, Jout + s * m * n);
   }
 }
 
-template <int K>
+template <int K, bool P>
 static void project_batch(const ccp_model* M, double* x, int64_t count, uint8_t* ok, uint8_t* conv,
                           int32_t* iters, double* resid, int nthreads) {
   constexpr int n = 7 * K, m = 2 * (K - 1);
@@ -56,7 +69,7 @@ static void project_batch(const ccp_model* M, double* x, int64_t count, uint8_t*
     double f[m];
     int32_t it;
     bool c, o;
-    ccp_project_one<K>(*M, x + s * n, f, &it, &c, &o);
+    ccp_project_one<K, P>(*M, x + s * n, f, &it, &c, &o);
     if (ok) ok[s] = o;
     if (conv) conv[s] = c;
     if (iters) iters[s] = it;
@@ -76,9 +89,11 @@ int ob_default_desc(int32_t n_arms, const int32_t* arm_index, ccp_model_desc* d)
 }
 
 void ob_set_reference(ccp_model* M, const double* q_start) {
-  if (M->n_arms == 2) ccp_reference_chain<2>(*M, q_start);
-  else ccp_reference_chain<3>(*M, q_start);
+#define OB_CALL(K, P) ccp_reference_chain<K, P>(*M, q_start)
+  OB_DISPATCH(M, OB_CALL);
+#undef OB_CALL
 }
+int ob_is_panda_alpha(const ccp_model* M) { return M->panda_alpha; }
 void ob_get_reference(const ccp_model* M, int pair, double* t0, double* q0) {
   memcpy(t0, M->ref[pair].t0, 3 * sizeof(double));
   memcpy(q0, M->ref[pair].q0, 4 * sizeof(double));
@@ -89,20 +104,23 @@ void ob_set_options(ccp_model* M, double step, int max_iter, double margin) {
 }
 
 void ob_function_batch(const ccp_model* M, const double* x, int64_t count, double* f) {
-  if (M->n_arms == 2) function_batch<2>(M, x, count, f);
-  else function_batch<3>(M, x, count, f);
+#define OB_CALL(K, P) function_batch<K, P>(M, x, count, f, nullptr)
+  OB_DISPATCH(M, OB_CALL);
+#undef OB_CALL
 }
 
 void ob_jacobian_batch(const ccp_model* M, const double* x, int64_t count, double* J) {
-  if (M->n_arms == 2) jacobian_batch<2>(M, x, count, J);
-  else jacobian_batch<3>(M, x, count, J);
+#define OB_CALL(K, P) jacobian_batch<K, P>(M, x, count, J)
+  OB_DISPATCH(M, OB_CALL);
+#undef OB_CALL
 }
 
 // x: AOS count x n, updated in place
 void ob_project_batch(const ccp_model* M, double* x, int64_t count, uint8_t* ok, uint8_t* conv,
                       int32_t* iters, double* resid, int nthreads) {
-  if (M->n_arms == 2) project_batch<2>(M, x, count, ok, conv, iters, resid, nthreads);
-  else project_batch<3>(M, x, count, ok, conv, iters, resid, nthreads);
+#define OB_CALL(K, P) project_batch<K, P>(M, x, count, ok, conv, iters, resid, nthreads)
+  OB_DISPATCH(M, OB_CALL);
+#undef OB_CALL
 }
 
 void ob_joint_valid_batch(const ccp_model* M, const double* x, int64_t count, uint8_t* out) {
@@ -111,18 +129,9 @@ void ob_joint_valid_batch(const ccp_model* M, const double* x, int64_t count, ui
     out[s] = M->n_arms == 2 ? ccp_joint_valid<2>(*M, x + s * n) : ccp_joint_valid<3>(*M, x + s * n);
 }
 void ob_is_satisfied_batch(const ccp_model* M, const double* x, int64_t count, uint8_t* out) {
-  const int n = 7 * M->n_arms;
-  for (int64_t s = 0; s < count; ++s) {
-    if (M->n_arms == 2) {
-      ccp_fwd<2> F;
-      ccp_forward<2>(*M, x + s * n, F);
-      out[s] = ccp_is_satisfied<2>(*M, F.f);
-    } else {
-      ccp_fwd<3> F;
-      ccp_forward<3>(*M, x + s * n, F);
-      out[s] = ccp_is_satisfied<3>(*M, F.f);
-    }
-  }
+#define OB_CALL(K, P) function_batch<K, P>(M, x, count, nullptr, out)
+  OB_DISPATCH(M, OB_CALL);
+#undef OB_CALL
 }
 
 void ob_arm_fk_batch(const ccp_model* M, int arm, const double* q, int64_t count, double* T, double* J) {

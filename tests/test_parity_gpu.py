@@ -201,6 +201,7 @@ def test_edge_cases(constraints):
     r3 = c.projectBatch(seeds[:32])
     assert r3.iters.max() == 3 and np.array_equal(_bits(r3.x[:5]), _bits(B.project(seeds[:32])["x"][:5]))
     c.setOptions()
+    B.set_options()
     # tolerance change is honoured
     c.setTolerance(1e-2, 5e-2)
     B.set_tolerance(1e-2, 5e-2)
