@@ -16,7 +16,18 @@ from .constraint import (  # noqa: F401
     make_model_desc,
 )
 
+from .state_space import (  # noqa: F401,E402
+    GeodesicResult,
+    KinematicChainSpace,
+    jy_ProjectedStateSampler,
+    jy_ProjectedStateSpace,
+)
+
 __all__ = [
+    "GeodesicResult",
+    "KinematicChainSpace",
+    "jy_ProjectedStateSampler",
+    "jy_ProjectedStateSpace",
     "ArmModel",
     "KinematicChainConstraint",
     "PandaModel",

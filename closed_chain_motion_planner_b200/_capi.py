@@ -85,6 +85,7 @@ SYMBOLS = {
     "ccp_arm_jacobian_batch": (C.c_int, [_H, _I32, _P, _I64, _I32, _P, _P]),
     "ccp_generate_seeds": (C.c_int, [_H, C.POINTER(SamplerArgs), _I64, _I32, _P, _P]),
     "ccp_sample_project_batch": (C.c_int, [_H, C.POINTER(SamplerArgs), _I64, _I32, _P, _P, _P, _P, _P, _P]),
+    "ccp_geodesic_batch": (C.c_int, [_H, _P, _P, _I64, C.c_double, C.c_double, _I32, _P, _P, _P, _P, _P]),
     "ccp_enforce_bounds_batch": (C.c_int, [_H, _P, _I64, _I32, _P]),
     "ccp_project_batch_host": (C.c_int, [_H, _P, _I64, _P, _P, _P, _P, _P]),
     "ccp_function_batch_host": (C.c_int, [_H, _P, _I64, _P]),

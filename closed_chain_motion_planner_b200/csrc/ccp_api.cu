@@ -616,6 +616,32 @@ int ccp_sample_project_batch(ccp_handle* h, const ccp_sampler_args* a, int64_t c
   return launch_project(h, A, layout, (cudaStream_t)stream);
 }
 
+int ccp_geodesic_batch(ccp_handle* h, const double* from_dev, const double* to_dev, int64_t edges, double delta,
+                       double lambda, int32_t max_states, double* states_dev, int32_t* n_states_dev,
+                       uint8_t* reached_dev, int32_t* iters_dev, void* stream) {
+  int rc = check_common(h, from_dev, edges, CCP_LAYOUT_AOS);
+  if (rc) return rc;
+  if (edges > 0 && (!to_dev || !states_dev || !n_states_dev || !reached_dev))
+    return set_err(h, CCP_ERR_INVALID, "%s", "null geodesic buffer");
+  if (!(delta > 0) || !(lambda > 0) || max_states < 1) return set_err(h, CCP_ERR_INVALID, "%s", "bad geodesic parameters");
+  if (!h->has_ref) return set_err(h, CCP_ERR_STATE, "%s", "geodesic before ccp_set_reference (setInitialPosition)");
+  if (edges == 0) return CCP_OK;
+  device_guard g(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned slot;
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    slot = h->launch_seq++ % CCP_NUM_COUNTERS;
+    h->launches++;
+  }
+  unsigned long long* counter = h->d_counters + slot;
+  CCP_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+  cudaError_t e = ccp_launch_geodesic(h->sm_count, h->model, from_dev, to_dev, edges, delta, lambda, max_states, states_dev,
+                                      n_states_dev, reached_dev, iters_dev, counter, st);
+  if (e != cudaSuccess) return set_err(h, CCP_ERR_CUDA, "geodesic kernel launch: %s", cudaGetErrorString(e));
+  return CCP_OK;
+}
+
 int ccp_enforce_bounds_batch(ccp_handle* h, double* x_dev, int64_t count, int32_t layout, void* stream) {
   int rc = check_common(h, x_dev, count, layout);
   if (rc) return rc;
@@ -651,12 +677,17 @@ int ccp_project_batch_host(ccp_handle* h, const double* seeds_host, int64_t coun
   uint8_t* dok = (uint8_t*)((char*)dit + sizeof(int32_t) * (size_t)count);
   uint8_t* dcv = dok + (size_t)count;
   // chunking: big enough to fill the persistent grid several times over, small enough to overlap
+  // each chunk should still give every lane of the persistent grid a couple of seeds (148 SMs x 384 lanes)
   int64_t chunk = count;
-  const int64_t min_chunk = (int64_t)h->sm_count * 512 * 4;
-  if (count >= 4 * min_chunk) {
-    int64_t parts = count / min_chunk;
-    if (parts > 16) parts = 16;
-    chunk = (count + parts - 1) / parts;
+  {
+    static int env_parts = -1;
+    if (env_parts < 0) {
+      const char* e = getenv("CCP_HOST_CHUNKS");
+      env_parts = e ? atoi(e) : 0;
+    }
+    int64_t parts = env_parts > 0 ? env_parts : count / ((int64_t)h->sm_count * 384 * 4);
+    if (parts > 8) parts = 8;
+    if (parts > 1) chunk = (count + parts - 1) / parts;
   }
   int ci = 0;
   for (int64_t off = 0; off < count; off += chunk, ++ci) {

@@ -128,17 +128,18 @@ CCP_HD void ccp_sincos(double x, double* s_out, double* c_out) {
 }
 
 // atan2(y, x) for y >= 0, x >= 0 (the only case angularDistance needs).  Result in [0, pi/2].
-// min/max -> t in [0,1]; shift by atan(0), pi/8 or pi/4 so |t'| <= tan(pi/16); 12-term series.
+// min/max -> t in [0,1]; shift by atan(0), pi/8 or pi/4 so |t'| <= tan(pi/16); 12-term series; one division.
 CCP_HD double ccp_atan2_pos(double y, double x) {
   const bool inv = y > x;
   const double num = inv ? x : y;
   const double den = inv ? y : x;
-  double t = (den > 0.0) ? num / den : 0.0;
-  const bool hi = t > 0x1.561b82ab7f990p-1;   // tan(3 pi/16)
-  const bool mid = t > 0x1.975f5e0553158p-3;  // tan(pi/16)
+  // t = num/den in [0,1] is never formed: the region tests and the shifted argument
+  // t' = (t - t0)/(1 + t t0) = (num - t0 den)/(den + t0 num) need ONE division in total
+  const bool hi = num > 0x1.561b82ab7f990p-1 * den;   // t > tan(3 pi/16)
+  const bool mid = num > 0x1.975f5e0553158p-3 * den;  // t > tan(pi/16)
   const double t0 = hi ? 1.0 : (mid ? 0x1.a827999fcef32p-2 : 0.0);   // 1, tan(pi/8), 0
   const double off = hi ? 0x1.921fb54442d18p-1 : (mid ? 0x1.921fb54442d18p-2 : 0.0);  // pi/4, pi/8, 0
-  double tr = (t - t0) / CCP_FMA(t, t0, 1.0);
+  double tr = (den > 0.0) ? CCP_FMA(-t0, den, num) / CCP_FMA(t0, num, den) : 0.0;
   double z = tr * tr;
   double p = CCP_FMA(z, -0x1.642c8590b2164p-5, 0x1.8618618618618p-5);  // -1/23, 1/21
   p = CCP_FMA(z, p, -0x1.af286bca1af28p-5);                            // -1/19
@@ -292,13 +293,19 @@ CCP_HD void ccp_qmul_link_rx(const ccp_link& L, double* q) {
 // Per-sample storage of the 7K (sin, cos) pairs between the passes.  The host build and the simple
 // kernels keep them in a local array; the projection kernel keeps them in shared memory
 // ([slot][thread], conflict-free) to free ~56 registers.
+// The forward pass also leaves, per joint, the (x, y) components of the lever arm to the EE-0 origin
+// expressed in that joint's frame (rx, ry): the Jacobian pass reads them instead of recomputing them.
 template <int K>
 struct ccp_sc_local {
-  double v[K][CCPC_DOF][2];
+  double v[K][CCPC_DOF][4];
   CCP_HD double& s(int a, int i) { return v[a][i][0]; }
   CCP_HD double& c(int a, int i) { return v[a][i][1]; }
+  CCP_HD double& rx(int a, int i) { return v[a][i][2]; }
+  CCP_HD double& ry(int a, int i) { return v[a][i][3]; }
   CCP_HD double s(int a, int i) const { return v[a][i][0]; }
   CCP_HD double c(int a, int i) const { return v[a][i][1]; }
+  CCP_HD double rx(int a, int i) const { return v[a][i][2]; }
+  CCP_HD double ry(int a, int i) const { return v[a][i][3]; }
 };
 
 // ------------------------------------------------------------------------------------------
@@ -346,12 +353,19 @@ CCP_HD void ccp_forward(const ccp_model& M, const XT& x, SC& S, ccp_fwd<K>& F) {
   double r[3] = {0.0, 0.0, M.arm[0].fl};
   {
     const ccp_arm& A = M.arm[0];
+    S.rx(0, 6) = r[0]; S.ry(0, 6) = r[1];
     ccp_down_pt<PANDA, 6>(A.link[6], S.s(0, 6), S.c(0, 6), r);
+    S.rx(0, 5) = r[0]; S.ry(0, 5) = r[1];
     ccp_down_pt<PANDA, 5>(A.link[5], S.s(0, 5), S.c(0, 5), r);
+    S.rx(0, 4) = r[0]; S.ry(0, 4) = r[1];
     ccp_down_pt<PANDA, 4>(A.link[4], S.s(0, 4), S.c(0, 4), r);
+    S.rx(0, 3) = r[0]; S.ry(0, 3) = r[1];
     ccp_down_pt<PANDA, 3>(A.link[3], S.s(0, 3), S.c(0, 3), r);
+    S.rx(0, 2) = r[0]; S.ry(0, 2) = r[1];
     ccp_down_pt<PANDA, 2>(A.link[2], S.s(0, 2), S.c(0, 2), r);
+    S.rx(0, 1) = r[0]; S.ry(0, 1) = r[1];
     ccp_down_pt<PANDA, 1>(A.link[1], S.s(0, 1), S.c(0, 1), r);
+    S.rx(0, 0) = r[0]; S.ry(0, 0) = r[1];
     ccp_down_pt<PANDA, 0>(A.link[0], S.s(0, 0), S.c(0, 0), r);
   }
   double p0[3];
@@ -370,12 +384,19 @@ CCP_HD void ccp_forward(const ccp_model& M, const XT& x, SC& S, ccp_fwd<K>& F) {
     v[1] = CCP_FMA(A.Rwb[1], e0, CCP_FMA(A.Rwb[4], e1, A.Rwb[7] * e2));
     v[2] = CCP_FMA(A.Rwb[2], e0, CCP_FMA(A.Rwb[5], e1, A.Rwb[8] * e2));
     ccp_up_pt<PANDA, 0>(A.link[0], S.s(a, 0), S.c(a, 0), v);
+    S.rx(a, 0) = v[0]; S.ry(a, 0) = v[1];
     ccp_up_pt<PANDA, 1>(A.link[1], S.s(a, 1), S.c(a, 1), v);
+    S.rx(a, 1) = v[0]; S.ry(a, 1) = v[1];
     ccp_up_pt<PANDA, 2>(A.link[2], S.s(a, 2), S.c(a, 2), v);
+    S.rx(a, 2) = v[0]; S.ry(a, 2) = v[1];
     ccp_up_pt<PANDA, 3>(A.link[3], S.s(a, 3), S.c(a, 3), v);
+    S.rx(a, 3) = v[0]; S.ry(a, 3) = v[1];
     ccp_up_pt<PANDA, 4>(A.link[4], S.s(a, 4), S.c(a, 4), v);
+    S.rx(a, 4) = v[0]; S.ry(a, 4) = v[1];
     ccp_up_pt<PANDA, 5>(A.link[5], S.s(a, 5), S.c(a, 5), v);
+    S.rx(a, 5) = v[0]; S.ry(a, 5) = v[1];
     ccp_up_pt<PANDA, 6>(A.link[6], S.s(a, 6), S.c(a, 6), v);
+    S.rx(a, 6) = v[0]; S.ry(a, 6) = v[1];
     v[2] -= A.fl;
     ccp_rot2t(A.cphi, A.sphi, v[0], v[1]);
     double* tc = F.tc[a - 1];
@@ -454,9 +475,10 @@ struct ccp_jac {
 };
 
 template <bool PANDA, int I, bool ARM0, class SC, class JT>
-CCP_HD void ccp_jac_link(const ccp_arm& A, int a, int p, const SC& S, double* r, double* w, double* m, JT& J) {
-  // joint I sees (r, w, m) in frame I:  d f0 / d q = +-(r x w)_z,  d f1 / d q = +-m_z  (+ on arm 0)
-  const double cz = CCP_FMA(r[0], w[1], -(r[1] * w[0]));
+CCP_HD void ccp_jac_link(const ccp_arm& A, int a, int p, const SC& S, double* w, double* m, JT& J) {
+  // joint I sees (r, w, m) in frame I:  d f0 / d q = +-(r x w)_z,  d f1 / d q = +-m_z  (+ on arm 0);
+  // r = lever arm to the EE-0 origin, left behind by the forward pass
+  const double cz = CCP_FMA(S.rx(a, I), w[1], -(S.ry(a, I) * w[0]));
   if (ARM0) {
     J.z(p, 0, I) = cz;
     J.z(p, 1, I) = m[2];
@@ -466,20 +488,19 @@ CCP_HD void ccp_jac_link(const ccp_arm& A, int a, int p, const SC& S, double* r,
   }
   if (I > 0) {
     const double s = S.s(a, I), c = S.c(a, I);
-    ccp_down_pt<PANDA, I>(A.link[I], s, c, r);
     ccp_down_vec<PANDA, I>(A.link[I], s, c, w);
     ccp_down_vec<PANDA, I>(A.link[I], s, c, m);
   }
 }
 template <bool PANDA, bool ARM0, class SC, class JT>
-CCP_HD void ccp_jac_arm(const ccp_arm& A, int a, int p, const SC& S, double* r, double* w, double* m, JT& J) {
-  ccp_jac_link<PANDA, 6, ARM0>(A, a, p, S, r, w, m, J);
-  ccp_jac_link<PANDA, 5, ARM0>(A, a, p, S, r, w, m, J);
-  ccp_jac_link<PANDA, 4, ARM0>(A, a, p, S, r, w, m, J);
-  ccp_jac_link<PANDA, 3, ARM0>(A, a, p, S, r, w, m, J);
-  ccp_jac_link<PANDA, 2, ARM0>(A, a, p, S, r, w, m, J);
-  ccp_jac_link<PANDA, 1, ARM0>(A, a, p, S, r, w, m, J);
-  ccp_jac_link<PANDA, 0, ARM0>(A, a, p, S, r, w, m, J);
+CCP_HD void ccp_jac_arm(const ccp_arm& A, int a, int p, const SC& S, double* w, double* m, JT& J) {
+  ccp_jac_link<PANDA, 6, ARM0>(A, a, p, S, w, m, J);
+  ccp_jac_link<PANDA, 5, ARM0>(A, a, p, S, w, m, J);
+  ccp_jac_link<PANDA, 4, ARM0>(A, a, p, S, w, m, J);
+  ccp_jac_link<PANDA, 3, ARM0>(A, a, p, S, w, m, J);
+  ccp_jac_link<PANDA, 2, ARM0>(A, a, p, S, w, m, J);
+  ccp_jac_link<PANDA, 1, ARM0>(A, a, p, S, w, m, J);
+  ccp_jac_link<PANDA, 0, ARM0>(A, a, p, S, w, m, J);
 }
 
 template <int K, bool PANDA, class SC, class JT>
@@ -500,26 +521,22 @@ CCP_HD void ccp_jacobian(const ccp_model& M, const SC& S, const ccp_fwd<K>& F, J
     // arm a: frame EE_a -> frame 7 -> ... -> frame 1
     {
       const ccp_arm& A = M.arm[a];
-      double r[3] = {tc[0], tc[1], tc[2]};
       double w[3] = {u[0], u[1], u[2]};
       double m[3] = {n[0], n[1], n[2]};
-      ccp_rot2(A.cphi, A.sphi, r[0], r[1]);
-      r[2] += A.fl;
       ccp_rot2(A.cphi, A.sphi, w[0], w[1]);
       ccp_rot2(A.cphi, A.sphi, m[0], m[1]);
-      ccp_jac_arm<PANDA, false>(A, a, p, S, r, w, m, J);
+      ccp_jac_arm<PANDA, false>(A, a, p, S, w, m, J);
     }
     // arm 0: u, n rotated into EE_0's frame by R_c^T, lever arm starts at the EE-0 origin
     {
       const ccp_arm& A = M.arm[0];
-      double r[3] = {0.0, 0.0, A.fl};
       double w[3] = {u[0], u[1], u[2]};
       double m[3] = {n[0], n[1], n[2]};
       ccp_qrot_inv(F.qc[p], w);
       ccp_qrot_inv(F.qc[p], m);
       ccp_rot2(A.cphi, A.sphi, w[0], w[1]);
       ccp_rot2(A.cphi, A.sphi, m[0], m[1]);
-      ccp_jac_arm<PANDA, true>(A, 0, p, S, r, w, m, J);
+      ccp_jac_arm<PANDA, true>(A, 0, p, S, w, m, J);
     }
   }
 }
@@ -552,8 +569,30 @@ CCP_HD void ccp_newton_step(const ccp_model& M, const ccp_fwd<K>& F, const JT& J
           }
           G[I][Jx] = acc;
         }
+  double y[m];
+  if (m == 2) {
+    // 2x2: Cramer's rule, one division.  A vanished row (g_kk = 0) or dependent rows (det <= 0) drop row 1 / the
+    // vanished row, exactly what the L D L^T path below does.
+    const double g00 = G[0][0], g01 = G[1][0], g11 = G[1][1];
+    const double det = CCP_FMA(g00, g11, -(g01 * g01));
+    const bool k0 = g00 > 0.0, k1 = g11 > 0.0;
+    if (k0 && k1 && det > 0.0) {
+      const double inv = 1.0 / det;
+      y[0] = CCP_FMA(g11, F.f[0], -(g01 * F.f[1])) * inv;
+      y[1] = CCP_FMA(g00, F.f[1], -(g01 * F.f[0])) * inv;
+    } else if (k0) {
+      y[0] = F.f[0] / g00;
+      y[1] = 0.0;
+    } else if (k1) {
+      y[0] = 0.0;
+      y[1] = F.f[1] / g11;
+    } else {
+      y[0] = 0.0;
+      y[1] = 0.0;
+    }
+  } else {
   // L D L^T with row dropping.  Lm is unit lower triangular, D the pivots.
-  double D[m], invD[m], y[m];
+  double D[m], invD[m];
   double Lm[m][m];
 #pragma unroll
   for (int k = 0; k < m; ++k) {
@@ -587,6 +626,7 @@ CCP_HD void ccp_newton_step(const ccp_model& M, const ccp_fwd<K>& F, const JT& J
 #pragma unroll
     for (int j = k + 1; j < m; ++j) v = CCP_FMA(-Lm[j][k], y[j], v);
     y[k] = (invD[k] != 0.0) ? v : 0.0;
+  }
   }
   // x -= step * J^T y
 #pragma unroll
@@ -763,4 +803,54 @@ CCP_HD double ccp_uniform01(uint64_t seed, uint64_t sample, uint32_t lane) {
 CCP_HD double ccp_seed_uniform(const ccp_model& M, uint64_t seed, uint64_t sample, int j) {
   const int i = j % CCPC_DOF;
   return CCP_FMA(ccp_uniform01(seed, sample, (uint32_t)j), M.ub[i] - M.lb[i], M.lb[i]);
+}
+
+// ------------------------------------------------------------------------------------------
+// discreteGeodesic building blocks (jy_ProjectedStateSpace.cpp:32-96)
+// ------------------------------------------------------------------------------------------
+// KinematicChainSpace::interpolate, one joint (KinematicChain.h:145-171): the short way round when
+// |to - from| > pi, wrapped back into [-pi, pi].
+CCP_HD double ccp_interpolate_joint(double from, double to, double t) {
+  const double PI = 3.14159265358979323846;
+  double diff = to - from;
+  if (fabs(diff) <= PI) return CCP_FMA(diff, t, from);
+  if (diff > 0.0) diff = 2.0 * PI - diff;
+  else diff = -2.0 * PI - diff;
+  double v = CCP_FMA(-diff, t, from);
+  if (v > PI) v -= 2.0 * PI;
+  else if (v < -PI) v += 2.0 * PI;
+  return v;
+}
+// RealVectorStateSpace::distance (Euclidean), sequential accumulation
+template <int N, class XA, class XB>
+CCP_HD double ccp_distance(const XA& a, const XB& b) {
+  double acc = 0.0;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const double d = a[j] - b[j];
+    acc = CCP_FMA(d, d, acc);
+  }
+  return sqrt(acc);
+}
+
+// Bookkeeping of one geodesic after the projection of `scratch` finished (jy_ProjectedStateSpace.cpp:65-90).
+// Returns 0 = keep walking (scratch accepted, `dist` updated), 1 = stop: reached (dist < delta after accepting),
+// 2 = stop: break (projection failed / deviated / wandered / no progress).  On 0 and 1 the caller stores scratch.
+struct ccp_geo_state {
+  double dist;   // distance(previous, to)
+  double total;  // accumulated arc length
+  double max;    // dist0 * lambda
+};
+template <int N, class XP, class XS, class XT>
+CCP_HD int ccp_geodesic_advance(ccp_geo_state& g, bool projected_ok, const XP& previous, const XS& scratch, const XT& to,
+                                double delta, double lambda) {
+  if (!projected_ok) return 2;                                  // not on manifold
+  const double step = ccp_distance<N>(previous, scratch);
+  if (step > lambda * delta) return 2;                          // deviated
+  g.total += step;
+  if (g.total > g.max) return 2;                                // wandered too far
+  const double newDist = ccp_distance<N>(scratch, to);
+  if (newDist >= g.dist) return 2;                              // no closer than before
+  g.dist = newDist;
+  return (g.dist >= delta) ? 0 : 1;
 }

@@ -1,0 +1,144 @@
+// ccp_geodesic.cu — batched discreteGeodesic (jy_ProjectedStateSpace.cpp:32-96): the planner's real consumer of
+// project (stefanBiPRM.cpp:315; checkMotion at :397,:463).  One thread walks one edge: interpolate by delta toward
+// `to` (KinematicChain.h:145-171), project, check deviation / arc length / progress, repeat.  The steps of an edge
+// are sequential, so the parallelism is across edges; like the projection kernel this is a persistent lane-refill
+// loop whose trip is ONE Newton iteration, so edges of different length and projections of different difficulty
+// do not idle the warp.  The state validity check (MoveIt collision, jy_ProjectedStateSpace.cpp:66) is a host
+// concern: this is the `interpolate = true` walk; callers validate the returned states lazily.
+#include "ccp_device.cuh"
+#include "ccp_internal.h"
+
+struct ccp_geodesic_args {
+  const double* from;  // AOS [edges][n]
+  const double* to;    // AOS [edges][n]
+  double* states;      // AOS [edges][max_states][n]; states[e][0] = from
+  int32_t* n_states;   // [edges]
+  uint8_t* reached;    // [edges] discreteGeodesic's return value (dist <= delta)
+  int32_t* total_iters;  // [edges] Newton iterations spent on the edge (may be null)
+  unsigned long long* counter;
+  long long edges;
+  int max_states;
+  double delta, lambda;
+};
+
+template <int K, bool PANDA>
+__global__ void __launch_bounds__(128, 3)
+ccp_geodesic_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ ccp_geodesic_args A) {
+  constexpr int n = CCPC_DOF * K;
+  double x[n];
+  ccp_sc_local<K> S;
+  ccp_jac<K> J;
+  ccp_geo_state g;
+  g.dist = g.total = g.max = 0.0;
+  int it = 0, ns = 0, iters_sum = 0;
+  long long e = -1;
+  bool need_edge = true;
+  for (;;) {
+    if (need_edge) {
+      // ---- start the next edge (jy_ProjectedStateSpace.cpp:35-50) ----
+      e = claim_next(A.counter);
+      if (e >= A.edges) break;
+      const double* fr = A.from + e * n;
+      const double* to = A.to + e * n;
+      double* out = A.states + (e * A.max_states) * n;
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < n; ++j) {
+        const double a = __ldg(fr + j), b = __ldg(to + j);
+        out[j] = a;
+        const double d = a - b;
+        acc = CCP_FMA(d, d, acc);
+        x[j] = a;
+      }
+      g.dist = sqrt(acc);
+      g.total = 0.0;
+      g.max = g.dist * A.lambda;
+      ns = 1;
+      iters_sum = 0;
+      if (g.dist <= A.delta) {  // already there
+        A.n_states[e] = 1;
+        A.reached[e] = 1;
+        if (A.total_iters) A.total_iters[e] = 0;
+        continue;
+      }
+      const double t = A.delta / g.dist;
+#pragma unroll
+      for (int j = 0; j < n; ++j) x[j] = ccp_interpolate_joint(x[j], __ldg(to + j), t);
+      it = 0;
+      need_edge = false;
+    }
+    ccp_fwd<K> F;
+    ccp_forward<K, PANDA>(M, x, S, F);
+    const bool cont = ccp_needs_step<K>(M, F.f) && it < M.max_iter;
+    if (cont) {
+      ++it;
+      ccp_jacobian<K, PANDA>(M, S, F, J);
+      ccp_newton_step<K>(M, F, J, x);
+    } else {
+      // ---- the projection of this step finished: bookkeeping of the walk ----
+      iters_sum += it;
+      const bool okk = ccp_converged<K>(M, F.f) && ccp_joint_valid<K>(M, x);
+      const double* to = A.to + e * n;
+      double* out = A.states + (e * A.max_states) * n;
+      const double* prev = out + (long long)(ns - 1) * n;
+      double tov[n], pv[n];
+#pragma unroll
+      for (int j = 0; j < n; ++j) {
+        tov[j] = __ldg(to + j);
+        pv[j] = prev[j];
+      }
+      int code = ccp_geodesic_advance<n>(g, okk, pv, x, tov, A.delta, A.lambda);
+      bool overflow = false;
+      if (code != 2) {
+        if (ns < A.max_states) {
+#pragma unroll
+          for (int j = 0; j < n; ++j) out[(long long)ns * n + j] = x[j];
+          ++ns;
+        } else {
+          code = 2;  // out of room: report as not reached
+          overflow = true;
+        }
+      }
+      if (code == 0) {
+        const double t = A.delta / g.dist;
+#pragma unroll
+        for (int j = 0; j < n; ++j) x[j] = ccp_interpolate_joint(x[j], tov[j], t);
+        it = 0;
+      } else {
+        A.n_states[e] = ns;
+        A.reached[e] = (!overflow && g.dist <= A.delta) ? 1 : 0;  // return dist <= tolerance (jy_ProjectedStateSpace.cpp:95)
+        if (A.total_iters) A.total_iters[e] = iters_sum;
+        need_edge = true;
+      }
+    }
+  }
+}
+
+cudaError_t ccp_launch_geodesic(int sm_count, const ccp_model& M, const double* from, const double* to, long long edges,
+                                double delta, double lambda, int max_states, double* states, int32_t* n_states,
+                                uint8_t* reached, int32_t* total_iters, unsigned long long* counter, cudaStream_t st) {
+  ccp_geodesic_args A;
+  A.from = from;
+  A.to = to;
+  A.states = states;
+  A.n_states = n_states;
+  A.reached = reached;
+  A.total_iters = total_iters;
+  A.counter = counter;
+  A.edges = edges;
+  A.max_states = max_states;
+  A.delta = delta;
+  A.lambda = lambda;
+  long long need = (edges + 127) / 128;
+  long long cap = (long long)sm_count * 3;
+  int grid = (int)(need < cap ? need : cap);
+  if (grid < 1) grid = 1;
+  if (M.n_arms == 2) {
+    if (M.panda_alpha) ccp_geodesic_kernel<2, true><<<grid, 128, 0, st>>>(M, A);
+    else ccp_geodesic_kernel<2, false><<<grid, 128, 0, st>>>(M, A);
+  } else {
+    if (M.panda_alpha) ccp_geodesic_kernel<3, true><<<grid, 128, 0, st>>>(M, A);
+    else ccp_geodesic_kernel<3, false><<<grid, 128, 0, st>>>(M, A);
+  }
+  return cudaGetLastError();
+}

@@ -15,10 +15,15 @@
 template <int K, int BLOCK>
 struct ccp_sc_smem {
   double* base;  // &smem[threadIdx.x]
-  __device__ __forceinline__ double& s(int a, int i) { return base[((a * CCPC_DOF + i) * 2 + 0) * BLOCK]; }
-  __device__ __forceinline__ double& c(int a, int i) { return base[((a * CCPC_DOF + i) * 2 + 1) * BLOCK]; }
-  __device__ __forceinline__ double s(int a, int i) const { return base[((a * CCPC_DOF + i) * 2 + 0) * BLOCK]; }
-  __device__ __forceinline__ double c(int a, int i) const { return base[((a * CCPC_DOF + i) * 2 + 1) * BLOCK]; }
+  __device__ __forceinline__ double& at(int a, int i, int k) const { return base[((a * CCPC_DOF + i) * 4 + k) * BLOCK]; }
+  __device__ __forceinline__ double& s(int a, int i) { return at(a, i, 0); }
+  __device__ __forceinline__ double& c(int a, int i) { return at(a, i, 1); }
+  __device__ __forceinline__ double& rx(int a, int i) { return at(a, i, 2); }
+  __device__ __forceinline__ double& ry(int a, int i) { return at(a, i, 3); }
+  __device__ __forceinline__ double s(int a, int i) const { return at(a, i, 0); }
+  __device__ __forceinline__ double c(int a, int i) const { return at(a, i, 1); }
+  __device__ __forceinline__ double rx(int a, int i) const { return at(a, i, 2); }
+  __device__ __forceinline__ double ry(int a, int i) const { return at(a, i, 3); }
 };
 
 // the Jacobian rows (28 (K-1) doubles) and the state x (7K doubles) can live there too
@@ -43,7 +48,7 @@ struct ccp_x_smem {
 template <int K, int BLOCK, int SM>
 constexpr size_t ccp_proj_smem_bytes() {
   return sizeof(double) * BLOCK *
-         (((SM & CCP_SM_SC) ? 2 * CCPC_DOF * K : 0) + ((SM & CCP_SM_J) ? 4 * CCPC_DOF * (K - 1) : 0) +
+         (((SM & CCP_SM_SC) ? 4 * CCPC_DOF * K : 0) + ((SM & CCP_SM_J) ? 4 * CCPC_DOF * (K - 1) : 0) +
           ((SM & CCP_SM_X) ? CCPC_DOF * K : 0));
 }
 
@@ -60,7 +65,7 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
   typename std::conditional<(SM & CCP_SM_SC) != 0, ccp_sc_smem<K, BLOCK>, ccp_sc_local<K>>::type S;
   if constexpr ((SM & CCP_SM_SC) != 0) {
     S.base = sm_next;
-    sm_next += 2 * CCPC_DOF * K * BLOCK;
+    sm_next += 4 * CCPC_DOF * K * BLOCK;
   }
   typename std::conditional<(SM & CCP_SM_J) != 0, ccp_jac_smem<K, BLOCK>, ccp_jac<K>>::type J;
   if constexpr ((SM & CCP_SM_J) != 0) {
@@ -169,7 +174,7 @@ static cudaError_t launch_project_g(int sm_count, const ccp_model& M, const ccp_
   if constexpr (K == 2) {
     switch (proj_variant()) {
       case 1: return launch_project_v<K, PANDA, SOA, GEN, 128, 3, CCP_SM_SC>(sm_count, M, A, st);
-      case 2: return launch_project_v<K, PANDA, SOA, GEN, 128, 4, CCP_SM_SC | CCP_SM_X>(sm_count, M, A, st);
+      case 2: return launch_project_v<K, PANDA, SOA, GEN, 128, 4, CCP_SM_SC>(sm_count, M, A, st);
       case 3: return launch_project_v<K, PANDA, SOA, GEN, 128, 3, CCP_SM_SC | CCP_SM_J>(sm_count, M, A, st);
       case 4: return launch_project_v<K, PANDA, SOA, GEN, 64, 6, 0>(sm_count, M, A, st);
       case 5: return launch_project_v<K, PANDA, SOA, GEN, 256, 2, CCP_SM_SC | CCP_SM_J>(sm_count, M, A, st);

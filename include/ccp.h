@@ -176,6 +176,23 @@ int ccp_sample_project_batch(ccp_handle* h, const ccp_sampler_args* a, int64_t c
 /* ≙ KinematicChainSpace::enforceBounds (KinematicChain.h:118-130), in place.                */
 int ccp_enforce_bounds_batch(ccp_handle* h, double* x_dev, int64_t count, int32_t layout, void* stream);
 
+/* ---- batched manifold traversal --------------------------------------------------------- */
+/* ≙ jy_ProjectedStateSpace::discreteGeodesic(from, to, interpolate = true, &geodesic)
+ * (jy_ProjectedStateSpace.cpp:32-96) for `edges` independent edges: walk from `from` toward `to` in steps of
+ * `delta` (KinematicChainSpace::interpolate, KinematicChain.h:145-171), projecting every step; stop when the
+ * projection fails, the step deviates by more than lambda*delta, the arc length exceeds lambda*dist, or no progress
+ * is made.  The state-validity check of the reference (MoveIt collision, :66) is NOT run: validate the returned states
+ * on the host (lazily).  Reference constants: delta 0.25, lambda 2.0 (ConstrainedPlanningCommon.cpp:118-119).
+ *   from_dev, to_dev : AOS double[edges][n]
+ *   states_dev       : AOS double[edges][max_states][n]; states[e][0] = from[e], then the accepted projections
+ *   n_states_dev     : int32[edges]  number of valid states of edge e (>= 1)
+ *   reached_dev      : uint8[edges]  discreteGeodesic's return value
+ *   iters_dev        : int32[edges]  Newton iterations spent on the edge, or NULL
+ * An edge that needs more than max_states states is reported as not reached.                              */
+int ccp_geodesic_batch(ccp_handle* h, const double* from_dev, const double* to_dev, int64_t edges, double delta,
+                       double lambda, int32_t max_states, double* states_dev, int32_t* n_states_dev,
+                       uint8_t* reached_dev, int32_t* iters_dev, void* stream);
+
 /* ---- host-buffer entry points (what a planner that owns host states calls) -------------- */
 /* Same as ccp_project_batch but all pointers are HOST memory, AOS double[count][n]
  * (the gathered OMPL states).  Copies in, projects, copies out; synchronous.                */

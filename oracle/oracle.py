@@ -134,6 +134,25 @@ class OracleA:
             self.lib.oa_arm_jacobian(self._buf, C.c_int(arm), _dp(q[i]), _dp(J[i]))
         return J.reshape(-1, 6, 7)
 
+    def discrete_geodesic(self, frm, to, delta=0.25, lam=2.0, fd=True, max_states=64, nthreads=1):
+        """jy_ProjectedStateSpace::discreteGeodesic(interpolate=true) per edge -> (reached, n_states, states)."""
+        frm, to = _as_states(frm, self.n), _as_states(to, self.n)
+        e = frm.shape[0]
+        states = np.zeros((e, max_states, self.n))
+        ns = np.zeros(e, np.int32)
+        rc = np.zeros(e, np.uint8)
+        self.lib.oa_discrete_geodesic_batch(self._buf, _dp(frm), _dp(to), C.c_int64(e), C.c_double(delta), C.c_double(lam),
+                                            C.c_int(1 if fd else 0), C.c_int(max_states), _dp(states), _dp(ns), _dp(rc),
+                                            C.c_int(nthreads))
+        return rc, ns, states
+
+    def interpolate(self, frm, to, t):
+        frm = np.ascontiguousarray(frm, dtype=np.float64)
+        to = np.ascontiguousarray(to, dtype=np.float64)
+        out = np.zeros_like(frm)
+        self.lib.oa_interpolate(_dp(frm), _dp(to), C.c_double(t), _dp(out), C.c_int(frm.size))
+        return out
+
     def seeds_uniform(self, seed, first, count):
         x = np.zeros((count, self.n))
         self.lib.oa_seeds_uniform(self._buf, C.c_uint64(seed), C.c_int64(first), C.c_int64(count), _dp(x))
@@ -220,6 +239,17 @@ class OracleB:
         J = np.zeros((q.shape[0], 42))
         self.lib.ob_arm_fk_batch(self._buf, C.c_int(arm), _dp(q), C.c_int64(q.shape[0]), _dp(T), _dp(J))
         return T.reshape(-1, 3, 4), J.reshape(-1, 6, 7)
+
+    def discrete_geodesic(self, frm, to, delta=0.25, lam=2.0, max_states=64):
+        frm, to = _as_states(frm, self.n), _as_states(to, self.n)
+        e = frm.shape[0]
+        states = np.zeros((e, max_states, self.n))
+        ns = np.zeros(e, np.int32)
+        rc = np.zeros(e, np.uint8)
+        it = np.zeros(e, np.int32)
+        self.lib.ob_geodesic_batch(self._buf, _dp(frm), _dp(to), C.c_int64(e), C.c_double(delta), C.c_double(lam),
+                                   C.c_int(max_states), _dp(states), _dp(ns), _dp(rc), _dp(it))
+        return rc, ns, states, it
 
     def seeds_uniform(self, seed, first, count):
         x = np.zeros((count, self.n))

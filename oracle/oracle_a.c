@@ -5,11 +5,15 @@
  * links or calls this file.  It is used by tests/, __graft_entry__.smoke() and the cpu_baseline /
  * --impl reference legs of bench.py.
  *
- * PARITY STATUS: "parity unpinned" by reference tests (the reference has none) and
- * the reference cannot be compiled here (needs OMPL, RBDL, Eigen, Boost, ROS, yaml-cpp: none are
- * installed, no network).  This file is pinned instead against the reference's only dumped
- * artefacts, debug/dumbbell_path.txt and debug/Wine_Bottle_path.txt (tests/golden/), the EE
- * poses quoted in config/ *.yaml comments, and Franka's published flange pose.
+ * PARITY STATUS: the reference has no tests and cannot be compiled here (needs OMPL,
+ * RBDL, Eigen, Boost, ROS, yaml-cpp: none are installed, no network), so nothing is pinned by
+ * reference TESTS.  It IS pinned by reference OUTPUTS: debug/dumbbell_path.txt and
+ * debug/Wine_Bottle_path.txt (tests/golden/) are path.interpolate() dumps whose interior rows are
+ * states of discreteGeodesic between consecutive roadmap vertices, i.e. real outputs of the
+ * reference's project().  oa_discrete_geodesic re-walks those edges and reproduces all 25 rows to
+ * the 6 printed digits (tests/test_geodesic_golden.py).  Further pins: row 0 = start_joint, the
+ * tolerance band of every interior row, the EE poses quoted in config/ *.yaml comments, Franka's
+ * published flange pose.
  *
  * It restates, in plain C with libm, the arithmetic of (paths relative to the reference root):
  *   - PandaModel::initModel / transformDH        src/kinematics/panda_rbdl.cpp:73-161
@@ -577,4 +581,76 @@ int oa_max_threads(void) {
 #else
   return 1;
 #endif
+}
+
+/* ---------- manifold traversal ---------- */
+/* KinematicChainSpace::interpolate, KinematicChain.h:145-171 */
+void oa_interpolate(const double* from, const double* to, double t, double* state, int n) {
+  const double pi = 3.14159265358979323846;
+  for (int i = 0; i < n; ++i) {
+    double diff = to[i] - from[i];
+    if (fabs(diff) <= pi) state[i] = from[i] + diff * t;
+    else {
+      if (diff > 0.0) diff = 2.0 * pi - diff;
+      else diff = -2.0 * pi - diff;
+      state[i] = from[i] - diff * t;
+      if (state[i] > pi) state[i] -= 2.0 * pi;
+      else if (state[i] < -pi) state[i] += 2.0 * pi;
+    }
+  }
+}
+/* RealVectorStateSpace::distance */
+static double oa_distance(const double* a, const double* b, int n) {
+  double dist = 0.0;
+  for (int i = 0; i < n; ++i) {
+    double diff = a[i] - b[i];
+    dist += diff * diff;
+  }
+  return sqrt(dist);
+}
+/* jy_ProjectedStateSpace::discreteGeodesic(from, to, interpolate = true, &geodesic), jy_ProjectedStateSpace.cpp:32-96.
+ * states: max_states x n, states[0] = from.  Returns the reference's bool; *n_states = geodesic->size().
+ * (With interpolate = true the validity checker is never consulted, :66.)                                   */
+int oa_discrete_geodesic(const oa_model* M, const double* from, const double* to, double delta_, double lambda_,
+                         int use_fd, int max_states, double* states, int* n_states) {
+  const int n = OA_DOF * M->n_arms;
+  int ns = 0;
+  memcpy(states, from, sizeof(double) * n);
+  ns = 1;
+  const double tolerance = delta_;
+  double dist, step, total = 0;
+  if ((dist = oa_distance(from, to, n)) <= tolerance) { *n_states = ns; return 1; }
+  const double max = dist * lambda_;
+  double previous[OA_DOF * OA_MAX_ARMS], scratch[OA_DOF * OA_MAX_ARMS];
+  memcpy(previous, from, sizeof(double) * n);
+  do {
+    oa_interpolate(previous, to, delta_ / dist, scratch, n);
+    if (!oa_project(M, scratch, use_fd, NULL, NULL, NULL) || (step = oa_distance(previous, scratch, n)) > lambda_ * delta_)
+      break;
+    total += step;
+    if (total > max) break;
+    const double newDist = oa_distance(scratch, to, n);
+    if (newDist >= dist) break;
+    dist = newDist;
+    memcpy(previous, scratch, sizeof(double) * n);
+    if (ns >= max_states) break; /* out of room (not in the reference; mirrors the engine's cap) */
+    memcpy(states + (size_t)ns * n, scratch, sizeof(double) * n);
+    ++ns;
+  } while (dist >= tolerance);
+  *n_states = ns;
+  return dist <= tolerance;
+}
+void oa_discrete_geodesic_batch(const oa_model* M, const double* from, const double* to, int64_t edges, double delta_,
+                                double lambda_, int use_fd, int max_states, double* states, int32_t* n_states,
+                                uint8_t* reached, int nthreads) {
+  const int n = OA_DOF * M->n_arms;
+  (void)nthreads;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads > 0 ? nthreads : 1)
+  for (int64_t e = 0; e < edges; ++e) {
+    int ns = 0;
+    int r = oa_discrete_geodesic(M, from + e * n, to + e * n, delta_, lambda_, use_fd, max_states,
+                                 states + (size_t)e * max_states * n, &ns);
+    n_states[e] = ns;
+    reached[e] = (uint8_t)r;
+  }
 }

@@ -76,6 +76,64 @@ static void project_batch(const ccp_model* M, double* x, int64_t count, uint8_t*
     if (resid) for (int k = 0; k < m; ++k) resid[s * m + k] = f[k];
   }
 }
+
+// host twin of ccp_geodesic_kernel (same calls, same order)
+template <int K, bool P>
+static void geodesic_batch(const ccp_model* M, const double* from, const double* to, int64_t edges, double delta,
+                           double lambda, int max_states, double* states, int32_t* n_states, uint8_t* reached,
+                           int32_t* total_iters) {
+  constexpr int n = 7 * K, m = 2 * (K - 1);
+#pragma omp parallel for schedule(dynamic, 8)
+  for (int64_t e = 0; e < edges; ++e) {
+    const double* fr = from + e * n;
+    const double* tov = to + e * n;
+    double* out = states + (size_t)e * max_states * n;
+    double x[n];
+    double acc = 0.0;
+    for (int j = 0; j < n; ++j) {
+      out[j] = fr[j];
+      const double d = fr[j] - tov[j];
+      acc = CCP_FMA(d, d, acc);
+      x[j] = fr[j];
+    }
+    ccp_geo_state g;
+    g.dist = sqrt(acc);
+    g.total = 0.0;
+    g.max = g.dist * lambda;
+    int ns = 1, iters_sum = 0;
+    bool overflow = false;
+    if (g.dist <= delta) {
+      n_states[e] = 1;
+      reached[e] = 1;
+      if (total_iters) total_iters[e] = 0;
+      continue;
+    }
+    for (;;) {
+      const double t = delta / g.dist;
+      for (int j = 0; j < n; ++j) x[j] = ccp_interpolate_joint(x[j], tov[j], t);
+      double f[m];
+      int32_t it;
+      bool cv, okk;
+      ccp_project_one<K, P>(*M, x, f, &it, &cv, &okk);
+      iters_sum += it;
+      const double* prev = out + (size_t)(ns - 1) * n;
+      int code = ccp_geodesic_advance<n>(g, okk, prev, x, tov, delta, lambda);
+      if (code != 2) {
+        if (ns < max_states) {
+          for (int j = 0; j < n; ++j) out[(size_t)ns * n + j] = x[j];
+          ++ns;
+        } else {
+          code = 2;
+          overflow = true;
+        }
+      }
+      if (code != 0) break;
+    }
+    n_states[e] = ns;
+    reached[e] = (!overflow && g.dist <= delta) ? 1 : 0;
+    if (total_iters) total_iters[e] = iters_sum;
+  }
+}
 }  // namespace
 
 extern "C" {
@@ -130,6 +188,14 @@ void ob_joint_valid_batch(const ccp_model* M, const double* x, int64_t count, ui
 }
 void ob_is_satisfied_batch(const ccp_model* M, const double* x, int64_t count, uint8_t* out) {
 #define OB_CALL(K, P) function_batch<K, P>(M, x, count, nullptr, out)
+  OB_DISPATCH(M, OB_CALL);
+#undef OB_CALL
+}
+
+void ob_geodesic_batch(const ccp_model* M, const double* from, const double* to, int64_t edges, double delta,
+                       double lambda, int max_states, double* states, int32_t* n_states, uint8_t* reached,
+                       int32_t* total_iters) {
+#define OB_CALL(K, P) geodesic_batch<K, P>(M, from, to, edges, delta, lambda, max_states, states, n_states, reached, total_iters)
   OB_DISPATCH(M, OB_CALL);
 #undef OB_CALL
 }
