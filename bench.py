@@ -321,7 +321,8 @@ def main():
         e2e = {"value": oe.item() / te.item(), "unit": UNIT, "h2d_bytes_per_step": count * n * 8,
                "d2h_bytes_per_step": count * (n * 8 + 1 + 4), "steps": e_steps,
                "projections_per_s": world * count * e_steps / te.item(),
-               "api": "ccp_project_batch_host (pinned host AOS states in, states + ok + iters out)"}
+               "api": "ccp_project_batch_host: pinned host AOS states in, states + ok + iters out; one persistent kernel "
+                      "consumes seed chunks as the copy engine lands them and finished chunks stream back"}
 
     if rank != 0:
         if world > 1:

@@ -51,7 +51,12 @@ struct ccp_handle {
   size_t d_stage_bytes;
   cudaStream_t hstream[3];
   cudaEvent_t ev0, ev1;
+  // streaming host path: device flags [ready | done | error], mapped pinned host flags, a pinned constant 1
+  int* d_flags;
+  int* h_flags;      // cudaHostAlloc(mapped): [0..63] host_done, [64] = 1
+  int* h_flags_dev;  // device alias of h_flags
   std::mutex mu;
+  std::mutex host_mu;  // the *_host entry points share the stage and the streaming flags: one at a time
   char err[512];
 };
 
@@ -310,6 +315,13 @@ int ccp_create(const ccp_model_desc* model, int32_t device, ccp_handle** out) {
   for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&nh->hstream[i], cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreate(&nh->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&nh->ev1);
+  nh->d_flags = nullptr;
+  nh->h_flags = nullptr;
+  nh->h_flags_dev = nullptr;
+  if (e == cudaSuccess) e = cudaMalloc(&nh->d_flags, sizeof(int) * 256);
+  if (e == cudaSuccess) e = cudaHostAlloc((void**)&nh->h_flags, sizeof(int) * 128, cudaHostAllocMapped);
+  if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&nh->h_flags_dev, nh->h_flags, 0);
+  if (e == cudaSuccess) nh->h_flags[64] = 1;
   if (e != cudaSuccess) {
     set_err(nullptr, CCP_ERR_CUDA, "ccp_create: %s", cudaGetErrorString(e));
     delete nh;
@@ -325,6 +337,8 @@ void ccp_destroy(ccp_handle* h) {
   cudaDeviceSynchronize();
   if (h->d_counters) cudaFree(h->d_counters);
   if (h->d_stage) cudaFree(h->d_stage);
+  if (h->d_flags) cudaFree(h->d_flags);
+  if (h->h_flags) cudaFreeHost(h->h_flags);
   for (int i = 0; i < 3; ++i) cudaStreamDestroy(h->hstream[i]);
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
@@ -664,6 +678,7 @@ int ccp_project_batch_host(ccp_handle* h, const double* seeds_host, int64_t coun
   if (rc) return rc;
   if (!h->has_ref) return set_err(h, CCP_ERR_STATE, "%s", "project before ccp_set_reference (setInitialPosition)");
   if (count == 0) return CCP_OK;
+  std::lock_guard<std::mutex> host_lock(h->host_mu);
   device_guard g(h->device);
   const int n = CCPC_DOF * h->model.n_arms, m = 2 * (h->model.n_arms - 1);
   const size_t per = sizeof(double) * n + sizeof(double) * m + 8 /* ok, conv, pad */ + sizeof(int32_t) + 4;
@@ -676,45 +691,83 @@ int ccp_project_batch_host(ccp_handle* h, const double* seeds_host, int64_t coun
   int32_t* dit = (int32_t*)((char*)dres + sizeof(double) * m * (size_t)count);
   uint8_t* dok = (uint8_t*)((char*)dit + sizeof(int32_t) * (size_t)count);
   uint8_t* dcv = dok + (size_t)count;
-  // chunking: big enough to fill the persistent grid several times over, small enough to overlap
-  // each chunk should still give every lane of the persistent grid a couple of seeds (148 SMs x 384 lanes)
-  int64_t chunk = count;
+  // ---- streaming pipeline -------------------------------------------------------------------------
+  // ONE persistent projection kernel runs over the whole batch while the copy engines stream the seeds in
+  // chunk by chunk (stream C) and the finished chunks out (stream D):
+  //   C: H2D chunk 0, flag 0, H2D chunk 1, flag 1, ...          (flag c = stream-ordered 4-byte copy)
+  //   K: kernel; a lane that claims a sample of chunk c waits for flag c; the last sample finished in
+  //      chunk c raises a mapped host flag
+  //   D: when the host sees that flag it enqueues the D2H copies of chunk c
+  // so the copies hide behind the kernel and there is one launch tail, not one per chunk.
+  int parts;
   {
     static int env_parts = -1;
     if (env_parts < 0) {
       const char* e = getenv("CCP_HOST_CHUNKS");
       env_parts = e ? atoi(e) : 0;
     }
-    int64_t parts = env_parts > 0 ? env_parts : count / ((int64_t)h->sm_count * 384 * 4);
-    if (parts > 8) parts = 8;
-    if (parts > 1) chunk = (count + parts - 1) / parts;
+    parts = env_parts > 0 ? env_parts : (int)(count / ((int64_t)h->sm_count * 384 * 2));  // measured best: 8 at 1 M
+    if (parts > 8 && env_parts <= 0) parts = 8;
+    if (parts > 32) parts = 32;
+    if (parts < 1) parts = 1;
   }
-  int ci = 0;
-  for (int64_t off = 0; off < count; off += chunk, ++ci) {
-    const int64_t c = (count - off < chunk) ? (count - off) : chunk;
-    cudaStream_t st = h->hstream[ci % 3];
-    CCP_CUDA(cudaMemcpyAsync(dx + off * n, seeds_host + off * n, sizeof(double) * n * c, cudaMemcpyHostToDevice, st));
+  int64_t chunk = (count + parts - 1) / parts;
+  chunk = (chunk + 7) / 8 * 8;
+  parts = (int)((count + chunk - 1) / chunk);
+  cudaStream_t sC = h->hstream[0], sK = h->hstream[1], sD = h->hstream[2];
+  int* d_ready = h->d_flags;
+  unsigned int* d_done = (unsigned int*)(h->d_flags + 64);
+  int* d_error = h->d_flags + 128;
+  for (int c = 0; c < parts; ++c) h->h_flags[c] = 0;
+  CCP_CUDA(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * 256, sK));
+  CCP_CUDA(cudaEventRecord(h->ev0, sK));
+  CCP_CUDA(cudaStreamWaitEvent(sC, h->ev0, 0));
+  {
     ccp_project_args A;
     memset(&A, 0, sizeof A);
-    A.seeds = dx + off * n;
-    A.x_out = dx + off * n;
-    A.ok = dok + off;
-    A.conv = dcv + off;
-    A.iters = dit + off;
-    A.resid = dres + off * m;
-    A.count = c;
+    A.seeds = dx;
+    A.x_out = dx;
+    A.ok = dok;
+    A.conv = dcv;
+    A.iters = dit;
+    A.resid = resid_host ? dres : nullptr;
+    A.count = count;
     A.gen_mode = -1;
-    rc = launch_project(h, A, CCP_LAYOUT_AOS, st);
+    A.ready = d_ready;
+    A.done = d_done;
+    A.host_done = h->h_flags_dev;
+    A.error = d_error;
+    A.chunk = chunk;
+    rc = launch_project(h, A, CCP_LAYOUT_AOS, sK);  // first: it overlaps even blocking (pageable) copies
     if (rc) return rc;
-    if (x_out_host)
-      CCP_CUDA(cudaMemcpyAsync(x_out_host + off * n, dx + off * n, sizeof(double) * n * c, cudaMemcpyDeviceToHost, st));
-    if (ok_host) CCP_CUDA(cudaMemcpyAsync(ok_host + off, dok + off, (size_t)c, cudaMemcpyDeviceToHost, st));
-    if (converged_host) CCP_CUDA(cudaMemcpyAsync(converged_host + off, dcv + off, (size_t)c, cudaMemcpyDeviceToHost, st));
-    if (iters_host) CCP_CUDA(cudaMemcpyAsync(iters_host + off, dit + off, sizeof(int32_t) * c, cudaMemcpyDeviceToHost, st));
-    if (resid_host)
-      CCP_CUDA(cudaMemcpyAsync(resid_host + off * m, dres + off * m, sizeof(double) * m * c, cudaMemcpyDeviceToHost, st));
   }
-  for (int i = 0; i < 3; ++i) CCP_CUDA(cudaStreamSynchronize(h->hstream[i]));
+  for (int c = 0; c < parts; ++c) {
+    const int64_t off = (int64_t)c * chunk;
+    const int64_t cn = (count - off < chunk) ? (count - off) : chunk;
+    CCP_CUDA(cudaMemcpyAsync(dx + off * n, seeds_host + off * n, sizeof(double) * n * cn, cudaMemcpyHostToDevice, sC));
+    CCP_CUDA(cudaMemcpyAsync(d_ready + c, h->h_flags + 64, sizeof(int), cudaMemcpyHostToDevice, sC));
+  }
+  for (int c = 0; c < parts; ++c) {
+    const int64_t off = (int64_t)c * chunk;
+    const int64_t cn = (count - off < chunk) ? (count - off) : chunk;
+    volatile int* flag = h->h_flags + c;
+    while (*flag == 0) {
+      if (cudaStreamQuery(sK) != cudaErrorNotReady) break;  // kernel finished (or failed): nothing more will be flagged
+    }
+    if (x_out_host)
+      CCP_CUDA(cudaMemcpyAsync(x_out_host + off * n, dx + off * n, sizeof(double) * n * cn, cudaMemcpyDeviceToHost, sD));
+    if (ok_host) CCP_CUDA(cudaMemcpyAsync(ok_host + off, dok + off, (size_t)cn, cudaMemcpyDeviceToHost, sD));
+    if (converged_host) CCP_CUDA(cudaMemcpyAsync(converged_host + off, dcv + off, (size_t)cn, cudaMemcpyDeviceToHost, sD));
+    if (iters_host) CCP_CUDA(cudaMemcpyAsync(iters_host + off, dit + off, sizeof(int32_t) * cn, cudaMemcpyDeviceToHost, sD));
+    if (resid_host)
+      CCP_CUDA(cudaMemcpyAsync(resid_host + off * m, dres + off * m, sizeof(double) * m * cn, cudaMemcpyDeviceToHost, sD));
+  }
+  int err = 0;
+  CCP_CUDA(cudaStreamSynchronize(sK));
+  CCP_CUDA(cudaStreamSynchronize(sC));
+  CCP_CUDA(cudaMemcpyAsync(&err, d_error, sizeof(int), cudaMemcpyDeviceToHost, sD));
+  CCP_CUDA(cudaStreamSynchronize(sD));
+  if (err) return set_err(h, CCP_ERR_CUDA, "%s", "streaming projection: a seed chunk never arrived (wait bound tripped)");
   return CCP_OK;
 }
 

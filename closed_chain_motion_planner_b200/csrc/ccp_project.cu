@@ -76,10 +76,16 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
   if constexpr ((SM & CCP_SM_X) != 0) x.base = sm_next;
   int it = 0;
   long long idx = claim_next(A.counter);
+  if (!GEN && !SOA && A.ready) wait_chunk_ready(A, idx, idx < A.count);
   if (idx < A.count) {
     if (!GEN) {
+      if (!SOA && A.ready) {
 #pragma unroll
-      for (int j = 0; j < n; ++j) x[j] = ld_elem<SOA>(A.seeds, idx, j, A.count, n);
+        for (int j = 0; j < n; ++j) x[j] = __ldcg(A.seeds + idx * n + j);
+      } else {
+#pragma unroll
+        for (int j = 0; j < n; ++j) x[j] = ld_elem<SOA>(A.seeds, idx, j, A.count, n);
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < n; ++j) x[j] = make_seed<K>(M, A, idx, j);
@@ -119,12 +125,28 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
           for (int j = 0; j < n; ++j) A.compact[slot * n + j] = x[j];
         }
       }
+      if (!GEN && !SOA && A.done) {
+        // streaming: count this sample into its chunk; the last one tells the host the chunk can be copied out
+        __threadfence();
+        const long long c = idx / A.chunk;
+        const long long in_chunk = (A.count - c * A.chunk < A.chunk) ? (A.count - c * A.chunk) : A.chunk;
+        if ((long long)atomicAdd(A.done + c, 1u) + 1 == in_chunk) {
+          __threadfence_system();
+          A.host_done[c] = 1;
+        }
+      }
       idx = claim_next(A.counter);
       it = 0;
+      if (!GEN && !SOA && A.ready) wait_chunk_ready(A, idx, idx < A.count);
       if (idx < A.count) {
         if (!GEN) {
+          if (!SOA && A.ready) {
 #pragma unroll
-          for (int j = 0; j < n; ++j) x[j] = ld_elem<SOA>(A.seeds, idx, j, A.count, n);
+            for (int j = 0; j < n; ++j) x[j] = __ldcg(A.seeds + idx * n + j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < n; ++j) x[j] = ld_elem<SOA>(A.seeds, idx, j, A.count, n);
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < n; ++j) x[j] = make_seed<K>(M, A, idx, j);
