@@ -163,6 +163,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--layout", default="aos", choices=["aos", "soa"])
+    ap.add_argument("--streams", type=int, default=1,
+                    help="independent seed batches of consecutive steps are issued round-robin on this many CUDA streams")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

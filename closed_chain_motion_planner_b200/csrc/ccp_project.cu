@@ -199,6 +199,7 @@ static cudaError_t launch_project_g(int sm_count, const ccp_model& M, const ccp_
       case 2: return launch_project_v<K, PANDA, SOA, GEN, 128, 4, CCP_SM_SC>(sm_count, M, A, st);
       case 3: return launch_project_v<K, PANDA, SOA, GEN, 128, 3, CCP_SM_SC | CCP_SM_J>(sm_count, M, A, st);
       case 4: return launch_project_v<K, PANDA, SOA, GEN, 64, 6, 0>(sm_count, M, A, st);
+      case 7: return launch_project_v<K, PANDA, SOA, GEN, 32, 12, 0>(sm_count, M, A, st);
       case 5: return launch_project_v<K, PANDA, SOA, GEN, 256, 2, CCP_SM_SC | CCP_SM_J>(sm_count, M, A, st);
       case 6: return launch_project_v<K, PANDA, SOA, GEN, 128, 2, 0>(sm_count, M, A, st);
       default: break;
