@@ -241,6 +241,8 @@ struct device_guard {
 static int launch_project(ccp_handle* h, ccp_project_args& A, int layout, cudaStream_t st) {
   if (!h->has_ref) return set_err(h, CCP_ERR_STATE, "%s", "project before ccp_set_reference (setInitialPosition)");
   if (A.count == 0) return CCP_OK;
+  if (A.count > 0x7fff0000LL)
+    return set_err(h, CCP_ERR_INVALID, "%s", "more than 2^31 - 65536 samples in one call: split the batch");
   unsigned slot;
   {
     std::lock_guard<std::mutex> lk(h->mu);

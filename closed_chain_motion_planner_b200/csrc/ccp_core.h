@@ -49,6 +49,7 @@ struct ccp_link {
   double sa, ca;      // sin/cos alpha
   double sha, cha;    // sin/cos alpha/2
   double qoff;        // theta offset (calibration dh.col(2))
+  double hqoff;       // half of it (the quaternion chain works on half angles)
 };
 
 struct ccp_arm {
@@ -93,21 +94,34 @@ CCP_HD int32_t ccp_lo32(double t) {
 #endif
 }
 
-// sin and cos of x.  Cody-Waite reduction by pi/2 in three pieces (33+33+53 bits), then the
-// classic degree-13/14 minimax kernels on [-pi/4, pi/4] (coefficients: Sun fdlibm k_sin/k_cos).
-// < 1 ulp for |x| < ~1e6, degrades gracefully (and identically on host and device) beyond.
+// v with its sign bit XORed by bit 31 of `flip` (an integer-pipe operation: a negation written as -v
+// is a DADD on the FP64 pipe)
+CCP_HD double ccp_xor_sign(double v, uint32_t flip) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(__double2hiint(v) ^ (int)(flip & 0x80000000u), __double2loint(v));
+#else
+  uint64_t u;
+  memcpy(&u, &v, sizeof u);
+  u ^= (uint64_t)(flip & 0x80000000u) << 32;
+  memcpy(&v, &u, sizeof u);
+  return v;
+#endif
+}
+
+// sin and cos of x.  Cody-Waite reduction by pi/2 in two pieces (33 bits, then the next 53: k PIO2_1 is
+// exact for |k| < 2^20, the second product is rounded once), then degree-13/14 minimax kernels on
+// [-pi/4, pi/4] (coefficients: Sun fdlibm k_sin/k_cos), cos in plain Horner form.  19 FP64 instructions,
+// <= 1.5 ulp for |x| < ~1e5; degrades gracefully (and identically on host and device) beyond.
 CCP_HD void ccp_sincos(double x, double* s_out, double* c_out) {
   const double TWO_OVER_PI = 0x1.45f306dc9c883p-1;
   const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: round-to-nearest-integer trick
   const double PIO2_1 = 0x1.921fb54400000p+0;
-  const double PIO2_2 = 0x1.0b4611a600000p-34;
-  const double PIO2_3 = 0x1.3198a2e037073p-69;
+  const double PIO2_2 = 0x1.0b4611a626331p-34;  // pi/2 - PIO2_1 to 53 bits
   double t = CCP_FMA(x, TWO_OVER_PI, MAGIC);
-  int32_t q = ccp_lo32(t);
+  const uint32_t q = (uint32_t)ccp_lo32(t);
   double k = t - MAGIC;
   double r = CCP_FMA(-k, PIO2_1, x);
   r = CCP_FMA(-k, PIO2_2, r);
-  r = CCP_FMA(-k, PIO2_3, r);
   double z = r * r;
   double ps = CCP_FMA(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
   ps = CCP_FMA(z, ps, 2.75573137070700676789e-06);
@@ -119,12 +133,13 @@ CCP_HD void ccp_sincos(double x, double* s_out, double* c_out) {
   pc = CCP_FMA(z, pc, 2.48015872894767294178e-05);
   pc = CCP_FMA(z, pc, -1.38888888888741095749e-03);
   pc = CCP_FMA(z, pc, 4.16666666666666019037e-02);
+  pc = CCP_FMA(z, pc, -0.5);
   double sr = CCP_FMA(r * z, ps, r);
-  double cr = CCP_FMA(z * z, pc, CCP_FMA(z, -0.5, 1.0));
-  double s = (q & 1) ? cr : sr;
-  double c = (q & 1) ? sr : cr;
-  *s_out = (q & 2) ? -s : s;
-  *c_out = ((q + 1) & 2) ? -c : c;
+  double cr = CCP_FMA(z, pc, 1.0);
+  double s = (q & 1u) ? cr : sr;
+  double c = (q & 1u) ? sr : cr;
+  *s_out = ccp_xor_sign(s, q << 30);         // quadrants 2, 3
+  *c_out = ccp_xor_sign(c, (q + 1u) << 30);  // quadrants 1, 2
 }
 
 // atan2(y, x) for y >= 0, x >= 0 (the only case angularDistance needs).  Result in [0, pi/2].
@@ -207,18 +222,17 @@ CCP_HD void ccp_qmul_conj_right(const double* a, const double* b, double* r) {
 }
 // v <- R(q)^T v  (rotate by the conjugate of unit quaternion q)
 CCP_HD void ccp_qrot_inv(const double* q, double* v) {
-  // a = -vec(q);  t = 2 (a x v);  v' = v + w t + a x t
+  // a = -vec(q);  t = a x v;  v' = v + 2 (w t + a x t)
   const double ax = -q[1], ay = -q[2], az = -q[3];
-  double tx = CCP_FMA(ay, v[2], -(az * v[1]));
-  double ty = CCP_FMA(az, v[0], -(ax * v[2]));
-  double tz = CCP_FMA(ax, v[1], -(ay * v[0]));
-  tx = tx + tx; ty = ty + ty; tz = tz + tz;
-  double cx = CCP_FMA(ay, tz, -(az * ty));
-  double cy = CCP_FMA(az, tx, -(ax * tz));
-  double cz = CCP_FMA(ax, ty, -(ay * tx));
-  v[0] = CCP_FMA(q[0], tx, v[0]) + cx;
-  v[1] = CCP_FMA(q[0], ty, v[1]) + cy;
-  v[2] = CCP_FMA(q[0], tz, v[2]) + cz;
+  const double tx = CCP_FMA(ay, v[2], -(az * v[1]));
+  const double ty = CCP_FMA(az, v[0], -(ax * v[2]));
+  const double tz = CCP_FMA(ax, v[1], -(ay * v[0]));
+  const double ex = CCP_FMA(q[0], tx, CCP_FMA(ay, tz, -(az * ty)));
+  const double ey = CCP_FMA(q[0], ty, CCP_FMA(az, tx, -(ax * tz)));
+  const double ez = CCP_FMA(q[0], tz, CCP_FMA(ax, ty, -(ay * tx)));
+  v[0] = CCP_FMA(2.0, ex, v[0]);
+  v[1] = CCP_FMA(2.0, ey, v[1]);
+  v[2] = CCP_FMA(2.0, ez, v[2]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -252,8 +266,22 @@ CCP_HD void ccp_down_vec(const ccp_link& L, double s, double c, double* v) {
 }
 template <bool PANDA, int I>
 CCP_HD void ccp_down_pt(const ccp_link& L, double s, double c, double* r) {
-  ccp_down_vec<PANDA, I>(L, s, c, r);
-  r[0] += L.tx;
+  // as ccp_down_vec, with the x translation folded into the rotation's FMA chain
+  const double nx = CCP_FMA(c, r[0], CCP_FMA(-s, r[1], L.tx));
+  const double ny = CCP_FMA(s, r[0], c * r[1]);
+  r[0] = nx;
+  r[1] = ny;
+  if (!PANDA) {
+    ccp_rot2(L.ca, L.sa, r[1], r[2]);
+  } else if (ccp_panda_sgn<I>::value > 0) {
+    const double y = r[1];
+    r[1] = -r[2];
+    r[2] = y;
+  } else if (ccp_panda_sgn<I>::value < 0) {
+    const double y = r[1];
+    r[1] = r[2];
+    r[2] = -y;
+  }
   if (!PANDA || ccp_panda_sgn<I>::value != 0) r[1] += L.ty;
   if (!PANDA || ccp_panda_sgn<I>::value == 0) r[2] += L.tz;
 }
@@ -323,7 +351,7 @@ struct ccp_fwd {
 template <bool PANDA, int I, class SC, class XT>
 CCP_HD void ccp_fwd_link_quat(const ccp_arm& A, int a, const XT& x, double* q, SC& S) {
   const ccp_link& L = A.link[I];
-  double h = 0.5 * (x[a * CCPC_DOF + I] + L.qoff);
+  double h = CCP_FMA(0.5, x[a * CCPC_DOF + I], L.hqoff);
   double sh, ch;
   ccp_sincos(h, &sh, &ch);
   ccp_qmul_link_rx<PANDA, I>(L, q);
@@ -461,8 +489,10 @@ CCP_HD bool ccp_joint_valid(const ccp_model& M, const XT& x) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Jacobian pass.  Ja[p][row][i]: d f_{2p+row} / d q(arm p+1, joint i);
-//                 J0[p][row][i]: d f_{2p+row} / d q(arm 0,   joint i).
+// Jacobian pass.  J0[p][row][i]:  d f_{2p+row} / d q(arm 0,   joint i);
+//                 Ja[p][row][i]: -d f_{2p+row} / d q(arm p+1, joint i)  — stored with the opposite sign: the
+//                 Gram matrix only sees products of two Ja entries and the update adds instead of subtracting,
+//                 so no negation is ever executed (bit-identical to storing the signed value).
 // ------------------------------------------------------------------------------------------
 template <int K>
 struct ccp_jac {
@@ -483,8 +513,8 @@ CCP_HD void ccp_jac_link(const ccp_arm& A, int a, int p, const SC& S, double* w,
     J.z(p, 0, I) = cz;
     J.z(p, 1, I) = m[2];
   } else {
-    J.a(p, 0, I) = -cz;
-    J.a(p, 1, I) = -m[2];
+    J.a(p, 0, I) = cz;
+    J.a(p, 1, I) = m[2];
   }
   if (I > 0) {
     const double s = S.s(a, I), c = S.c(a, I);
@@ -644,7 +674,7 @@ CCP_HD void ccp_newton_step(const ccp_model& M, const ccp_fwd<K>& F, const JT& J
 #pragma unroll
     for (int i = 0; i < CCPC_DOF; ++i) {
       double dx = CCP_FMA(J.a(p, 1, i), y[2 * p + 1], J.a(p, 0, i) * y[2 * p]);
-      x[(p + 1) * CCPC_DOF + i] = CCP_FMA(-M.step, dx, x[(p + 1) * CCPC_DOF + i]);
+      x[(p + 1) * CCPC_DOF + i] = CCP_FMA(M.step, dx, x[(p + 1) * CCPC_DOF + i]);  // Ja holds -J
     }
 }
 
@@ -661,7 +691,7 @@ CCP_HD void ccp_jac_dense(const ccp_jac<K>& J, double* out) {
 #pragma unroll
       for (int i = 0; i < CCPC_DOF; ++i) {
         out[(2 * p + r) * n + i] = J.J0[p][r][i];
-        out[(2 * p + r) * n + (p + 1) * CCPC_DOF + i] = J.Ja[p][r][i];
+        out[(2 * p + r) * n + (p + 1) * CCPC_DOF + i] = -J.Ja[p][r][i];
       }
 }
 

@@ -83,6 +83,7 @@ static inline int ccp_pack_model(const ccp_model_desc* d, ccp_model* M) {
       L.ty = -1.0 * L.sa * s.dh_d[i];
       L.tz = L.ca * s.dh_d[i];
       L.qoff = s.dh_theta_offset[i];
+      L.hqoff = 0.5 * s.dh_theta_offset[i];
     }
     for (int r = 0; r < 3; ++r) {
       for (int c = 0; c < 3; ++c) A.Rwb[3 * r + c] = s.t_wb[4 * r + c];

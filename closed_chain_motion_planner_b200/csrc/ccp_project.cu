@@ -47,20 +47,113 @@ struct ccp_x_smem {
 #define CCP_SM_X 4
 template <int K, int BLOCK, int SM>
 constexpr size_t ccp_proj_smem_bytes() {
-  return sizeof(double) * BLOCK *
-         (((SM & CCP_SM_SC) ? 4 * CCPC_DOF * K : 0) + ((SM & CCP_SM_J) ? 4 * CCPC_DOF * (K - 1) : 0) +
-          ((SM & CCP_SM_X) ? CCPC_DOF * K : 0));
+  // staging arrays; the tail exchange ([7K + 1][BLOCK] doubles) aliases them
+  constexpr size_t stage = ((SM & CCP_SM_SC) ? 4 * CCPC_DOF * K : 0) + ((SM & CCP_SM_J) ? 4 * CCPC_DOF * (K - 1) : 0);
+  constexpr size_t exch = CCPC_DOF * K + 1;
+  return sizeof(double) * BLOCK * (stage > exch ? stage : exch);
+}
+
+// ------------------------------------------------------------------------------------------
+// work distribution
+// ------------------------------------------------------------------------------------------
+// A warp owns a private CHUNK of sample indices (shared memory: [next, end)).  Lanes whose sample just finished
+// take the next indices from it; only when it runs dry does the warp's leader touch the global work counter
+// (one atomic per CCP_CLAIM_CHUNK samples instead of one per refill, and off the refill's critical path most of
+// the time) and prefetch the new chunk's seed lines into L2.
+#define CCP_CLAIM_CHUNK 32u
+
+// how many trips pass between two tail rendezvous of the block
+#define CCP_TAIL_PERIOD 4
+
+template <int K, bool SOA, bool GEN>
+__device__ __forceinline__ unsigned claim_chunked(unsigned* chunk, const ccp_project_args& A, unsigned count,
+                                                   unsigned first_dynamic, volatile int* s_tail) {
+  constexpr int n = CCPC_DOF * K;
+  const unsigned mask = __activemask();
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(mask) - 1;
+  const unsigned need = __popc(mask);
+  const unsigned rank = __popc(mask & ((1u << lane) - 1u));
+  unsigned base0 = 0, left = 0, base1 = count;
+  if (lane == leader) {
+    base0 = chunk[0];
+    left = chunk[1] - base0;
+    if (left >= need) {
+      chunk[0] = base0 + need;
+    } else {
+      unsigned end1 = count;
+      if (!*s_tail) {
+        base1 = first_dynamic + atomicAdd((unsigned int*)A.counter, CCP_CLAIM_CHUNK);
+        if (base1 > count) base1 = count;
+        end1 = (count - base1 < CCP_CLAIM_CHUNK) ? count : base1 + CCP_CLAIM_CHUNK;
+        if (end1 - base1 < CCP_CLAIM_CHUNK) *s_tail = 1;  // the batch has run dry: the block enters its tail
+        if (!GEN && end1 > base1) {
+          if (!SOA) {
+            const char* p = (const char*)(A.seeds + (size_t)base1 * n);
+            const unsigned bytes = (end1 - base1) * n * 8u;
+            for (unsigned o = 0; o < bytes; o += 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+          } else {
+#pragma unroll
+            for (int j = 0; j < n; ++j) {
+              const char* p = (const char*)(A.seeds + (size_t)j * count + base1);
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
+            }
+          }
+        }
+      }
+      const unsigned take = need - left;  // <= 32 = CCP_CLAIM_CHUNK
+      chunk[0] = (end1 - base1 < take) ? end1 : base1 + take;
+      chunk[1] = end1;
+    }
+  }
+  base0 = __shfl_sync(mask, base0, leader);
+  left = __shfl_sync(mask, left, leader);
+  base1 = __shfl_sync(mask, base1, leader);
+  // an index past the chunk's end is >= count: the lane stays without work
+  return (rank < left) ? base0 + rank : base1 + (rank - left);
+}
+
+template <int K, bool SOA, bool GEN, class XT>
+__device__ __forceinline__ void load_seed(const ccp_model& M, const ccp_project_args& A, unsigned idx, unsigned count,
+                                          XT& x) {
+  constexpr int n = CCPC_DOF * K;
+  if (!GEN) {
+    if (!SOA && A.ready) {
+#pragma unroll
+      for (int j = 0; j < n; ++j) x[j] = __ldcg(A.seeds + (size_t)idx * n + j);
+    } else {
+#pragma unroll
+      for (int j = 0; j < n; ++j) x[j] = ld_elem<SOA>(A.seeds, idx, j, count, n);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < n; ++j) x[j] = make_seed<K>(M, A, idx, j);
+  }
 }
 
 // GEN = false: seeds are read from memory (project).  GEN = true: seeds come from the counter-based
 // generator and the sampler epilogue (wrap) is compiled in (sample_project).
 // PANDA: structured stock-Panda link code (ccp_core.h).  SM: which per-sample arrays are staged in
 // shared memory (CCP_SM_* bits) instead of registers.
+//
+// Loop structure.  One trip = one Newton iteration of the lane's current sample (ConstraintFunction.h:68-73).
+// A lane whose sample leaves the loop writes its result and takes the next index (lane refill), so the
+// 0..250-iteration spread does not idle the warp while there is work.  When the batch runs dry the block
+// enters its TAIL: every CCP_TAIL_PERIOD trips the warps meet at a barrier, and as soon as the samples still
+// iterating fit in fewer warps they are packed into the lowest warps through shared memory ((x, it, index) is
+// the whole state of a sample between trips).  Emptied warps wait at the barrier and issue nothing, so the last
+// samples run at one-warp-per-scheduler latency instead of sharing the FP64 pipe with warps that carry one or
+// two live lanes each.  Which lane ran a sample never affects its result.
 template <int K, bool PANDA, bool SOA, bool GEN, int BLOCK, int MINB, int SM>
 __global__ void __launch_bounds__(BLOCK, MINB)
 ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ ccp_project_args A) {
   constexpr int n = CCPC_DOF * K, m = 2 * (K - 1);
+  constexpr int NW = BLOCK / 32;
   extern __shared__ double ccp_smem[];
+  __shared__ int s_tail;
+  __shared__ int s_wcnt[NW];
+  __shared__ unsigned s_chunk[NW][2];
   double* sm_next = ccp_smem + threadIdx.x;
   typename std::conditional<(SM & CCP_SM_SC) != 0, ccp_sc_smem<K, BLOCK>, ccp_sc_local<K>>::type S;
   if constexpr ((SM & CCP_SM_SC) != 0) {
@@ -72,85 +165,126 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
     J.base = sm_next;
     sm_next += 4 * CCPC_DOF * (K - 1) * BLOCK;
   }
-  typename std::conditional<(SM & CCP_SM_X) != 0, ccp_x_smem<BLOCK>, double[n]>::type x;
-  if constexpr ((SM & CCP_SM_X) != 0) x.base = sm_next;
-  int it = 0;
-  long long idx = claim_next(A.counter);
-  if (!GEN && !SOA && A.ready) wait_chunk_ready(A, idx, idx < A.count);
-  if (idx < A.count) {
-    if (!GEN) {
-      if (!SOA && A.ready) {
-#pragma unroll
-        for (int j = 0; j < n; ++j) x[j] = __ldcg(A.seeds + idx * n + j);
-      } else {
-#pragma unroll
-        for (int j = 0; j < n; ++j) x[j] = ld_elem<SOA>(A.seeds, idx, j, A.count, n);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < n; ++j) x[j] = make_seed<K>(M, A, idx, j);
-    }
+  double x[n];
+  const unsigned count = (unsigned)A.count;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // The first chunk of every warp is static and interleaved over the blocks (chunk c -> block c % grid, warp
+  // c / grid), so a batch smaller than the machine spreads one warp per SM before any SM gets a second one; the
+  // global counter hands out what lies beyond those gridDim.x * NW chunks.
+  const unsigned static_chunks = gridDim.x * NW;
+  const unsigned first_dynamic = (count / CCP_CLAIM_CHUNK < static_chunks) ? count : static_chunks * CCP_CLAIM_CHUNK;
+  if (threadIdx.x == 0) s_tail = (first_dynamic >= count) ? 1 : 0;
+  if (lane == 0) {
+    const unsigned long long b0 = (unsigned long long)(warp * gridDim.x + blockIdx.x) * CCP_CLAIM_CHUNK;
+    const unsigned lo = b0 < count ? (unsigned)b0 : count;
+    s_chunk[warp][0] = lo;
+    s_chunk[warp][1] = (count - lo < CCP_CLAIM_CHUNK) ? count : lo + CCP_CLAIM_CHUNK;
   }
-  while (idx < A.count) {
-    ccp_fwd<K> F;
-    ccp_forward<K, PANDA>(M, x, S, F);
-    const bool cont = ccp_needs_step<K>(M, F.f) && it < M.max_iter;
-    if (cont) {
-      ++it;
-      ccp_jacobian<K, PANDA>(M, S, F, J);
-      ccp_newton_step<K>(M, F, J, x);
-    } else {
-      // ---- epilogue of this sample (ConstraintFunction.h:75-81), then refill the lane ----
-      const bool cv = ccp_converged<K>(M, F.f);
-      const bool okk = cv && ccp_joint_valid<K>(M, x);
-      if (GEN && A.wrap) {
-#pragma unroll
-        for (int j = 0; j < n; ++j) x[j] = ccp_wrap_pi(x[j]);
-      }
-      if (A.x_out) {
-#pragma unroll
-        for (int j = 0; j < n; ++j) st_elem<SOA>(A.x_out, idx, j, A.count, n, x[j]);
-      }
-      if (A.ok) A.ok[idx] = okk;
-      if (A.conv) A.conv[idx] = cv;
-      if (A.iters) A.iters[idx] = it;
-      if (A.resid) {
-#pragma unroll
-        for (int k = 0; k < m; ++k) st_elem<SOA>(A.resid, idx, k, A.count, m, F.f[k]);
-      }
-      if (A.n_ok && okk) {
-        const unsigned long long slot = atomicAdd(A.n_ok, 1ULL);
-        if (A.compact) {
-#pragma unroll
-          for (int j = 0; j < n; ++j) A.compact[slot * n + j] = x[j];
+  __syncthreads();
+  int it = 0;
+  unsigned idx = claim_chunked<K, SOA, GEN>(s_chunk[warp], A, count, first_dynamic, &s_tail);
+  if (!GEN && !SOA && A.ready) wait_chunk_ready(A, idx, idx < count);
+  if (idx < count) load_seed<K, SOA, GEN>(M, A, idx, count, x);
+  bool tail = false;
+  int since = 0;
+  for (;;) {
+    if (!tail) tail = *(volatile int*)&s_tail != 0;
+    if (tail) {
+      if (since == 0) {
+        // ---- tail rendezvous ----
+        if (idx >= count) {  // what is left of the warp's private chunk
+          idx = claim_chunked<K, SOA, GEN>(s_chunk[warp], A, count, first_dynamic, &s_tail);
+          it = 0;
+          if (!GEN && !SOA && A.ready) wait_chunk_ready(A, idx, idx < count);
+          if (idx < count) load_seed<K, SOA, GEN>(M, A, idx, count, x);
         }
-      }
-      if (!GEN && !SOA && A.done) {
-        // streaming: count this sample into its chunk; the last one tells the host the chunk can be copied out
-        __threadfence();
-        const long long c = idx / A.chunk;
-        const long long in_chunk = (A.count - c * A.chunk < A.chunk) ? (A.count - c * A.chunk) : A.chunk;
-        if ((long long)atomicAdd(A.done + c, 1u) + 1 == in_chunk) {
-          __threadfence_system();
-          A.host_done[c] = 1;
+        __syncwarp();
+        const bool active = idx < count;
+        const int total = __syncthreads_count(active);
+        if (total == 0) break;
+        const unsigned bal = __ballot_sync(0xffffffffu, active);
+        if (lane == 0) s_wcnt[warp] = __popc(bal);
+        __syncthreads();
+        int before = 0, nonempty = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+          const int c = s_wcnt[w];
+          nonempty += c > 0;
+          before += (w < warp) ? c : 0;
         }
-      }
-      idx = claim_next(A.counter);
-      it = 0;
-      if (!GEN && !SOA && A.ready) wait_chunk_ready(A, idx, idx < A.count);
-      if (idx < A.count) {
-        if (!GEN) {
-          if (!SOA && A.ready) {
+        if (nonempty > (total + 31) / 32) {
+          // pack the live samples into the lowest warps
+          double* ex = ccp_smem;  // [n + 1][BLOCK]; aliases the staging arrays, which are dead between trips
+          if (active) {
+            const int slot = before + __popc(bal & ((1u << lane) - 1u));
 #pragma unroll
-            for (int j = 0; j < n; ++j) x[j] = __ldcg(A.seeds + idx * n + j);
-          } else {
-#pragma unroll
-            for (int j = 0; j < n; ++j) x[j] = ld_elem<SOA>(A.seeds, idx, j, A.count, n);
+            for (int j = 0; j < n; ++j) ex[j * BLOCK + slot] = x[j];
+            ex[n * BLOCK + slot] = __hiloint2double(it, (int)idx);
           }
-        } else {
+          __syncthreads();
+          if ((int)threadIdx.x < total) {
 #pragma unroll
-          for (int j = 0; j < n; ++j) x[j] = make_seed<K>(M, A, idx, j);
+            for (int j = 0; j < n; ++j) x[j] = ex[j * BLOCK + threadIdx.x];
+            const double pk = ex[n * BLOCK + threadIdx.x];
+            it = __double2hiint(pk);
+            idx = (unsigned)__double2loint(pk);
+          } else {
+            idx = count;
+          }
+          if constexpr (SM != 0) __syncthreads();  // the staging arrays are about to be written again
         }
+        since = CCP_TAIL_PERIOD;
+      }
+      --since;
+    }
+    if (idx < count) {
+      ccp_fwd<K> F;
+      ccp_forward<K, PANDA>(M, x, S, F);
+      const bool cont = ccp_needs_step<K>(M, F.f) && it < M.max_iter;
+      if (cont) {
+        ++it;
+        ccp_jacobian<K, PANDA>(M, S, F, J);
+        ccp_newton_step<K>(M, F, J, x);
+      } else {
+        // ---- epilogue of this sample (ConstraintFunction.h:75-81), then refill the lane ----
+        const bool cv = ccp_converged<K>(M, F.f);
+        const bool okk = cv && ccp_joint_valid<K>(M, x);
+        if (GEN && A.wrap) {
+#pragma unroll
+          for (int j = 0; j < n; ++j) x[j] = ccp_wrap_pi(x[j]);
+        }
+        if (A.x_out) {
+#pragma unroll
+          for (int j = 0; j < n; ++j) st_elem<SOA>(A.x_out, idx, j, count, n, x[j]);
+        }
+        if (A.ok) A.ok[idx] = okk;
+        if (A.conv) A.conv[idx] = cv;
+        if (A.iters) A.iters[idx] = it;
+        if (A.resid) {
+#pragma unroll
+          for (int k = 0; k < m; ++k) st_elem<SOA>(A.resid, idx, k, count, m, F.f[k]);
+        }
+        if (A.n_ok && okk) {
+          const unsigned long long slot = atomicAdd(A.n_ok, 1ULL);
+          if (A.compact) {
+#pragma unroll
+            for (int j = 0; j < n; ++j) A.compact[slot * n + j] = x[j];
+          }
+        }
+        if (!GEN && !SOA && A.done) {
+          // streaming: count this sample into its chunk; the last one tells the host the chunk can be copied out
+          __threadfence();
+          const long long c = idx / A.chunk;
+          const long long in_chunk = (A.count - c * A.chunk < A.chunk) ? (A.count - c * A.chunk) : A.chunk;
+          if ((long long)atomicAdd(A.done + c, 1u) + 1 == in_chunk) {
+            __threadfence_system();
+            A.host_done[c] = 1;
+          }
+        }
+        idx = claim_chunked<K, SOA, GEN>(s_chunk[warp], A, count, first_dynamic, &s_tail);
+        it = 0;
+        if (!GEN && !SOA && A.ready) wait_chunk_ready(A, idx, idx < count);
+        if (idx < count) load_seed<K, SOA, GEN>(M, A, idx, count, x);
       }
     }
   }
@@ -165,7 +299,9 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
 // among the compiled configurations for tuning; the default is the best one measured on B200.
 template <int K, bool PANDA, bool SOA, bool GEN, int BLOCK, int MINB, int SM>
 static cudaError_t launch_project_v(int sm_count, const ccp_model& M, const ccp_project_args& A, cudaStream_t st) {
-  long long need = (A.count + BLOCK - 1) / BLOCK;
+  // persistent grid: MINB blocks per SM; a small batch is spread one warp's worth (32 samples) per block so that
+  // it runs at one-warp-per-scheduler latency on many SMs instead of crowding a few
+  long long need = (A.count + 31) / 32;
   long long cap = (long long)sm_count * MINB;
   int grid = (int)(need < cap ? need : cap);
   if (grid < 1) grid = 1;
@@ -195,21 +331,18 @@ static cudaError_t launch_project_g(int sm_count, const ccp_model& M, const ccp_
 #ifdef CCP_TUNE
   if constexpr (K == 2) {
     switch (proj_variant()) {
-      case 1: return launch_project_v<K, PANDA, SOA, GEN, 128, 3, CCP_SM_SC>(sm_count, M, A, st);
-      case 2: return launch_project_v<K, PANDA, SOA, GEN, 128, 4, CCP_SM_SC>(sm_count, M, A, st);
-      case 3: return launch_project_v<K, PANDA, SOA, GEN, 128, 3, CCP_SM_SC | CCP_SM_J>(sm_count, M, A, st);
-      case 4: return launch_project_v<K, PANDA, SOA, GEN, 64, 6, 0>(sm_count, M, A, st);
-      case 7: return launch_project_v<K, PANDA, SOA, GEN, 32, 12, 0>(sm_count, M, A, st);
-      case 5: return launch_project_v<K, PANDA, SOA, GEN, 256, 2, CCP_SM_SC | CCP_SM_J>(sm_count, M, A, st);
-      case 6: return launch_project_v<K, PANDA, SOA, GEN, 128, 2, 0>(sm_count, M, A, st);
+      case 1: return launch_project_v<K, PANDA, SOA, GEN, 128, 3, 0>(sm_count, M, A, st);
+      case 2: return launch_project_v<K, PANDA, SOA, GEN, 192, 2, 0>(sm_count, M, A, st);
+      case 3: return launch_project_v<K, PANDA, SOA, GEN, 256, 1, 0>(sm_count, M, A, st);
+      case 4: return launch_project_v<K, PANDA, SOA, GEN, 512, 1, CCP_SM_SC>(sm_count, M, A, st);
       default: break;
     }
   }
 #endif
-  // measured on B200 (profiles/): 3 resident blocks of 128 threads per SM, everything in registers
-  // (168 regs, no spills) beats every shared-memory staging variant for K = 2
-  if constexpr (K == 2) return launch_project_v<K, PANDA, SOA, GEN, 128, 3, 0>(sm_count, M, A, st);
-  else return launch_project_v<K, PANDA, SOA, GEN, 128, 2, CCP_SM_SC>(sm_count, M, A, st);
+  // One block per SM so the tail packing sees every live sample of the SM.  K = 2: 12 warps, everything in
+  // registers (168, no spills); measured on B200 (profiles/) against shared-memory staging variants.
+  if constexpr (K == 2) return launch_project_v<K, PANDA, SOA, GEN, 384, 1, 0>(sm_count, M, A, st);
+  else return launch_project_v<K, PANDA, SOA, GEN, 256, 1, CCP_SM_SC>(sm_count, M, A, st);
 }
 
 #define CCP_CAT_(a, b, c, d) a##b##c##d
