@@ -158,13 +158,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="dumbbell")
     ap.add_argument("--count", type=int, default=1_000_000, help="seeds per rank per step")
-    ap.add_argument("--cpu-sample", type=int, default=6000, help="seeds of the cpu_baseline leg")
-    ap.add_argument("--ref-sample", type=int, default=4000, help="seeds per step of --impl reference")
+    ap.add_argument("--cpu-sample", type=int, default=100000, help="seeds of the cpu_baseline leg")
+    ap.add_argument("--ref-sample", type=int, default=20000, help="seeds per step of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--layout", default="aos", choices=["aos", "soa"])
-    ap.add_argument("--streams", type=int, default=1,
-                    help="independent seed batches of consecutive steps are issued round-robin on this many CUDA streams")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="every launch runs its own stragglers to completion (ccp_project_batch) instead of parking them "
+                         "for the next launch (ccp_project_batch_pipelined + one ccp_project_flush)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -207,37 +208,65 @@ def main():
                               near_host=None)
         assert lib.ccp_generate_seeds(h, C.byref(a), count, layout, t.data_ptr(), stream) == 0
         batches.append(t)
-    x_out = torch.empty(shape, dtype=torch.float64, device=dev)
-    ok = torch.empty(count, dtype=torch.uint8, device=dev)
-    cv = torch.empty(count, dtype=torch.uint8, device=dev)
-    iters = torch.empty(count, dtype=torch.int32, device=dev)
-    compact = torch.empty((count, n), dtype=torch.float64, device=dev)
-    n_ok = torch.zeros(1, dtype=torch.int64, device=dev)
+    # Outputs.  Steps are PIPELINED (ccp_project_batch_pipelined): the <= ~1e5 samples still iterating when a
+    # step's seed list runs dry are carried into the next launch instead of idling the GPU, so a step's per-seed
+    # outputs are complete one launch later and every step in flight needs its own arrays (ring of R sets); one
+    # ccp_project_flush inside the timed region completes the last step.  --no-pipeline: every launch runs its
+    # own stragglers to completion (one output set would do; the ring is kept for symmetry).
+    pipelined = not args.no_pipeline
+    R = 3
+    outs = []
+    for r in range(R):
+        outs.append(dict(x=torch.empty(shape, dtype=torch.float64, device=dev),
+                         ok=torch.empty(count, dtype=torch.uint8, device=dev),
+                         cv=torch.empty(count, dtype=torch.uint8, device=dev),
+                         it=torch.empty(count, dtype=torch.int32, device=dev),
+                         compact=torch.empty((count, n), dtype=torch.float64, device=dev),
+                         n_ok=torch.zeros(1, dtype=torch.int64, device=dev)))
     from closed_chain_motion_planner_b200.dist import gather_capacity, gather_converged
 
     cap = gather_capacity(count)
     pool = torch.empty((world, cap, n), dtype=torch.float64, device=dev) if world > 1 else None
     counts_all = torch.zeros(world, dtype=torch.int64, device=dev)
     max_count_seen = torch.zeros(1, dtype=torch.int64, device=dev)
+    project = lib.ccp_project_batch_pipelined if pipelined else lib.ccp_project_batch
 
-    def step(i, ev0=None, ev1=None):
-        n_ok.zero_()
-        if ev0 is not None:
-            ev0.record()
-        rc = lib.ccp_project_batch(h, batches[i % n_batches].data_ptr(), count, layout, x_out.data_ptr(), ok.data_ptr(),
-                                   cv.data_ptr(), iters.data_ptr(), None, compact.data_ptr(), n_ok.data_ptr(), stream)
-        assert rc == 0, lib.ccp_last_error(h)
-        if ev1 is not None:
-            ev1.record()
+    def exchange(o):
         if world > 1:
             # the path's one exchange step: converged counts + compacted converged states (fixed capacity,
             # no host sync), NCCL all-gather over NVLink
-            gather_converged(compact, n_ok, cap, None, pool, counts_all)
+            gather_converged(o["compact"], o["n_ok"], cap, None, pool, counts_all)
             torch.maximum(max_count_seen, counts_all.max().view(1), out=max_count_seen)
 
+    def step(i, ev0=None, ev1=None):
+        o = outs[i % R]
+        o["n_ok"].zero_()
+        if ev0 is not None:
+            ev0.record()
+        rc = project(h, batches[i % n_batches].data_ptr(), count, layout, o["x"].data_ptr(), o["ok"].data_ptr(),
+                     o["cv"].data_ptr(), o["it"].data_ptr(), None, o["compact"].data_ptr(), o["n_ok"].data_ptr(), stream)
+        assert rc == 0, lib.ccp_last_error(h)
+        if ev1 is not None:
+            ev1.record()
+        exchange(o)
+        return o
+
+    def flush(i, ev0=None, ev1=None):
+        o = outs[i % R]
+        o["n_ok"].zero_()
+        if ev0 is not None:
+            ev0.record()
+        rc = lib.ccp_project_flush(h, o["compact"].data_ptr(), o["n_ok"].data_ptr(), stream)
+        assert rc == 0, lib.ccp_last_error(h)
+        if ev1 is not None:
+            ev1.record()
+        exchange(o)
+        return o
+
     for i in range(args.warmup):
-        step(i)
-        _ = (n_ok.clone(), iters.sum(dtype=torch.int64))  # same (torch) bookkeeping ops as the timed loop: loads them once
+        o = step(i)
+        _ = (o["n_ok"].clone(), o["it"].sum(dtype=torch.int64))  # same (torch) bookkeeping ops as the timed loop: loads them once
+    flush(args.warmup)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -247,18 +276,28 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = c.launchCount()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps + 1)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     total_ok = 0
     total_flops = 0.0
     total_iters = 0
     fl_iter, fl_tail = c.algorithmicFlops()
     t_begin.record()
-    per_step_stats = []
+    ok_counts, iter_sums = [], []
+    prev = None
     for s in range(args.steps):
-        step(args.warmup + s, *evs[s])
-        # per-step result read: the converged count (8 bytes) — keeps the kernel honest, stays on device
-        per_step_stats.append((n_ok.clone(), iters.sum(dtype=torch.int64)))
+        o = step(args.warmup + s, *evs[s])
+        # per-step result reads, on device: the states that finished in this launch (8 bytes) and the iteration
+        # total of the step whose outputs this launch completed (pipelined: the previous step's)
+        ok_counts.append(o["n_ok"].clone())
+        done = prev if pipelined else o
+        if done is not None:
+            iter_sums.append(done["it"].sum(dtype=torch.int64))
+        prev = o
+    if pipelined:
+        o = flush(args.warmup + args.steps, *evs[args.steps])
+        ok_counts.append(o["n_ok"].clone())
+        iter_sums.append(prev["it"].sum(dtype=torch.int64))
     t_end.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -269,10 +308,11 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     ms_total = t_begin.elapsed_time(t_end)
-    kernel_ms = [a.elapsed_time(b) for a, b in evs]
-    for nk, its in per_step_stats:
-        total_ok += int(nk.item())
-        total_iters += int(its.item())
+    n_timed_launches = args.steps + (1 if pipelined else 0)
+    kernel_ms = [a.elapsed_time(b) for a, b in evs[:n_timed_launches]]
+    total_ok = sum(int(v.item()) for v in ok_counts)
+    total_iters = sum(int(v.item()) for v in iter_sums)
+    assert len(iter_sums) == args.steps
     total_flops = total_iters * fl_iter + args.steps * count * fl_tail
 
     # max over ranks of the timed region; sums over ranks of the work
@@ -341,6 +381,14 @@ def main():
     except OSError:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    # dram bytes read + written per launch of the projection kernel, from the committed `ncu --set full` capture
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if tr.get("config") == args.config and tr.get("count") == count:
+            traffic = tr.get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
     alg_bytes = (2 * n * 8 + 1 + 1 + 4) * count  # seeds in, states out, ok, converged, iters
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -350,15 +398,17 @@ def main():
                    "seeds_per_gpu_per_step": count, "arms": c.k_, "layout": args.layout,
                    "tolerances": [1e-3, 5e-3], "step": 0.30, "max_iter": 250,
                    "l2": f"inputs+outputs {2 * count * n * 8 / 1e6:.0f} MB per step exceed the 126 MB L2; seed batches rotate over {n_batches} buffers",
+                   "launches": ("pipelined: ccp_project_batch_pipelined per step (stragglers carried into the next launch) + one "
+                                "ccp_project_flush, all inside the timed region") if pipelined else "ccp_project_batch per step",
                    "exchange": "none" if world == 1 else "NCCL all_gather of counts + padded compacted converged states per step"},
         "projections_per_s": world * count * args.steps / secs,
         "ok_fraction": ok_all / (world * count * args.steps),
         "mean_iters": iters_all / (world * count * args.steps),
         "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": peak_flops / 1e12, "unit": "TFLOP/s",
-                     "frac": achieved / peak_flops, "traffic": None,
+                     "frac": achieved / peak_flops, "traffic": traffic,
                      "peak_source": "measured in this run: ccp_fp64_peak_probe (register-only DFMA chains, best of 5)",
                      "flops_per_iteration": fl_iter, "flops_per_tail": fl_tail,
-                     "kernel_ms_per_launch": kernel_ms_sum_max / args.steps,
+                     "kernel_ms_per_launch": kernel_ms_sum_max / n_timed_launches, "kernel_launches_timed": n_timed_launches,
                      "hbm": {"achieved_gbs": alg_bytes / (ksecs / args.steps) / 1e9, "peak_gbs": hbm_peak,
                              "frac": alg_bytes / (ksecs / args.steps) / 1e9 / hbm_peak,
                              "algorithmic_bytes_per_projection": 2 * n * 8 + 6,

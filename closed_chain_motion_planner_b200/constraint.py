@@ -302,11 +302,13 @@ class KinematicChainConstraint:
         return count, torch.cuda.current_stream(X.device).cuda_stream
 
     def projectBatch(self, X, layout: int = CCP_LAYOUT_AOS, out=None, want_resid: bool = True,
-                     compact=None, n_ok=None) -> ProjectResult:
+                     compact=None, n_ok=None, pipelined: bool = False) -> ProjectResult:
         """Batched project().  numpy (count, n) -> host path; torch CUDA tensor -> device path (async on the
         current stream).  `out` (device path) may alias X for in-place projection.  Device path only:
         `compact` ((>=count, n) float64) receives the ok states densely packed by the kernel epilogue and
-        `n_ok` (int64[1], zeroed by the caller) their count."""
+        `n_ok` (int64[1], zeroed by the caller) their count.  `pipelined=True` (device path) parks the samples
+        still iterating when the batch runs dry instead of idling the GPU on them: the result tensors are
+        complete only after the next non-pipelined projectBatch or flush() (ccp_project_batch_pipelined)."""
         self._need()
         m = self.getCoDimension()
         if _is_torch(X):
@@ -321,7 +323,8 @@ class KinematicChainConstraint:
             if want_resid:
                 shape = (count, m) if layout == CCP_LAYOUT_AOS else (m, count)
                 rs = torch.empty(shape, dtype=torch.float64, device=X.device)
-            _check(self._lib, self._h, self._lib.ccp_project_batch(
+            fn = self._lib.ccp_project_batch_pipelined if pipelined else self._lib.ccp_project_batch
+            _check(self._lib, self._h, fn(
                 self._h, X.data_ptr(), count, layout, xo.data_ptr(), ok.data_ptr(), cv.data_ptr(), it.data_ptr(),
                 rs.data_ptr() if rs is not None else None,
                 compact.data_ptr() if compact is not None else None,
@@ -342,6 +345,21 @@ class KinematicChainConstraint:
             self._h, X.ctypes.data, count, xo.ctypes.data, ok.ctypes.data, cv.ctypes.data, it.ctypes.data,
             rs.ctypes.data))
         return ProjectResult(xo, ok, cv, it, rs)
+
+    def flush(self, compact=None, n_ok=None, stream=None):
+        """Completes the samples parked by pipelined projections (ccp_project_flush); async on the current stream."""
+        self._need()
+        if stream is None:
+            import torch
+
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        _check(self._lib, self._h, self._lib.ccp_project_flush(
+            self._h, compact.data_ptr() if compact is not None else None,
+            n_ok.data_ptr() if n_ok is not None else None, stream))
+
+    def pipelineOpen(self) -> bool:
+        self._need()
+        return self._lib.ccp_project_pipeline_open(self._h) == 1
 
     def functionBatch(self, X, layout: int = CCP_LAYOUT_AOS):
         self._need()

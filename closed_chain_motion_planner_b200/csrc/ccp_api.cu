@@ -55,6 +55,16 @@ struct ccp_handle {
   int* d_flags;
   int* h_flags;      // cudaHostAlloc(mapped): [0..63] host_done, [64] = 1
   int* h_flags_dev;  // device alias of h_flags
+  // pipelined projection launches: two park buffers (the launch adopts from one and parks into the other),
+  // their record counters, and the table of output descriptors by launch slot
+  ccp_park_rec* d_park[2];
+  unsigned* d_park_count;  // [2]
+  ccp_out_desc* d_desc;    // [CCP_NUM_DESC]
+  size_t park_capacity;    // records per buffer
+  int park_cur;            // buffer holding the parked samples of the last pipelined launch
+  bool pipeline_open;      // parked samples exist
+  int pipe_sig;            // layout | gen << 1 of the launches in the pipeline (same kernel instantiation)
+  int pipe_launches;       // pipelined launches since the pipeline opened (slot ring safety)
   std::mutex mu;
   std::mutex host_mu;  // the *_host entry points share the stage and the streaming flags: one at a time
   char err[512];
@@ -238,21 +248,23 @@ struct device_guard {
   }
 };
 
-static int launch_project(ccp_handle* h, ccp_project_args& A, int layout, cudaStream_t st) {
-  if (!h->has_ref) return set_err(h, CCP_ERR_STATE, "%s", "project before ccp_set_reference (setInitialPosition)");
-  if (A.count == 0) return CCP_OK;
-  if (A.count > 0x7fff0000LL)
-    return set_err(h, CCP_ERR_INVALID, "%s", "more than 2^31 - 65536 samples in one call: split the batch");
-  unsigned slot;
-  {
-    std::lock_guard<std::mutex> lk(h->mu);
-    slot = h->launch_seq++ % CCP_NUM_COUNTERS;
-    h->launches++;
-  }
-  A.counter = h->d_counters + slot;
-  CCP_CUDA(cudaMemsetAsync(A.counter, 0, sizeof(unsigned long long), st));
+// Pipelined launches need the park buffers: every lane can park its live sample plus (its share of) the unstarted
+// rest of its warp's private chunk, so 2 records per resident thread bound a launch's parking.
+static int ensure_pipeline(ccp_handle* h) {
+  if (h->d_park[0]) return CCP_OK;
+  const size_t cap = (size_t)h->sm_count * 512 * 2;
+  CCP_CUDA(cudaMalloc(&h->d_park[0], cap * sizeof(ccp_park_rec)));
+  CCP_CUDA(cudaMalloc(&h->d_park[1], cap * sizeof(ccp_park_rec)));
+  CCP_CUDA(cudaMalloc(&h->d_park_count, 2 * sizeof(unsigned)));
+  CCP_CUDA(cudaMalloc(&h->d_desc, CCP_NUM_DESC * sizeof(ccp_out_desc)));
+  CCP_CUDA(cudaMemset(h->d_park_count, 0, 2 * sizeof(unsigned)));
+  CCP_CUDA(cudaMemset(h->d_desc, 0, CCP_NUM_DESC * sizeof(ccp_out_desc)));
+  h->park_capacity = cap;
+  return CCP_OK;
+}
+
+static int dispatch_project(ccp_handle* h, ccp_project_args& A, bool soa, cudaStream_t st) {
   cudaError_t e = cudaSuccess;
-  const bool soa = layout == CCP_LAYOUT_SOA;
   if (h->model.n_arms == 2)
     e = h->model.panda_alpha ? ccp_launch_project_K2_P1(h->sm_count, h->model, A, soa, st)
                              : ccp_launch_project_K2_P0(h->sm_count, h->model, A, soa, st);
@@ -260,6 +272,62 @@ static int launch_project(ccp_handle* h, ccp_project_args& A, int layout, cudaSt
     e = h->model.panda_alpha ? ccp_launch_project_K3_P1(h->sm_count, h->model, A, soa, st)
                              : ccp_launch_project_K3_P0(h->sm_count, h->model, A, soa, st);
   if (e != cudaSuccess) return set_err(h, CCP_ERR_CUDA, "project kernel launch: %s", cudaGetErrorString(e));
+  return CCP_OK;
+}
+
+// One projection launch.  defer = true: pipelined (the samples still iterating when the work runs dry are parked
+// for the next launch).  A launch that finds the pipeline open adopts the parked samples first; a launch that is
+// not itself deferred completes them and thereby closes the pipeline.
+static int launch_project(ccp_handle* h, ccp_project_args& A, int layout, cudaStream_t st, bool defer = false) {
+  if (!h->has_ref) return set_err(h, CCP_ERR_STATE, "%s", "project before ccp_set_reference (setInitialPosition)");
+  if (A.count > 0x7fff0000LL)
+    return set_err(h, CCP_ERR_INVALID, "%s", "more than 2^31 - 65536 samples in one call: split the batch");
+  const bool soa = layout == CCP_LAYOUT_SOA;
+  const int sig = (soa ? 1 : 0) | (A.gen_mode >= 0 ? 2 : 0);
+  if (h->pipeline_open && sig != h->pipe_sig) {
+    // parked samples belong to another kernel instantiation (layout / generator): complete them first
+    ccp_project_args F;
+    memset(&F, 0, sizeof F);
+    F.gen_mode = (h->pipe_sig & 2) ? 0 : -1;
+    int rc = launch_project(h, F, (h->pipe_sig & 1) ? CCP_LAYOUT_SOA : CCP_LAYOUT_AOS, st, false);
+    if (rc) return rc;
+  }
+  if (A.count == 0 && !h->pipeline_open) return CCP_OK;
+  if (defer && h->pipe_launches >= CCP_NUM_DESC / 2) defer = false;  // a parked sample must find its launch's slot
+  unsigned slot;
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    slot = h->launch_seq++ % CCP_NUM_COUNTERS;
+    h->launches++;
+  }
+  A.counter = h->d_counters + slot;
+  A.slot = slot % CCP_NUM_DESC;
+  CCP_CUDA(cudaMemsetAsync(A.counter, 0, sizeof(unsigned long long), st));
+  if (defer || h->pipeline_open) {
+    int rc = ensure_pipeline(h);
+    if (rc) return rc;
+    A.desc_table = h->d_desc;
+    if (h->pipeline_open) {
+      A.adopt = h->d_park[h->park_cur];
+      A.adopt_count = h->d_park_count + h->park_cur;
+    }
+    if (defer) {
+      A.park = h->d_park[1 - h->park_cur];
+      A.park_count = h->d_park_count + (1 - h->park_cur);
+      CCP_CUDA(cudaMemsetAsync(A.park_count, 0, sizeof(unsigned), st));
+    }
+  }
+  int rc = dispatch_project(h, A, soa, st);
+  if (rc) return rc;
+  if (defer) {
+    h->pipeline_open = true;
+    h->pipe_sig = sig;
+    h->pipe_launches++;
+    h->park_cur = 1 - h->park_cur;
+  } else {
+    h->pipeline_open = false;
+    h->pipe_launches = 0;
+  }
   return CCP_OK;
 }
 
@@ -309,6 +377,14 @@ int ccp_create(const ccp_model_desc* model, int32_t device, ccp_handle** out) {
   nh->launch_seq = 0;
   nh->d_stage = nullptr;
   nh->d_stage_bytes = 0;
+  nh->d_park[0] = nh->d_park[1] = nullptr;
+  nh->d_park_count = nullptr;
+  nh->d_desc = nullptr;
+  nh->park_capacity = 0;
+  nh->park_cur = 0;
+  nh->pipeline_open = false;
+  nh->pipe_sig = 0;
+  nh->pipe_launches = 0;
   nh->err[0] = 0;
   device_guard g(device);
   cudaError_t e = g.ok ? cudaSuccess : cudaErrorInvalidDevice;
@@ -340,6 +416,10 @@ void ccp_destroy(ccp_handle* h) {
   if (h->d_counters) cudaFree(h->d_counters);
   if (h->d_stage) cudaFree(h->d_stage);
   if (h->d_flags) cudaFree(h->d_flags);
+  if (h->d_park[0]) cudaFree(h->d_park[0]);
+  if (h->d_park[1]) cudaFree(h->d_park[1]);
+  if (h->d_park_count) cudaFree(h->d_park_count);
+  if (h->d_desc) cudaFree(h->d_desc);
   if (h->h_flags) cudaFreeHost(h->h_flags);
   for (int i = 0; i < 3; ++i) cudaStreamDestroy(h->hstream[i]);
   cudaEventDestroy(h->ev0);
@@ -352,8 +432,15 @@ int ccp_n_arms(const ccp_handle* h) { return h ? h->model.n_arms : CCP_ERR_INVAL
 int ccp_device(const ccp_handle* h) { return h ? h->device : CCP_ERR_INVALID; }
 int64_t ccp_launch_count(const ccp_handle* h) { return h ? h->launches : 0; }
 
+#define CCP_NO_OPEN_PIPELINE(h)                                                                                   \
+  do {                                                                                                             \
+    if ((h)->pipeline_open)                                                                                        \
+      return set_err((h), CCP_ERR_STATE, "%s", "pipelined projections are in flight: call ccp_project_flush first"); \
+  } while (0)
+
 int ccp_set_reference(ccp_handle* h, const double* q_start_host) {
   if (!h || !q_start_host) return h ? set_err(h, CCP_ERR_INVALID, "%s", "null q_start") : CCP_ERR_INVALID;
+  CCP_NO_OPEN_PIPELINE(h);
   device_guard g(h->device);
   const int n = CCPC_DOF * h->model.n_arms;
   double* dq = nullptr;
@@ -390,6 +477,7 @@ int ccp_set_tolerance(ccp_handle* h, double tol_position, double tol_rotation) {
   if (!h) return CCP_ERR_INVALID;
   if (!(tol_position > 0) || !(tol_rotation > 0))
     return set_err(h, CCP_ERR_INVALID, "%s", "setTolerance: tolerance must be positive.");
+  CCP_NO_OPEN_PIPELINE(h);
   h->model.tol_p = tol_position;
   h->model.tol_r = tol_rotation;
   return CCP_OK;
@@ -397,8 +485,9 @@ int ccp_set_tolerance(ccp_handle* h, double tol_position, double tol_rotation) {
 
 int ccp_set_options(ccp_handle* h, const ccp_options* opt) {
   if (!h || !opt) return CCP_ERR_INVALID;
-  if (!(opt->step > 0) || opt->max_iter < 0 || !(opt->joint_margin >= 0))
-    return set_err(h, CCP_ERR_INVALID, "%s", "bad options");
+  if (!(opt->step > 0) || opt->max_iter < 0 || opt->max_iter > 65535 || !(opt->joint_margin >= 0))
+    return set_err(h, CCP_ERR_INVALID, "%s", "bad options (step > 0, 0 <= max_iter <= 65535, joint_margin >= 0)");
+  CCP_NO_OPEN_PIPELINE(h);
   h->model.step = opt->step;
   h->model.max_iter = opt->max_iter;
   h->model.margin = opt->joint_margin;
@@ -555,6 +644,64 @@ int ccp_project_batch(ccp_handle* h, const double* seeds_dev, int64_t count, int
   return launch_project(h, A, layout, (cudaStream_t)stream);
 }
 
+static int fill_sampler_args(ccp_handle* h, const ccp_sampler_args* a, int64_t count, ccp_project_args* A);
+
+int ccp_project_batch_pipelined(ccp_handle* h, const double* seeds_dev, int64_t count, int32_t layout, double* x_out_dev,
+                                uint8_t* ok_dev, uint8_t* converged_dev, int32_t* iters_dev, double* resid_dev,
+                                double* compact_dev, int64_t* n_ok_dev, void* stream) {
+  int rc = check_common(h, seeds_dev, count, layout);
+  if (rc) return rc;
+  if (compact_dev && !n_ok_dev) return set_err(h, CCP_ERR_INVALID, "%s", "compact output needs n_ok");
+  device_guard g(h->device);
+  ccp_project_args A;
+  memset(&A, 0, sizeof A);
+  A.seeds = seeds_dev;
+  A.x_out = x_out_dev;
+  A.ok = ok_dev;
+  A.conv = converged_dev;
+  A.iters = iters_dev;
+  A.resid = resid_dev;
+  A.compact = compact_dev;
+  A.n_ok = (unsigned long long*)n_ok_dev;
+  A.count = count;
+  A.gen_mode = -1;
+  return launch_project(h, A, layout, (cudaStream_t)stream, true);
+}
+
+int ccp_sample_project_batch_pipelined(ccp_handle* h, const ccp_sampler_args* a, int64_t count, int32_t layout,
+                                       double* x_out_dev, uint8_t* ok_dev, int32_t* iters_dev, double* compact_dev,
+                                       int64_t* n_ok_dev, void* stream) {
+  if (!h) return CCP_ERR_INVALID;
+  if (count < 0) return set_err(h, CCP_ERR_INVALID, "%s", "negative count");
+  if (layout != CCP_LAYOUT_AOS && layout != CCP_LAYOUT_SOA) return set_err(h, CCP_ERR_INVALID, "%s", "bad layout");
+  if (compact_dev && !n_ok_dev) return set_err(h, CCP_ERR_INVALID, "%s", "compact output needs n_ok");
+  ccp_project_args A;
+  int rc = fill_sampler_args(h, a, count, &A);
+  if (rc) return rc;
+  A.x_out = x_out_dev;
+  A.ok = ok_dev;
+  A.iters = iters_dev;
+  A.compact = compact_dev;
+  A.n_ok = (unsigned long long*)n_ok_dev;
+  device_guard g(h->device);
+  return launch_project(h, A, layout, (cudaStream_t)stream, true);
+}
+
+int ccp_project_flush(ccp_handle* h, double* compact_dev, int64_t* n_ok_dev, void* stream) {
+  if (!h) return CCP_ERR_INVALID;
+  if (compact_dev && !n_ok_dev) return set_err(h, CCP_ERR_INVALID, "%s", "compact output needs n_ok");
+  if (!h->pipeline_open) return CCP_OK;
+  device_guard g(h->device);
+  ccp_project_args A;
+  memset(&A, 0, sizeof A);
+  A.gen_mode = (h->pipe_sig & 2) ? 0 : -1;
+  A.compact = compact_dev;
+  A.n_ok = (unsigned long long*)n_ok_dev;
+  return launch_project(h, A, (h->pipe_sig & 1) ? CCP_LAYOUT_SOA : CCP_LAYOUT_AOS, (cudaStream_t)stream, false);
+}
+
+int ccp_project_pipeline_open(const ccp_handle* h) { return h ? (h->pipeline_open ? 1 : 0) : CCP_ERR_INVALID; }
+
 int ccp_project_batch_timed(ccp_handle* h, const double* seeds_dev, int64_t count, int32_t layout, double* x_out_dev,
                             uint8_t* ok_dev, uint8_t* converged_dev, int32_t* iters_dev, double* resid_dev,
                             double* compact_dev, int64_t* n_ok_dev, void* stream, float* kernel_ms) {
@@ -680,6 +827,7 @@ int ccp_project_batch_host(ccp_handle* h, const double* seeds_host, int64_t coun
   if (rc) return rc;
   if (!h->has_ref) return set_err(h, CCP_ERR_STATE, "%s", "project before ccp_set_reference (setInitialPosition)");
   if (count == 0) return CCP_OK;
+  CCP_NO_OPEN_PIPELINE(h);  // this call runs on the handle's private streams
   std::lock_guard<std::mutex> host_lock(h->host_mu);
   device_guard g(h->device);
   const int n = CCPC_DOF * h->model.n_arms, m = 2 * (h->model.n_arms - 1);

@@ -23,6 +23,29 @@ __device__ __forceinline__ void st_elem(double* __restrict__ base, long long idx
 // ------------------------------------------------------------------------------------------
 // projection kernel
 // ------------------------------------------------------------------------------------------
+// Output arrays of one launch, kept in a device table indexed by launch slot: a sample that a pipelined launch
+// carried over to its successor still reports into the arrays of the launch it came from.
+struct ccp_out_desc {
+  double* x_out;
+  uint8_t* ok;
+  uint8_t* conv;
+  int32_t* iters;
+  double* resid;
+  long long count;  // SOA stride of those arrays
+  int wrap;
+  int pad;
+};
+#define CCP_NUM_DESC 64
+
+// A sample between two trips is (x, iteration count, index, launch slot): what a pipelined launch parks when
+// its seed list runs dry and what the next launch adopts.
+struct ccp_park_rec {
+  unsigned idx;
+  int it_slot;  // iterations so far | slot << 16
+  double x[CCPC_DOF * CCPC_MAX_ARMS];
+};
+#define CCP_NO_SAMPLE 0xffffffffu
+
 struct ccp_project_args {
   const double* seeds;  // nullptr when gen_mode >= 0
   double* x_out;
@@ -46,6 +69,14 @@ struct ccp_project_args {
   volatile int* host_done;      // [chunks] mapped pinned host flags: chunk c fully projected
   int* error;                   // set when the safety bound of the wait loop tripped
   long long chunk;              // samples per chunk (multiple of 8: chunks never share a 128 B line)
+  // pipelined launches (ccp_project_batch_pipelined): adopt the samples the previous launch parked, park the
+  // samples still iterating when this launch's work runs dry instead of idling the machine on them
+  const ccp_park_rec* adopt;    // nullptr = nothing to adopt
+  const unsigned* adopt_count;
+  ccp_park_rec* park;           // nullptr = run every sample to completion
+  unsigned* park_count;
+  ccp_out_desc* desc_table;     // [CCP_NUM_DESC]
+  unsigned slot;                // this launch's entry of desc_table
 };
 
 // Wait until the chunk(s) holding the samples just claimed by this warp's finishing lanes have landed.

@@ -56,46 +56,55 @@ constexpr size_t ccp_proj_smem_bytes() {
 // ------------------------------------------------------------------------------------------
 // work distribution
 // ------------------------------------------------------------------------------------------
-// A warp owns a private CHUNK of sample indices (shared memory: [next, end)).  Lanes whose sample just finished
-// take the next indices from it; only when it runs dry does the warp's leader touch the global work counter
-// (one atomic per CCP_CLAIM_CHUNK samples instead of one per refill, and off the refill's critical path most of
-// the time) and prefetch the new chunk's seed lines into L2.
+// The work items of a launch are numbered u = 0 .. total-1: first the samples adopted from the previous
+// (pipelined) launch, then this launch's own seeds.  A warp owns a private CHUNK of work numbers (shared
+// memory: [next, end)).  Lanes whose sample just finished take the next numbers from it; only when it runs dry
+// does the warp's leader touch the global work counter (one atomic per CCP_CLAIM_CHUNK samples instead of one
+// per refill, and off the refill's critical path most of the time) and prefetch the new chunk's seed lines
+// into L2.
 #define CCP_CLAIM_CHUNK 32u
 
 // how many trips pass between two tail rendezvous of the block
 #define CCP_TAIL_PERIOD 4
 
+struct ccp_work {
+  unsigned total;          // adopted + own
+  unsigned n_adopt;
+  unsigned first_dynamic;  // work numbers below this are handed out statically
+};
+
 template <int K, bool SOA, bool GEN>
-__device__ __forceinline__ unsigned claim_chunked(unsigned* chunk, const ccp_project_args& A, unsigned count,
-                                                   unsigned first_dynamic, volatile int* s_tail) {
+__device__ __forceinline__ unsigned claim_chunked(unsigned* chunk, const ccp_project_args& A, const ccp_work& W,
+                                                   volatile int* s_tail) {
   constexpr int n = CCPC_DOF * K;
   const unsigned mask = __activemask();
   const int lane = threadIdx.x & 31;
   const int leader = __ffs(mask) - 1;
   const unsigned need = __popc(mask);
   const unsigned rank = __popc(mask & ((1u << lane) - 1u));
-  unsigned base0 = 0, left = 0, base1 = count;
+  unsigned base0 = 0, left = 0, base1 = W.total;
   if (lane == leader) {
     base0 = chunk[0];
     left = chunk[1] - base0;
     if (left >= need) {
       chunk[0] = base0 + need;
     } else {
-      unsigned end1 = count;
+      unsigned end1 = W.total;
       if (!*s_tail) {
-        base1 = first_dynamic + atomicAdd((unsigned int*)A.counter, CCP_CLAIM_CHUNK);
-        if (base1 > count) base1 = count;
-        end1 = (count - base1 < CCP_CLAIM_CHUNK) ? count : base1 + CCP_CLAIM_CHUNK;
-        if (end1 - base1 < CCP_CLAIM_CHUNK) *s_tail = 1;  // the batch has run dry: the block enters its tail
-        if (!GEN && end1 > base1) {
+        base1 = W.first_dynamic + atomicAdd((unsigned int*)A.counter, CCP_CLAIM_CHUNK);
+        if (base1 > W.total) base1 = W.total;
+        end1 = (W.total - base1 < CCP_CLAIM_CHUNK) ? W.total : base1 + CCP_CLAIM_CHUNK;
+        if (end1 - base1 < CCP_CLAIM_CHUNK) *s_tail = 1;  // the work has run dry: the block enters its tail
+        if (!GEN && end1 > base1 && base1 >= W.n_adopt) {
+          const unsigned i0 = base1 - W.n_adopt;
           if (!SOA) {
-            const char* p = (const char*)(A.seeds + (size_t)base1 * n);
+            const char* p = (const char*)(A.seeds + (size_t)i0 * n);
             const unsigned bytes = (end1 - base1) * n * 8u;
             for (unsigned o = 0; o < bytes; o += 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
           } else {
 #pragma unroll
             for (int j = 0; j < n; ++j) {
-              const char* p = (const char*)(A.seeds + (size_t)j * count + base1);
+              const char* p = (const char*)(A.seeds + (size_t)j * (size_t)A.count + i0);
               asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
               asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
             }
@@ -110,21 +119,36 @@ __device__ __forceinline__ unsigned claim_chunked(unsigned* chunk, const ccp_pro
   base0 = __shfl_sync(mask, base0, leader);
   left = __shfl_sync(mask, left, leader);
   base1 = __shfl_sync(mask, base1, leader);
-  // an index past the chunk's end is >= count: the lane stays without work
+  // a number past the chunk's end is >= total: the lane stays without work
   return (rank < left) ? base0 + rank : base1 + (rank - left);
 }
 
-template <int K, bool SOA, bool GEN, class XT>
-__device__ __forceinline__ void load_seed(const ccp_model& M, const ccp_project_args& A, unsigned idx, unsigned count,
-                                          XT& x) {
+// Work number u -> the lane's sample: state x, index within its launch, iteration count | launch slot << 16.
+template <int K, bool SOA, bool GEN>
+__device__ __forceinline__ void load_sample(const ccp_model& M, const ccp_project_args& A, const ccp_work& W, unsigned u,
+                                            double* x, unsigned& idx, int& it) {
   constexpr int n = CCPC_DOF * K;
+  if (u >= W.total) {
+    idx = CCP_NO_SAMPLE;
+    return;
+  }
+  if (u < W.n_adopt) {
+    const ccp_park_rec* r = A.adopt + u;
+    idx = __ldcg(&r->idx);
+    it = __ldcg(&r->it_slot);
+#pragma unroll
+    for (int j = 0; j < n; ++j) x[j] = __ldcg(&r->x[j]);
+    return;
+  }
+  idx = u - W.n_adopt;
+  it = (int)(A.slot << 16);
   if (!GEN) {
     if (!SOA && A.ready) {
 #pragma unroll
       for (int j = 0; j < n; ++j) x[j] = __ldcg(A.seeds + (size_t)idx * n + j);
     } else {
 #pragma unroll
-      for (int j = 0; j < n; ++j) x[j] = ld_elem<SOA>(A.seeds, idx, j, count, n);
+      for (int j = 0; j < n; ++j) x[j] = ld_elem<SOA>(A.seeds, idx, j, A.count, n);
     }
   } else {
 #pragma unroll
@@ -138,13 +162,17 @@ __device__ __forceinline__ void load_seed(const ccp_model& M, const ccp_project_
 // shared memory (CCP_SM_* bits) instead of registers.
 //
 // Loop structure.  One trip = one Newton iteration of the lane's current sample (ConstraintFunction.h:68-73).
-// A lane whose sample leaves the loop writes its result and takes the next index (lane refill), so the
-// 0..250-iteration spread does not idle the warp while there is work.  When the batch runs dry the block
-// enters its TAIL: every CCP_TAIL_PERIOD trips the warps meet at a barrier, and as soon as the samples still
-// iterating fit in fewer warps they are packed into the lowest warps through shared memory ((x, it, index) is
-// the whole state of a sample between trips).  Emptied warps wait at the barrier and issue nothing, so the last
-// samples run at one-warp-per-scheduler latency instead of sharing the FP64 pipe with warps that carry one or
-// two live lanes each.  Which lane ran a sample never affects its result.
+// A lane whose sample leaves the loop writes its result and takes the next work number (lane refill), so the
+// 0..250-iteration spread does not idle the warp while there is work.  When the work runs dry the block enters
+// its TAIL:
+//   * complete mode (A.park == nullptr): every CCP_TAIL_PERIOD trips the warps meet at a barrier, and as soon as
+//     the samples still iterating fit in fewer warps they are packed into the lowest warps through shared memory
+//     ((x, it, index) is the whole state of a sample between trips).  Emptied warps wait at the barrier and issue
+//     nothing, so the last samples run at one-warp-per-scheduler latency instead of sharing the FP64 pipe with
+//     warps that carry one or two live lanes each.
+//   * pipelined mode (A.park != nullptr): the warp writes its live samples to the park buffer and exits; the next
+//     launch adopts them as its first work items.  No lane ever idles on a straggler.
+// Which lane (or launch) ran a sample never affects its result.
 template <int K, bool PANDA, bool SOA, bool GEN, int BLOCK, int MINB, int SM>
 __global__ void __launch_bounds__(BLOCK, MINB)
 ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ ccp_project_args A) {
@@ -166,40 +194,84 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
     sm_next += 4 * CCPC_DOF * (K - 1) * BLOCK;
   }
   double x[n];
-  const unsigned count = (unsigned)A.count;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  ccp_work W;
+  W.n_adopt = A.adopt ? __ldcg(A.adopt_count) : 0u;
+  W.total = W.n_adopt + (unsigned)A.count;
   // The first chunk of every warp is static and interleaved over the blocks (chunk c -> block c % grid, warp
   // c / grid), so a batch smaller than the machine spreads one warp per SM before any SM gets a second one; the
   // global counter hands out what lies beyond those gridDim.x * NW chunks.
   const unsigned static_chunks = gridDim.x * NW;
-  const unsigned first_dynamic = (count / CCP_CLAIM_CHUNK < static_chunks) ? count : static_chunks * CCP_CLAIM_CHUNK;
-  if (threadIdx.x == 0) s_tail = (first_dynamic >= count) ? 1 : 0;
+  W.first_dynamic = (W.total / CCP_CLAIM_CHUNK < static_chunks) ? W.total : static_chunks * CCP_CLAIM_CHUNK;
+  if (threadIdx.x == 0) {
+    s_tail = (W.first_dynamic >= W.total) ? 1 : 0;
+    if (blockIdx.x == 0 && A.park) {  // successors find this launch's output arrays by slot
+      ccp_out_desc d;
+      d.x_out = A.x_out; d.ok = A.ok; d.conv = A.conv; d.iters = A.iters; d.resid = A.resid;
+      d.count = A.count; d.wrap = A.wrap; d.pad = 0;
+      A.desc_table[A.slot] = d;
+    }
+  }
   if (lane == 0) {
     const unsigned long long b0 = (unsigned long long)(warp * gridDim.x + blockIdx.x) * CCP_CLAIM_CHUNK;
-    const unsigned lo = b0 < count ? (unsigned)b0 : count;
+    const unsigned lo = b0 < W.total ? (unsigned)b0 : W.total;
     s_chunk[warp][0] = lo;
-    s_chunk[warp][1] = (count - lo < CCP_CLAIM_CHUNK) ? count : lo + CCP_CLAIM_CHUNK;
+    s_chunk[warp][1] = (W.total - lo < CCP_CLAIM_CHUNK) ? W.total : lo + CCP_CLAIM_CHUNK;
   }
   __syncthreads();
   int it = 0;
-  unsigned idx = claim_chunked<K, SOA, GEN>(s_chunk[warp], A, count, first_dynamic, &s_tail);
-  if (!GEN && !SOA && A.ready) wait_chunk_ready(A, idx, idx < count);
-  if (idx < count) load_seed<K, SOA, GEN>(M, A, idx, count, x);
+  unsigned idx = CCP_NO_SAMPLE;
+  {
+    const unsigned u = claim_chunked<K, SOA, GEN>(s_chunk[warp], A, W, &s_tail);
+    if (!GEN && !SOA && A.ready) wait_chunk_ready(A, u, u < W.total);
+    load_sample<K, SOA, GEN>(M, A, W, u, x, idx, it);
+  }
   bool tail = false;
   int since = 0;
   for (;;) {
     if (!tail) tail = *(volatile int*)&s_tail != 0;
     if (tail) {
-      if (since == 0) {
-        // ---- tail rendezvous ----
-        if (idx >= count) {  // what is left of the warp's private chunk
-          idx = claim_chunked<K, SOA, GEN>(s_chunk[warp], A, count, first_dynamic, &s_tail);
-          it = 0;
-          if (!GEN && !SOA && A.ready) wait_chunk_ready(A, idx, idx < count);
-          if (idx < count) load_seed<K, SOA, GEN>(M, A, idx, count, x);
+      if (A.park) {
+        // ---- pipelined mode: once few enough of the warp's lanes still carry a sample, park what the warp
+        // holds (live samples, then the unstarted rest of its private chunk) and leave.  A launch that outgrew
+        // its static allotment parks the moment its work runs dry (every other warp is still full, nothing is
+        // gained by waiting); a launch smaller than the machine keeps iterating until half the lanes are free,
+        // so it makes progress and the parked set stays bounded (<= 16 per warp) however many follow.
+        if (idx == CCP_NO_SAMPLE) {
+          const unsigned u = claim_chunked<K, SOA, GEN>(s_chunk[warp], A, W, &s_tail);
+          load_sample<K, SOA, GEN>(M, A, W, u, x, idx, it);
         }
         __syncwarp();
-        const bool active = idx < count;
+        const int park_at = (W.first_dynamic < W.total) ? 32 : 16;
+        if (__popc(__ballot_sync(0xffffffffu, idx != CCP_NO_SAMPLE)) <= park_at) {
+          for (;;) {
+            const bool live = idx != CCP_NO_SAMPLE;
+            const unsigned bal = __ballot_sync(0xffffffffu, live);
+            if (bal == 0u) break;
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(A.park_count, (unsigned)__popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (live) {
+              ccp_park_rec* r = A.park + base + __popc(bal & ((1u << lane) - 1u));
+              r->idx = idx;
+              r->it_slot = it;
+#pragma unroll
+              for (int j = 0; j < n; ++j) r->x[j] = x[j];
+            }
+            const unsigned u = claim_chunked<K, SOA, GEN>(s_chunk[warp], A, W, &s_tail);
+            load_sample<K, SOA, GEN>(M, A, W, u, x, idx, it);
+          }
+          return;
+        }
+      } else if (since == 0) {
+        // ---- complete mode: tail rendezvous ----
+        if (idx == CCP_NO_SAMPLE) {  // what is left of the warp's private chunk
+          const unsigned u = claim_chunked<K, SOA, GEN>(s_chunk[warp], A, W, &s_tail);
+          if (!GEN && !SOA && A.ready) wait_chunk_ready(A, u, u < W.total);
+          load_sample<K, SOA, GEN>(M, A, W, u, x, idx, it);
+        }
+        __syncwarp();
+        const bool active = idx != CCP_NO_SAMPLE;
         const int total = __syncthreads_count(active);
         if (total == 0) break;
         const unsigned bal = __ballot_sync(0xffffffffu, active);
@@ -229,7 +301,7 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
             it = __double2hiint(pk);
             idx = (unsigned)__double2loint(pk);
           } else {
-            idx = count;
+            idx = CCP_NO_SAMPLE;
           }
           if constexpr (SM != 0) __syncthreads();  // the staging arrays are about to be written again
         }
@@ -237,10 +309,10 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
       }
       --since;
     }
-    if (idx < count) {
+    if (idx != CCP_NO_SAMPLE) {
       ccp_fwd<K> F;
       ccp_forward<K, PANDA>(M, x, S, F);
-      const bool cont = ccp_needs_step<K>(M, F.f) && it < M.max_iter;
+      const bool cont = ccp_needs_step<K>(M, F.f) && (it & 0xffff) < M.max_iter;
       if (cont) {
         ++it;
         ccp_jacobian<K, PANDA>(M, S, F, J);
@@ -249,21 +321,32 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
         // ---- epilogue of this sample (ConstraintFunction.h:75-81), then refill the lane ----
         const bool cv = ccp_converged<K>(M, F.f);
         const bool okk = cv && ccp_joint_valid<K>(M, x);
-        if (GEN && A.wrap) {
+        // the sample reports into the arrays of the launch it was submitted with
+        ccp_out_desc D;
+        if (((unsigned)it >> 16) == A.slot) {
+          D.x_out = A.x_out; D.ok = A.ok; D.conv = A.conv; D.iters = A.iters; D.resid = A.resid;
+          D.count = A.count; D.wrap = A.wrap;
+        } else {
+          const ccp_out_desc* T = A.desc_table + ((unsigned)it >> 16);
+          D.x_out = T->x_out; D.ok = T->ok; D.conv = T->conv; D.iters = T->iters; D.resid = T->resid;
+          D.count = T->count; D.wrap = T->wrap;
+        }
+        if (GEN && D.wrap) {
 #pragma unroll
           for (int j = 0; j < n; ++j) x[j] = ccp_wrap_pi(x[j]);
         }
-        if (A.x_out) {
+        if (D.x_out) {
 #pragma unroll
-          for (int j = 0; j < n; ++j) st_elem<SOA>(A.x_out, idx, j, count, n, x[j]);
+          for (int j = 0; j < n; ++j) st_elem<SOA>(D.x_out, idx, j, D.count, n, x[j]);
         }
-        if (A.ok) A.ok[idx] = okk;
-        if (A.conv) A.conv[idx] = cv;
-        if (A.iters) A.iters[idx] = it;
-        if (A.resid) {
+        if (D.ok) D.ok[idx] = okk;
+        if (D.conv) D.conv[idx] = cv;
+        if (D.iters) D.iters[idx] = it & 0xffff;
+        if (D.resid) {
 #pragma unroll
-          for (int k = 0; k < m; ++k) st_elem<SOA>(A.resid, idx, k, count, m, F.f[k]);
+          for (int k = 0; k < m; ++k) st_elem<SOA>(D.resid, idx, k, D.count, m, F.f[k]);
         }
+        // the compacted stream is a stream: a state is appended to the buffer of the launch it finished in
         if (A.n_ok && okk) {
           const unsigned long long slot = atomicAdd(A.n_ok, 1ULL);
           if (A.compact) {
@@ -281,10 +364,9 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
             A.host_done[c] = 1;
           }
         }
-        idx = claim_chunked<K, SOA, GEN>(s_chunk[warp], A, count, first_dynamic, &s_tail);
-        it = 0;
-        if (!GEN && !SOA && A.ready) wait_chunk_ready(A, idx, idx < count);
-        if (idx < count) load_seed<K, SOA, GEN>(M, A, idx, count, x);
+        const unsigned u = claim_chunked<K, SOA, GEN>(s_chunk[warp], A, W, &s_tail);
+        if (!GEN && !SOA && A.ready) wait_chunk_ready(A, u, u < W.total);
+        load_sample<K, SOA, GEN>(M, A, W, u, x, idx, it);
       }
     }
   }
@@ -303,6 +385,7 @@ static cudaError_t launch_project_v(int sm_count, const ccp_model& M, const ccp_
   // it runs at one-warp-per-scheduler latency on many SMs instead of crowding a few
   long long need = (A.count + 31) / 32;
   long long cap = (long long)sm_count * MINB;
+  if (A.adopt) need = cap;  // how many samples the previous launch parked is only known on the device
   int grid = (int)(need < cap ? need : cap);
   if (grid < 1) grid = 1;
   constexpr size_t smem = ccp_proj_smem_bytes<K, BLOCK, SM>();

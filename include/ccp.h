@@ -129,6 +129,27 @@ int ccp_project_batch(ccp_handle* h, const double* seeds_dev, int64_t count, int
                       int32_t* iters_dev, double* resid_dev, double* compact_dev,
                       int64_t* n_ok_dev, void* stream);
 
+/* Pipelined form of ccp_project_batch for a caller that projects batch after batch on ONE stream (the planner's
+ * batched sampler refilling its pool, jy_ProjectedStateSpace.cpp:10-29).  Iteration counts spread 0..max_iter, so
+ * when a batch's seed list runs dry a few samples are still iterating and the rest of the GPU would idle on them;
+ * this call instead PARKS them (state, iteration count, index) and returns, and the next ccp_project_batch[_pipelined]
+ * / ccp_sample_project_batch[_pipelined] / ccp_project_flush on the same handle adopts them as its first work items.
+ * Results are bit-identical to ccp_project_batch.  Contract:
+ *   - per-seed outputs (x_out, ok, converged, iters, resid) of a pipelined call are complete only after a later
+ *     non-pipelined projection call or ccp_project_flush on the same stream; the arrays must stay valid until then;
+ *   - compact_dev / n_ok_dev form a STREAM: a converged state is appended to the buffer of the launch it FINISHED
+ *     in (so a launch may append a few states of its predecessor), ccp_project_flush appends the last ones;
+ *   - all launches of an open pipeline use one stream; setters (set_reference/tolerance/options) return
+ *     CCP_ERR_STATE while the pipeline is open.                                                            */
+int ccp_project_batch_pipelined(ccp_handle* h, const double* seeds_dev, int64_t count, int32_t layout,
+                                double* x_out_dev, uint8_t* ok_dev, uint8_t* converged_dev,
+                                int32_t* iters_dev, double* resid_dev, double* compact_dev,
+                                int64_t* n_ok_dev, void* stream);
+/* Completes every parked sample (compact_dev / n_ok_dev may be NULL).  No-op when nothing is parked.        */
+int ccp_project_flush(ccp_handle* h, double* compact_dev, int64_t* n_ok_dev, void* stream);
+/* 1 when parked samples exist, 0 otherwise.                                                                */
+int ccp_project_pipeline_open(const ccp_handle* h);
+
 /* ≙ isSatisfied (ConstraintFunction.h:114-120): finite and f0 <= tol1 and f1 <= tol2.       */
 int ccp_is_satisfied_batch(ccp_handle* h, const double* x_dev, int64_t count, int32_t layout,
                            uint8_t* out_dev, void* stream);
@@ -173,6 +194,10 @@ int ccp_generate_seeds(ccp_handle* h, const ccp_sampler_args* a, int64_t count, 
 int ccp_sample_project_batch(ccp_handle* h, const ccp_sampler_args* a, int64_t count, int32_t layout,
                              double* x_out_dev, uint8_t* ok_dev, int32_t* iters_dev,
                              double* compact_dev, int64_t* n_ok_dev, void* stream);
+/* Pipelined form (see ccp_project_batch_pipelined): the pool refill never waits on a batch's stragglers.     */
+int ccp_sample_project_batch_pipelined(ccp_handle* h, const ccp_sampler_args* a, int64_t count, int32_t layout,
+                                       double* x_out_dev, uint8_t* ok_dev, int32_t* iters_dev,
+                                       double* compact_dev, int64_t* n_ok_dev, void* stream);
 /* ≙ KinematicChainSpace::enforceBounds (KinematicChain.h:118-130), in place.                */
 int ccp_enforce_bounds_batch(ccp_handle* h, double* x_dev, int64_t count, int32_t layout, void* stream);
 
