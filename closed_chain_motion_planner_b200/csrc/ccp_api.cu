@@ -37,6 +37,14 @@
 // handle
 // ------------------------------------------------------------------------------------------
 #define CCP_NUM_COUNTERS 64
+#define CCP_HOST_MAX_CHUNKS 24  /* < CCP_NUM_DESC / 2: every chunk launch of a host call stays pipelined */
+
+// per-launch device record (ring of CCP_NUM_COUNTERS): zeroed by ONE stream-ordered memset before the launch
+struct ccp_launch_rec {
+  unsigned long long work;  // dynamic work counter of the projection / geodesic kernel
+  unsigned parked;          // samples the (pipelined) launch parked
+  unsigned pad;
+};
 
 struct ccp_handle {
   int device;
@@ -44,21 +52,18 @@ struct ccp_handle {
   bool has_ref;
   ccp_model model;  // host image; passed BY VALUE to every kernel
   long long launches;
-  unsigned long long* d_counters;  // CCP_NUM_COUNTERS work counters (one per in-flight launch)
+  ccp_launch_rec* d_counters;  // CCP_NUM_COUNTERS launch records: work counter + parked-sample counter
   unsigned launch_seq;
   // grow-only device staging for the *_host entry points
   void* d_stage;
   size_t d_stage_bytes;
   cudaStream_t hstream[3];
   cudaEvent_t ev0, ev1;
-  // streaming host path: device flags [ready | done | error], mapped pinned host flags, a pinned constant 1
-  int* d_flags;
-  int* h_flags;      // cudaHostAlloc(mapped): [0..63] host_done, [64] = 1
-  int* h_flags_dev;  // device alias of h_flags
+  cudaEvent_t ev_chunk_in[CCP_HOST_MAX_CHUNKS], ev_chunk_k[CCP_HOST_MAX_CHUNKS];  // host path: chunk landed / projected
   // pipelined projection launches: two park buffers (the launch adopts from one and parks into the other),
   // their record counters, and the table of output descriptors by launch slot
   ccp_park_rec* d_park[2];
-  unsigned* d_park_count;  // [2]
+  unsigned prev_slot;      // launch slot whose record counts the parked samples in d_park[park_cur]
   ccp_out_desc* d_desc;    // [CCP_NUM_DESC]
   size_t park_capacity;    // records per buffer
   int park_cur;            // buffer holding the parked samples of the last pipelined launch
@@ -255,9 +260,7 @@ static int ensure_pipeline(ccp_handle* h) {
   const size_t cap = (size_t)h->sm_count * 512 * 2;
   CCP_CUDA(cudaMalloc(&h->d_park[0], cap * sizeof(ccp_park_rec)));
   CCP_CUDA(cudaMalloc(&h->d_park[1], cap * sizeof(ccp_park_rec)));
-  CCP_CUDA(cudaMalloc(&h->d_park_count, 2 * sizeof(unsigned)));
   CCP_CUDA(cudaMalloc(&h->d_desc, CCP_NUM_DESC * sizeof(ccp_out_desc)));
-  CCP_CUDA(cudaMemset(h->d_park_count, 0, 2 * sizeof(unsigned)));
   CCP_CUDA(cudaMemset(h->d_desc, 0, CCP_NUM_DESC * sizeof(ccp_out_desc)));
   h->park_capacity = cap;
   return CCP_OK;
@@ -300,21 +303,20 @@ static int launch_project(ccp_handle* h, ccp_project_args& A, int layout, cudaSt
     slot = h->launch_seq++ % CCP_NUM_COUNTERS;
     h->launches++;
   }
-  A.counter = h->d_counters + slot;
+  A.counter = &h->d_counters[slot].work;
   A.slot = slot % CCP_NUM_DESC;
-  CCP_CUDA(cudaMemsetAsync(A.counter, 0, sizeof(unsigned long long), st));
+  CCP_CUDA(cudaMemsetAsync(h->d_counters + slot, 0, sizeof(ccp_launch_rec), st));
   if (defer || h->pipeline_open) {
     int rc = ensure_pipeline(h);
     if (rc) return rc;
     A.desc_table = h->d_desc;
     if (h->pipeline_open) {
       A.adopt = h->d_park[h->park_cur];
-      A.adopt_count = h->d_park_count + h->park_cur;
+      A.adopt_count = &h->d_counters[h->prev_slot].parked;
     }
     if (defer) {
       A.park = h->d_park[1 - h->park_cur];
-      A.park_count = h->d_park_count + (1 - h->park_cur);
-      CCP_CUDA(cudaMemsetAsync(A.park_count, 0, sizeof(unsigned), st));
+      A.park_count = &h->d_counters[slot].parked;
     }
   }
   int rc = dispatch_project(h, A, soa, st);
@@ -324,6 +326,7 @@ static int launch_project(ccp_handle* h, ccp_project_args& A, int layout, cudaSt
     h->pipe_sig = sig;
     h->pipe_launches++;
     h->park_cur = 1 - h->park_cur;
+    h->prev_slot = slot;
   } else {
     h->pipeline_open = false;
     h->pipe_launches = 0;
@@ -378,7 +381,7 @@ int ccp_create(const ccp_model_desc* model, int32_t device, ccp_handle** out) {
   nh->d_stage = nullptr;
   nh->d_stage_bytes = 0;
   nh->d_park[0] = nh->d_park[1] = nullptr;
-  nh->d_park_count = nullptr;
+  nh->prev_slot = 0;
   nh->d_desc = nullptr;
   nh->park_capacity = 0;
   nh->park_cur = 0;
@@ -389,17 +392,14 @@ int ccp_create(const ccp_model_desc* model, int32_t device, ccp_handle** out) {
   device_guard g(device);
   cudaError_t e = g.ok ? cudaSuccess : cudaErrorInvalidDevice;
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&nh->sm_count, cudaDevAttrMultiProcessorCount, device);
-  if (e == cudaSuccess) e = cudaMalloc(&nh->d_counters, CCP_NUM_COUNTERS * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&nh->d_counters, CCP_NUM_COUNTERS * sizeof(ccp_launch_rec));
   for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&nh->hstream[i], cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreate(&nh->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&nh->ev1);
-  nh->d_flags = nullptr;
-  nh->h_flags = nullptr;
-  nh->h_flags_dev = nullptr;
-  if (e == cudaSuccess) e = cudaMalloc(&nh->d_flags, sizeof(int) * 256);
-  if (e == cudaSuccess) e = cudaHostAlloc((void**)&nh->h_flags, sizeof(int) * 128, cudaHostAllocMapped);
-  if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&nh->h_flags_dev, nh->h_flags, 0);
-  if (e == cudaSuccess) nh->h_flags[64] = 1;
+  for (int i = 0; i < CCP_HOST_MAX_CHUNKS && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&nh->ev_chunk_in[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&nh->ev_chunk_k[i], cudaEventDisableTiming);
+  }
   if (e != cudaSuccess) {
     set_err(nullptr, CCP_ERR_CUDA, "ccp_create: %s", cudaGetErrorString(e));
     delete nh;
@@ -415,12 +415,13 @@ void ccp_destroy(ccp_handle* h) {
   cudaDeviceSynchronize();
   if (h->d_counters) cudaFree(h->d_counters);
   if (h->d_stage) cudaFree(h->d_stage);
-  if (h->d_flags) cudaFree(h->d_flags);
   if (h->d_park[0]) cudaFree(h->d_park[0]);
   if (h->d_park[1]) cudaFree(h->d_park[1]);
-  if (h->d_park_count) cudaFree(h->d_park_count);
   if (h->d_desc) cudaFree(h->d_desc);
-  if (h->h_flags) cudaFreeHost(h->h_flags);
+  for (int i = 0; i < CCP_HOST_MAX_CHUNKS; ++i) {
+    cudaEventDestroy(h->ev_chunk_in[i]);
+    cudaEventDestroy(h->ev_chunk_k[i]);
+  }
   for (int i = 0; i < 3; ++i) cudaStreamDestroy(h->hstream[i]);
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
@@ -797,8 +798,8 @@ int ccp_geodesic_batch(ccp_handle* h, const double* from_dev, const double* to_d
     slot = h->launch_seq++ % CCP_NUM_COUNTERS;
     h->launches++;
   }
-  unsigned long long* counter = h->d_counters + slot;
-  CCP_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+  unsigned long long* counter = &h->d_counters[slot].work;
+  CCP_CUDA(cudaMemsetAsync(h->d_counters + slot, 0, sizeof(ccp_launch_rec), st));
   cudaError_t e = ccp_launch_geodesic(h->sm_count, h->model, from_dev, to_dev, edges, delta, lambda, max_states, states_dev,
                                       n_states_dev, reached_dev, iters_dev, counter, st);
   if (e != cudaSuccess) return set_err(h, CCP_ERR_CUDA, "geodesic kernel launch: %s", cudaGetErrorString(e));
@@ -818,16 +819,20 @@ int ccp_enforce_bounds_batch(ccp_handle* h, double* x_dev, int64_t count, int32_
 }
 
 // ---- host-buffer entry points ------------------------------------------------------------
-// Chunked 3-stage pipeline over the handle's private streams: H2D(i) | project(i) | D2H(i).
-// With pinned caller buffers the copies overlap the kernels; with pageable buffers CUDA stages
-// them internally and the call is still correct.
+// ccp_project_batch_host: the batch is cut into chunks that flow through three private streams,
+//   C: H2D chunk 0 | H2D chunk 1 | ...
+//   K:      project 0 | project 1 | ... | flush            (PIPELINED launches: a chunk's stragglers are parked and
+//   D:                 D2H chunk 0 | ...        | D2H last   adopted by the next chunk's launch, so there is ONE tail
+// for the whole call however fine the chunks are, and chunk c's outputs are complete after launch c + 1).  Everything
+// is ordered by events; the host only waits at the end.  With pinned caller buffers the copies run at PCIe rate
+// behind the kernels; with pageable buffers CUDA stages them and the call is still correct.
 int ccp_project_batch_host(ccp_handle* h, const double* seeds_host, int64_t count, double* x_out_host,
                            uint8_t* ok_host, uint8_t* converged_host, int32_t* iters_host, double* resid_host) {
   int rc = check_common(h, seeds_host, count, CCP_LAYOUT_AOS);
   if (rc) return rc;
   if (!h->has_ref) return set_err(h, CCP_ERR_STATE, "%s", "project before ccp_set_reference (setInitialPosition)");
   if (count == 0) return CCP_OK;
-  CCP_NO_OPEN_PIPELINE(h);  // this call runs on the handle's private streams
+  CCP_NO_OPEN_PIPELINE(h);  // this call runs its own pipeline on the handle's private streams
   std::lock_guard<std::mutex> host_lock(h->host_mu);
   device_guard g(h->device);
   const int n = CCPC_DOF * h->model.n_arms, m = 2 * (h->model.n_arms - 1);
@@ -841,14 +846,8 @@ int ccp_project_batch_host(ccp_handle* h, const double* seeds_host, int64_t coun
   int32_t* dit = (int32_t*)((char*)dres + sizeof(double) * m * (size_t)count);
   uint8_t* dok = (uint8_t*)((char*)dit + sizeof(int32_t) * (size_t)count);
   uint8_t* dcv = dok + (size_t)count;
-  // ---- streaming pipeline -------------------------------------------------------------------------
-  // ONE persistent projection kernel runs over the whole batch while the copy engines stream the seeds in
-  // chunk by chunk (stream C) and the finished chunks out (stream D):
-  //   C: H2D chunk 0, flag 0, H2D chunk 1, flag 1, ...          (flag c = stream-ordered 4-byte copy)
-  //   K: kernel; a lane that claims a sample of chunk c waits for flag c; the last sample finished in
-  //      chunk c raises a mapped host flag
-  //   D: when the host sees that flag it enqueues the D2H copies of chunk c
-  // so the copies hide behind the kernel and there is one launch tail, not one per chunk.
+  // chunking: a chunk a little larger than the resident lane count keeps every lane busy within a launch; the
+  // first H2D and the last D2H (the parts nothing hides) shrink with the chunk
   int parts;
   {
     static int env_parts = -1;
@@ -856,54 +855,18 @@ int ccp_project_batch_host(ccp_handle* h, const double* seeds_host, int64_t coun
       const char* e = getenv("CCP_HOST_CHUNKS");
       env_parts = e ? atoi(e) : 0;
     }
-    parts = env_parts > 0 ? env_parts : (int)(count / ((int64_t)h->sm_count * 384 * 2));  // measured best: 8 at 1 M
-    if (parts > 8 && env_parts <= 0) parts = 8;
-    if (parts > 32) parts = 32;
+    const int64_t lanes = (int64_t)h->sm_count * 384;
+    parts = env_parts > 0 ? env_parts : (int)(count / (lanes + lanes / 8));
+    if (parts > CCP_HOST_MAX_CHUNKS) parts = CCP_HOST_MAX_CHUNKS;
     if (parts < 1) parts = 1;
   }
   int64_t chunk = (count + parts - 1) / parts;
-  chunk = (chunk + 7) / 8 * 8;
+  chunk = (chunk + 15) / 16 * 16;  // chunks never share a 128 B line of any output array
   parts = (int)((count + chunk - 1) / chunk);
   cudaStream_t sC = h->hstream[0], sK = h->hstream[1], sD = h->hstream[2];
-  int* d_ready = h->d_flags;
-  unsigned int* d_done = (unsigned int*)(h->d_flags + 64);
-  int* d_error = h->d_flags + 128;
-  for (int c = 0; c < parts; ++c) h->h_flags[c] = 0;
-  CCP_CUDA(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * 256, sK));
-  CCP_CUDA(cudaEventRecord(h->ev0, sK));
-  CCP_CUDA(cudaStreamWaitEvent(sC, h->ev0, 0));
-  {
-    ccp_project_args A;
-    memset(&A, 0, sizeof A);
-    A.seeds = dx;
-    A.x_out = dx;
-    A.ok = dok;
-    A.conv = dcv;
-    A.iters = dit;
-    A.resid = resid_host ? dres : nullptr;
-    A.count = count;
-    A.gen_mode = -1;
-    A.ready = d_ready;
-    A.done = d_done;
-    A.host_done = h->h_flags_dev;
-    A.error = d_error;
-    A.chunk = chunk;
-    rc = launch_project(h, A, CCP_LAYOUT_AOS, sK);  // first: it overlaps even blocking (pageable) copies
-    if (rc) return rc;
-  }
-  for (int c = 0; c < parts; ++c) {
+  auto copy_out = [&](int c) -> int {
     const int64_t off = (int64_t)c * chunk;
     const int64_t cn = (count - off < chunk) ? (count - off) : chunk;
-    CCP_CUDA(cudaMemcpyAsync(dx + off * n, seeds_host + off * n, sizeof(double) * n * cn, cudaMemcpyHostToDevice, sC));
-    CCP_CUDA(cudaMemcpyAsync(d_ready + c, h->h_flags + 64, sizeof(int), cudaMemcpyHostToDevice, sC));
-  }
-  for (int c = 0; c < parts; ++c) {
-    const int64_t off = (int64_t)c * chunk;
-    const int64_t cn = (count - off < chunk) ? (count - off) : chunk;
-    volatile int* flag = h->h_flags + c;
-    while (*flag == 0) {
-      if (cudaStreamQuery(sK) != cudaErrorNotReady) break;  // kernel finished (or failed): nothing more will be flagged
-    }
     if (x_out_host)
       CCP_CUDA(cudaMemcpyAsync(x_out_host + off * n, dx + off * n, sizeof(double) * n * cn, cudaMemcpyDeviceToHost, sD));
     if (ok_host) CCP_CUDA(cudaMemcpyAsync(ok_host + off, dok + off, (size_t)cn, cudaMemcpyDeviceToHost, sD));
@@ -911,13 +874,46 @@ int ccp_project_batch_host(ccp_handle* h, const double* seeds_host, int64_t coun
     if (iters_host) CCP_CUDA(cudaMemcpyAsync(iters_host + off, dit + off, sizeof(int32_t) * cn, cudaMemcpyDeviceToHost, sD));
     if (resid_host)
       CCP_CUDA(cudaMemcpyAsync(resid_host + off * m, dres + off * m, sizeof(double) * m * cn, cudaMemcpyDeviceToHost, sD));
+    return CCP_OK;
+  };
+  for (int c = 0; c < parts; ++c) {
+    const int64_t off = (int64_t)c * chunk;
+    const int64_t cn = (count - off < chunk) ? (count - off) : chunk;
+    CCP_CUDA(cudaMemcpyAsync(dx + off * n, seeds_host + off * n, sizeof(double) * n * cn, cudaMemcpyHostToDevice, sC));
+    CCP_CUDA(cudaEventRecord(h->ev_chunk_in[c], sC));
+    CCP_CUDA(cudaStreamWaitEvent(sK, h->ev_chunk_in[c], 0));
+    ccp_project_args A;
+    memset(&A, 0, sizeof A);
+    A.seeds = dx + off * n;
+    A.x_out = dx + off * n;
+    A.ok = dok + off;
+    A.conv = dcv + off;
+    A.iters = dit + off;
+    A.resid = resid_host ? dres + off * m : nullptr;
+    A.count = cn;
+    A.gen_mode = -1;
+    rc = launch_project(h, A, CCP_LAYOUT_AOS, sK, /*defer=*/parts > 1);
+    if (rc) return rc;
+    CCP_CUDA(cudaEventRecord(h->ev_chunk_k[c], sK));
+    if (c > 0) {  // launch c completed chunk c - 1
+      CCP_CUDA(cudaStreamWaitEvent(sD, h->ev_chunk_k[c], 0));
+      rc = copy_out(c - 1);
+      if (rc) return rc;
+    }
   }
-  int err = 0;
-  CCP_CUDA(cudaStreamSynchronize(sK));
-  CCP_CUDA(cudaStreamSynchronize(sC));
-  CCP_CUDA(cudaMemcpyAsync(&err, d_error, sizeof(int), cudaMemcpyDeviceToHost, sD));
+  if (h->pipeline_open) {
+    ccp_project_args F;
+    memset(&F, 0, sizeof F);
+    F.gen_mode = -1;
+    rc = launch_project(h, F, CCP_LAYOUT_AOS, sK, false);
+    if (rc) return rc;
+  }
+  CCP_CUDA(cudaEventRecord(h->ev1, sK));
+  CCP_CUDA(cudaStreamWaitEvent(sD, h->ev1, 0));
+  rc = copy_out(parts - 1);
+  if (rc) return rc;
   CCP_CUDA(cudaStreamSynchronize(sD));
-  if (err) return set_err(h, CCP_ERR_CUDA, "%s", "streaming projection: a seed chunk never arrived (wait bound tripped)");
+  CCP_CUDA(cudaStreamSynchronize(sK));
   return CCP_OK;
 }
 

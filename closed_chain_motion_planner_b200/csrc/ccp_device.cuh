@@ -63,12 +63,6 @@ struct ccp_project_args {
   long long first_index;
   double distance;
   double near[CCPC_DOF * CCPC_MAX_ARMS];
-  // streaming (host entry point): the seeds arrive chunk by chunk over PCIe WHILE the kernel runs
-  const int* ready;             // [chunks] set to 1 by a stream-ordered copy after chunk c landed; nullptr = off
-  unsigned int* done;           // [chunks] finished samples per chunk
-  volatile int* host_done;      // [chunks] mapped pinned host flags: chunk c fully projected
-  int* error;                   // set when the safety bound of the wait loop tripped
-  long long chunk;              // samples per chunk (multiple of 8: chunks never share a 128 B line)
   // pipelined launches (ccp_project_batch_pipelined): adopt the samples the previous launch parked, park the
   // samples still iterating when this launch's work runs dry instead of idling the machine on them
   const ccp_park_rec* adopt;    // nullptr = nothing to adopt
@@ -78,29 +72,6 @@ struct ccp_project_args {
   ccp_out_desc* desc_table;     // [CCP_NUM_DESC]
   unsigned slot;                // this launch's entry of desc_table
 };
-
-// Wait until the chunk(s) holding the samples just claimed by this warp's finishing lanes have landed.
-// One lane per warp polls (copies are stream-ordered, so the highest chunk implies the lower ones).
-__device__ __forceinline__ void wait_chunk_ready(const ccp_project_args& A, long long idx, bool valid) {
-  const unsigned mask = __activemask();
-  const int lane = threadIdx.x & 31;
-  const int leader = __ffs(mask) - 1;
-  const int c = valid ? (int)(idx / A.chunk) : 0;
-  const int cmax = __reduce_max_sync(mask, c);
-  if (lane == leader) {
-    const volatile int* f = A.ready + cmax;
-    unsigned spins = 0;
-    while (*f == 0) {
-      __nanosleep(500);
-      if (++spins > (1u << 22)) {  // ~2 s: never hang the GPU on a lost copy
-        *A.error = 1;
-        break;
-      }
-    }
-  }
-  __syncwarp(mask);
-  __threadfence();
-}
 
 // warp-aggregated claim of the next sample index by the lanes currently finishing
 __device__ __forceinline__ long long claim_next(unsigned long long* counter) {

@@ -143,13 +143,8 @@ __device__ __forceinline__ void load_sample(const ccp_model& M, const ccp_projec
   idx = u - W.n_adopt;
   it = (int)(A.slot << 16);
   if (!GEN) {
-    if (!SOA && A.ready) {
 #pragma unroll
-      for (int j = 0; j < n; ++j) x[j] = __ldcg(A.seeds + (size_t)idx * n + j);
-    } else {
-#pragma unroll
-      for (int j = 0; j < n; ++j) x[j] = ld_elem<SOA>(A.seeds, idx, j, A.count, n);
-    }
+    for (int j = 0; j < n; ++j) x[j] = ld_elem<SOA>(A.seeds, idx, j, A.count, n);
   } else {
 #pragma unroll
     for (int j = 0; j < n; ++j) x[j] = make_seed<K>(M, A, idx, j);
@@ -223,7 +218,6 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
   unsigned idx = CCP_NO_SAMPLE;
   {
     const unsigned u = claim_chunked<K, SOA, GEN>(s_chunk[warp], A, W, &s_tail);
-    if (!GEN && !SOA && A.ready) wait_chunk_ready(A, u, u < W.total);
     load_sample<K, SOA, GEN>(M, A, W, u, x, idx, it);
   }
   bool tail = false;
@@ -267,7 +261,6 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
         // ---- complete mode: tail rendezvous ----
         if (idx == CCP_NO_SAMPLE) {  // what is left of the warp's private chunk
           const unsigned u = claim_chunked<K, SOA, GEN>(s_chunk[warp], A, W, &s_tail);
-          if (!GEN && !SOA && A.ready) wait_chunk_ready(A, u, u < W.total);
           load_sample<K, SOA, GEN>(M, A, W, u, x, idx, it);
         }
         __syncwarp();
@@ -354,19 +347,13 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
             for (int j = 0; j < n; ++j) A.compact[slot * n + j] = x[j];
           }
         }
-        if (!GEN && !SOA && A.done) {
-          // streaming: count this sample into its chunk; the last one tells the host the chunk can be copied out
-          __threadfence();
-          const long long c = idx / A.chunk;
-          const long long in_chunk = (A.count - c * A.chunk < A.chunk) ? (A.count - c * A.chunk) : A.chunk;
-          if ((long long)atomicAdd(A.done + c, 1u) + 1 == in_chunk) {
-            __threadfence_system();
-            A.host_done[c] = 1;
-          }
-        }
+        // Has the global counter run dry?  Private chunks keep a warp supplied for ~50 more trips, so without
+        // this look (issued before the refill's loads, consumed after them) a block would notice the end of the
+        // work long after the blocks around it, and a pipelined launch would wait on it with SMs idle.
+        const unsigned handed_out = tail ? 0u : __ldcg((const unsigned*)A.counter);
         const unsigned u = claim_chunked<K, SOA, GEN>(s_chunk[warp], A, W, &s_tail);
-        if (!GEN && !SOA && A.ready) wait_chunk_ready(A, u, u < W.total);
         load_sample<K, SOA, GEN>(M, A, W, u, x, idx, it);
+        if (!tail && handed_out >= W.total - W.first_dynamic) s_tail = 1;
       }
     }
   }
