@@ -104,11 +104,13 @@ ccp_function_kernel(const __grid_constant__ ccp_model M, const double* __restric
     ccp_fwd<K> F;
     ccp_sc_local<K> S;
     ccp_forward<K, PANDA>(M, x, S, F);
+    double fv[m];
+    ccp_residual<K>(F, fv, nullptr);
     if (f) {
 #pragma unroll
-      for (int k = 0; k < m; ++k) st_elem<SOA>(f, idx, k, count, m, F.f[k]);
+      for (int k = 0; k < m; ++k) st_elem<SOA>(f, idx, k, count, m, fv[k]);
     }
-    if (satisfied) satisfied[idx] = ccp_is_satisfied<K>(M, F.f);
+    if (satisfied) satisfied[idx] = ccp_is_satisfied<K>(M, fv);
   }
 }
 
@@ -128,7 +130,7 @@ ccp_jacobian_kernel(const __grid_constant__ ccp_model M, const double* __restric
     ccp_forward<K, PANDA>(M, x, S, F);
     ccp_jacobian<K, PANDA>(M, S, F, J);
     double D[m * n];
-    ccp_jac_dense<K>(J, D);
+    ccp_jac_dense<K>(F, J, D);
 #pragma unroll
     for (int k = 0; k < m * n; ++k) st_elem<SOA>(Jout, idx, k, count, m * n, D[k]);
   }
@@ -479,8 +481,7 @@ int ccp_set_tolerance(ccp_handle* h, double tol_position, double tol_rotation) {
   if (!(tol_position > 0) || !(tol_rotation > 0))
     return set_err(h, CCP_ERR_INVALID, "%s", "setTolerance: tolerance must be positive.");
   CCP_NO_OPEN_PIPELINE(h);
-  h->model.tol_p = tol_position;
-  h->model.tol_r = tol_rotation;
+  ccp_model_set_tolerance(&h->model, tol_position, tol_rotation);
   return CCP_OK;
 }
 

@@ -18,12 +18,17 @@
 //               q_Rx(alpha_i) (x) q_Rz(theta_i/2): half-angle sincos, no rot->quat conversion.
 //   position    the EE-0 origin is pushed DOWN arm 0 (tip -> base), through the world, and UP
 //               arm a (base -> tip): 3-vector recursions only, no 3x3 products.
-//   residual    f0 = |t_c - t_0|,  f1 = 2 atan2(|vec d|, |d_w|),  d = q_c (x) conj(q_0).
-//   jacobian    with u = (t_c - t_0)/f0 and n = sign(d_w) vec(d)/|vec d| (both in EE-a's frame):
-//               carry (r, w, m) = (lever arm to EE-0, u, n) down each arm; at joint i
-//               df0/dq_i = -+ (r x w)_z, df1/dq_i = -+ m_z (+ on arm 0, - on arm a).
-//   step        x -= step * J^T (J J^T)^-1 f, (J J^T) factored as L D L^T in registers; rows that
-//               vanish or make D_k <= 0 are dropped (what JacobiSVD's rank threshold does).
+//   residual    e = t_c - t_0, d = q_c (x) conj(q_0):  f0 = |e|,  f1 = 2 atan2(|vec d|, |d_w|).
+//   loop tests  on the squares, so no sqrt / atan2 sits between an evaluation and the decision to step:
+//               f0 > tol1  <=>  |e|^2 > tol1^2 ;  f1 > tol2  <=>  |vec d|^2 > tan^2(tol2/2) d_w^2.
+//   jacobian    UNNORMALISED gradient rows  g0 = f0 grad f0 = e . de/dq ,  g1 = s |vec d| grad f1
+//               (s = sign d_w):  carry (r, w, m) = (lever arm to EE-0, e, vec d) down each arm; at
+//               joint i  g0_i = -+ (r x w)_z,  g1_i = -+ m_z  (+ on arm 0, - on arm a).  No division by
+//               f0 or |vec d|: with D = diag(1/f0, s/|vec d|), J = D g and
+//   step        x -= step J^T (J J^T)^-1 f = step g^T (g g^T)^-1 (f0^2, s |vec d| f1): the same minimum-norm
+//               Newton step; (g g^T) is solved by Cramer (2x2) or L D L^T (4x4) in registers; rows that
+//               vanish or make D_k <= 0 are dropped (what JacobiSVD's rank threshold does).  sqrt and
+//               atan2 are only needed for the right-hand side, so they overlap the Jacobian pass.
 #pragma once
 
 #include <math.h>
@@ -74,12 +79,23 @@ struct ccp_model {
                         //    EXACTLY (no alpha calibration): the kernels use the structured link code
   int32_t reserved;
   double tol_p, tol_r;  // tolerance1_, tolerance2_
+  double tol_p2;        // tol_p^2
+  double tan2_r;        // tan^2(tol_r / 2): f1 > tol_r  <=>  |vec d|^2 > tan2_r d_w^2   (0 < tol_r < pi)
   double step;          // 0.30
   double margin;        // 1e-3
   double lb[CCPC_DOF], ub[CCPC_DOF];
   ccp_arm arm[CCPC_MAX_ARMS];
   ccp_pair_ref ref[CCPC_MAX_ARMS - 1];
 };
+
+// setTolerance (ConstraintFunction.h:104-112) + the derived thresholds of the loop tests.  Host only (libm tan).
+static inline void ccp_model_set_tolerance(ccp_model* M, double tol_p, double tol_r) {
+  M->tol_p = tol_p;
+  M->tol_r = tol_r;
+  M->tol_p2 = tol_p * tol_p;
+  const double t = tan(0.5 * tol_r);
+  M->tan2_r = (0.5 * tol_r < 1.5707963267948966) ? t * t : HUGE_VAL;  // f1 <= pi always
+}
 
 // ------------------------------------------------------------------------------------------
 // Elementary functions
@@ -344,9 +360,23 @@ struct ccp_fwd {
   double tc[K - 1][3];        // translation of chain a:  R_a^T (p_0 - p_a)
   double qc[K - 1][4];        // rotation of chain a:     conj(q_a) (x) q_0   (unit)
   double d[K - 1][4];         // qc (x) conj(q_ref)
-  double f[2 * (K - 1)];      // (f0, f1) per pair
-  double sv[K - 1];           // |vec d|
+  double e[K - 1][3];         // tc - t_ref
+  double e2[K - 1];           // |e|^2        (f0 = sqrt(e2))
+  double sv2[K - 1];          // |vec d|^2    (f1 = 2 atan2(sqrt(sv2), |d_w|))
 };
+
+// the residual values function() reports (ConstraintFunction.h:84-102), and |vec d|
+template <int K>
+CCP_HD void ccp_residual(const ccp_fwd<K>& F, double* f, double* sv_out) {
+#pragma unroll
+  for (int p = 0; p < K - 1; ++p) {
+    f[2 * p] = sqrt(F.e2[p]);
+    const double sv = sqrt(F.sv2[p]);
+    const double atn = ccp_atan2_pos(sv, fabs(F.d[p][0]));
+    f[2 * p + 1] = atn + atn;
+    if (sv_out) sv_out[p] = sv;
+  }
+}
 
 template <bool PANDA, int I, class SC, class XT>
 CCP_HD void ccp_fwd_link_quat(const ccp_arm& A, int a, const XT& x, double* q, SC& S) {
@@ -437,30 +467,30 @@ CCP_HD void ccp_forward(const ccp_model& M, const XT& x, SC& S, ccp_fwd<K>& F) {
     ccp_qmul_conj_right(qc, M.ref[a - 1].q0, F.d[a - 1]);
     const double* d = F.d[a - 1];
     const double* t0 = M.ref[a - 1].t0;
-    double ex = tc[0] - t0[0], ey = tc[1] - t0[1], ez = tc[2] - t0[2];
-    F.f[2 * (a - 1)] = sqrt(CCP_FMA(ex, ex, CCP_FMA(ey, ey, ez * ez)));
-    double sv = sqrt(CCP_FMA(d[1], d[1], CCP_FMA(d[2], d[2], d[3] * d[3])));
-    F.sv[a - 1] = sv;
-    double atn = ccp_atan2_pos(sv, fabs(d[0]));
-    F.f[2 * (a - 1) + 1] = atn + atn;
+    const double ex = tc[0] - t0[0], ey = tc[1] - t0[1], ez = tc[2] - t0[2];
+    F.e[a - 1][0] = ex; F.e[a - 1][1] = ey; F.e[a - 1][2] = ez;
+    F.e2[a - 1] = CCP_FMA(ex, ex, CCP_FMA(ey, ey, ez * ez));
+    F.sv2[a - 1] = CCP_FMA(d[1], d[1], CCP_FMA(d[2], d[2], d[3] * d[3]));
   }
 }
 
-// Loop test of project(): `(f0 > tol1) || (f1 > tol2)` for any pair (ConstraintFunction.h:68).
+// Loop test of project(): `(f0 > tol1) || (f1 > tol2)` for any pair (ConstraintFunction.h:68), on the squares.
 template <int K>
-CCP_HD bool ccp_needs_step(const ccp_model& M, const double* f) {
+CCP_HD bool ccp_needs_step(const ccp_model& M, const ccp_fwd<K>& F) {
   bool any = false;
 #pragma unroll
-  for (int a = 0; a < K - 1; ++a) any = any || (f[2 * a] > M.tol_p) || (f[2 * a + 1] > M.tol_r);
+  for (int a = 0; a < K - 1; ++a)
+    any = any || (F.e2[a] > M.tol_p2) || (F.sv2[a] > M.tan2_r * (F.d[a][0] * F.d[a][0]));
   return any;
 }
 // Success test of project() (ConstraintFunction.h:75): norm1 is the 0/1 flag `f0 > tol1`, so
 // `norm1 < tol1` means f0 <= tol1; norm2 = f1 must be STRICTLY below tol2.  NaNs fail.
 template <int K>
-CCP_HD bool ccp_converged(const ccp_model& M, const double* f) {
+CCP_HD bool ccp_converged(const ccp_model& M, const ccp_fwd<K>& F) {
   bool all = true;
 #pragma unroll
-  for (int a = 0; a < K - 1; ++a) all = all && (f[2 * a] <= M.tol_p) && (f[2 * a + 1] < M.tol_r);
+  for (int a = 0; a < K - 1; ++a)
+    all = all && (F.e2[a] <= M.tol_p2) && (F.sv2[a] < M.tan2_r * (F.d[a][0] * F.d[a][0]));
   return all;
 }
 // isSatisfied (ConstraintFunction.h:114-120): finite, f0 <= tol1, f1 <= tol2.
@@ -538,30 +568,22 @@ CCP_HD void ccp_jacobian(const ccp_model& M, const SC& S, const ccp_fwd<K>& F, J
 #pragma unroll
   for (int p = 0; p < K - 1; ++p) {
     const int a = p + 1;
-    const double* tc = F.tc[p];
-    const double* t0 = M.ref[p].t0;
+    const double* e = F.e[p];
     const double* d = F.d[p];
-    const double f0 = F.f[2 * p];
-    const double sv = F.sv[p];
-    const double inv_f0 = (f0 > 0.0) ? 1.0 / f0 : 0.0;
-    double inv_sv = (sv > 0.0) ? 1.0 / sv : 0.0;
-    inv_sv = (d[0] < 0.0) ? -inv_sv : inv_sv;
-    double u[3] = {(tc[0] - t0[0]) * inv_f0, (tc[1] - t0[1]) * inv_f0, (tc[2] - t0[2]) * inv_f0};
-    double n[3] = {d[1] * inv_sv, d[2] * inv_sv, d[3] * inv_sv};
     // arm a: frame EE_a -> frame 7 -> ... -> frame 1
     {
       const ccp_arm& A = M.arm[a];
-      double w[3] = {u[0], u[1], u[2]};
-      double m[3] = {n[0], n[1], n[2]};
+      double w[3] = {e[0], e[1], e[2]};
+      double m[3] = {d[1], d[2], d[3]};
       ccp_rot2(A.cphi, A.sphi, w[0], w[1]);
       ccp_rot2(A.cphi, A.sphi, m[0], m[1]);
       ccp_jac_arm<PANDA, false>(A, a, p, S, w, m, J);
     }
-    // arm 0: u, n rotated into EE_0's frame by R_c^T, lever arm starts at the EE-0 origin
+    // arm 0: e, vec d rotated into EE_0's frame by R_c^T, lever arm starts at the EE-0 origin
     {
       const ccp_arm& A = M.arm[0];
-      double w[3] = {u[0], u[1], u[2]};
-      double m[3] = {n[0], n[1], n[2]};
+      double w[3] = {e[0], e[1], e[2]};
+      double m[3] = {d[1], d[2], d[3]};
       ccp_qrot_inv(F.qc[p], w);
       ccp_qrot_inv(F.qc[p], m);
       ccp_rot2(A.cphi, A.sphi, w[0], w[1]);
@@ -577,9 +599,19 @@ CCP_HD void ccp_jacobian(const ccp_model& M, const SC& S, const ccp_fwd<K>& F, J
 template <int K, class JT, class XT>
 CCP_HD void ccp_newton_step(const ccp_model& M, const ccp_fwd<K>& F, const JT& J, XT& x) {
   constexpr int m = 2 * (K - 1);
+  // right-hand side D^-1 f = (f0^2, s |vec d| f1) per pair: the only place sqrt and atan2 are needed
+  double rhs[m];
+#pragma unroll
+  for (int p = 0; p < K - 1; ++p) {
+    const double sv = sqrt(F.sv2[p]);
+    const double atn = ccp_atan2_pos(sv, fabs(F.d[p][0]));
+    const double h = sv * (atn + atn);
+    rhs[2 * p] = F.e2[p];
+    rhs[2 * p + 1] = (F.d[p][0] < 0.0) ? -h : h;
+  }
   double G[m][m];
-  // Gram matrix, lower triangle.  Rows of the same pair share both arms' columns; rows of
-  // different pairs only share arm 0's columns.
+  // Gram matrix of the rows, lower triangle.  Rows of the same pair share both arms' columns; rows of
+  // different pairs only share arm 0's columns.  The two arms' partial sums are independent chains.
 #pragma unroll
   for (int p = 0; p < K - 1; ++p)
 #pragma unroll
@@ -590,12 +622,14 @@ CCP_HD void ccp_newton_step(const ccp_model& M, const ccp_fwd<K>& F, const JT& J
         for (int rj = 0; rj < 2; ++rj) {
           const int I = 2 * p + ri, Jx = 2 * pp + rj;
           if (Jx > I) continue;
-          double acc = 0.0;
+          double acc = J.z(p, ri, 0) * J.z(pp, rj, 0);
 #pragma unroll
-          for (int i = 0; i < CCPC_DOF; ++i) acc = CCP_FMA(J.z(p, ri, i), J.z(pp, rj, i), acc);
+          for (int i = 1; i < CCPC_DOF; ++i) acc = CCP_FMA(J.z(p, ri, i), J.z(pp, rj, i), acc);
           if (pp == p) {
+            double acca = J.a(p, ri, 0) * J.a(p, rj, 0);
 #pragma unroll
-            for (int i = 0; i < CCPC_DOF; ++i) acc = CCP_FMA(J.a(p, ri, i), J.a(p, rj, i), acc);
+            for (int i = 1; i < CCPC_DOF; ++i) acca = CCP_FMA(J.a(p, ri, i), J.a(p, rj, i), acca);
+            acc = acc + acca;
           }
           G[I][Jx] = acc;
         }
@@ -608,14 +642,14 @@ CCP_HD void ccp_newton_step(const ccp_model& M, const ccp_fwd<K>& F, const JT& J
     const bool k0 = g00 > 0.0, k1 = g11 > 0.0;
     if (k0 && k1 && det > 0.0) {
       const double inv = 1.0 / det;
-      y[0] = CCP_FMA(g11, F.f[0], -(g01 * F.f[1])) * inv;
-      y[1] = CCP_FMA(g00, F.f[1], -(g01 * F.f[0])) * inv;
+      y[0] = CCP_FMA(g11, rhs[0], -(g01 * rhs[1])) * inv;
+      y[1] = CCP_FMA(g00, rhs[1], -(g01 * rhs[0])) * inv;
     } else if (k0) {
-      y[0] = F.f[0] / g00;
+      y[0] = rhs[0] / g00;
       y[1] = 0.0;
     } else if (k1) {
       y[0] = 0.0;
-      y[1] = F.f[1] / g11;
+      y[1] = rhs[1] / g11;
     } else {
       y[0] = 0.0;
       y[1] = 0.0;
@@ -643,7 +677,7 @@ CCP_HD void ccp_newton_step(const ccp_model& M, const ccp_fwd<K>& F, const JT& J
   // forward substitution L z = f, scale by D^-1, back substitution L^T y = z
 #pragma unroll
   for (int k = 0; k < m; ++k) {
-    double v = F.f[k];
+    double v = rhs[k];
 #pragma unroll
     for (int j = 0; j < k; ++j) v = CCP_FMA(-Lm[k][j], y[j], v);
     y[k] = v;
@@ -678,21 +712,28 @@ CCP_HD void ccp_newton_step(const ccp_model& M, const ccp_fwd<K>& F, const JT& J
     }
 }
 
-// Dense m x n Jacobian (row-major) from the compact form: the layout jacobian() returns.
+// Dense m x n Jacobian (row-major), the layout jacobian() returns: J = D g with D = diag(1/f0, s/|vec d|)
+// (a row whose residual vanishes is 0), arm-a entries with their sign restored.
 template <int K>
-CCP_HD void ccp_jac_dense(const ccp_jac<K>& J, double* out) {
+CCP_HD void ccp_jac_dense(const ccp_fwd<K>& F, const ccp_jac<K>& J, double* out) {
   constexpr int m = 2 * (K - 1), n = CCPC_DOF * K;
 #pragma unroll
   for (int i = 0; i < m * n; ++i) out[i] = 0.0;
 #pragma unroll
-  for (int p = 0; p < K - 1; ++p)
+  for (int p = 0; p < K - 1; ++p) {
+    const double f0 = sqrt(F.e2[p]), sv = sqrt(F.sv2[p]);
+    double sc[2];
+    sc[0] = (f0 > 0.0) ? 1.0 / f0 : 0.0;
+    sc[1] = (sv > 0.0) ? 1.0 / sv : 0.0;
+    sc[1] = (F.d[p][0] < 0.0) ? -sc[1] : sc[1];
 #pragma unroll
     for (int r = 0; r < 2; ++r)
 #pragma unroll
       for (int i = 0; i < CCPC_DOF; ++i) {
-        out[(2 * p + r) * n + i] = J.J0[p][r][i];
-        out[(2 * p + r) * n + (p + 1) * CCPC_DOF + i] = -J.Ja[p][r][i];
+        out[(2 * p + r) * n + i] = J.J0[p][r][i] * sc[r];
+        out[(2 * p + r) * n + (p + 1) * CCPC_DOF + i] = -(J.Ja[p][r][i] * sc[r]);
       }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -708,15 +749,14 @@ CCP_HD void ccp_project_one(const ccp_model& M, double* x, double* f_out, int32_
   ccp_sc_local<K> S;
   int32_t it = 0;
   ccp_forward<K, PANDA>(M, x, S, F);
-  while (ccp_needs_step<K>(M, F.f) && it < M.max_iter) {
+  while (ccp_needs_step<K>(M, F) && it < M.max_iter) {
     ++it;
     ccp_jacobian<K, PANDA>(M, S, F, J);
     ccp_newton_step<K>(M, F, J, x);
     ccp_forward<K, PANDA>(M, x, S, F);
   }
-  const bool conv = ccp_converged<K>(M, F.f);
-#pragma unroll
-  for (int k = 0; k < 2 * (K - 1); ++k) f_out[k] = F.f[k];
+  const bool conv = ccp_converged<K>(M, F);
+  ccp_residual<K>(F, f_out, nullptr);
   *iters = it;
   *converged = conv;
   *ok = conv && ccp_joint_valid<K>(M, x);

@@ -69,7 +69,7 @@ ccp_geodesic_kernel(const __grid_constant__ ccp_model M, const __grid_constant__
     }
     ccp_fwd<K> F;
     ccp_forward<K, PANDA>(M, x, S, F);
-    const bool cont = ccp_needs_step<K>(M, F.f) && it < M.max_iter;
+    const bool cont = ccp_needs_step<K>(M, F) && it < M.max_iter;
     if (cont) {
       ++it;
       ccp_jacobian<K, PANDA>(M, S, F, J);
@@ -77,7 +77,7 @@ ccp_geodesic_kernel(const __grid_constant__ ccp_model M, const __grid_constant__
     } else {
       // ---- the projection of this step finished: bookkeeping of the walk ----
       iters_sum += it;
-      const bool okk = ccp_converged<K>(M, F.f) && ccp_joint_valid<K>(M, x);
+      const bool okk = ccp_converged<K>(M, F) && ccp_joint_valid<K>(M, x);
       const double* to = A.to + e * n;
       double* out = A.states + (e * A.max_states) * n;
       const double* prev = out + (long long)(ns - 1) * n;

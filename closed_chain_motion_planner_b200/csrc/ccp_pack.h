@@ -47,8 +47,7 @@ static inline int ccp_pack_model(const ccp_model_desc* d, ccp_model* M) {
   memset(M, 0, sizeof *M);
   M->n_arms = d->n_arms;
   M->max_iter = 250;  // ConstraintFunction.h:26
-  M->tol_p = 1e-3;    // ConstrainedPlanningCommon.cpp:120
-  M->tol_r = 5e-3;    // ConstrainedPlanningCommon.cpp:121
+  ccp_model_set_tolerance(M, 1e-3, 5e-3);  // ConstrainedPlanningCommon.cpp:120-121
   M->step = 0.30;     // ConstraintFunction.h:71
   M->margin = 1e-3;   // ConstraintFunction.h:45
   for (int i = 0; i < CCP_DOF; ++i) {

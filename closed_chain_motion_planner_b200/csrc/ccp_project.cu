@@ -305,14 +305,14 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
     if (idx != CCP_NO_SAMPLE) {
       ccp_fwd<K> F;
       ccp_forward<K, PANDA>(M, x, S, F);
-      const bool cont = ccp_needs_step<K>(M, F.f) && (it & 0xffff) < M.max_iter;
+      const bool cont = ccp_needs_step<K>(M, F) && (it & 0xffff) < M.max_iter;
       if (cont) {
         ++it;
         ccp_jacobian<K, PANDA>(M, S, F, J);
         ccp_newton_step<K>(M, F, J, x);
       } else {
         // ---- epilogue of this sample (ConstraintFunction.h:75-81), then refill the lane ----
-        const bool cv = ccp_converged<K>(M, F.f);
+        const bool cv = ccp_converged<K>(M, F);
         const bool okk = cv && ccp_joint_valid<K>(M, x);
         // the sample reports into the arrays of the launch it was submitted with
         ccp_out_desc D;
@@ -336,8 +336,10 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
         if (D.conv) D.conv[idx] = cv;
         if (D.iters) D.iters[idx] = it & 0xffff;
         if (D.resid) {
+          double fv[m];
+          ccp_residual<K>(F, fv, nullptr);
 #pragma unroll
-          for (int k = 0; k < m; ++k) st_elem<SOA>(D.resid, idx, k, D.count, m, F.f[k]);
+          for (int k = 0; k < m; ++k) st_elem<SOA>(D.resid, idx, k, D.count, m, fv[k]);
         }
         // the compacted stream is a stream: a state is appended to the buffer of the launch it finished in
         if (A.n_ok && okk) {

@@ -40,8 +40,10 @@ static void function_batch(const ccp_model* M, const double* x, int64_t count, d
     ccp_fwd<K> F;
     ccp_sc_local<K> S;
     ccp_forward<K, P>(*M, x + s * n, S, F);
-    if (f) for (int k = 0; k < m; ++k) f[s * m + k] = F.f[k];
-    if (sat) sat[s] = ccp_is_satisfied<K>(*M, F.f);
+    double fv[m];
+    ccp_residual<K>(F, fv, nullptr);
+    if (f) for (int k = 0; k < m; ++k) f[s * m + k] = fv[k];
+    if (sat) sat[s] = ccp_is_satisfied<K>(*M, fv);
   }
 }
 
@@ -55,7 +57,7 @@ static void jacobian_batch(const ccp_model* M, const double* x, int64_t count, d
     ccp_sc_local<K> S;
     ccp_forward<K, P>(*M, x + s * n, S, F);
     ccp_jacobian<K, P>(*M, S, F, J);
-    ccp_jac_dense<K>(J, Jout + s * m * n);
+    ccp_jac_dense<K>(F, J, Jout + s * m * n);
   }
 }
 
@@ -156,7 +158,7 @@ void ob_get_reference(const ccp_model* M, int pair, double* t0, double* q0) {
   memcpy(t0, M->ref[pair].t0, 3 * sizeof(double));
   memcpy(q0, M->ref[pair].q0, 4 * sizeof(double));
 }
-void ob_set_tolerance(ccp_model* M, double t1, double t2) { M->tol_p = t1; M->tol_r = t2; }
+void ob_set_tolerance(ccp_model* M, double t1, double t2) { ccp_model_set_tolerance(M, t1, t2); }
 void ob_set_options(ccp_model* M, double step, int max_iter, double margin) {
   M->step = step; M->max_iter = max_iter; M->margin = margin;
 }

@@ -19,6 +19,8 @@ st = collections.Counter()
 thr = collections.Counter()
 tot = 0
 for r in rows[2:]:
+    if r and r[0] == "Address":  # the report holds further views / launches: the first SASS view is enough
+        break
     if len(r) < len(hdr):
         continue
     m = re.match(r"\s*(?:@!?U?P\w+\s+)?([A-Z0-9_]+)", r[ci["Source"]])
@@ -37,3 +39,19 @@ if warp_iters:
 stot = sum(st.values())
 for op, n in ex.most_common(24):
     print(f"  {op:10s} {n:>14,} {100*n/tot:5.1f}%  lanes {thr[op]/max(n,1):5.1f}  stall-samples {100*st[op]/max(stot,1):5.1f}%")
+
+# where the not-issued stall samples fall, by reason
+reasons = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
+rs = collections.Counter()
+for r in rows[2:]:
+    if r and r[0] == "Address":
+        break
+    if len(r) < len(hdr):
+        continue
+    for k in reasons:
+        try:
+            rs[k] += int(r[ci[k]] or 0)
+        except ValueError:
+            pass
+tot_s = sum(rs.values())
+print("stall samples by reason: " + ", ".join(f"{k[6:]} {100*v/max(tot_s,1):.1f}%" for k, v in rs.most_common(10)))
