@@ -163,6 +163,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--layout", default="aos", choices=["aos", "soa"])
+    ap.add_argument("--nccl-gather", action="store_true",
+                    help="N > 1: collect the converged states with NCCL all-gathers instead of the kernel's fused peer stores")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="every launch runs its own stragglers to completion (ccp_project_batch) instead of parking them "
                          "for the next launch (ccp_project_batch_pipelined + one ccp_project_flush)")
@@ -223,44 +225,67 @@ def main():
                          it=torch.empty(count, dtype=torch.int32, device=dev),
                          compact=torch.empty((count, n), dtype=torch.float64, device=dev),
                          n_ok=torch.zeros(1, dtype=torch.int64, device=dev)))
-    from closed_chain_motion_planner_b200.dist import gather_capacity, gather_converged
+    from closed_chain_motion_planner_b200.dist import PeerPool, gather_capacity, gather_converged
 
+    # The path's one exchange step: every rank collects the converged states of all ranks.
+    #   fused (default): the projection kernel's epilogue stores each converged state straight into every rank's
+    #     pool in symmetric memory (NVLink P2P stores, ccp_set_gather_peers); an 8-byte count all-gather follows;
+    #   --nccl-gather / no peer memory: NCCL all-gather of the counts and of the padded compacted states.
     cap = gather_capacity(count)
-    pool = torch.empty((world, cap, n), dtype=torch.float64, device=dev) if world > 1 else None
+    peer_pools = None
+    exchange_kind = "none"
+    if world > 1:
+        exchange_kind = "nccl"
+        if not args.nccl_gather:
+            try:
+                peer_pools = [PeerPool(c, cap) for _ in range(R)]
+                exchange_kind = "fused"
+            except Exception as e:  # every rank fails alike (no P2P on the node)
+                if rank == 0:
+                    print(f"peer memory unavailable ({e!r}); NCCL gather", file=sys.stderr)
+    pool = torch.empty((world, cap, n), dtype=torch.float64, device=dev) if exchange_kind == "nccl" else None
     counts_all = torch.zeros(world, dtype=torch.int64, device=dev)
-    max_count_seen = torch.zeros(1, dtype=torch.int64, device=dev)
+    max_counts = torch.zeros(world, dtype=torch.int64, device=dev)
     project = lib.ccp_project_batch_pipelined if pipelined else lib.ccp_project_batch
 
-    def exchange(o):
-        if world > 1:
-            # the path's one exchange step: converged counts + compacted converged states (fixed capacity,
-            # no host sync), NCCL all-gather over NVLink
+    def pre_launch(i):
+        if exchange_kind == "fused":
+            peer_pools[i % R].attach()
+
+    def exchange(i, o):
+        if exchange_kind == "fused":
+            cts = peer_pools[i % R].exchange_counts(o["n_ok"])
+            torch.maximum(max_counts, cts, out=max_counts)
+        elif exchange_kind == "nccl":
             gather_converged(o["compact"], o["n_ok"], cap, None, pool, counts_all)
-            torch.maximum(max_count_seen, counts_all.max().view(1), out=max_count_seen)
+            torch.maximum(max_counts, counts_all, out=max_counts)
 
     def step(i, ev0=None, ev1=None):
         o = outs[i % R]
         o["n_ok"].zero_()
+        pre_launch(i)
         if ev0 is not None:
             ev0.record()
         rc = project(h, batches[i % n_batches].data_ptr(), count, layout, o["x"].data_ptr(), o["ok"].data_ptr(),
-                     o["cv"].data_ptr(), o["it"].data_ptr(), None, o["compact"].data_ptr(), o["n_ok"].data_ptr(), stream)
+                     o["cv"].data_ptr(), o["it"].data_ptr(), None,
+                     None if exchange_kind == "fused" else o["compact"].data_ptr(), o["n_ok"].data_ptr(), stream)
         assert rc == 0, lib.ccp_last_error(h)
         if ev1 is not None:
             ev1.record()
-        exchange(o)
+        exchange(i, o)
         return o
 
     def flush(i, ev0=None, ev1=None):
         o = outs[i % R]
         o["n_ok"].zero_()
+        pre_launch(i)
         if ev0 is not None:
             ev0.record()
-        rc = lib.ccp_project_flush(h, o["compact"].data_ptr(), o["n_ok"].data_ptr(), stream)
+        rc = lib.ccp_project_flush(h, None if exchange_kind == "fused" else o["compact"].data_ptr(), o["n_ok"].data_ptr(), stream)
         assert rc == 0, lib.ccp_last_error(h)
         if ev1 is not None:
             ev1.record()
-        exchange(o)
+        exchange(i, o)
         return o
 
     for i in range(args.warmup):
@@ -304,7 +329,7 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     launches = c.launchCount() - launches0
-    assert int(max_count_seen.item()) <= cap, "gather capacity overflow"
+    assert int(max_counts.max().item()) <= cap, "gather capacity overflow"
     clocks = sampler.stop() if rank == 0 else None
 
     ms_total = t_begin.elapsed_time(t_end)
@@ -401,7 +426,10 @@ def main():
                    "l2": f"inputs+outputs {2 * count * n * 8 / 1e6:.0f} MB per step exceed the 126 MB L2; seed batches rotate over {n_batches} buffers",
                    "launches": ("pipelined: ccp_project_batch_pipelined per step (stragglers carried into the next launch) + one "
                                 "ccp_project_flush, all inside the timed region") if pipelined else "ccp_project_batch per step",
-                   "exchange": "none" if world == 1 else "NCCL all_gather of counts + padded compacted converged states per step"},
+                   "exchange": {"none": "none",
+                                "fused": "per step: the projection kernel stores every converged state into all ranks' pools "
+                                         "(symmetric memory, NVLink P2P stores) + 8-byte NCCL all_gather of the counts",
+                                "nccl": "per step: NCCL all_gather of counts + padded compacted converged states"}[exchange_kind]},
         "projections_per_s": world * count * args.steps / secs,
         "ok_fraction": ok_all / (world * count * args.steps),
         "mean_iters": iters_all / (world * count * args.steps),

@@ -70,6 +70,10 @@ struct ccp_handle {
   bool pipeline_open;      // parked samples exist
   int pipe_sig;            // layout | gen << 1 of the launches in the pipeline (same kernel instantiation)
   int pipe_launches;       // pipelined launches since the pipeline opened (slot ring safety)
+  // fused all-gather target (ccp_set_gather_peers)
+  double* peer_pool[CCP_MAX_PEERS];
+  int peer_world, peer_rank;
+  long long peer_cap;
   std::mutex mu;
   std::mutex host_mu;  // the *_host entry points share the stage and the streaming flags: one at a time
   char err[512];
@@ -307,6 +311,12 @@ static int launch_project(ccp_handle* h, ccp_project_args& A, int layout, cudaSt
   }
   A.counter = &h->d_counters[slot].work;
   A.slot = slot % CCP_NUM_DESC;
+  if (h->peer_world > 0 && A.n_ok) {
+    A.peer_world = h->peer_world;
+    A.peer_row0 = (long long)h->peer_rank * h->peer_cap;
+    A.peer_cap = h->peer_cap;
+    for (int p = 0; p < h->peer_world; ++p) A.peer_pool[p] = h->peer_pool[p];
+  }
   CCP_CUDA(cudaMemsetAsync(h->d_counters + slot, 0, sizeof(ccp_launch_rec), st));
   if (defer || h->pipeline_open) {
     int rc = ensure_pipeline(h);
@@ -384,6 +394,9 @@ int ccp_create(const ccp_model_desc* model, int32_t device, ccp_handle** out) {
   nh->d_stage_bytes = 0;
   nh->d_park[0] = nh->d_park[1] = nullptr;
   nh->prev_slot = 0;
+  nh->peer_world = 0;
+  nh->peer_rank = 0;
+  nh->peer_cap = 0;
   nh->d_desc = nullptr;
   nh->park_capacity = 0;
   nh->park_cur = 0;
@@ -700,6 +713,24 @@ int ccp_project_flush(ccp_handle* h, double* compact_dev, int64_t* n_ok_dev, voi
   A.compact = compact_dev;
   A.n_ok = (unsigned long long*)n_ok_dev;
   return launch_project(h, A, (h->pipe_sig & 1) ? CCP_LAYOUT_SOA : CCP_LAYOUT_AOS, (cudaStream_t)stream, false);
+}
+
+int ccp_set_gather_peers(ccp_handle* h, int32_t world, int32_t rank, const uint64_t* pool_dev_ptrs, int64_t capacity) {
+  if (!h) return CCP_ERR_INVALID;
+  if (world == 0) {
+    h->peer_world = 0;
+    return CCP_OK;
+  }
+  if (world < 1 || world > CCP_MAX_PEERS || rank < 0 || rank >= world || !pool_dev_ptrs || capacity < 1)
+    return set_err(h, CCP_ERR_INVALID, "%s", "gather peers: 1 <= world <= 8, 0 <= rank < world, capacity >= 1");
+  for (int p = 0; p < world; ++p) {
+    if (!pool_dev_ptrs[p]) return set_err(h, CCP_ERR_INVALID, "%s", "gather peers: null pool pointer");
+    h->peer_pool[p] = (double*)(uintptr_t)pool_dev_ptrs[p];
+  }
+  h->peer_world = world;
+  h->peer_rank = rank;
+  h->peer_cap = capacity;
+  return CCP_OK;
 }
 
 int ccp_project_pipeline_open(const ccp_handle* h) { return h ? (h->pipeline_open ? 1 : 0) : CCP_ERR_INVALID; }

@@ -36,6 +36,7 @@ struct ccp_out_desc {
   int pad;
 };
 #define CCP_NUM_DESC 64
+#define CCP_MAX_PEERS 8
 
 // A sample between two trips is (x, iteration count, index, launch slot): what a pipelined launch parks when
 // its seed list runs dry and what the next launch adopts.
@@ -63,6 +64,12 @@ struct ccp_project_args {
   long long first_index;
   double distance;
   double near[CCPC_DOF * CCPC_MAX_ARMS];
+  // fused all-gather of the converged states (ccp_set_gather_peers): the epilogue also stores an ok state into row
+  // peer_row0 + slot of EVERY rank's pool (peer-mapped device memory: P2P stores over NVLink)
+  double* peer_pool[CCP_MAX_PEERS];
+  int peer_world;               // 0 = off
+  long long peer_row0;          // rank * capacity
+  long long peer_cap;           // rows per rank in a pool
   // pipelined launches (ccp_project_batch_pipelined): adopt the samples the previous launch parked, park the
   // samples still iterating when this launch's work runs dry instead of idling the machine on them
   const ccp_park_rec* adopt;    // nullptr = nothing to adopt

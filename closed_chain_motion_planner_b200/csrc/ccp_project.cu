@@ -48,9 +48,10 @@ struct ccp_x_smem {
 template <int K, int BLOCK, int SM>
 constexpr size_t ccp_proj_smem_bytes() {
   // staging arrays; the tail exchange ([7K + 1][BLOCK] doubles) aliases them
+  // x (CCP_SM_X) is live between trips, so it sits after the exchange area
   constexpr size_t stage = ((SM & CCP_SM_SC) ? 4 * CCPC_DOF * K : 0) + ((SM & CCP_SM_J) ? 4 * CCPC_DOF * (K - 1) : 0);
   constexpr size_t exch = CCPC_DOF * K + 1;
-  return sizeof(double) * BLOCK * (stage > exch ? stage : exch);
+  return sizeof(double) * BLOCK * ((stage > exch ? stage : exch) + ((SM & CCP_SM_X) ? CCPC_DOF * K : 0));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -124,9 +125,9 @@ __device__ __forceinline__ unsigned claim_chunked(unsigned* chunk, const ccp_pro
 }
 
 // Work number u -> the lane's sample: state x, index within its launch, iteration count | launch slot << 16.
-template <int K, bool SOA, bool GEN>
+template <int K, bool SOA, bool GEN, class XT>
 __device__ __forceinline__ void load_sample(const ccp_model& M, const ccp_project_args& A, const ccp_work& W, unsigned u,
-                                            double* x, unsigned& idx, int& it) {
+                                            XT& x, unsigned& idx, int& it) {
   constexpr int n = CCPC_DOF * K;
   if (u >= W.total) {
     idx = CCP_NO_SAMPLE;
@@ -188,7 +189,12 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
     J.base = sm_next;
     sm_next += 4 * CCPC_DOF * (K - 1) * BLOCK;
   }
-  double x[n];
+  typename std::conditional<(SM & CCP_SM_X) != 0, ccp_x_smem<BLOCK>, double[n]>::type x;
+  if constexpr ((SM & CCP_SM_X) != 0) {
+    constexpr int stage = ((SM & CCP_SM_SC) ? 4 * CCPC_DOF * K : 0) + ((SM & CCP_SM_J) ? 4 * CCPC_DOF * (K - 1) : 0);
+    constexpr int exch = CCPC_DOF * K + 1;
+    x.base = ccp_smem + threadIdx.x + (stage > exch ? stage : exch) * BLOCK;
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   ccp_work W;
   W.n_adopt = A.adopt ? __ldcg(A.adopt_count) : 0u;
@@ -348,6 +354,15 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < n; ++j) A.compact[slot * n + j] = x[j];
           }
+          // fused all-gather: the state goes straight into this rank's rows of every peer's pool (NVLink P2P
+          // stores, fire and forget; visible to the peers when this kernel has completed)
+          if (A.peer_world > 0 && (long long)slot < A.peer_cap) {
+            for (int p = 0; p < A.peer_world; ++p) {
+              double* row = A.peer_pool[p] + (A.peer_row0 + (long long)slot) * n;
+#pragma unroll
+              for (int j = 0; j < n; ++j) row[j] = x[j];
+            }
+          }
         }
         // Has the global counter run dry?  Private chunks keep a warp supplied for ~50 more trips, so without
         // this look (issued before the refill's loads, consumed after them) a block would notice the end of the
@@ -406,7 +421,8 @@ static cudaError_t launch_project_g(int sm_count, const ccp_model& M, const ccp_
       case 1: return launch_project_v<K, PANDA, SOA, GEN, 128, 3, 0>(sm_count, M, A, st);
       case 2: return launch_project_v<K, PANDA, SOA, GEN, 192, 2, 0>(sm_count, M, A, st);
       case 3: return launch_project_v<K, PANDA, SOA, GEN, 256, 1, 0>(sm_count, M, A, st);
-      case 4: return launch_project_v<K, PANDA, SOA, GEN, 512, 1, CCP_SM_SC>(sm_count, M, A, st);
+      case 4: return launch_project_v<K, PANDA, SOA, GEN, 384, 1, CCP_SM_X>(sm_count, M, A, st);
+      case 5: return launch_project_v<K, PANDA, SOA, GEN, 448, 1, CCP_SM_X>(sm_count, M, A, st);
       default: break;
     }
   }

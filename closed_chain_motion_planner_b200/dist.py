@@ -3,10 +3,16 @@
 Every projection is independent, so the path shards trivially: rank r owns a contiguous slice of the
 counter-based seed stream (no seed exchange — seed i depends only on (rng_seed, i)) and projects it with
 the same kernel.  The ONE exchange step is collecting the converged states for the planner's batched
-sampler: an all-gather of the per-rank converged counts followed by an all-gather of the per-rank
-compacted (densely packed by the kernel epilogue) converged states, padded to a fixed capacity so that
-no host synchronisation is needed to size the collective.  torch.distributed is the plumbing (NCCL over
-NVLink/NVSwitch on GPUs; gloo in the CPU tests of this host logic).
+sampler.  Two implementations:
+
+  PeerPool (GPUs)     the all-gather is FUSED into the projection kernel: every rank's pool lives in peer-mapped
+                      (symmetric) device memory and the kernel's epilogue stores each converged state straight into
+                      its rows of every rank's pool over NVLink (ccp_set_gather_peers); only the 8-byte counts are
+                      exchanged afterwards (one tiny NCCL all-gather, which also orders the stores for the readers).
+  gather_converged    NCCL all-gather of the counts and of the compacted states padded to a fixed capacity — the
+                      fallback when peer memory cannot be mapped, and what the gloo CPU tests exercise.
+
+torch.distributed is the plumbing (NCCL over NVLink/NVSwitch on GPUs; gloo in the CPU tests of this host logic).
 """
 from __future__ import annotations
 
@@ -52,6 +58,55 @@ def gather_converged(compact, n_ok, capacity: int, group=None, pool=None, counts
     return pool, counts
 
 
+class PeerPool:
+    """Every rank's pool of converged states in symmetric (peer-mapped) device memory + the engine hook that makes
+    the projection kernel write into all of them.
+
+    pool[r, :counts[r]] holds rank r's converged states once `exchange_counts` has run after the projection
+    launch(es) on the same stream.  A pool must not be written by a new projection before every rank has finished
+    reading it (any later collective of the group, e.g. the next exchange_counts, is such a point).
+    """
+
+    def __init__(self, constraint, capacity: int, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        self.c = constraint
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        if self.world > 8:
+            raise ValueError("PeerPool spans one NVLink domain of at most 8 GPUs")
+        self.capacity = int(capacity)
+        self.n = constraint.getAmbientDimension()
+        dev = torch.device("cuda", constraint.device)
+        self.pool = symm.empty((self.world, self.capacity, self.n), dtype=torch.float64, device=dev)
+        self.handle = symm.rendezvous(self.pool, self.group)
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.counts = torch.zeros(self.world, dtype=torch.int64, device=dev)
+
+    def attach(self):
+        """Point the engine's fused gather at this pool (host-side state only; applies to later launches)."""
+        import ctypes as C
+
+        arr = (C.c_uint64 * self.world)(*self.ptrs)
+        rc = self.c._lib.ccp_set_gather_peers(self.c._h, self.world, self.rank, arr, self.capacity)
+        if rc != 0:
+            raise RuntimeError(self.c._lib.ccp_last_error(self.c._h).decode())
+
+    def detach(self):
+        self.c._lib.ccp_set_gather_peers(self.c._h, 0, 0, None, 0)
+
+    def exchange_counts(self, n_ok):
+        """All-gather of the 8-byte converged counts (async on the current stream).  Ordered after the projection
+        kernels of this rank on the stream, so a rank that sees counts[r] also sees rank r's rows."""
+        import torch.distributed as dist
+
+        dist.all_gather_into_tensor(self.counts, n_ok.view(1), group=self.group)
+        return self.counts
+
+
 def unpack_pool(pool, counts):
     """Drop the padding: (sum(counts), n) tensor of all ranks' converged states, rank-major.
     Raises if a rank overflowed its capacity (its count exceeds the rows that were gathered)."""
@@ -71,13 +126,30 @@ class ShardedSampleProjector:
     kernel call with no collective.
     """
 
-    def __init__(self, constraint, group=None):
+    def __init__(self, constraint, group=None, fused: bool = True):
         import torch.distributed as dist
 
         self.c = constraint
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.fused = fused and 1 < self.world <= 8
+        self._peer = None  # PeerPool, (re)allocated when the capacity grows
+        self.fused_error = None
+
+    def _peer_pool(self, cap):
+        """The symmetric pool for the fused gather, or None when peer memory cannot be mapped (collective: every
+        rank takes the same branch because the allocation either works on the whole node or on none of it)."""
+        if not self.fused:
+            return None
+        if self._peer is None or self._peer.capacity < cap:
+            try:
+                self._peer = PeerPool(self.c, cap, self.group)
+            except Exception as e:  # no P2P / symmetric memory on this box: NCCL gather instead
+                self.fused = False
+                self.fused_error = repr(e)
+                self._peer = None
+        return self._peer
 
     def sample_project(self, rng_seed: int, first_index: int, total: int, mode: int = 0, distance: float = 0.0,
                        near=None, wrap_bounds: bool = False):
@@ -102,6 +174,22 @@ class ShardedSampleProjector:
                                  wrap_bounds=1 if wrap_bounds else 0, distance=distance,
                                  near_host=None if near_arr is None else near_arr.ctypes.data_as(C.POINTER(C.c_double)))
         stream = torch.cuda.current_stream(dev).cuda_stream
+        peer = self._peer_pool(cap) if self.world > 1 else None
+        if peer is not None:
+            # fused: the kernel stores the converged states into every rank's pool; no local compact buffer needed
+            import torch.distributed as dist
+
+            dist.barrier(group=self.group)  # nobody is still reading the pool of the previous call
+            peer.attach()
+            try:
+                rc = c._lib.ccp_sample_project_batch(c._h, C.byref(args), count, _capi.CCP_LAYOUT_AOS, None, None, None,
+                                                     None, n_ok.data_ptr(), stream)
+            finally:
+                peer.detach()
+            if rc != 0:
+                raise _capi.CcpError(c._lib.ccp_last_error(c._h).decode())
+            counts = peer.exchange_counts(n_ok)
+            return unpack_pool(peer.pool[:, :cap], counts), counts.clone()
         rc = c._lib.ccp_sample_project_batch(c._h, C.byref(args), count, _capi.CCP_LAYOUT_AOS, None, None, None,
                                              compact.data_ptr(), n_ok.data_ptr(), stream)
         if rc != 0:

@@ -150,6 +150,17 @@ int ccp_project_flush(ccp_handle* h, double* compact_dev, int64_t* n_ok_dev, voi
 /* 1 when parked samples exist, 0 otherwise.                                                                */
 int ccp_project_pipeline_open(const ccp_handle* h);
 
+/* ---- fused all-gather of the converged states (multi-GPU sampler) --------------------------------
+ * pool_dev_ptrs[p] is the address, valid ON THIS DEVICE, of rank p's pool: double[world][capacity][n] in
+ * peer-mapped memory (CUDA P2P / symmetric memory; pool_dev_ptrs[rank] is this rank's own pool).  While peers are
+ * set, every projection call that passes n_ok_dev also stores each ok state into row rank*capacity + slot of EVERY
+ * rank's pool from the kernel's epilogue (slot = the value n_ok had): the all-gather of the states is done by the
+ * projection kernel itself, store by store over NVLink, overlapped with the arithmetic, and only the 8-byte counts
+ * remain to be exchanged.  States beyond `capacity` are counted but not stored (overflow is visible in n_ok).
+ * A peer may read this rank's rows once the projection kernel has completed (e.g. after the count exchange that
+ * follows it on the same stream).  world = 0 switches the mode off.                                           */
+int ccp_set_gather_peers(ccp_handle* h, int32_t world, int32_t rank, const uint64_t* pool_dev_ptrs, int64_t capacity);
+
 /* ≙ isSatisfied (ConstraintFunction.h:114-120): finite and f0 <= tol1 and f1 <= tol2.       */
 int ccp_is_satisfied_batch(ccp_handle* h, const double* x_dev, int64_t count, int32_t layout,
                            uint8_t* out_dev, void* stream);

@@ -25,9 +25,25 @@ WORKER = textwrap.dedent(
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     c = pkg.KinematicChainConstraint.from_config("stefan", device=local)
     total = 40001
+    # fused path (the kernel stores into every rank's symmetric pool over NVLink) against the NCCL gather
     sp = ShardedSampleProjector(c)
     states, counts = sp.sample_project(rng_seed=3, first_index=1000, total=total)
     torch.cuda.synchronize()
+    assert sp.fused, "fused peer-store gather unavailable: " + str(sp.fused_error)
+    sn = ShardedSampleProjector(c, fused=False)
+    states_n, counts_n = sn.sample_project(rng_seed=3, first_index=1000, total=total)
+    torch.cuda.synchronize()
+    assert torch.equal(counts, counts_n)
+    off = 0
+    for rr in range(world):  # same rows per rank region (order within a region is unspecified)
+        k = int(counts[rr])
+        a, b = states[off:off + k].cpu().numpy(), states_n[off:off + k].cpu().numpy()
+        srt = lambda m: m[np.lexsort(m.T[::-1])]
+        assert np.array_equal(srt(a), srt(b))
+        off += k
+    states2, counts2 = sp.sample_project(rng_seed=4, first_index=0, total=total // 2)  # pool reuse
+    torch.cuda.synchronize()
+    assert int(counts2.sum()) == states2.shape[0]
     assert counts.shape == (world,) and int(counts.sum()) == states.shape[0]
     # every rank holds the same gathered pool
     chk = states.sum(dim=0).clone()
