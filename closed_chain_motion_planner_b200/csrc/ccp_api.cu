@@ -70,6 +70,7 @@ struct ccp_handle {
   bool pipeline_open;      // parked samples exist
   int pipe_sig;            // layout | gen << 1 of the launches in the pipeline (same kernel instantiation)
   int pipe_launches;       // pipelined launches since the pipeline opened (slot ring safety)
+  cudaMemPool_t pool;  // stream-ordered scratch of the sampler path; keeps its memory between calls
   // fused all-gather target (ccp_set_gather_peers)
   double* peer_pool[CCP_MAX_PEERS];
   int peer_world, peer_rank;
@@ -292,12 +293,13 @@ static int launch_project(ccp_handle* h, ccp_project_args& A, int layout, cudaSt
   if (A.count > 0x7fff0000LL)
     return set_err(h, CCP_ERR_INVALID, "%s", "more than 2^31 - 65536 samples in one call: split the batch");
   const bool soa = layout == CCP_LAYOUT_SOA;
-  const int sig = (soa ? 1 : 0) | (A.gen_mode >= 0 ? 2 : 0);
+  const int sig = soa ? 1 : 0;
+  if (A.seed_stride == 0) A.seed_stride = A.count;
+  if (A.out_stride == 0) A.out_stride = A.count;
   if (h->pipeline_open && sig != h->pipe_sig) {
-    // parked samples belong to another kernel instantiation (layout / generator): complete them first
+    // parked samples belong to the other kernel instantiation (layout): complete them first
     ccp_project_args F;
     memset(&F, 0, sizeof F);
-    F.gen_mode = (h->pipe_sig & 2) ? 0 : -1;
     int rc = launch_project(h, F, (h->pipe_sig & 1) ? CCP_LAYOUT_SOA : CCP_LAYOUT_AOS, st, false);
     if (rc) return rc;
   }
@@ -411,6 +413,20 @@ int ccp_create(const ccp_model_desc* model, int32_t device, ccp_handle** out) {
   for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&nh->hstream[i], cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreate(&nh->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&nh->ev1);
+  nh->pool = nullptr;
+  if (e == cudaSuccess) {
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof props);
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    e = cudaMemPoolCreate(&nh->pool, &props);
+    if (e == cudaSuccess) {
+      unsigned long long keep = ~0ULL;  // never trim at synchronisation points: the scratch is reused by every call
+      e = cudaMemPoolSetAttribute(nh->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   for (int i = 0; i < CCP_HOST_MAX_CHUNKS && e == cudaSuccess; ++i) {
     e = cudaEventCreateWithFlags(&nh->ev_chunk_in[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&nh->ev_chunk_k[i], cudaEventDisableTiming);
@@ -430,6 +446,7 @@ void ccp_destroy(ccp_handle* h) {
   cudaDeviceSynchronize();
   if (h->d_counters) cudaFree(h->d_counters);
   if (h->d_stage) cudaFree(h->d_stage);
+  if (h->pool) cudaMemPoolDestroy(h->pool);
   if (h->d_park[0]) cudaFree(h->d_park[0]);
   if (h->d_park[1]) cudaFree(h->d_park[1]);
   if (h->d_desc) cudaFree(h->d_desc);
@@ -655,7 +672,6 @@ int ccp_project_batch(ccp_handle* h, const double* seeds_dev, int64_t count, int
   A.compact = compact_dev;
   A.n_ok = (unsigned long long*)n_ok_dev;
   A.count = count;
-  A.gen_mode = -1;
   return launch_project(h, A, layout, (cudaStream_t)stream);
 }
 
@@ -679,27 +695,17 @@ int ccp_project_batch_pipelined(ccp_handle* h, const double* seeds_dev, int64_t 
   A.compact = compact_dev;
   A.n_ok = (unsigned long long*)n_ok_dev;
   A.count = count;
-  A.gen_mode = -1;
   return launch_project(h, A, layout, (cudaStream_t)stream, true);
 }
+
+static int sample_project_impl(ccp_handle* h, const ccp_sampler_args* a, int64_t count, int32_t layout, double* x_out_dev,
+                               uint8_t* ok_dev, int32_t* iters_dev, double* compact_dev, int64_t* n_ok_dev, void* stream,
+                               bool defer);
 
 int ccp_sample_project_batch_pipelined(ccp_handle* h, const ccp_sampler_args* a, int64_t count, int32_t layout,
                                        double* x_out_dev, uint8_t* ok_dev, int32_t* iters_dev, double* compact_dev,
                                        int64_t* n_ok_dev, void* stream) {
-  if (!h) return CCP_ERR_INVALID;
-  if (count < 0) return set_err(h, CCP_ERR_INVALID, "%s", "negative count");
-  if (layout != CCP_LAYOUT_AOS && layout != CCP_LAYOUT_SOA) return set_err(h, CCP_ERR_INVALID, "%s", "bad layout");
-  if (compact_dev && !n_ok_dev) return set_err(h, CCP_ERR_INVALID, "%s", "compact output needs n_ok");
-  ccp_project_args A;
-  int rc = fill_sampler_args(h, a, count, &A);
-  if (rc) return rc;
-  A.x_out = x_out_dev;
-  A.ok = ok_dev;
-  A.iters = iters_dev;
-  A.compact = compact_dev;
-  A.n_ok = (unsigned long long*)n_ok_dev;
-  device_guard g(h->device);
-  return launch_project(h, A, layout, (cudaStream_t)stream, true);
+  return sample_project_impl(h, a, count, layout, x_out_dev, ok_dev, iters_dev, compact_dev, n_ok_dev, stream, true);
 }
 
 int ccp_project_flush(ccp_handle* h, double* compact_dev, int64_t* n_ok_dev, void* stream) {
@@ -709,7 +715,6 @@ int ccp_project_flush(ccp_handle* h, double* compact_dev, int64_t* n_ok_dev, voi
   device_guard g(h->device);
   ccp_project_args A;
   memset(&A, 0, sizeof A);
-  A.gen_mode = (h->pipe_sig & 2) ? 0 : -1;
   A.compact = compact_dev;
   A.n_ok = (unsigned long long*)n_ok_dev;
   return launch_project(h, A, (h->pipe_sig & 1) ? CCP_LAYOUT_SOA : CCP_LAYOUT_AOS, (cudaStream_t)stream, false);
@@ -793,23 +798,82 @@ int ccp_generate_seeds(ccp_handle* h, const ccp_sampler_args* a, int64_t count, 
   return CCP_OK;
 }
 
-int ccp_sample_project_batch(ccp_handle* h, const ccp_sampler_args* a, int64_t count, int32_t layout,
-                             double* x_out_dev, uint8_t* ok_dev, int32_t* iters_dev, double* compact_dev,
-                             int64_t* n_ok_dev, void* stream) {
+}  // extern "C"
+template <int K, bool SOA>
+static void launch_seed_kernel(const ccp_handle* h, const ccp_project_args& A, double* out, cudaStream_t st) {
+  const int grid = grid_for(h, A.count, 128, 8);
+  ccp_seed_kernel<K, SOA><<<grid, 128, 0, st>>>(h->model, A, out);
+}
+extern "C" {
+
+// sample -> project -> (wrap) -> compact.  The seeds of a chunk are generated by the seed kernel into a
+// stream-ordered scratch buffer (their HBM round trip is ~0.1 % of the projection time) and projected by the same
+// kernel as caller-provided seeds; a batch larger than CCP_SAMPLE_CHUNK is cut into pipelined launches so the
+// scratch stays small and there is one tail for the whole call.
+#define CCP_SAMPLE_CHUNK (2 * 1024 * 1024)
+static int sample_project_impl(ccp_handle* h, const ccp_sampler_args* a, int64_t count, int32_t layout, double* x_out_dev,
+                               uint8_t* ok_dev, int32_t* iters_dev, double* compact_dev, int64_t* n_ok_dev, void* stream,
+                               bool defer) {
   if (!h) return CCP_ERR_INVALID;
   if (count < 0) return set_err(h, CCP_ERR_INVALID, "%s", "negative count");
   if (layout != CCP_LAYOUT_AOS && layout != CCP_LAYOUT_SOA) return set_err(h, CCP_ERR_INVALID, "%s", "bad layout");
   if (compact_dev && !n_ok_dev) return set_err(h, CCP_ERR_INVALID, "%s", "compact output needs n_ok");
-  ccp_project_args A;
-  int rc = fill_sampler_args(h, a, count, &A);
+  if (!h->has_ref) return set_err(h, CCP_ERR_STATE, "%s", "project before ccp_set_reference (setInitialPosition)");
+  ccp_project_args S;
+  int rc = fill_sampler_args(h, a, count, &S);
   if (rc) return rc;
-  A.x_out = x_out_dev;
-  A.ok = ok_dev;
-  A.iters = iters_dev;
-  A.compact = compact_dev;
-  A.n_ok = (unsigned long long*)n_ok_dev;
   device_guard g(h->device);
-  return launch_project(h, A, layout, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (count == 0) {
+    if (!defer && h->pipeline_open) {
+      ccp_project_args F;
+      memset(&F, 0, sizeof F);
+      F.compact = compact_dev;
+      F.n_ok = (unsigned long long*)n_ok_dev;
+      return launch_project(h, F, layout, st, false);
+    }
+    return CCP_OK;
+  }
+  const int n = CCPC_DOF * h->model.n_arms;
+  const bool soa = layout == CCP_LAYOUT_SOA;
+  const int64_t chunk = count < CCP_SAMPLE_CHUNK ? count : CCP_SAMPLE_CHUNK;
+  double* scratch = nullptr;
+  CCP_CUDA(cudaMallocFromPoolAsync((void**)&scratch, sizeof(double) * n * (size_t)chunk, h->pool, st));
+  for (int64_t off = 0; off < count && rc == CCP_OK; off += chunk) {
+    const int64_t cn = (count - off < chunk) ? (count - off) : chunk;
+    S.count = cn;
+    S.first_index = a->first_index + off;
+    if (h->model.n_arms == 2) {
+      if (soa) launch_seed_kernel<2, true>(h, S, scratch, st); else launch_seed_kernel<2, false>(h, S, scratch, st);
+    } else {
+      if (soa) launch_seed_kernel<3, true>(h, S, scratch, st); else launch_seed_kernel<3, false>(h, S, scratch, st);
+    }
+    h->launches++;
+    ccp_project_args A;
+    memset(&A, 0, sizeof A);
+    A.seeds = scratch;
+    A.seed_stride = cn;
+    A.count = cn;
+    A.out_stride = count;
+    A.wrap = a->wrap_bounds;
+    A.x_out = x_out_dev ? (soa ? x_out_dev + off : x_out_dev + off * n) : nullptr;
+    A.ok = ok_dev ? ok_dev + off : nullptr;
+    A.iters = iters_dev ? iters_dev + off : nullptr;
+    A.compact = compact_dev;
+    A.n_ok = (unsigned long long*)n_ok_dev;
+    const bool last = off + cn >= count;
+    rc = launch_project(h, A, layout, st, defer || !last);
+  }
+  cudaError_t e = cudaFreeAsync(scratch, st);
+  if (rc) return rc;
+  if (e != cudaSuccess) return set_err(h, CCP_ERR_CUDA, "cudaFreeAsync: %s", cudaGetErrorString(e));
+  return CCP_OK;
+}
+
+int ccp_sample_project_batch(ccp_handle* h, const ccp_sampler_args* a, int64_t count, int32_t layout,
+                             double* x_out_dev, uint8_t* ok_dev, int32_t* iters_dev, double* compact_dev,
+                             int64_t* n_ok_dev, void* stream) {
+  return sample_project_impl(h, a, count, layout, x_out_dev, ok_dev, iters_dev, compact_dev, n_ok_dev, stream, false);
 }
 
 int ccp_geodesic_batch(ccp_handle* h, const double* from_dev, const double* to_dev, int64_t edges, double delta,
@@ -923,7 +987,6 @@ int ccp_project_batch_host(ccp_handle* h, const double* seeds_host, int64_t coun
     A.iters = dit + off;
     A.resid = resid_host ? dres + off * m : nullptr;
     A.count = cn;
-    A.gen_mode = -1;
     rc = launch_project(h, A, CCP_LAYOUT_AOS, sK, /*defer=*/parts > 1);
     if (rc) return rc;
     CCP_CUDA(cudaEventRecord(h->ev_chunk_k[c], sK));
@@ -936,7 +999,6 @@ int ccp_project_batch_host(ccp_handle* h, const double* seeds_host, int64_t coun
   if (h->pipeline_open) {
     ccp_project_args F;
     memset(&F, 0, sizeof F);
-    F.gen_mode = -1;
     rc = launch_project(h, F, CCP_LAYOUT_AOS, sK, false);
     if (rc) return rc;
   }

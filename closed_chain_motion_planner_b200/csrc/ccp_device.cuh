@@ -58,7 +58,9 @@ struct ccp_project_args {
   unsigned long long* n_ok;    // appended-to counter for `compact`
   unsigned long long* counter; // work counter (zeroed before launch)
   long long count;
-  int gen_mode;  // -1 load seeds; 0 uniform; 1 uniform-near; 2 gaussian
+  long long seed_stride;  // SOA: element stride between joints of `seeds` (= count unless the launch is a chunk)
+  long long out_stride;   // SOA: same for x_out / resid
+  int gen_mode;  // seed kernel only: 0 uniform; 1 uniform-near; 2 gaussian
   int wrap;
   unsigned long long rng_seed;
   long long first_index;
@@ -101,6 +103,9 @@ __device__ __forceinline__ double gauss01(unsigned long long seed, unsigned long
   ccp_sincos(6.283185307179586476925 * u2, &s, &c);
   return sqrt(-2.0 * log(u1)) * c;
 }
+
+// out-of-line enforceBounds wrap: the epilogue calls it per joint instead of inlining fmod's slow path 7K times
+static __device__ __noinline__ double ccp_wrap_pi_call(double v) { return ccp_wrap_pi(v); }
 
 template <int K>
 __device__ __forceinline__ double make_seed(const ccp_model& M, const ccp_project_args& A, long long idx, int j) {

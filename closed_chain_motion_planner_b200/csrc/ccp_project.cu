@@ -74,7 +74,7 @@ struct ccp_work {
   unsigned first_dynamic;  // work numbers below this are handed out statically
 };
 
-template <int K, bool SOA, bool GEN>
+template <int K, bool SOA>
 __device__ __forceinline__ unsigned claim_chunked(unsigned* chunk, const ccp_project_args& A, const ccp_work& W,
                                                    volatile int* s_tail) {
   constexpr int n = CCPC_DOF * K;
@@ -96,7 +96,7 @@ __device__ __forceinline__ unsigned claim_chunked(unsigned* chunk, const ccp_pro
         if (base1 > W.total) base1 = W.total;
         end1 = (W.total - base1 < CCP_CLAIM_CHUNK) ? W.total : base1 + CCP_CLAIM_CHUNK;
         if (end1 - base1 < CCP_CLAIM_CHUNK) *s_tail = 1;  // the work has run dry: the block enters its tail
-        if (!GEN && end1 > base1 && base1 >= W.n_adopt) {
+        if (end1 > base1 && base1 >= W.n_adopt) {
           const unsigned i0 = base1 - W.n_adopt;
           if (!SOA) {
             const char* p = (const char*)(A.seeds + (size_t)i0 * n);
@@ -105,7 +105,7 @@ __device__ __forceinline__ unsigned claim_chunked(unsigned* chunk, const ccp_pro
           } else {
 #pragma unroll
             for (int j = 0; j < n; ++j) {
-              const char* p = (const char*)(A.seeds + (size_t)j * (size_t)A.count + i0);
+              const char* p = (const char*)(A.seeds + (size_t)j * (size_t)A.seed_stride + i0);
               asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
               asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
             }
@@ -125,7 +125,7 @@ __device__ __forceinline__ unsigned claim_chunked(unsigned* chunk, const ccp_pro
 }
 
 // Work number u -> the lane's sample: state x, index within its launch, iteration count | launch slot << 16.
-template <int K, bool SOA, bool GEN, class XT>
+template <int K, bool SOA, class XT>
 __device__ __forceinline__ void load_sample(const ccp_model& M, const ccp_project_args& A, const ccp_work& W, unsigned u,
                                             XT& x, unsigned& idx, int& it) {
   constexpr int n = CCPC_DOF * K;
@@ -143,17 +143,10 @@ __device__ __forceinline__ void load_sample(const ccp_model& M, const ccp_projec
   }
   idx = u - W.n_adopt;
   it = (int)(A.slot << 16);
-  if (!GEN) {
 #pragma unroll
-    for (int j = 0; j < n; ++j) x[j] = ld_elem<SOA>(A.seeds, idx, j, A.count, n);
-  } else {
-#pragma unroll
-    for (int j = 0; j < n; ++j) x[j] = make_seed<K>(M, A, idx, j);
-  }
+  for (int j = 0; j < n; ++j) x[j] = ld_elem<SOA>(A.seeds, idx, j, A.seed_stride, n);
 }
 
-// GEN = false: seeds are read from memory (project).  GEN = true: seeds come from the counter-based
-// generator and the sampler epilogue (wrap) is compiled in (sample_project).
 // PANDA: structured stock-Panda link code (ccp_core.h).  SM: which per-sample arrays are staged in
 // shared memory (CCP_SM_* bits) instead of registers.
 //
@@ -169,7 +162,7 @@ __device__ __forceinline__ void load_sample(const ccp_model& M, const ccp_projec
 //   * pipelined mode (A.park != nullptr): the warp writes its live samples to the park buffer and exits; the next
 //     launch adopts them as its first work items.  No lane ever idles on a straggler.
 // Which lane (or launch) ran a sample never affects its result.
-template <int K, bool PANDA, bool SOA, bool GEN, int BLOCK, int MINB, int SM>
+template <int K, bool PANDA, bool SOA, int BLOCK, int MINB, int SM>
 __global__ void __launch_bounds__(BLOCK, MINB)
 ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ ccp_project_args A) {
   constexpr int n = CCPC_DOF * K, m = 2 * (K - 1);
@@ -209,7 +202,7 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
     if (blockIdx.x == 0 && A.park) {  // successors find this launch's output arrays by slot
       ccp_out_desc d;
       d.x_out = A.x_out; d.ok = A.ok; d.conv = A.conv; d.iters = A.iters; d.resid = A.resid;
-      d.count = A.count; d.wrap = A.wrap; d.pad = 0;
+      d.count = A.out_stride; d.wrap = A.wrap; d.pad = 0;
       A.desc_table[A.slot] = d;
     }
   }
@@ -223,8 +216,8 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
   int it = 0;
   unsigned idx = CCP_NO_SAMPLE;
   {
-    const unsigned u = claim_chunked<K, SOA, GEN>(s_chunk[warp], A, W, &s_tail);
-    load_sample<K, SOA, GEN>(M, A, W, u, x, idx, it);
+    const unsigned u = claim_chunked<K, SOA>(s_chunk[warp], A, W, &s_tail);
+    load_sample<K, SOA>(M, A, W, u, x, idx, it);
   }
   bool tail = false;
   int since = 0;
@@ -238,8 +231,8 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
         // gained by waiting); a launch smaller than the machine keeps iterating until half the lanes are free,
         // so it makes progress and the parked set stays bounded (<= 16 per warp) however many follow.
         if (idx == CCP_NO_SAMPLE) {
-          const unsigned u = claim_chunked<K, SOA, GEN>(s_chunk[warp], A, W, &s_tail);
-          load_sample<K, SOA, GEN>(M, A, W, u, x, idx, it);
+          const unsigned u = claim_chunked<K, SOA>(s_chunk[warp], A, W, &s_tail);
+          load_sample<K, SOA>(M, A, W, u, x, idx, it);
         }
         __syncwarp();
         const int park_at = (W.first_dynamic < W.total) ? 32 : 16;
@@ -258,16 +251,16 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
 #pragma unroll
               for (int j = 0; j < n; ++j) r->x[j] = x[j];
             }
-            const unsigned u = claim_chunked<K, SOA, GEN>(s_chunk[warp], A, W, &s_tail);
-            load_sample<K, SOA, GEN>(M, A, W, u, x, idx, it);
+            const unsigned u = claim_chunked<K, SOA>(s_chunk[warp], A, W, &s_tail);
+            load_sample<K, SOA>(M, A, W, u, x, idx, it);
           }
           return;
         }
       } else if (since == 0) {
         // ---- complete mode: tail rendezvous ----
         if (idx == CCP_NO_SAMPLE) {  // what is left of the warp's private chunk
-          const unsigned u = claim_chunked<K, SOA, GEN>(s_chunk[warp], A, W, &s_tail);
-          load_sample<K, SOA, GEN>(M, A, W, u, x, idx, it);
+          const unsigned u = claim_chunked<K, SOA>(s_chunk[warp], A, W, &s_tail);
+          load_sample<K, SOA>(M, A, W, u, x, idx, it);
         }
         __syncwarp();
         const bool active = idx != CCP_NO_SAMPLE;
@@ -324,15 +317,15 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
         ccp_out_desc D;
         if (((unsigned)it >> 16) == A.slot) {
           D.x_out = A.x_out; D.ok = A.ok; D.conv = A.conv; D.iters = A.iters; D.resid = A.resid;
-          D.count = A.count; D.wrap = A.wrap;
+          D.count = A.out_stride; D.wrap = A.wrap;
         } else {
           const ccp_out_desc* T = A.desc_table + ((unsigned)it >> 16);
           D.x_out = T->x_out; D.ok = T->ok; D.conv = T->conv; D.iters = T->iters; D.resid = T->resid;
           D.count = T->count; D.wrap = T->wrap;
         }
-        if (GEN && D.wrap) {
+        if (D.wrap) {  // the sampler's enforceBounds (KinematicChain.h:118-130); one out-of-line copy of the fmod code
 #pragma unroll
-          for (int j = 0; j < n; ++j) x[j] = ccp_wrap_pi(x[j]);
+          for (int j = 0; j < n; ++j) x[j] = ccp_wrap_pi_call(x[j]);
         }
         if (D.x_out) {
 #pragma unroll
@@ -368,8 +361,8 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
         // this look (issued before the refill's loads, consumed after them) a block would notice the end of the
         // work long after the blocks around it, and a pipelined launch would wait on it with SMs idle.
         const unsigned handed_out = tail ? 0u : __ldcg((const unsigned*)A.counter);
-        const unsigned u = claim_chunked<K, SOA, GEN>(s_chunk[warp], A, W, &s_tail);
-        load_sample<K, SOA, GEN>(M, A, W, u, x, idx, it);
+        const unsigned u = claim_chunked<K, SOA>(s_chunk[warp], A, W, &s_tail);
+        load_sample<K, SOA>(M, A, W, u, x, idx, it);
         if (!tail && handed_out >= W.total - W.first_dynamic) s_tail = 1;
       }
     }
@@ -383,7 +376,7 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
 // projection launch configuration: BLOCK threads, MINB resident blocks per SM (persistent grid), and
 // which per-sample arrays live in shared memory.  CCP_PROJ_VARIANT (environment, read once) selects
 // among the compiled configurations for tuning; the default is the best one measured on B200.
-template <int K, bool PANDA, bool SOA, bool GEN, int BLOCK, int MINB, int SM>
+template <int K, bool PANDA, bool SOA, int BLOCK, int MINB, int SM>
 static cudaError_t launch_project_v(int sm_count, const ccp_model& M, const ccp_project_args& A, cudaStream_t st) {
   // persistent grid: MINB blocks per SM; a small batch is spread one warp's worth (32 samples) per block so that
   // it runs at one-warp-per-scheduler latency on many SMs instead of crowding a few
@@ -393,7 +386,7 @@ static cudaError_t launch_project_v(int sm_count, const ccp_model& M, const ccp_
   int grid = (int)(need < cap ? need : cap);
   if (grid < 1) grid = 1;
   constexpr size_t smem = ccp_proj_smem_bytes<K, BLOCK, SM>();
-  auto kern = ccp_project_kernel<K, PANDA, SOA, GEN, BLOCK, MINB, SM>;
+  auto kern = ccp_project_kernel<K, PANDA, SOA, BLOCK, MINB, SM>;
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -413,24 +406,32 @@ static int proj_variant() {
   return v;
 }
 
-template <int K, bool PANDA, bool SOA, bool GEN>
+template <int K, bool PANDA, bool SOA>
 static cudaError_t launch_project_g(int sm_count, const ccp_model& M, const ccp_project_args& A, cudaStream_t st) {
 #ifdef CCP_TUNE
   if constexpr (K == 2) {
     switch (proj_variant()) {
-      case 1: return launch_project_v<K, PANDA, SOA, GEN, 128, 3, 0>(sm_count, M, A, st);
-      case 2: return launch_project_v<K, PANDA, SOA, GEN, 192, 2, 0>(sm_count, M, A, st);
-      case 3: return launch_project_v<K, PANDA, SOA, GEN, 256, 1, 0>(sm_count, M, A, st);
-      case 4: return launch_project_v<K, PANDA, SOA, GEN, 384, 1, CCP_SM_X>(sm_count, M, A, st);
-      case 5: return launch_project_v<K, PANDA, SOA, GEN, 448, 1, CCP_SM_X>(sm_count, M, A, st);
+      case 1: return launch_project_v<K, PANDA, SOA, 128, 3, 0>(sm_count, M, A, st);
+      case 2: return launch_project_v<K, PANDA, SOA, 192, 2, 0>(sm_count, M, A, st);
+      case 3: return launch_project_v<K, PANDA, SOA, 256, 1, 0>(sm_count, M, A, st);
+      case 4: return launch_project_v<K, PANDA, SOA, 384, 1, CCP_SM_X>(sm_count, M, A, st);
+      case 5: return launch_project_v<K, PANDA, SOA, 448, 1, CCP_SM_X>(sm_count, M, A, st);
+      default: break;
+    }
+  } else {
+    switch (proj_variant()) {
+      case 1: return launch_project_v<K, PANDA, SOA, 320, 1, CCP_SM_SC>(sm_count, M, A, st);
+      case 2: return launch_project_v<K, PANDA, SOA, 192, 1, CCP_SM_SC>(sm_count, M, A, st);
+      case 3: return launch_project_v<K, PANDA, SOA, 128, 2, CCP_SM_SC>(sm_count, M, A, st);
+      case 4: return launch_project_v<K, PANDA, SOA, 256, 1, 0>(sm_count, M, A, st);
       default: break;
     }
   }
 #endif
   // One block per SM so the tail packing sees every live sample of the SM.  K = 2: 12 warps, everything in
   // registers (168, no spills); measured on B200 (profiles/) against shared-memory staging variants.
-  if constexpr (K == 2) return launch_project_v<K, PANDA, SOA, GEN, 384, 1, 0>(sm_count, M, A, st);
-  else return launch_project_v<K, PANDA, SOA, GEN, 256, 1, CCP_SM_SC>(sm_count, M, A, st);
+  if constexpr (K == 2) return launch_project_v<K, PANDA, SOA, 384, 1, 0>(sm_count, M, A, st);
+  else return launch_project_v<K, PANDA, SOA, 256, 1, CCP_SM_SC>(sm_count, M, A, st);
 }
 
 #define CCP_CAT_(a, b, c, d) a##b##c##d
@@ -440,8 +441,7 @@ cudaError_t CCP_CAT(ccp_launch_project_K, CCP_TU_K, _P, CCP_TU_PANDA)(int sm_cou
                                                                      cudaStream_t st) {
   constexpr int K = CCP_TU_K;
   constexpr bool PANDA = CCP_TU_PANDA != 0;
-  const bool gen = A.gen_mode >= 0;
-  if (soa) return gen ? launch_project_g<K, PANDA, true, true>(sm_count, M, A, st) : launch_project_g<K, PANDA, true, false>(sm_count, M, A, st);
-  return gen ? launch_project_g<K, PANDA, false, true>(sm_count, M, A, st) : launch_project_g<K, PANDA, false, false>(sm_count, M, A, st);
+  if (soa) return launch_project_g<K, PANDA, true>(sm_count, M, A, st);
+  return launch_project_g<K, PANDA, false>(sm_count, M, A, st);
 }
 

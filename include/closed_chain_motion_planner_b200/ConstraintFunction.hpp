@@ -160,6 +160,24 @@ class KinematicChainConstraint {
                             compact_dev, n_ok_dev, stream));
   }
 
+  // Pipelined form for a caller that projects batch after batch on one stream (the batched sampler): the samples
+  // still iterating when a batch runs dry are carried into the next launch instead of idling the GPU on them.
+  // Per-seed outputs are complete after the next non-pipelined projection or flushProjections().
+  void projectBatchDevicePipelined(const double* seeds_dev, int64_t count, ccp_layout layout, double* x_out_dev,
+                                   uint8_t* ok_dev, uint8_t* converged_dev, int32_t* iters_dev, double* resid_dev,
+                                   double* compact_dev, int64_t* n_ok_dev, void* stream) const {
+    check(ccp_project_batch_pipelined(need(), seeds_dev, count, layout, x_out_dev, ok_dev, converged_dev, iters_dev,
+                                      resid_dev, compact_dev, n_ok_dev, stream));
+  }
+  void flushProjections(double* compact_dev, int64_t* n_ok_dev, void* stream) const {
+    check(ccp_project_flush(need(), compact_dev, n_ok_dev, stream));
+  }
+  // Multi-GPU sampler: make the projection kernel store every converged state into all ranks' pools
+  // (peer-mapped device memory) — the all-gather of the states fused into the kernel.  world = 0 switches it off.
+  void setGatherPeers(int world, int rank, const uint64_t* pool_dev_ptrs, int64_t capacity) const {
+    check(ccp_set_gather_peers(need(), world, rank, pool_dev_ptrs, capacity));
+  }
+
   ccp_handle* handle() const { return h_; }
 
  private:
