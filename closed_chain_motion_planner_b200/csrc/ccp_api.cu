@@ -294,6 +294,7 @@ static int launch_project(ccp_handle* h, ccp_project_args& A, int layout, cudaSt
     return set_err(h, CCP_ERR_INVALID, "%s", "more than 2^31 - 65536 samples in one call: split the batch");
   const bool soa = layout == CCP_LAYOUT_SOA;
   const int sig = soa ? 1 : 0;
+  A.stage_seeds = (A.seeds && (((uintptr_t)A.seeds) & 15u) == 0) ? 1 : 0;
   if (A.seed_stride == 0) A.seed_stride = A.count;
   if (A.out_stride == 0) A.out_stride = A.count;
   if (h->pipeline_open && sig != h->pipe_sig) {

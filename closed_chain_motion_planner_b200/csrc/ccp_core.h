@@ -504,17 +504,22 @@ CCP_HD bool ccp_is_satisfied(const ccp_model& M, const double* f) {
   }
   return all;
 }
-// jointValid (ConstraintFunction.h:43-55)
+// jointValid (ConstraintFunction.h:43-55).  Per-arm partial results are independent chains (the epilogue runs with
+// a few lanes and the rest of the warp waiting behind it: latency matters there, not throughput).
 template <int K, class XT>
 CCP_HD bool ccp_joint_valid(const ccp_model& M, const XT& x) {
   bool ok = true;
 #pragma unroll
-  for (int a = 0; a < K; ++a)
+  for (int a = 0; a < K; ++a) {
+    bool lo = true, hi = true;
 #pragma unroll
     for (int i = 0; i < CCPC_DOF; ++i) {
-      double v = x[a * CCPC_DOF + i];
-      ok = ok && !(v < M.lb[i] + M.margin) && !(v > M.ub[i] - M.margin);
+      const double v = x[a * CCPC_DOF + i];
+      lo = lo && !(v < M.lb[i] + M.margin);
+      hi = hi && !(v > M.ub[i] - M.margin);
     }
+    ok = ok && lo && hi;
+  }
   return ok;
 }
 

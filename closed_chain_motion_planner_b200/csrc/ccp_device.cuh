@@ -60,6 +60,7 @@ struct ccp_project_args {
   long long count;
   long long seed_stride;  // SOA: element stride between joints of `seeds` (= count unless the launch is a chunk)
   long long out_stride;   // SOA: same for x_out / resid
+  int stage_seeds;  // 1: `seeds` is 16-byte aligned, chunks of it may be bulk-copied to shared memory
   int gen_mode;  // seed kernel only: 0 uniform; 1 uniform-near; 2 gaussian
   int wrap;
   unsigned long long rng_seed;

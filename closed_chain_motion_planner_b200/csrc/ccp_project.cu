@@ -45,13 +45,17 @@ struct ccp_x_smem {
 #define CCP_SM_SC 1
 #define CCP_SM_J 2
 #define CCP_SM_X 4
+// doubles in front of the seed staging area: max(staging arrays, tail exchange) + state x
+template <int K, int BLOCK, int SM>
+__host__ __device__ constexpr int ccp_proj_stage_offset() {
+  constexpr int stage = ((SM & CCP_SM_SC) ? 4 * CCPC_DOF * K : 0) + ((SM & CCP_SM_J) ? 4 * CCPC_DOF * (K - 1) : 0);
+  constexpr int exch = CCPC_DOF * K + 1;
+  return BLOCK * ((stage > exch ? stage : exch) + ((SM & CCP_SM_X) ? CCPC_DOF * K : 0));
+}
 template <int K, int BLOCK, int SM>
 constexpr size_t ccp_proj_smem_bytes() {
-  // staging arrays; the tail exchange ([7K + 1][BLOCK] doubles) aliases them
-  // x (CCP_SM_X) is live between trips, so it sits after the exchange area
-  constexpr size_t stage = ((SM & CCP_SM_SC) ? 4 * CCPC_DOF * K : 0) + ((SM & CCP_SM_J) ? 4 * CCPC_DOF * (K - 1) : 0);
-  constexpr size_t exch = CCPC_DOF * K + 1;
-  return sizeof(double) * BLOCK * ((stage > exch ? stage : exch) + ((SM & CCP_SM_X) ? CCPC_DOF * K : 0));
+  // + per warp two seed buffers of one claim chunk (32 states) each
+  return sizeof(double) * ((size_t)ccp_proj_stage_offset<K, BLOCK, SM>() + (size_t)(BLOCK / 32) * 2 * 32 * CCPC_DOF * K);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -61,8 +65,7 @@ constexpr size_t ccp_proj_smem_bytes() {
 // (pipelined) launch, then this launch's own seeds.  A warp owns a private CHUNK of work numbers (shared
 // memory: [next, end)).  Lanes whose sample just finished take the next numbers from it; only when it runs dry
 // does the warp's leader touch the global work counter (one atomic per CCP_CLAIM_CHUNK samples instead of one
-// per refill, and off the refill's critical path most of the time) and prefetch the new chunk's seed lines
-// into L2.
+// per refill) and start the bulk copy of the new chunk's seeds into shared memory.
 #define CCP_CLAIM_CHUNK 32u
 
 // how many trips pass between two tail rendezvous of the block
@@ -74,21 +77,78 @@ struct ccp_work {
   unsigned first_dynamic;  // work numbers below this are handed out statically
 };
 
+// Per-warp chunk state (shared memory).  The seeds of a chunk are STAGED in shared memory by one bulk-copy (TMA,
+// cp.async.bulk + mbarrier) issued by the warp's leader the moment the chunk is claimed, so a refill reads its seed
+// with a shared-memory load instead of waiting ~1 us on HBM/L2 with the other 31 lanes of the warp stalled behind
+// it.  Two buffers alternate (chunk q uses buffer q & 1): lanes that took the last numbers of the old chunk still
+// read it while the copy of the new one is in flight.
+struct ccp_warp_chunk {
+  unsigned next, end;    // private work numbers [next, end)
+  unsigned seq;          // chunks claimed so far
+  unsigned base[2];      // first work number of the chunk in buffer b
+  unsigned staged[2];    // 1: buffer b holds (or is receiving) that chunk's seeds
+  unsigned parity[2];    // mbarrier phase parity that completes buffer b's current copy
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// leader only: start the bulk copy of work numbers [base, end) into buffer b, if they are plain seeds of this launch
+// and the copy meets TMA's 16-byte rules
 template <int K, bool SOA>
-__device__ __forceinline__ unsigned claim_chunked(unsigned* chunk, const ccp_project_args& A, const ccp_work& W,
-                                                   volatile int* s_tail) {
+__device__ __forceinline__ void stage_chunk(ccp_warp_chunk* wc, int b, unsigned base, unsigned end, double* buf,
+                                            unsigned long long* mbar, const ccp_project_args& A, const ccp_work& W) {
+  constexpr int n = CCPC_DOF * K;
+  wc->base[b] = base;
+  wc->staged[b] = 0u;
+  if (!A.stage_seeds || end <= base || base < W.n_adopt) return;
+  const unsigned i0 = base - W.n_adopt, cnt = end - base;
+  const unsigned dst = smem_u32(buf), bar = smem_u32(mbar);
+  if (!SOA) {
+    const unsigned bytes = cnt * n * 8u;
+    if (((i0 * (unsigned)(n * 8)) | bytes) & 15u) return;
+    const double* src = A.seeds + (size_t)i0 * n;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+  } else {
+    if ((i0 | cnt | (unsigned)A.seed_stride) & 1u) return;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(cnt * 8u * n) : "memory");
+#pragma unroll 1
+    for (int j = 0; j < n; ++j) {
+      const double* src = A.seeds + (size_t)j * (size_t)A.seed_stride + i0;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       dst + (unsigned)j * CCP_CLAIM_CHUNK * 8u),
+                   "l"(src), "r"(cnt * 8u), "r"(bar)
+                   : "memory");
+    }
+  }
+  wc->staged[b] = 1u;
+  wc->parity[b] ^= 1u;  // the phase this copy completes
+}
+
+// Lanes whose sample just finished take the next work numbers.  Returns the number (>= total: none left) and, in
+// `buf_sel`, which of the warp's two seed buffers belongs to the chunk the number came from.
+template <int K, bool SOA>
+__device__ __forceinline__ unsigned claim_chunked(ccp_warp_chunk* wc, double* stage, unsigned long long* mbar,
+                                                   const ccp_project_args& A, const ccp_work& W, volatile int* s_tail,
+                                                   int& buf_sel) {
   constexpr int n = CCPC_DOF * K;
   const unsigned mask = __activemask();
   const int lane = threadIdx.x & 31;
   const int leader = __ffs(mask) - 1;
   const unsigned need = __popc(mask);
   const unsigned rank = __popc(mask & ((1u << lane) - 1u));
-  unsigned base0 = 0, left = 0, base1 = W.total;
+  unsigned base0 = 0, left = 0, base1 = W.total, seq = 0;
   if (lane == leader) {
-    base0 = chunk[0];
-    left = chunk[1] - base0;
+    base0 = wc->next;
+    left = wc->end - base0;
+    seq = wc->seq;
     if (left >= need) {
-      chunk[0] = base0 + need;
+      wc->next = base0 + need;
+      left = need;  // everybody is served from the current chunk
     } else {
       unsigned end1 = W.total;
       if (!*s_tail) {
@@ -96,38 +156,32 @@ __device__ __forceinline__ unsigned claim_chunked(unsigned* chunk, const ccp_pro
         if (base1 > W.total) base1 = W.total;
         end1 = (W.total - base1 < CCP_CLAIM_CHUNK) ? W.total : base1 + CCP_CLAIM_CHUNK;
         if (end1 - base1 < CCP_CLAIM_CHUNK) *s_tail = 1;  // the work has run dry: the block enters its tail
-        if (end1 > base1 && base1 >= W.n_adopt) {
-          const unsigned i0 = base1 - W.n_adopt;
-          if (!SOA) {
-            const char* p = (const char*)(A.seeds + (size_t)i0 * n);
-            const unsigned bytes = (end1 - base1) * n * 8u;
-            for (unsigned o = 0; o < bytes; o += 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
-          } else {
-#pragma unroll
-            for (int j = 0; j < n; ++j) {
-              const char* p = (const char*)(A.seeds + (size_t)j * (size_t)A.seed_stride + i0);
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
-            }
-          }
-        }
       }
+      seq += 1u;
+      const int b = (int)(seq & 1u);
+      stage_chunk<K, SOA>(wc, b, base1, end1, stage + b * (int)CCP_CLAIM_CHUNK * n, mbar + b, A, W);
       const unsigned take = need - left;  // <= 32 = CCP_CLAIM_CHUNK
-      chunk[0] = (end1 - base1 < take) ? end1 : base1 + take;
-      chunk[1] = end1;
+      wc->next = (end1 - base1 < take) ? end1 : base1 + take;
+      wc->end = end1;
+      wc->seq = seq;
     }
   }
   base0 = __shfl_sync(mask, base0, leader);
   left = __shfl_sync(mask, left, leader);
   base1 = __shfl_sync(mask, base1, leader);
-  // a number past the chunk's end is >= total: the lane stays without work
-  return (rank < left) ? base0 + rank : base1 + (rank - left);
+  seq = __shfl_sync(mask, seq, leader);
+  // lanes ranked below `left` are served from the chunk that was current on entry; if a new chunk was claimed
+  // (seq advanced) that is the previous buffer.  A number past the chunk's end is >= total: no work for the lane.
+  const bool from_old = rank < left;
+  buf_sel = (int)((from_old && left < need) ? ((seq - 1u) & 1u) : (seq & 1u));
+  return from_old ? base0 + rank : base1 + (rank - left);
 }
 
 // Work number u -> the lane's sample: state x, index within its launch, iteration count | launch slot << 16.
 template <int K, bool SOA, class XT>
 __device__ __forceinline__ void load_sample(const ccp_model& M, const ccp_project_args& A, const ccp_work& W, unsigned u,
-                                            XT& x, unsigned& idx, int& it) {
+                                            const ccp_warp_chunk* wc, const double* stage, unsigned long long* mbar,
+                                            int buf_sel, XT& x, unsigned& idx, int& it) {
   constexpr int n = CCPC_DOF * K;
   if (u >= W.total) {
     idx = CCP_NO_SAMPLE;
@@ -143,6 +197,23 @@ __device__ __forceinline__ void load_sample(const ccp_model& M, const ccp_projec
   }
   idx = u - W.n_adopt;
   it = (int)(A.slot << 16);
+  if (wc->staged[buf_sel]) {
+    // the chunk's seeds are (being) copied to shared memory: wait for the copy's mbarrier phase, then read
+    const unsigned bar = smem_u32(mbar + buf_sel), parity = wc->parity[buf_sel];
+    unsigned done = 0;
+    do {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(bar), "r"(parity)
+          : "memory");
+    } while (!done);
+    const double* src = stage + buf_sel * (int)CCP_CLAIM_CHUNK * n;
+    const unsigned k = u - wc->base[buf_sel];
+#pragma unroll
+    for (int j = 0; j < n; ++j) x[j] = SOA ? src[j * (int)CCP_CLAIM_CHUNK + k] : src[k * n + j];
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < n; ++j) x[j] = ld_elem<SOA>(A.seeds, idx, j, A.seed_stride, n);
 }
@@ -167,10 +238,11 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ ccp_project_args A) {
   constexpr int n = CCPC_DOF * K, m = 2 * (K - 1);
   constexpr int NW = BLOCK / 32;
-  extern __shared__ double ccp_smem[];
+  extern __shared__ __align__(16) double ccp_smem[];
   __shared__ int s_tail;
   __shared__ int s_wcnt[NW];
-  __shared__ unsigned s_chunk[NW][2];
+  __shared__ ccp_warp_chunk s_chunk[NW];
+  __shared__ __align__(8) unsigned long long s_mbar[NW][2];
   double* sm_next = ccp_smem + threadIdx.x;
   typename std::conditional<(SM & CCP_SM_SC) != 0, ccp_sc_smem<K, BLOCK>, ccp_sc_local<K>>::type S;
   if constexpr ((SM & CCP_SM_SC) != 0) {
@@ -206,18 +278,34 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
       A.desc_table[A.slot] = d;
     }
   }
+  // seed staging area: [NW][2][CCP_CLAIM_CHUNK * n] doubles behind the exchange / staging arrays
+  ccp_warp_chunk* wc = &s_chunk[warp];
+  unsigned long long* mbar = s_mbar[warp];
+  double* stage = ccp_smem + ccp_proj_stage_offset<K, BLOCK, SM>() + warp * (2 * (int)CCP_CLAIM_CHUNK * n);
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar + 1)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    wc->parity[0] = wc->parity[1] = 1u;  // stage_chunk flips it: the first copy into a buffer completes phase 0
+    wc->staged[0] = wc->staged[1] = 0u;
+  }
+  __syncthreads();
   if (lane == 0) {
     const unsigned long long b0 = (unsigned long long)(warp * gridDim.x + blockIdx.x) * CCP_CLAIM_CHUNK;
     const unsigned lo = b0 < W.total ? (unsigned)b0 : W.total;
-    s_chunk[warp][0] = lo;
-    s_chunk[warp][1] = (W.total - lo < CCP_CLAIM_CHUNK) ? W.total : lo + CCP_CLAIM_CHUNK;
+    const unsigned hi = (W.total - lo < CCP_CLAIM_CHUNK) ? W.total : lo + CCP_CLAIM_CHUNK;
+    wc->next = lo;
+    wc->end = hi;
+    wc->seq = 0u;
+    stage_chunk<K, SOA>(wc, 0, lo, hi, stage, mbar, A, W);
   }
   __syncthreads();
   int it = 0;
   unsigned idx = CCP_NO_SAMPLE;
   {
-    const unsigned u = claim_chunked<K, SOA>(s_chunk[warp], A, W, &s_tail);
-    load_sample<K, SOA>(M, A, W, u, x, idx, it);
+    int bsel;
+    const unsigned u = claim_chunked<K, SOA>(wc, stage, mbar, A, W, &s_tail, bsel);
+    load_sample<K, SOA>(M, A, W, u, wc, stage, mbar, bsel, x, idx, it);
   }
   bool tail = false;
   int since = 0;
@@ -231,8 +319,9 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
         // gained by waiting); a launch smaller than the machine keeps iterating until half the lanes are free,
         // so it makes progress and the parked set stays bounded (<= 16 per warp) however many follow.
         if (idx == CCP_NO_SAMPLE) {
-          const unsigned u = claim_chunked<K, SOA>(s_chunk[warp], A, W, &s_tail);
-          load_sample<K, SOA>(M, A, W, u, x, idx, it);
+          int bsel;
+          const unsigned u = claim_chunked<K, SOA>(wc, stage, mbar, A, W, &s_tail, bsel);
+          load_sample<K, SOA>(M, A, W, u, wc, stage, mbar, bsel, x, idx, it);
         }
         __syncwarp();
         const int park_at = (W.first_dynamic < W.total) ? 32 : 16;
@@ -251,16 +340,18 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
 #pragma unroll
               for (int j = 0; j < n; ++j) r->x[j] = x[j];
             }
-            const unsigned u = claim_chunked<K, SOA>(s_chunk[warp], A, W, &s_tail);
-            load_sample<K, SOA>(M, A, W, u, x, idx, it);
+            int bsel;
+            const unsigned u = claim_chunked<K, SOA>(wc, stage, mbar, A, W, &s_tail, bsel);
+            load_sample<K, SOA>(M, A, W, u, wc, stage, mbar, bsel, x, idx, it);
           }
           return;
         }
       } else if (since == 0) {
         // ---- complete mode: tail rendezvous ----
         if (idx == CCP_NO_SAMPLE) {  // what is left of the warp's private chunk
-          const unsigned u = claim_chunked<K, SOA>(s_chunk[warp], A, W, &s_tail);
-          load_sample<K, SOA>(M, A, W, u, x, idx, it);
+          int bsel;
+          const unsigned u = claim_chunked<K, SOA>(wc, stage, mbar, A, W, &s_tail, bsel);
+          load_sample<K, SOA>(M, A, W, u, wc, stage, mbar, bsel, x, idx, it);
         }
         __syncwarp();
         const bool active = idx != CCP_NO_SAMPLE;
@@ -358,12 +449,13 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
           }
         }
         // Has the global counter run dry?  Private chunks keep a warp supplied for ~50 more trips, so without
-        // this look (issued before the refill's loads, consumed after them) a block would notice the end of the
-        // work long after the blocks around it, and a pipelined launch would wait on it with SMs idle.
-        const unsigned handed_out = tail ? 0u : __ldcg((const unsigned*)A.counter);
-        const unsigned u = claim_chunked<K, SOA>(s_chunk[warp], A, W, &s_tail);
-        load_sample<K, SOA>(M, A, W, u, x, idx, it);
-        if (!tail && handed_out >= W.total - W.first_dynamic) s_tail = 1;
+        // this look a block would notice the end of the work long after the blocks around it, and a pipelined
+        // launch would wait on it with SMs idle.  (Complete launches pack their tail anyway and skip the look.)
+        const unsigned handed_out = (tail || !A.park) ? 0u : __ldcg((const unsigned*)A.counter);
+        int bsel;
+        const unsigned u = claim_chunked<K, SOA>(wc, stage, mbar, A, W, &s_tail, bsel);
+        load_sample<K, SOA>(M, A, W, u, wc, stage, mbar, bsel, x, idx, it);
+        if (!tail && A.park && handed_out >= W.total - W.first_dynamic) s_tail = 1;
       }
     }
   }
@@ -423,15 +515,18 @@ static cudaError_t launch_project_g(int sm_count, const ccp_model& M, const ccp_
       case 1: return launch_project_v<K, PANDA, SOA, 320, 1, CCP_SM_SC>(sm_count, M, A, st);
       case 2: return launch_project_v<K, PANDA, SOA, 192, 1, CCP_SM_SC>(sm_count, M, A, st);
       case 3: return launch_project_v<K, PANDA, SOA, 128, 2, CCP_SM_SC>(sm_count, M, A, st);
-      case 4: return launch_project_v<K, PANDA, SOA, 256, 1, 0>(sm_count, M, A, st);
+      case 4: return launch_project_v<K, PANDA, SOA, 256, 1, CCP_SM_SC>(sm_count, M, A, st);
+      case 5: return launch_project_v<K, PANDA, SOA, 288, 1, 0>(sm_count, M, A, st);
+      case 6: return launch_project_v<K, PANDA, SOA, 320, 1, 0>(sm_count, M, A, st);
       default: break;
     }
   }
 #endif
   // One block per SM so the tail packing sees every live sample of the SM.  K = 2: 12 warps, everything in
-  // registers (168, no spills); measured on B200 (profiles/) against shared-memory staging variants.
+  // registers (168, no spills); K = 3: 8 warps at 255 registers.  Both measured on B200 (profiles/)
+  // against shared-memory staging and other block shapes.
   if constexpr (K == 2) return launch_project_v<K, PANDA, SOA, 384, 1, 0>(sm_count, M, A, st);
-  else return launch_project_v<K, PANDA, SOA, 256, 1, CCP_SM_SC>(sm_count, M, A, st);
+  else return launch_project_v<K, PANDA, SOA, 256, 1, 0>(sm_count, M, A, st);
 }
 
 #define CCP_CAT_(a, b, c, d) a##b##c##d
