@@ -101,7 +101,7 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def cpu_baseline(config: str, sample: int, threads: int):
+def cpu_baseline(config: str, sample: int, threads: int, with_engine_arithmetic: bool = False):
     """Oracle A (reference-faithful restatement) on the first `sample` Seeds-U of the workload."""
     import numpy as np
 
@@ -115,8 +115,22 @@ def cpu_baseline(config: str, sample: int, threads: int):
     t0 = time.perf_counter()
     r = A.project(seeds, fd=True, nthreads=threads)
     dt = time.perf_counter() - t0
-    return {"seconds": dt, "projections_per_s": sample / dt, "converged_per_s": float(r["ok"].sum()) / dt,
-            "ok_fraction": float(np.mean(r["ok"])), "mean_iters": float(np.mean(r["iters"]))}
+    out = {"seconds": dt, "projections_per_s": sample / dt, "converged_per_s": float(r["ok"].sum()) / dt,
+           "ok_fraction": float(np.mean(r["ok"])), "mean_iters": float(np.mean(r["iters"]))}
+    if with_engine_arithmetic:
+        # the engine's own arithmetic (analytic Jacobian, csrc/ccp_core.h compiled by g++) on the same cores and
+        # seeds: separates the algorithmic part of the GPU/CPU ratio from the hardware part
+        from closed_chain_motion_planner_b200._capi import default_model_desc
+        from oracle.oracle import OracleB
+
+        B = OracleB(default_model_desc(cfg.arm_indices))
+        B.set_initial_position(cfg.start)
+        t0 = time.perf_counter()
+        rb = B.project(seeds, nthreads=threads)
+        dtb = time.perf_counter() - t0
+        out["engine_arithmetic_on_cpu"] = {"projections_per_s": sample / dtb, "converged_per_s": float(rb["ok"].sum()) / dtb,
+                                           "seconds": dtb, "threads": threads}
+    return out
 
 
 def run_reference(args):
@@ -448,9 +462,10 @@ def main():
         line["e2e"] = e2e
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        cb = cpu_baseline(args.config, args.cpu_sample, threads)
+        cb = cpu_baseline(args.config, args.cpu_sample, threads, with_engine_arithmetic=True)
         line["cpu_baseline"] = {"value": cb["converged_per_s"], "unit": UNIT, "cores": threads, "kind": "port",
                                 "projections_per_s": cb["projections_per_s"], "mean_iters": cb["mean_iters"],
+                                "engine_arithmetic_on_cpu": cb.get("engine_arithmetic_on_cpu"),
                                 "sample": f"first {args.cpu_sample} Seeds-U of {args.config}, oracle A (reference-faithful FD "
                                           f"Jacobian + SVD solve) on {threads} threads, {cb['seconds']:.1f} s"}
     print(json.dumps(line), flush=True)
