@@ -48,6 +48,17 @@ class Options(C.Structure):
     ]
 
 
+class IkOptions(C.Structure):
+    _fields_ = [
+        ("max_iter", C.c_int32),
+        ("reserved", C.c_int32),
+        ("eps_pos", C.c_double),
+        ("eps_rot", C.c_double),
+        ("damping", C.c_double),
+        ("joint_margin", C.c_double),
+    ]
+
+
 class SamplerArgs(C.Structure):
     _fields_ = [
         ("rng_seed", C.c_uint64),
@@ -90,6 +101,9 @@ SYMBOLS = {
     "ccp_arm_jacobian_batch": (C.c_int, [_H, _I32, _P, _I64, _I32, _P, _P]),
     "ccp_generate_seeds": (C.c_int, [_H, C.POINTER(SamplerArgs), _I64, _I32, _P, _P]),
     "ccp_sample_project_batch": (C.c_int, [_H, C.POINTER(SamplerArgs), _I64, _I32, _P, _P, _P, _P, _P, _P]),
+    "ccp_ik_default_options": (None, [C.POINTER(IkOptions)]),
+    "ccp_ik_batch": (C.c_int, [_H, _I32, _P, _P, _I64, C.POINTER(IkOptions), _P, _P, _P, _P, _P]),
+    "ccp_ik_sample_batch": (C.c_int, [_H, _I32, _P, _I64, _I32, C.c_uint64, C.c_double, _P, C.POINTER(IkOptions), _P, _P, _P, _P]),
     "ccp_geodesic_batch": (C.c_int, [_H, _P, _P, _I64, C.c_double, C.c_double, _I32, _P, _P, _P, _P, _P]),
     "ccp_enforce_bounds_batch": (C.c_int, [_H, _P, _I64, _I32, _P]),
     "ccp_project_batch_host": (C.c_int, [_H, _P, _I64, _P, _P, _P, _P, _P]),

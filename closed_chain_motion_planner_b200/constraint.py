@@ -496,6 +496,71 @@ class PandaModel:
         T, _ = self._fk(q, True, False)
         return T[..., :3, 3]
 
+    # ---- batched pose IK (goal sampling; ik_task.cpp:16-49, panda_tracik.cpp:62-88,140-158) ----
+    def _ik_opts(self, **kw):
+        o = _capi.IkOptions()
+        self._c._lib.ccp_ik_default_options(C.byref(o))
+        for k, v in kw.items():
+            if v is not None:
+                setattr(o, k, v)
+        return o
+
+    def ikBatch(self, targets, seeds, max_iter=None, eps_pos=None, eps_rot=None, damping=None, joint_margin=None):
+        """One damped-Newton IK solve per (target, seed) pair on the GPU.  targets: (count, 3, 4) or (count, 4, 4) EE
+        poses in the arm's base frame (what getTransform returns); seeds: (count, 7).  Returns dict(q, ok, iters, err)
+        as numpy arrays (torch CUDA tensors in -> torch CUDA tensors out)."""
+        import torch
+
+        c = self._c
+        is_t = _is_torch(targets)
+        dev = torch.device("cuda", c.device)
+        T = targets if is_t else torch.from_numpy(np.ascontiguousarray(targets, dtype=np.float64))
+        T = T.to(dev)[..., :3, :].reshape(-1, 12).contiguous()
+        q0 = seeds if _is_torch(seeds) else torch.from_numpy(np.ascontiguousarray(seeds, dtype=np.float64))
+        q0 = q0.to(dev).reshape(-1, 7).contiguous()
+        cnt = T.shape[0]
+        if q0.shape[0] != cnt:
+            raise ValueError("one seed per target")
+        q = torch.empty((cnt, 7), dtype=torch.float64, device=dev)
+        ok = torch.empty(cnt, dtype=torch.uint8, device=dev)
+        it = torch.empty(cnt, dtype=torch.int32, device=dev)
+        err = torch.empty((cnt, 2), dtype=torch.float64, device=dev)
+        o = self._ik_opts(max_iter=max_iter, eps_pos=eps_pos, eps_rot=eps_rot, damping=damping, joint_margin=joint_margin)
+        _check(c._lib, c._h, c._lib.ccp_ik_batch(c._h, 0, T.data_ptr(), q0.data_ptr(), cnt, C.byref(o), q.data_ptr(),
+                                                 ok.data_ptr(), it.data_ptr(), err.data_ptr(),
+                                                 torch.cuda.current_stream(dev).cuda_stream))
+        res = dict(q=q, ok=ok, iters=it, err=err)
+        return res if is_t else {k: v.cpu().numpy() for k, v in res.items()}
+
+    def ikSampleBatch(self, targets, restarts: int = 15, rng_seed: int = 0, sigma: float = 0.3, q_ref=None, **opts):
+        """The goal sampler's per-arm loop for a batch of targets (jy_ConstrainedValidStateSampler.h:63-189): `restarts`
+        solves per target side by side (restart 0 from q_ref if given, the rest from N(mid-range, sigma) clipped to the
+        limits); the seeded solution wins, else the successful one nearest to q_ref.  Returns dict(q, ok, n_success)."""
+        import torch
+
+        c = self._c
+        is_t = _is_torch(targets)
+        dev = torch.device("cuda", c.device)
+        T = targets if is_t else torch.from_numpy(np.ascontiguousarray(targets, dtype=np.float64))
+        T = T.to(dev)[..., :3, :].reshape(-1, 12).contiguous()
+        cnt = T.shape[0]
+        ref = None
+        if q_ref is not None:
+            ref = q_ref if _is_torch(q_ref) else torch.from_numpy(np.ascontiguousarray(q_ref, dtype=np.float64))
+            ref = ref.to(dev).reshape(-1, 7).contiguous()
+            if ref.shape[0] != cnt:
+                raise ValueError("one reference configuration per target")
+        q = torch.zeros((cnt, 7), dtype=torch.float64, device=dev)
+        ok = torch.empty(cnt, dtype=torch.uint8, device=dev)
+        ns = torch.empty(cnt, dtype=torch.int32, device=dev)
+        o = self._ik_opts(**opts)
+        _check(c._lib, c._h, c._lib.ccp_ik_sample_batch(c._h, 0, T.data_ptr(), cnt, restarts, rng_seed, sigma,
+                                                        ref.data_ptr() if ref is not None else None, C.byref(o),
+                                                        q.data_ptr(), ok.data_ptr(), ns.data_ptr(),
+                                                        torch.cuda.current_stream(dev).cuda_stream))
+        res = dict(q=q, ok=ok, n_success=ns)
+        return res if is_t else {k: v.cpu().numpy() for k, v in res.items()}
+
     def getJacobianMatrix(self, q) -> np.ndarray:
         """panda_rbdl.cpp:9-22: 6x7, rows [linear; angular]."""
         _, J = self._fk(q, False, True)

@@ -29,6 +29,7 @@
 #include "ccp_device.cuh"
 #include "ccp_internal.h"
 #include "ccp_flops.h"
+#include "ccp_ik.h"
 #include "ccp_pack.h"
 
 #define CCP_VERSION_STRING "ccp-b200 0.1 (sm_100a)"
@@ -900,6 +901,72 @@ int ccp_geodesic_batch(ccp_handle* h, const double* from_dev, const double* to_d
   cudaError_t e = ccp_launch_geodesic(h->sm_count, h->model, from_dev, to_dev, edges, delta, lambda, max_states, states_dev,
                                       n_states_dev, reached_dev, iters_dev, counter, st);
   if (e != cudaSuccess) return set_err(h, CCP_ERR_CUDA, "geodesic kernel launch: %s", cudaGetErrorString(e));
+  return CCP_OK;
+}
+
+// ---- batched pose IK (goal sampling) -------------------------------------------------------
+void ccp_ik_default_options(ccp_ik_options* o) {
+  if (!o) return;
+  o->max_iter = 200;
+  o->reserved = 0;
+  o->eps_pos = 1e-5;  // TRAC-IK's default eps on every twist component
+  o->eps_rot = 1e-5;
+  o->damping = 1e-4;
+  o->joint_margin = 1e-3;  // TrackIKAdaptor::isValid, panda_tracik.cpp:99-108
+}
+
+static int ik_options(ccp_handle* h, const ccp_ik_options* opt, ccp_ik_opt* O) {
+  ccp_ik_options d;
+  ccp_ik_default_options(&d);
+  if (opt) d = *opt;
+  if (d.max_iter < 0 || !(d.eps_pos > 0) || !(d.eps_rot > 0) || !(d.damping >= 0) || !(d.joint_margin >= 0))
+    return set_err(h, CCP_ERR_INVALID, "%s", "bad IK options");
+  O->max_iter = d.max_iter;
+  O->pad = 0;
+  O->eps_p = d.eps_pos;
+  O->eps_r = d.eps_rot;
+  O->lambda2 = d.damping;
+  O->margin = d.joint_margin;
+  return CCP_OK;
+}
+
+int ccp_ik_batch(ccp_handle* h, int32_t arm, const double* T_target_dev, const double* q_seed_dev, int64_t count,
+                 const ccp_ik_options* opt, double* q_out_dev, uint8_t* ok_dev, int32_t* iters_dev, double* err_dev,
+                 void* stream) {
+  if (!h) return CCP_ERR_INVALID;
+  if (count < 0) return set_err(h, CCP_ERR_INVALID, "%s", "negative count");
+  if (arm < 0 || arm >= h->model.n_arms) return set_err(h, CCP_ERR_INVALID, "%s", "arm index out of range");
+  if (count > 0 && (!T_target_dev || !q_seed_dev || !q_out_dev)) return set_err(h, CCP_ERR_INVALID, "%s", "null IK buffer");
+  ccp_ik_opt O;
+  int rc = ik_options(h, opt, &O);
+  if (rc) return rc;
+  if (count == 0) return CCP_OK;
+  device_guard g(h->device);
+  cudaError_t e = ccp_launch_ik(h->sm_count, h->model, arm, T_target_dev, q_seed_dev, count, O, q_out_dev, ok_dev, iters_dev,
+                                err_dev, (cudaStream_t)stream);
+  h->launches++;
+  if (e != cudaSuccess) return set_err(h, CCP_ERR_CUDA, "IK kernel launch: %s", cudaGetErrorString(e));
+  return CCP_OK;
+}
+
+int ccp_ik_sample_batch(ccp_handle* h, int32_t arm, const double* T_target_dev, int64_t n_targets, int32_t restarts,
+                        uint64_t rng_seed, double sigma, const double* q_ref_dev, const ccp_ik_options* opt,
+                        double* q_best_dev, uint8_t* ok_dev, int32_t* n_success_dev, void* stream) {
+  if (!h) return CCP_ERR_INVALID;
+  if (n_targets < 0) return set_err(h, CCP_ERR_INVALID, "%s", "negative count");
+  if (arm < 0 || arm >= h->model.n_arms) return set_err(h, CCP_ERR_INVALID, "%s", "arm index out of range");
+  if (restarts < 1 || restarts > 32) return set_err(h, CCP_ERR_INVALID, "%s", "IK restarts must be 1..32");
+  if (!(sigma >= 0)) return set_err(h, CCP_ERR_INVALID, "%s", "IK sigma must be >= 0");
+  if (n_targets > 0 && (!T_target_dev || !q_best_dev || !ok_dev)) return set_err(h, CCP_ERR_INVALID, "%s", "null IK buffer");
+  ccp_ik_opt O;
+  int rc = ik_options(h, opt, &O);
+  if (rc) return rc;
+  if (n_targets == 0) return CCP_OK;
+  device_guard g(h->device);
+  cudaError_t e = ccp_launch_ik_sample(h->sm_count, h->model, arm, T_target_dev, q_ref_dev, n_targets, restarts, rng_seed,
+                                       sigma, O, q_best_dev, ok_dev, n_success_dev, (cudaStream_t)stream);
+  h->launches++;
+  if (e != cudaSuccess) return set_err(h, CCP_ERR_CUDA, "IK sample kernel launch: %s", cudaGetErrorString(e));
   return CCP_OK;
 }
 

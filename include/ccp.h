@@ -229,6 +229,39 @@ int ccp_geodesic_batch(ccp_handle* h, const double* from_dev, const double* to_d
                        double lambda, int32_t max_states, double* states_dev, int32_t* n_states_dev,
                        uint8_t* reached_dev, int32_t* iters_dev, void* stream);
 
+/* ---- batched single-arm pose IK (goal sampling) ----------------------------------------------------------
+ * ≙ IKTask::solve / random_solve (src/base/constraints/ik_task.cpp:16-49) -> panda_ik::solve /
+ * TrackIKAdaptor::randomSolve (src/kinematics/panda_tracik.cpp:62-88,140-158) for a whole batch.  TRAC-IK is third
+ * party and not reproduced; the solver here is a damped Newton iteration on the 6-D pose error with joint-limit
+ * clamping (KDL ChainIkSolverPos_NR_JL's idea).  An answer is correct iff FK(q) hits the target within the tolerance
+ * inside the limits — that is the parity criterion (tests/test_ik_gpu.py, checked with the reference-faithful FK).
+ * Poses are those PandaModel::getTransform returns: the EE frame in the arm's BASE frame, row-major 3x4 [R|p]; the
+ * reference's t_b7 = t_wb^-1 * T_obj * t_o7 (ik_task.cpp:24) converts to it with the constant flange/hand offsets. */
+typedef struct ccp_ik_options {
+  int32_t max_iter;     /* 200 Newton steps per solve */
+  int32_t reserved;
+  double eps_pos;       /* 1e-5 m   on every position component (TRAC-IK default eps) */
+  double eps_rot;       /* 1e-5 rad on every rotation-error component */
+  double damping;       /* 1e-4: lambda^2 added to the diagonal of J J^T */
+  double joint_margin;  /* 1e-3: a solution must stay this far inside the limits (panda_tracik.cpp:99-108) */
+} ccp_ik_options;
+void ccp_ik_default_options(ccp_ik_options* o);
+/* One solve per (target, seed) pair.  T_target_dev double[count][12], q_seed_dev / q_out_dev double[count][7]
+ * (q_out = last iterate, also on failure), ok_dev uint8[count] (converged inside the limits), iters_dev int32[count]
+ * or NULL, err_dev double[count][2] = final (|p error|_inf, |rotation error|_inf) or NULL.  opt NULL = defaults.   */
+int ccp_ik_batch(ccp_handle* h, int32_t arm, const double* T_target_dev, const double* q_seed_dev, int64_t count,
+                 const ccp_ik_options* opt, double* q_out_dev, uint8_t* ok_dev, int32_t* iters_dev, double* err_dev,
+                 void* stream);
+/* ≙ the goal sampler's per-arm loop (jy_ConstrainedValidStateSampler.h:63-189): for each of n_targets targets run
+ * `restarts` (1..32) solves side by side — restart 0 from q_ref (if given), the others from N(mid-range, sigma) draws
+ * clipped to the limits (TrackIKAdaptor::getRandomConfig, sigma = 0.3 there) — and keep the seeded solution if it
+ * succeeded, else the successful one nearest to q_ref (without q_ref: the lowest-numbered successful restart).
+ * q_best_dev double[n_targets][7] (untouched where ok == 0), ok_dev uint8[n_targets], n_success_dev int32[n_targets]
+ * (how many restarts converged) or NULL.                                                                           */
+int ccp_ik_sample_batch(ccp_handle* h, int32_t arm, const double* T_target_dev, int64_t n_targets, int32_t restarts,
+                        uint64_t rng_seed, double sigma, const double* q_ref_dev, const ccp_ik_options* opt,
+                        double* q_best_dev, uint8_t* ok_dev, int32_t* n_success_dev, void* stream);
+
 /* ---- host-buffer entry points (what a planner that owns host states calls) -------------- */
 /* Same as ccp_project_batch but all pointers are HOST memory, AOS double[count][n]
  * (the gathered OMPL states).  Copies in, projects, copies out; synchronous.                */

@@ -240,6 +240,19 @@ class OracleB:
         self.lib.ob_arm_fk_batch(self._buf, C.c_int(arm), _dp(q), C.c_int64(q.shape[0]), _dp(T), _dp(J))
         return T.reshape(-1, 3, 4), J.reshape(-1, 6, 7)
 
+    def ik(self, arm, targets, seeds, max_iter=200, eps_pos=1e-5, eps_rot=1e-5, damping=1e-4, margin=1e-3):
+        """Host twin of ccp_ik_batch: targets (count, 12) row-major 3x4, seeds (count, 7)."""
+        T = np.ascontiguousarray(targets, dtype=np.float64).reshape(-1, 12)
+        q0 = _as_states(seeds, 7)
+        cnt = T.shape[0]
+        q = np.zeros((cnt, 7))
+        ok = np.zeros(cnt, np.uint8)
+        it = np.zeros(cnt, np.int32)
+        err = np.zeros((cnt, 2))
+        self.lib.ob_ik_batch(self._buf, C.c_int(arm), _dp(T), _dp(q0), C.c_int64(cnt), C.c_int(max_iter), C.c_double(eps_pos),
+                             C.c_double(eps_rot), C.c_double(damping), C.c_double(margin), _dp(q), _dp(ok), _dp(it), _dp(err))
+        return dict(q=q, ok=ok, iters=it, err=err)
+
     def discrete_geodesic(self, frm, to, delta=0.25, lam=2.0, max_states=64):
         frm, to = _as_states(frm, self.n), _as_states(to, self.n)
         e = frm.shape[0]

@@ -15,6 +15,7 @@
 
 #include "ccp.h"
 #include "ccp_core.h"
+#include "ccp_ik.h"
 #include "ccp_pack.h"
 
 #ifdef _OPENMP
@@ -200,6 +201,25 @@ void ob_geodesic_batch(const ccp_model* M, const double* from, const double* to,
 #define OB_CALL(K, P) geodesic_batch<K, P>(M, from, to, edges, delta, lambda, max_states, states, n_states, reached, total_iters)
   OB_DISPATCH(M, OB_CALL);
 #undef OB_CALL
+}
+
+// host twin of ccp_ik_kernel (explicit seeds)
+void ob_ik_batch(const ccp_model* M, int arm, const double* Tt, const double* qseed, int64_t count, int max_iter,
+                 double eps_p, double eps_r, double lambda2, double margin, double* qout, uint8_t* ok, int32_t* iters,
+                 double* err) {
+  ccp_ik_opt O;
+  O.max_iter = max_iter; O.pad = 0; O.eps_p = eps_p; O.eps_r = eps_r; O.lambda2 = lambda2; O.margin = margin;
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int64_t s = 0; s < count; ++s) {
+    double q[7], e[2];
+    for (int k = 0; k < 7; ++k) q[k] = qseed[7 * s + k];
+    int32_t it; bool okk;
+    ccp_ik_solve_one(M->arm[arm], M->lb, M->ub, Tt + 12 * s, q, O, &it, &okk, e);
+    for (int k = 0; k < 7; ++k) qout[7 * s + k] = q[k];
+    if (ok) ok[s] = okk;
+    if (iters) iters[s] = it;
+    if (err) { err[2 * s] = e[0]; err[2 * s + 1] = e[1]; }
+  }
 }
 
 void ob_arm_fk_batch(const ccp_model* M, int arm, const double* q, int64_t count, double* T, double* J) {
