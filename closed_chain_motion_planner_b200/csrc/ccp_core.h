@@ -124,38 +124,172 @@ CCP_HD double ccp_xor_sign(double v, uint32_t flip) {
 #endif
 }
 
-// sin and cos of x.  Cody-Waite reduction by pi/2 in two pieces (33 bits, then the next 53: k PIO2_1 is
-// exact for |k| < 2^20, the second product is rounded once), then degree-13/14 minimax kernels on
-// [-pi/4, pi/4] (coefficients: Sun fdlibm k_sin/k_cos), cos in plain Horner form.  19 FP64 instructions,
-// <= 1.5 ulp for |x| < ~1e5; degrades gracefully (and identically on host and device) beyond.
+// sin and cos of x by table + short series: x = k pi/64 + r with |r| <= pi/128 (Cody-Waite in two pieces: k P1 is
+// exact for |k| < 2^20, the second product is rounded once); (sin, cos)(k pi/64) come from a 128-entry table of
+// correctly rounded values, sin r / cos r - 1 from their Taylor series to r^7 / r^6 (truncation < 4e-18), and
+//     sin x = S + (S (cos r - 1) + C sin r),   cos x = C + (C (cos r - 1) - S sin r).
+// 16 FP64 instructions and one 16-byte table load; no quadrant selects.  <= 1.5 ulp for |x| < ~1e5; degrades
+// gracefully (and identically on host and device) beyond.
+#define CCP_SC_TABLE_ENTRIES \
+    {0x0.0p+0, 0x1.0000000000000p+0}, \
+    {0x1.91f65f10dd814p-5, 0x1.ff621e3796d7ep-1}, \
+    {0x1.917a6bc29b42cp-4, 0x1.fd88da3d12526p-1}, \
+    {0x1.2c8106e8e613ap-3, 0x1.fa7557f08a517p-1}, \
+    {0x1.8f8b83c69a60bp-3, 0x1.f6297cff75cb0p-1}, \
+    {0x1.f19f97b215f1bp-3, 0x1.f0a7efb9230d7p-1}, \
+    {0x1.294062ed59f06p-2, 0x1.e9f4156c62ddap-1}, \
+    {0x1.58f9a75ab1fddp-2, 0x1.e212104f686e5p-1}, \
+    {0x1.87de2a6aea963p-2, 0x1.d906bcf328d46p-1}, \
+    {0x1.b5d1009e15cc0p-2, 0x1.ced7af43cc773p-1}, \
+    {0x1.e2b5d3806f63bp-2, 0x1.c38b2f180bdb1p-1}, \
+    {0x1.073879922ffeep-1, 0x1.b728345196e3ep-1}, \
+    {0x1.1c73b39ae68c8p-1, 0x1.a9b66290ea1a3p-1}, \
+    {0x1.30ff7fce17035p-1, 0x1.9b3e047f38741p-1}, \
+    {0x1.44cf325091dd6p-1, 0x1.8bc806b151741p-1}, \
+    {0x1.57d69348ceca0p-1, 0x1.7b5df226aafafp-1}, \
+    {0x1.6a09e667f3bcdp-1, 0x1.6a09e667f3bcdp-1}, \
+    {0x1.7b5df226aafafp-1, 0x1.57d69348ceca0p-1}, \
+    {0x1.8bc806b151741p-1, 0x1.44cf325091dd6p-1}, \
+    {0x1.9b3e047f38741p-1, 0x1.30ff7fce17035p-1}, \
+    {0x1.a9b66290ea1a3p-1, 0x1.1c73b39ae68c8p-1}, \
+    {0x1.b728345196e3ep-1, 0x1.073879922ffeep-1}, \
+    {0x1.c38b2f180bdb1p-1, 0x1.e2b5d3806f63bp-2}, \
+    {0x1.ced7af43cc773p-1, 0x1.b5d1009e15cc0p-2}, \
+    {0x1.d906bcf328d46p-1, 0x1.87de2a6aea963p-2}, \
+    {0x1.e212104f686e5p-1, 0x1.58f9a75ab1fddp-2}, \
+    {0x1.e9f4156c62ddap-1, 0x1.294062ed59f06p-2}, \
+    {0x1.f0a7efb9230d7p-1, 0x1.f19f97b215f1bp-3}, \
+    {0x1.f6297cff75cb0p-1, 0x1.8f8b83c69a60bp-3}, \
+    {0x1.fa7557f08a517p-1, 0x1.2c8106e8e613ap-3}, \
+    {0x1.fd88da3d12526p-1, 0x1.917a6bc29b42cp-4}, \
+    {0x1.ff621e3796d7ep-1, 0x1.91f65f10dd814p-5}, \
+    {0x1.0000000000000p+0, 0x0.0p+0}, \
+    {0x1.ff621e3796d7ep-1, -0x1.91f65f10dd814p-5}, \
+    {0x1.fd88da3d12526p-1, -0x1.917a6bc29b42cp-4}, \
+    {0x1.fa7557f08a517p-1, -0x1.2c8106e8e613ap-3}, \
+    {0x1.f6297cff75cb0p-1, -0x1.8f8b83c69a60bp-3}, \
+    {0x1.f0a7efb9230d7p-1, -0x1.f19f97b215f1bp-3}, \
+    {0x1.e9f4156c62ddap-1, -0x1.294062ed59f06p-2}, \
+    {0x1.e212104f686e5p-1, -0x1.58f9a75ab1fddp-2}, \
+    {0x1.d906bcf328d46p-1, -0x1.87de2a6aea963p-2}, \
+    {0x1.ced7af43cc773p-1, -0x1.b5d1009e15cc0p-2}, \
+    {0x1.c38b2f180bdb1p-1, -0x1.e2b5d3806f63bp-2}, \
+    {0x1.b728345196e3ep-1, -0x1.073879922ffeep-1}, \
+    {0x1.a9b66290ea1a3p-1, -0x1.1c73b39ae68c8p-1}, \
+    {0x1.9b3e047f38741p-1, -0x1.30ff7fce17035p-1}, \
+    {0x1.8bc806b151741p-1, -0x1.44cf325091dd6p-1}, \
+    {0x1.7b5df226aafafp-1, -0x1.57d69348ceca0p-1}, \
+    {0x1.6a09e667f3bcdp-1, -0x1.6a09e667f3bcdp-1}, \
+    {0x1.57d69348ceca0p-1, -0x1.7b5df226aafafp-1}, \
+    {0x1.44cf325091dd6p-1, -0x1.8bc806b151741p-1}, \
+    {0x1.30ff7fce17035p-1, -0x1.9b3e047f38741p-1}, \
+    {0x1.1c73b39ae68c8p-1, -0x1.a9b66290ea1a3p-1}, \
+    {0x1.073879922ffeep-1, -0x1.b728345196e3ep-1}, \
+    {0x1.e2b5d3806f63bp-2, -0x1.c38b2f180bdb1p-1}, \
+    {0x1.b5d1009e15cc0p-2, -0x1.ced7af43cc773p-1}, \
+    {0x1.87de2a6aea963p-2, -0x1.d906bcf328d46p-1}, \
+    {0x1.58f9a75ab1fddp-2, -0x1.e212104f686e5p-1}, \
+    {0x1.294062ed59f06p-2, -0x1.e9f4156c62ddap-1}, \
+    {0x1.f19f97b215f1bp-3, -0x1.f0a7efb9230d7p-1}, \
+    {0x1.8f8b83c69a60bp-3, -0x1.f6297cff75cb0p-1}, \
+    {0x1.2c8106e8e613ap-3, -0x1.fa7557f08a517p-1}, \
+    {0x1.917a6bc29b42cp-4, -0x1.fd88da3d12526p-1}, \
+    {0x1.91f65f10dd814p-5, -0x1.ff621e3796d7ep-1}, \
+    {0x0.0p+0, -0x1.0000000000000p+0}, \
+    {-0x1.91f65f10dd814p-5, -0x1.ff621e3796d7ep-1}, \
+    {-0x1.917a6bc29b42cp-4, -0x1.fd88da3d12526p-1}, \
+    {-0x1.2c8106e8e613ap-3, -0x1.fa7557f08a517p-1}, \
+    {-0x1.8f8b83c69a60bp-3, -0x1.f6297cff75cb0p-1}, \
+    {-0x1.f19f97b215f1bp-3, -0x1.f0a7efb9230d7p-1}, \
+    {-0x1.294062ed59f06p-2, -0x1.e9f4156c62ddap-1}, \
+    {-0x1.58f9a75ab1fddp-2, -0x1.e212104f686e5p-1}, \
+    {-0x1.87de2a6aea963p-2, -0x1.d906bcf328d46p-1}, \
+    {-0x1.b5d1009e15cc0p-2, -0x1.ced7af43cc773p-1}, \
+    {-0x1.e2b5d3806f63bp-2, -0x1.c38b2f180bdb1p-1}, \
+    {-0x1.073879922ffeep-1, -0x1.b728345196e3ep-1}, \
+    {-0x1.1c73b39ae68c8p-1, -0x1.a9b66290ea1a3p-1}, \
+    {-0x1.30ff7fce17035p-1, -0x1.9b3e047f38741p-1}, \
+    {-0x1.44cf325091dd6p-1, -0x1.8bc806b151741p-1}, \
+    {-0x1.57d69348ceca0p-1, -0x1.7b5df226aafafp-1}, \
+    {-0x1.6a09e667f3bcdp-1, -0x1.6a09e667f3bcdp-1}, \
+    {-0x1.7b5df226aafafp-1, -0x1.57d69348ceca0p-1}, \
+    {-0x1.8bc806b151741p-1, -0x1.44cf325091dd6p-1}, \
+    {-0x1.9b3e047f38741p-1, -0x1.30ff7fce17035p-1}, \
+    {-0x1.a9b66290ea1a3p-1, -0x1.1c73b39ae68c8p-1}, \
+    {-0x1.b728345196e3ep-1, -0x1.073879922ffeep-1}, \
+    {-0x1.c38b2f180bdb1p-1, -0x1.e2b5d3806f63bp-2}, \
+    {-0x1.ced7af43cc773p-1, -0x1.b5d1009e15cc0p-2}, \
+    {-0x1.d906bcf328d46p-1, -0x1.87de2a6aea963p-2}, \
+    {-0x1.e212104f686e5p-1, -0x1.58f9a75ab1fddp-2}, \
+    {-0x1.e9f4156c62ddap-1, -0x1.294062ed59f06p-2}, \
+    {-0x1.f0a7efb9230d7p-1, -0x1.f19f97b215f1bp-3}, \
+    {-0x1.f6297cff75cb0p-1, -0x1.8f8b83c69a60bp-3}, \
+    {-0x1.fa7557f08a517p-1, -0x1.2c8106e8e613ap-3}, \
+    {-0x1.fd88da3d12526p-1, -0x1.917a6bc29b42cp-4}, \
+    {-0x1.ff621e3796d7ep-1, -0x1.91f65f10dd814p-5}, \
+    {-0x1.0000000000000p+0, 0x0.0p+0}, \
+    {-0x1.ff621e3796d7ep-1, 0x1.91f65f10dd814p-5}, \
+    {-0x1.fd88da3d12526p-1, 0x1.917a6bc29b42cp-4}, \
+    {-0x1.fa7557f08a517p-1, 0x1.2c8106e8e613ap-3}, \
+    {-0x1.f6297cff75cb0p-1, 0x1.8f8b83c69a60bp-3}, \
+    {-0x1.f0a7efb9230d7p-1, 0x1.f19f97b215f1bp-3}, \
+    {-0x1.e9f4156c62ddap-1, 0x1.294062ed59f06p-2}, \
+    {-0x1.e212104f686e5p-1, 0x1.58f9a75ab1fddp-2}, \
+    {-0x1.d906bcf328d46p-1, 0x1.87de2a6aea963p-2}, \
+    {-0x1.ced7af43cc773p-1, 0x1.b5d1009e15cc0p-2}, \
+    {-0x1.c38b2f180bdb1p-1, 0x1.e2b5d3806f63bp-2}, \
+    {-0x1.b728345196e3ep-1, 0x1.073879922ffeep-1}, \
+    {-0x1.a9b66290ea1a3p-1, 0x1.1c73b39ae68c8p-1}, \
+    {-0x1.9b3e047f38741p-1, 0x1.30ff7fce17035p-1}, \
+    {-0x1.8bc806b151741p-1, 0x1.44cf325091dd6p-1}, \
+    {-0x1.7b5df226aafafp-1, 0x1.57d69348ceca0p-1}, \
+    {-0x1.6a09e667f3bcdp-1, 0x1.6a09e667f3bcdp-1}, \
+    {-0x1.57d69348ceca0p-1, 0x1.7b5df226aafafp-1}, \
+    {-0x1.44cf325091dd6p-1, 0x1.8bc806b151741p-1}, \
+    {-0x1.30ff7fce17035p-1, 0x1.9b3e047f38741p-1}, \
+    {-0x1.1c73b39ae68c8p-1, 0x1.a9b66290ea1a3p-1}, \
+    {-0x1.073879922ffeep-1, 0x1.b728345196e3ep-1}, \
+    {-0x1.e2b5d3806f63bp-2, 0x1.c38b2f180bdb1p-1}, \
+    {-0x1.b5d1009e15cc0p-2, 0x1.ced7af43cc773p-1}, \
+    {-0x1.87de2a6aea963p-2, 0x1.d906bcf328d46p-1}, \
+    {-0x1.58f9a75ab1fddp-2, 0x1.e212104f686e5p-1}, \
+    {-0x1.294062ed59f06p-2, 0x1.e9f4156c62ddap-1}, \
+    {-0x1.f19f97b215f1bp-3, 0x1.f0a7efb9230d7p-1}, \
+    {-0x1.8f8b83c69a60bp-3, 0x1.f6297cff75cb0p-1}, \
+    {-0x1.2c8106e8e613ap-3, 0x1.fa7557f08a517p-1}, \
+    {-0x1.917a6bc29b42cp-4, 0x1.fd88da3d12526p-1}, \
+    {-0x1.91f65f10dd814p-5, 0x1.ff621e3796d7ep-1},
+
+static const double ccp_sc_table_host[128][2] = {CCP_SC_TABLE_ENTRIES};
+#if defined(__CUDACC__)
+static __device__ __align__(16) const double ccp_sc_table_dev[128][2] = {CCP_SC_TABLE_ENTRIES};
+#endif
+
 CCP_HD void ccp_sincos(double x, double* s_out, double* c_out) {
-  const double TWO_OVER_PI = 0x1.45f306dc9c883p-1;
+  const double SIXTYFOUR_OVER_PI = 0x1.45f306dc9c883p+4;
   const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: round-to-nearest-integer trick
-  const double PIO2_1 = 0x1.921fb54400000p+0;
-  const double PIO2_2 = 0x1.0b4611a626331p-34;  // pi/2 - PIO2_1 to 53 bits
-  double t = CCP_FMA(x, TWO_OVER_PI, MAGIC);
-  const uint32_t q = (uint32_t)ccp_lo32(t);
-  double k = t - MAGIC;
-  double r = CCP_FMA(-k, PIO2_1, x);
-  r = CCP_FMA(-k, PIO2_2, r);
-  double z = r * r;
-  double ps = CCP_FMA(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-  ps = CCP_FMA(z, ps, 2.75573137070700676789e-06);
-  ps = CCP_FMA(z, ps, -1.98412698298579493134e-04);
-  ps = CCP_FMA(z, ps, 8.33333333332248946124e-03);
-  ps = CCP_FMA(z, ps, -1.66666666666666324348e-01);
-  double pc = CCP_FMA(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-  pc = CCP_FMA(z, pc, -2.75573143513906633035e-07);
-  pc = CCP_FMA(z, pc, 2.48015872894767294178e-05);
-  pc = CCP_FMA(z, pc, -1.38888888888741095749e-03);
-  pc = CCP_FMA(z, pc, 4.16666666666666019037e-02);
+  const double P1 = 0x1.921fb54400000p-5;   // pi/64, leading 33 bits
+  const double P2 = 0x1.0b4611a626331p-39;  // pi/64 - P1 to 53 bits
+  const double t = CCP_FMA(x, SIXTYFOUR_OVER_PI, MAGIC);
+  const uint32_t idx = (uint32_t)ccp_lo32(t) & 127u;
+  const double k = t - MAGIC;
+  double r = CCP_FMA(-k, P1, x);
+  r = CCP_FMA(-k, P2, r);
+#if defined(__CUDA_ARCH__)
+  const double2 sc = __ldg(reinterpret_cast<const double2*>(&ccp_sc_table_dev[idx][0]));
+  const double S = sc.x, C = sc.y;
+#else
+  const double S = ccp_sc_table_host[idx][0], C = ccp_sc_table_host[idx][1];
+#endif
+  const double z = r * r;
+  double ps = CCP_FMA(z, -0x1.a01a01a01a01ap-13, 0x1.1111111111111p-7);  // -1/7!, 1/5!
+  ps = CCP_FMA(z, ps, -0x1.5555555555555p-3);                            // -1/3!
+  const double sr = CCP_FMA(r * z, ps, r);                               // sin r
+  double pc = CCP_FMA(z, -0x1.6c16c16c16c17p-10, 0x1.5555555555555p-5);  // -1/6!, 1/4!
   pc = CCP_FMA(z, pc, -0.5);
-  double sr = CCP_FMA(r * z, ps, r);
-  double cr = CCP_FMA(z, pc, 1.0);
-  double s = (q & 1u) ? cr : sr;
-  double c = (q & 1u) ? sr : cr;
-  *s_out = ccp_xor_sign(s, q << 30);         // quadrants 2, 3
-  *c_out = ccp_xor_sign(c, (q + 1u) << 30);  // quadrants 1, 2
+  const double cm1 = z * pc;                                             // cos r - 1
+  *s_out = CCP_FMA(C, sr, CCP_FMA(S, cm1, S));
+  *c_out = CCP_FMA(-S, sr, CCP_FMA(C, cm1, C));
 }
 
 // atan2(y, x) for y >= 0, x >= 0 (the only case angularDistance needs).  Result in [0, pi/2].
