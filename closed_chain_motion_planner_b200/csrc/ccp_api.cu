@@ -524,7 +524,7 @@ int ccp_set_options(ccp_handle* h, const ccp_options* opt) {
   CCP_NO_OPEN_PIPELINE(h);
   h->model.step = opt->step;
   h->model.max_iter = opt->max_iter;
-  h->model.margin = opt->joint_margin;
+  ccp_model_set_margin(&h->model, opt->joint_margin);
   return CCP_OK;
 }
 

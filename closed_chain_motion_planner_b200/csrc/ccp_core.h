@@ -84,9 +84,19 @@ struct ccp_model {
   double step;          // 0.30
   double margin;        // 1e-3
   double lb[CCPC_DOF], ub[CCPC_DOF];
+  double lbm[CCPC_DOF], ubm[CCPC_DOF];  // lb + margin, ub - margin (jointValid's thresholds, precomputed)
   ccp_arm arm[CCPC_MAX_ARMS];
   ccp_pair_ref ref[CCPC_MAX_ARMS - 1];
 };
+
+// joint margin (ConstraintFunction.h:45) + jointValid's thresholds
+static inline void ccp_model_set_margin(ccp_model* M, double margin) {
+  M->margin = margin;
+  for (int i = 0; i < CCPC_DOF; ++i) {
+    M->lbm[i] = M->lb[i] + margin;
+    M->ubm[i] = M->ub[i] - margin;
+  }
+}
 
 // setTolerance (ConstraintFunction.h:104-112) + the derived thresholds of the loop tests.  Host only (libm tan).
 static inline void ccp_model_set_tolerance(ccp_model* M, double tol_p, double tol_r) {
@@ -649,8 +659,8 @@ CCP_HD bool ccp_joint_valid(const ccp_model& M, const XT& x) {
 #pragma unroll
     for (int i = 0; i < CCPC_DOF; ++i) {
       const double v = x[a * CCPC_DOF + i];
-      lo = lo && !(v < M.lb[i] + M.margin);
-      hi = hi && !(v > M.ub[i] - M.margin);
+      lo = lo && !(v < M.lbm[i]);
+      hi = hi && !(v > M.ubm[i]);
     }
     ok = ok && lo && hi;
   }

@@ -49,11 +49,11 @@ static inline int ccp_pack_model(const ccp_model_desc* d, ccp_model* M) {
   M->max_iter = 250;  // ConstraintFunction.h:26
   ccp_model_set_tolerance(M, 1e-3, 5e-3);  // ConstrainedPlanningCommon.cpp:120-121
   M->step = 0.30;     // ConstraintFunction.h:71
-  M->margin = 1e-3;   // ConstraintFunction.h:45
   for (int i = 0; i < CCP_DOF; ++i) {
     M->lb[i] = d->lb[i];
     M->ub[i] = d->ub[i];
   }
+  ccp_model_set_margin(M, 1e-3);  // ConstraintFunction.h:45
   // Stock Panda alpha pattern on every arm (bitwise: no alpha calibration) -> structured link code.
   static const double kPi2 = 1.57079632679489661923;
   static const double kPandaAlpha[7] = {0.0, -1.0 * kPi2, kPi2, kPi2, -1.0 * kPi2, kPi2, kPi2};

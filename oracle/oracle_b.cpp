@@ -161,7 +161,7 @@ void ob_get_reference(const ccp_model* M, int pair, double* t0, double* q0) {
 }
 void ob_set_tolerance(ccp_model* M, double t1, double t2) { ccp_model_set_tolerance(M, t1, t2); }
 void ob_set_options(ccp_model* M, double step, int max_iter, double margin) {
-  M->step = step; M->max_iter = max_iter; M->margin = margin;
+  M->step = step; M->max_iter = max_iter; ccp_model_set_margin(M, margin);
 }
 
 void ob_function_batch(const ccp_model* M, const double* x, int64_t count, double* f) {
