@@ -1,0 +1,104 @@
+"""Edge cases of the projection entry points: empty / tiny / ragged batches, odd SoA strides and misaligned seed
+pointers (the TMA staging must fall back to plain loads), NaN seeds, in-place projection, the chunked sampler path."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import make_oracles
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def _bits(t):
+    return t.cpu().numpy().view(np.uint64)
+
+
+@pytest.fixture(scope="module")
+def setup():
+    import closed_chain_motion_planner_b200 as pkg
+
+    assert torch.cuda.is_available()
+    cfg, A, B = make_oracles("Wine_Bottle")
+    c = pkg.KinematicChainConstraint.from_config("Wine_Bottle", device=0)
+    return pkg, c, A, B
+
+
+@pytest.mark.parametrize("count", [0, 1, 31, 32, 33, 1023, 148 * 384 + 1])
+@pytest.mark.parametrize("layout", ["aos", "soa"])
+def test_ragged_counts_bit_exact(setup, count, layout):
+    pkg, c, A, B = setup
+    seeds = A.seeds_uniform(0, 0, max(count, 1))[:count]
+    rb = B.project(seeds, nthreads=8) if count else None
+    if layout == "aos":
+        r = c.projectBatch(torch.from_numpy(seeds).cuda().reshape(count, 14))
+        x = r.x.cpu().numpy()
+    else:
+        r = c.projectBatch(torch.from_numpy(np.ascontiguousarray(seeds.T)).cuda().reshape(14, count), layout=pkg.CCP_LAYOUT_SOA)
+        x = r.x.cpu().numpy().T
+    torch.cuda.synchronize()
+    assert r.ok.shape[0] == count
+    if count:
+        assert np.array_equal(x.view(np.uint64), rb["x"].view(np.uint64))
+        assert np.array_equal(r.iters.cpu().numpy(), rb["iters"]) and np.array_equal(r.ok.cpu().numpy(), rb["ok"])
+
+
+def test_misaligned_seed_pointer_and_in_place(setup):
+    """Seeds starting 8 bytes off a 16-byte boundary cannot be bulk-copied: the kernel must take the plain-load path,
+    with identical results; out may alias the seeds."""
+    pkg, c, A, B = setup
+    n = 70_000
+    seeds = A.seeds_uniform(0, 0, n)
+    ref = c.projectBatch(torch.from_numpy(seeds).cuda())
+    buf = torch.empty(n * 14 + 1, dtype=torch.float64, device="cuda")
+    view = buf[1:].view(n, 14)
+    assert view.data_ptr() % 16 == 8
+    view.copy_(torch.from_numpy(seeds))
+    r = c.projectBatch(view, out=view)  # misaligned AND in place
+    torch.cuda.synchronize()
+    assert np.array_equal(_bits(r.x), _bits(ref.x)) and torch.equal(r.iters, ref.iters)
+
+
+def test_nan_and_far_seeds_terminate(setup):
+    pkg, c, A, B = setup
+    seeds = A.seeds_uniform(0, 0, 4096)
+    seeds[5, 3] = np.nan
+    seeds[77, :] = np.inf
+    seeds[100, 0] = 1e9  # a joint angle far outside any sane range
+    r = c.projectBatch(torch.from_numpy(seeds).cuda())
+    torch.cuda.synchronize()
+    ok = r.ok.cpu().numpy()
+    assert ok[5] == 0 and ok[77] == 0
+    rb = B.project(seeds, nthreads=8)
+    good = np.ones(4096, bool)
+    good[[5, 77]] = False
+    assert np.array_equal(r.x.cpu().numpy()[good].view(np.uint64), rb["x"][good].view(np.uint64))
+    assert np.array_equal(ok, rb["ok"])
+
+
+@pytest.mark.parametrize("layout", ["aos", "soa"])
+def test_chunked_sampler_equals_explicit_seeds(setup, layout):
+    """ccp_sample_project_batch cuts batches above 2 M seeds into pipelined launches over a scratch seed buffer: the
+    per-seed outputs must equal projecting the explicitly generated seeds, also in SoA (strided chunk outputs)."""
+    pkg, c, A, B = setup
+    from closed_chain_motion_planner_b200 import _capi
+
+    n = 2 * 1024 * 1024 + 70_001
+    lay = pkg.CCP_LAYOUT_AOS if layout == "aos" else pkg.CCP_LAYOUT_SOA
+    shape = (n, 14) if layout == "aos" else (14, n)
+    st = torch.cuda.current_stream().cuda_stream
+    a = _capi.SamplerArgs(rng_seed=5, first_index=123, mode=0, wrap_bounds=0, distance=0.0, near_host=None)
+    seeds = torch.empty(shape, dtype=torch.float64, device="cuda")
+    assert c._lib.ccp_generate_seeds(c._h, C.byref(a), n, lay, seeds.data_ptr(), st) == 0
+    ref = c.projectBatch(seeds, layout=lay, want_resid=False)
+    x = torch.empty(shape, dtype=torch.float64, device="cuda")
+    ok = torch.empty(n, dtype=torch.uint8, device="cuda")
+    it = torch.empty(n, dtype=torch.int32, device="cuda")
+    n_ok = torch.zeros(1, dtype=torch.int64, device="cuda")
+    assert c._lib.ccp_sample_project_batch(c._h, C.byref(a), n, lay, x.data_ptr(), ok.data_ptr(), it.data_ptr(), None,
+                                           n_ok.data_ptr(), st) == 0
+    torch.cuda.synchronize()
+    assert not c.pipelineOpen()
+    assert torch.equal(ok, ref.ok) and torch.equal(it, ref.iters) and np.array_equal(_bits(x), _bits(ref.x))
+    assert int(n_ok) == int(ref.ok.sum())
