@@ -243,7 +243,8 @@ def main():
 
     # The path's one exchange step: every rank collects the converged states of all ranks.
     #   fused (default): the projection kernel's epilogue stores each converged state straight into every rank's
-    #     pool in symmetric memory (NVLink P2P stores, ccp_set_gather_peers); an 8-byte count all-gather follows;
+    #     pool in symmetric memory (NVLink P2P stores, ccp_set_gather_peers); the 8-byte counts follow the same way
+    #     (ccp_publish_count) and a device-side barrier of the symmetric-memory group orders them for the readers;
     #   --nccl-gather / no peer memory: NCCL all-gather of the counts and of the padded compacted states.
     cap = gather_capacity(count)
     peer_pools = None
@@ -442,7 +443,8 @@ def main():
                                 "ccp_project_flush, all inside the timed region") if pipelined else "ccp_project_batch per step",
                    "exchange": {"none": "none",
                                 "fused": "per step: the projection kernel stores every converged state into all ranks' pools "
-                                         "(symmetric memory, NVLink P2P stores) + 8-byte NCCL all_gather of the counts",
+                                         "(symmetric memory, NVLink P2P stores); the 8-byte counts follow by peer stores + the "
+                                         "symmetric-memory group's device-side barrier (no collective-library call in the step)",
                                 "nccl": "per step: NCCL all_gather of counts + padded compacted converged states"}[exchange_kind]},
         "projections_per_s": world * count * args.steps / secs,
         "ok_fraction": ok_all / (world * count * args.steps),

@@ -95,6 +95,7 @@ SYMBOLS = {
     "ccp_project_pipeline_open": (C.c_int, [_H]),
     "ccp_sample_project_batch_pipelined": (C.c_int, [_H, C.POINTER(SamplerArgs), _I64, _I32, _P, _P, _P, _P, _P, _P]),
     "ccp_set_gather_peers": (C.c_int, [_H, _I32, _I32, C.POINTER(C.c_uint64), _I64]),
+    "ccp_publish_count": (C.c_int, [_H, _P, _I32, _I32, C.POINTER(C.c_uint64), _P]),
     "ccp_is_satisfied_batch": (C.c_int, [_H, _P, _I64, _I32, _P, _P]),
     "ccp_joint_valid_batch": (C.c_int, [_H, _P, _I64, _I32, _P, _P]),
     "ccp_fk_batch": (C.c_int, [_H, _I32, _P, _I64, _I32, _P, _P]),

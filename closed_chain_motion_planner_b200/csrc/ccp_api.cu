@@ -228,6 +228,19 @@ __global__ void __launch_bounds__(256) ccp_dfma_probe_kernel(double* __restrict_
   if (s == 123.456) sink[0] = s;  // never true; keeps the chain alive
 }
 
+// one warp: this rank's converged count -> slot `rank` of every rank's count array (peer-mapped memory)
+struct ccp_count_peers {
+  long long* counts[CCP_MAX_PEERS];
+};
+__global__ void ccp_publish_count_kernel(const long long* __restrict__ n_ok, const __grid_constant__ ccp_count_peers P,
+                                         int world, int rank) {
+  const long long v = *n_ok;
+  if ((int)threadIdx.x < world) {
+    P.counts[threadIdx.x][rank] = v;
+    __threadfence_system();
+  }
+}
+
 // dispatch helper: (arms, structured alpha) -> template arguments
 #define CCP_DISPATCH_KP(h, CALL)                                                  \
   do {                                                                            \
@@ -737,6 +750,20 @@ int ccp_set_gather_peers(ccp_handle* h, int32_t world, int32_t rank, const uint6
   h->peer_world = world;
   h->peer_rank = rank;
   h->peer_cap = capacity;
+  return CCP_OK;
+}
+
+int ccp_publish_count(ccp_handle* h, const int64_t* n_ok_dev, int32_t world, int32_t rank, const uint64_t* counts_dev_ptrs,
+                      void* stream) {
+  if (!h) return CCP_ERR_INVALID;
+  if (world < 1 || world > CCP_MAX_PEERS || rank < 0 || rank >= world || !n_ok_dev || !counts_dev_ptrs)
+    return set_err(h, CCP_ERR_INVALID, "%s", "publish count: 1 <= world <= 8, 0 <= rank < world, non-null pointers");
+  ccp_count_peers P;
+  for (int p = 0; p < CCP_MAX_PEERS; ++p) P.counts[p] = p < world ? (long long*)(uintptr_t)counts_dev_ptrs[p] : nullptr;
+  device_guard g(h->device);
+  ccp_publish_count_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const long long*)n_ok_dev, P, world, rank);
+  h->launches++;
+  CCP_CUDA(cudaGetLastError());
   return CCP_OK;
 }
 

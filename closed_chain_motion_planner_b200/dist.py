@@ -84,7 +84,12 @@ class PeerPool:
         self.pool = symm.empty((self.world, self.capacity, self.n), dtype=torch.float64, device=dev)
         self.handle = symm.rendezvous(self.pool, self.group)
         self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
-        self.counts = torch.zeros(self.world, dtype=torch.int64, device=dev)
+        # the per-rank counts live in symmetric memory too: every rank stores its own count into all of them
+        self.counts = symm.empty((self.world,), dtype=torch.int64, device=dev)
+        self.counts.zero_()
+        self.counts_handle = symm.rendezvous(self.counts, self.group)
+        self.count_ptrs = [int(p) for p in self.counts_handle.buffer_ptrs]
+        self.use_nccl_counts = False
 
     def attach(self):
         """Point the engine's fused gather at this pool (host-side state only; applies to later launches)."""
@@ -99,11 +104,24 @@ class PeerPool:
         self.c._lib.ccp_set_gather_peers(self.c._h, 0, 0, None, 0)
 
     def exchange_counts(self, n_ok):
-        """All-gather of the 8-byte converged counts (async on the current stream).  Ordered after the projection
-        kernels of this rank on the stream, so a rank that sees counts[r] also sees rank r's rows."""
+        """Exchange of the 8-byte converged counts (async on the current stream): a one-warp kernel stores this
+        rank's count into every rank's count array, then the symmetric-memory group's device-side barrier — ordered
+        after the projection kernels of this rank on the stream, so once it has passed, counts[r] and rank r's rows
+        are both in place.  No collective-library call.  (use_nccl_counts = True: an NCCL all-gather instead.)"""
+        import ctypes as C
+
+        import torch
         import torch.distributed as dist
 
-        dist.all_gather_into_tensor(self.counts, n_ok.view(1), group=self.group)
+        if self.use_nccl_counts:
+            dist.all_gather_into_tensor(self.counts, n_ok.view(1), group=self.group)
+            return self.counts
+        arr = (C.c_uint64 * self.world)(*self.count_ptrs)
+        stream = torch.cuda.current_stream(self.pool.device).cuda_stream
+        rc = self.c._lib.ccp_publish_count(self.c._h, n_ok.data_ptr(), self.world, self.rank, arr, stream)
+        if rc != 0:
+            raise RuntimeError(self.c._lib.ccp_last_error(self.c._h).decode())
+        self.counts_handle.barrier(channel=0)
         return self.counts
 
 

@@ -160,6 +160,11 @@ int ccp_project_pipeline_open(const ccp_handle* h);
  * A peer may read this rank's rows once the projection kernel has completed (e.g. after the count exchange that
  * follows it on the same stream).  world = 0 switches the mode off.                                           */
 int ccp_set_gather_peers(ccp_handle* h, int32_t world, int32_t rank, const uint64_t* pool_dev_ptrs, int64_t capacity);
+/* Stores *n_ok_dev into slot `rank` of every rank's int64[world] count array (counts_dev_ptrs[p] = rank p's array,
+ * peer-mapped), stream-ordered after the projection launches that counted into n_ok_dev: with a barrier of the
+ * symmetric-memory group afterwards no collective library call is needed to exchange the counts.                */
+int ccp_publish_count(ccp_handle* h, const int64_t* n_ok_dev, int32_t world, int32_t rank,
+                      const uint64_t* counts_dev_ptrs, void* stream);
 
 /* ≙ isSatisfied (ConstraintFunction.h:114-120): finite and f0 <= tol1 and f1 <= tol2.       */
 int ccp_is_satisfied_batch(ccp_handle* h, const double* x_dev, int64_t count, int32_t layout,
