@@ -120,20 +120,6 @@ CCP_HD int32_t ccp_lo32(double t) {
 #endif
 }
 
-// v with its sign bit XORed by bit 31 of `flip` (an integer-pipe operation: a negation written as -v
-// is a DADD on the FP64 pipe)
-CCP_HD double ccp_xor_sign(double v, uint32_t flip) {
-#if defined(__CUDA_ARCH__)
-  return __hiloint2double(__double2hiint(v) ^ (int)(flip & 0x80000000u), __double2loint(v));
-#else
-  uint64_t u;
-  memcpy(&u, &v, sizeof u);
-  u ^= (uint64_t)(flip & 0x80000000u) << 32;
-  memcpy(&v, &u, sizeof u);
-  return v;
-#endif
-}
-
 // sin and cos of x by table + short series: x = k pi/64 + r with |r| <= pi/128 (Cody-Waite in two pieces: k P1 is
 // exact for |k| < 2^20, the second product is rounded once); (sin, cos)(k pi/64) come from a 128-entry table of
 // correctly rounded values, sin r / cos r - 1 from their Taylor series to r^7 / r^6 (truncation < 4e-18), and
@@ -648,23 +634,24 @@ CCP_HD bool ccp_is_satisfied(const ccp_model& M, const double* f) {
   }
   return all;
 }
-// jointValid (ConstraintFunction.h:43-55).  Per-arm partial results are independent chains (the epilogue runs with
-// a few lanes and the rest of the warp waiting behind it: latency matters there, not throughput).
+// jointValid (ConstraintFunction.h:43-55).  Branch-free (no short-circuit: the compiler would otherwise predicate a
+// chain of conditional loads), two independent accumulation chains per arm: the epilogue runs with a few lanes and
+// the rest of the warp waiting behind it, so its instruction count and latency both matter.
 template <int K, class XT>
 CCP_HD bool ccp_joint_valid(const ccp_model& M, const XT& x) {
-  bool ok = true;
+  unsigned bad = 0u;
 #pragma unroll
   for (int a = 0; a < K; ++a) {
-    bool lo = true, hi = true;
+    unsigned lo = 0u, hi = 0u;
 #pragma unroll
     for (int i = 0; i < CCPC_DOF; ++i) {
       const double v = x[a * CCPC_DOF + i];
-      lo = lo && !(v < M.lbm[i]);
-      hi = hi && !(v > M.ubm[i]);
+      lo |= (unsigned)(v < M.lbm[i]);
+      hi |= (unsigned)(v > M.ubm[i]);
     }
-    ok = ok && lo && hi;
+    bad |= lo | hi;
   }
-  return ok;
+  return bad == 0u;
 }
 
 // ------------------------------------------------------------------------------------------
