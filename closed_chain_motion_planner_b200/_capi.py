@@ -109,6 +109,9 @@ SYMBOLS = {
     "ccp_enforce_bounds_batch": (C.c_int, [_H, _P, _I64, _I32, _P]),
     "ccp_project_batch_host": (C.c_int, [_H, _P, _I64, _P, _P, _P, _P, _P]),
     "ccp_function_batch_host": (C.c_int, [_H, _P, _I64, _P]),
+    "ccp_sample_project_batch_host": (C.c_int, [_H, C.POINTER(SamplerArgs), _I64, _P, _P, _P, _P, _P]),
+    "ccp_geodesic_batch_host": (C.c_int, [_H, _P, _P, _I64, C.c_double, C.c_double, _I32, _P, _P, _P, _P]),
+    "ccp_ik_sample_batch_host": (C.c_int, [_H, _I32, _P, _I64, _I32, C.c_uint64, C.c_double, _P, C.POINTER(IkOptions), _P, _P, _P]),
     "ccp_jacobian_batch_host": (C.c_int, [_H, _P, _I64, _P]),
     "ccp_arm_fk_batch_host": (C.c_int, [_H, _I32, _P, _I64, _P, _P]),
     "ccp_fp64_peak_probe": (C.c_int, [_H, _I32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

@@ -1106,6 +1106,132 @@ int ccp_project_batch_host(ccp_handle* h, const double* seeds_host, int64_t coun
   return CCP_OK;
 }
 
+// Host-buffer forms of the sampler, the geodesic walk and the IK sampler: what a C++ planner that never touches CUDA
+// calls (include/closed_chain_motion_planner_b200/ProjectedStateSpace.hpp).  Device scratch comes from the handle's
+// stream-ordered pool; synchronous.
+int ccp_sample_project_batch_host(ccp_handle* h, const ccp_sampler_args* a, int64_t count, double* x_out_host,
+                                  uint8_t* ok_host, int32_t* iters_host, double* compact_host, int64_t* n_ok_host) {
+  if (!h) return CCP_ERR_INVALID;
+  if (count < 0) return set_err(h, CCP_ERR_INVALID, "%s", "negative count");
+  if (compact_host && !n_ok_host) return set_err(h, CCP_ERR_INVALID, "%s", "compact output needs n_ok");
+  if (count == 0) {
+    if (n_ok_host) *n_ok_host = 0;
+    return CCP_OK;
+  }
+  CCP_NO_OPEN_PIPELINE(h);
+  std::lock_guard<std::mutex> host_lock(h->host_mu);
+  device_guard g(h->device);
+  const int n = CCPC_DOF * h->model.n_arms;
+  cudaStream_t st = h->hstream[1];
+  const size_t xb = sizeof(double) * n * (size_t)count;
+  char* base = nullptr;
+  const size_t total = (x_out_host ? xb : 0) + (compact_host ? xb : 0) + sizeof(int32_t) * (size_t)count + (size_t)count + 64;
+  CCP_CUDA(cudaMallocFromPoolAsync((void**)&base, total, h->pool, st));
+  char* p = base;
+  double* dx = x_out_host ? (double*)p : nullptr;       p += x_out_host ? xb : 0;
+  double* dc = compact_host ? (double*)p : nullptr;     p += compact_host ? xb : 0;
+  long long* dn = (long long*)p;                         p += 16;
+  int32_t* dit = (int32_t*)p;                            p += sizeof(int32_t) * (size_t)count;
+  uint8_t* dok = (uint8_t*)p;
+  cudaError_t e = cudaMemsetAsync(dn, 0, 16, st);
+  int rc = CCP_OK;
+  if (e == cudaSuccess)
+    rc = sample_project_impl(h, a, count, CCP_LAYOUT_AOS, dx, ok_host ? dok : nullptr, iters_host ? dit : nullptr, dc,
+                             (compact_host || n_ok_host) ? (int64_t*)dn : nullptr, st, false);
+  long long nk = 0;
+  if (rc == CCP_OK && e == cudaSuccess && (compact_host || n_ok_host)) {
+    e = cudaMemcpyAsync(&nk, dn, sizeof nk, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess && n_ok_host) *n_ok_host = nk;
+    if (e == cudaSuccess && compact_host && nk > 0)
+      e = cudaMemcpyAsync(compact_host, dc, sizeof(double) * n * (size_t)nk, cudaMemcpyDeviceToHost, st);
+  }
+  if (rc == CCP_OK && e == cudaSuccess && x_out_host) e = cudaMemcpyAsync(x_out_host, dx, xb, cudaMemcpyDeviceToHost, st);
+  if (rc == CCP_OK && e == cudaSuccess && ok_host) e = cudaMemcpyAsync(ok_host, dok, (size_t)count, cudaMemcpyDeviceToHost, st);
+  if (rc == CCP_OK && e == cudaSuccess && iters_host)
+    e = cudaMemcpyAsync(iters_host, dit, sizeof(int32_t) * (size_t)count, cudaMemcpyDeviceToHost, st);
+  cudaFreeAsync(base, st);
+  cudaError_t e2 = cudaStreamSynchronize(st);
+  if (rc) return rc;
+  if (e != cudaSuccess || e2 != cudaSuccess)
+    return set_err(h, CCP_ERR_CUDA, "ccp_sample_project_batch_host: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+  return CCP_OK;
+}
+
+int ccp_geodesic_batch_host(ccp_handle* h, const double* from_host, const double* to_host, int64_t edges, double delta,
+                            double lambda, int32_t max_states, double* states_host, int32_t* n_states_host,
+                            uint8_t* reached_host, int32_t* iters_host) {
+  int rc = check_common(h, from_host, edges, CCP_LAYOUT_AOS);
+  if (rc) return rc;
+  if (edges > 0 && (!to_host || !states_host || !n_states_host || !reached_host))
+    return set_err(h, CCP_ERR_INVALID, "%s", "null geodesic buffer");
+  if (max_states < 1) return set_err(h, CCP_ERR_INVALID, "%s", "bad geodesic parameters");
+  if (edges == 0) return CCP_OK;
+  std::lock_guard<std::mutex> host_lock(h->host_mu);
+  device_guard g(h->device);
+  const int n = CCPC_DOF * h->model.n_arms;
+  cudaStream_t st = h->hstream[1];
+  const size_t eb = sizeof(double) * n * (size_t)edges, sb = eb * (size_t)max_states;
+  char* base = nullptr;
+  CCP_CUDA(cudaMallocFromPoolAsync((void**)&base, 2 * eb + sb + (2 * sizeof(int32_t) + 1) * (size_t)edges + 64, h->pool, st));
+  double* dfrom = (double*)base;
+  double* dto = (double*)(base + eb);
+  double* dst = (double*)(base + 2 * eb);
+  int32_t* dns = (int32_t*)(base + 2 * eb + sb);
+  int32_t* dit = dns + edges;
+  uint8_t* drc = (uint8_t*)(dit + edges);
+  cudaError_t e = cudaMemcpyAsync(dfrom, from_host, eb, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dto, to_host, eb, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) rc = ccp_geodesic_batch(h, dfrom, dto, edges, delta, lambda, max_states, dst, dns, drc, dit, st);
+  if (rc == CCP_OK && e == cudaSuccess) e = cudaMemcpyAsync(states_host, dst, sb, cudaMemcpyDeviceToHost, st);
+  if (rc == CCP_OK && e == cudaSuccess) e = cudaMemcpyAsync(n_states_host, dns, sizeof(int32_t) * (size_t)edges, cudaMemcpyDeviceToHost, st);
+  if (rc == CCP_OK && e == cudaSuccess) e = cudaMemcpyAsync(reached_host, drc, (size_t)edges, cudaMemcpyDeviceToHost, st);
+  if (rc == CCP_OK && e == cudaSuccess && iters_host)
+    e = cudaMemcpyAsync(iters_host, dit, sizeof(int32_t) * (size_t)edges, cudaMemcpyDeviceToHost, st);
+  cudaFreeAsync(base, st);
+  cudaError_t e2 = cudaStreamSynchronize(st);
+  if (rc) return rc;
+  if (e != cudaSuccess || e2 != cudaSuccess)
+    return set_err(h, CCP_ERR_CUDA, "ccp_geodesic_batch_host: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+  return CCP_OK;
+}
+
+int ccp_ik_sample_batch_host(ccp_handle* h, int32_t arm, const double* T_target_host, int64_t n_targets, int32_t restarts,
+                             uint64_t rng_seed, double sigma, const double* q_ref_host, const ccp_ik_options* opt,
+                             double* q_best_host, uint8_t* ok_host, int32_t* n_success_host) {
+  if (!h) return CCP_ERR_INVALID;
+  if (n_targets < 0) return set_err(h, CCP_ERR_INVALID, "%s", "negative count");
+  if (n_targets > 0 && (!T_target_host || !q_best_host || !ok_host)) return set_err(h, CCP_ERR_INVALID, "%s", "null IK buffer");
+  if (n_targets == 0) return CCP_OK;
+  std::lock_guard<std::mutex> host_lock(h->host_mu);
+  device_guard g(h->device);
+  cudaStream_t st = h->hstream[1];
+  const size_t tb = sizeof(double) * 12 * (size_t)n_targets, qb = sizeof(double) * 7 * (size_t)n_targets;
+  char* base = nullptr;
+  CCP_CUDA(cudaMallocFromPoolAsync((void**)&base, tb + 2 * qb + (sizeof(int32_t) + 1) * (size_t)n_targets + 64, h->pool, st));
+  double* dT = (double*)base;
+  double* dref = (double*)(base + tb);
+  double* dq = (double*)(base + tb + qb);
+  int32_t* dns = (int32_t*)(base + tb + 2 * qb);
+  uint8_t* dok = (uint8_t*)(dns + n_targets);
+  cudaError_t e = cudaMemcpyAsync(dT, T_target_host, tb, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && q_ref_host) e = cudaMemcpyAsync(dref, q_ref_host, qb, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(dq, 0, qb, st);
+  int rc = CCP_OK;
+  if (e == cudaSuccess)
+    rc = ccp_ik_sample_batch(h, arm, dT, n_targets, restarts, rng_seed, sigma, q_ref_host ? dref : nullptr, opt, dq, dok, dns, st);
+  if (rc == CCP_OK && e == cudaSuccess) e = cudaMemcpyAsync(q_best_host, dq, qb, cudaMemcpyDeviceToHost, st);
+  if (rc == CCP_OK && e == cudaSuccess) e = cudaMemcpyAsync(ok_host, dok, (size_t)n_targets, cudaMemcpyDeviceToHost, st);
+  if (rc == CCP_OK && e == cudaSuccess && n_success_host)
+    e = cudaMemcpyAsync(n_success_host, dns, sizeof(int32_t) * (size_t)n_targets, cudaMemcpyDeviceToHost, st);
+  cudaFreeAsync(base, st);
+  cudaError_t e2 = cudaStreamSynchronize(st);
+  if (rc) return rc;
+  if (e != cudaSuccess || e2 != cudaSuccess)
+    return set_err(h, CCP_ERR_CUDA, "ccp_ik_sample_batch_host: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+  return CCP_OK;
+}
+
 int ccp_function_batch_host(ccp_handle* h, const double* x_host, int64_t count, double* f_host) {
   int rc = check_common(h, x_host, count, CCP_LAYOUT_AOS);
   if (rc) return rc;

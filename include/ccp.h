@@ -274,6 +274,17 @@ int ccp_project_batch_host(ccp_handle* h, const double* seeds_host, int64_t coun
                            double* x_out_host, uint8_t* ok_host, uint8_t* converged_host,
                            int32_t* iters_host, double* resid_host);
 int ccp_function_batch_host(ccp_handle* h, const double* x_host, int64_t count, double* f_host);
+/* Host-buffer forms (AOS; synchronous) of ccp_sample_project_batch, ccp_geodesic_batch and ccp_ik_sample_batch, for a
+ * C++ planner that never touches CUDA (include/closed_chain_motion_planner_b200/ProjectedStateSpace.hpp).  Any output
+ * the device form allows to be NULL may be NULL; compact_host receives *n_ok_host rows.                            */
+int ccp_sample_project_batch_host(ccp_handle* h, const ccp_sampler_args* a, int64_t count, double* x_out_host,
+                                  uint8_t* ok_host, int32_t* iters_host, double* compact_host, int64_t* n_ok_host);
+int ccp_geodesic_batch_host(ccp_handle* h, const double* from_host, const double* to_host, int64_t edges, double delta,
+                            double lambda, int32_t max_states, double* states_host, int32_t* n_states_host,
+                            uint8_t* reached_host, int32_t* iters_host);
+int ccp_ik_sample_batch_host(ccp_handle* h, int32_t arm, const double* T_target_host, int64_t n_targets, int32_t restarts,
+                             uint64_t rng_seed, double sigma, const double* q_ref_host, const ccp_ik_options* opt,
+                             double* q_best_host, uint8_t* ok_host, int32_t* n_success_host);
 int ccp_jacobian_batch_host(ccp_handle* h, const double* x_host, int64_t count, double* J_host);
 /* ≙ PandaModel::getTransform / getJacobianMatrix for host 7-vectors (AOS): T_host double[count][12],
  * J_host double[count][42]; either output may be NULL.                                          */
