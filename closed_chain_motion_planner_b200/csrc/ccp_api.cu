@@ -53,8 +53,10 @@ struct ccp_handle {
   bool has_ref;
   ccp_model model;  // host image; passed BY VALUE to every kernel
   long long launches;
-  ccp_launch_rec* d_counters;  // CCP_NUM_COUNTERS launch records: work counter + parked-sample counter
-  unsigned launch_seq;
+  ccp_launch_rec* d_counters;  // 2 * CCP_NUM_COUNTERS launch records (work counter + parked-sample counter): the first
+                               // ring belongs to the projection launches (a parked sample's launch must keep its
+                               // record and descriptor slot until it is adopted), the second to the geodesic launches
+  unsigned launch_seq, geo_seq;
   // grow-only device staging for the *_host entry points
   void* d_stage;
   size_t d_stage_bytes;
@@ -407,6 +409,7 @@ int ccp_create(const ccp_model_desc* model, int32_t device, ccp_handle** out) {
   nh->has_ref = false;
   nh->launches = 0;
   nh->launch_seq = 0;
+  nh->geo_seq = 0;
   nh->d_stage = nullptr;
   nh->d_stage_bytes = 0;
   nh->d_park[0] = nh->d_park[1] = nullptr;
@@ -424,7 +427,7 @@ int ccp_create(const ccp_model_desc* model, int32_t device, ccp_handle** out) {
   device_guard g(device);
   cudaError_t e = g.ok ? cudaSuccess : cudaErrorInvalidDevice;
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&nh->sm_count, cudaDevAttrMultiProcessorCount, device);
-  if (e == cudaSuccess) e = cudaMalloc(&nh->d_counters, CCP_NUM_COUNTERS * sizeof(ccp_launch_rec));
+  if (e == cudaSuccess) e = cudaMalloc(&nh->d_counters, 2 * CCP_NUM_COUNTERS * sizeof(ccp_launch_rec));
   for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&nh->hstream[i], cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreate(&nh->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&nh->ev1);
@@ -920,7 +923,7 @@ int ccp_geodesic_batch(ccp_handle* h, const double* from_dev, const double* to_d
   unsigned slot;
   {
     std::lock_guard<std::mutex> lk(h->mu);
-    slot = h->launch_seq++ % CCP_NUM_COUNTERS;
+    slot = CCP_NUM_COUNTERS + h->geo_seq++ % CCP_NUM_COUNTERS;
     h->launches++;
   }
   unsigned long long* counter = &h->d_counters[slot].work;

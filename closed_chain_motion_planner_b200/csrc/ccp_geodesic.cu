@@ -33,10 +33,20 @@ ccp_geodesic_kernel(const __grid_constant__ ccp_model M, const __grid_constant__
   int it = 0, ns = 0, iters_sum = 0;
   long long e = -1;
   bool need_edge = true;
+  // The first edge of every lane is static and interleaved over the blocks (edge group g -> block g % grid, warp
+  // g / grid), so a batch smaller than the machine — the planner's usual k x new-vertices edges — spreads one warp
+  // per SM before any SM gets a second one; the global counter hands out what lies beyond.
+  const long long static_edges = (long long)gridDim.x * (blockDim.x / 32) * 32;
+  bool first = true;
   for (;;) {
     if (need_edge) {
       // ---- start the next edge (jy_ProjectedStateSpace.cpp:35-50) ----
-      e = claim_next(A.counter);
+      if (first) {
+        first = false;
+        e = ((long long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32 + (threadIdx.x & 31);
+      } else {
+        e = static_edges + claim_next(A.counter);
+      }
       if (e >= A.edges) break;
       const double* fr = A.from + e * n;
       const double* to = A.to + e * n;
@@ -129,7 +139,7 @@ cudaError_t ccp_launch_geodesic(int sm_count, const ccp_model& M, const double* 
   A.max_states = max_states;
   A.delta = delta;
   A.lambda = lambda;
-  long long need = (edges + 127) / 128;
+  long long need = (edges + 31) / 32;  // one warp's worth of edges per block before any block gets more
   long long cap = (long long)sm_count * 3;
   int grid = (int)(need < cap ? need : cap);
   if (grid < 1) grid = 1;
