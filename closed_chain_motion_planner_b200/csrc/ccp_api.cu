@@ -4,11 +4,12 @@
 // Kernel design (DESIGN.md has the long form):
 //   * one THREAD owns one sample: the matrices are 3-vectors and quaternions, nothing is a dense
 //     contraction, so every lane does useful FP64 work and no shuffles sit on the critical path;
-//   * the Newton loop is a persistent LANE-REFILL loop: the moment a lane's sample converges (or hits
-//     the 250-iteration cap) the lane writes its result and claims the next seed from a global
-//     counter, so the 18..250-iteration spread does not idle the warp;
-//   * the model (DH constants, frames, tolerances; 2.1 KB) is a __grid_constant__ kernel parameter:
-//     every use is an immediate constant-bank operand of the DFMA, no loads, no registers;
+//   * the Newton loop is a persistent LANE-REFILL loop (ccp_project.cu): the moment a lane's sample converges
+//     (or hits the 250-iteration cap) the lane writes its result and takes the next work number from its
+//     warp's private chunk, so the 0..250-iteration spread does not idle the warp; the launch tail is packed
+//     (complete launches) or parked for the next launch (pipelined launches);
+//   * the model (DH constants, frames, tolerances; 2.2 KB) is a __grid_constant__ kernel parameter:
+//     every use is a constant-bank operand, never a global load;
 //   * all arithmetic is the shared header ccp_core.h (explicit fma, --fmad=false).
 //
 // Reference behaviour replaced: KinematicChainConstraint::{function,jacobian,project,isSatisfied,
@@ -79,7 +80,7 @@ struct ccp_handle {
   int peer_world, peer_rank;
   long long peer_cap;
   std::mutex mu;
-  std::mutex host_mu;  // the *_host entry points share the stage and the streaming flags: one at a time
+  std::mutex host_mu;  // the *_host entry points share the stage buffer and the private streams: one at a time
   char err[512];
 };
 

@@ -1,5 +1,5 @@
 // ccp_core.h — the engine arithmetic of the closed-chain projection, written once as
-// __host__ __device__ code.  The CUDA kernels (ccp_kernels.cu) are the product; the SAME header
+// __host__ __device__ code.  The CUDA kernels (ccp_project.cu, ccp_geodesic.cu, ccp_api.cu) are the product; the SAME header
 // compiled by g++ (oracle/oracle_b.cpp, test infrastructure only) reproduces the device results
 // bit for bit, because
 //   * every fused multiply-add is an explicit fma() and nothing else may be contracted

@@ -158,9 +158,9 @@ class jy_ProjectedStateSpace:
 class jy_ProjectedStateSampler:
     """WrapperStateSampler + project + enforceBounds (jy_ProjectedStateSpace.cpp:10-29), batched.
 
-    sampleUniform() pops one state from a pool of PROJECTED states; an empty pool is refilled by one launch of
-    ccp_sample_project_batch (seeds generated on the device from the counter-based stream, projection, optional
-    [-pi,pi) wrap, compaction).  Unlike the reference — which ignores project()'s return value (:13) and hands failed
+    sampleUniform() pops one state from a pool of PROJECTED states; an empty pool is refilled by one call of
+    ccp_sample_project_batch (counter-based seed kernel, then the projection kernel with the optional [-pi,pi) wrap
+    and the compaction in its epilogue).  Unlike the reference — which ignores project()'s return value (:13) and hands failed
     projections to the planner — the pool only holds states with project()==true.  sampleUniformNear / sampleGaussian
     draw a small batch around the given state and return the first success (or the wrapped last iterate of the first
     draw if none succeeded, which is what the reference would have returned).
