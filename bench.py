@@ -380,7 +380,7 @@ def main():
         hit = torch.empty(count, dtype=torch.int32).pin_memory()
         hok_np = hok.numpy()
         torch.cuda.synchronize()
-        e_steps = max(3, min(args.steps, 5))
+        e_steps = max(3, min(args.steps, 10))
         zero_copy = os.environ.get("CCP_E2E_ZEROCOPY") == "1"  # experiment: kernel reads/writes pinned host memory
 
         def host_call():
