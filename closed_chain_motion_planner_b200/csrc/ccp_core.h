@@ -65,6 +65,11 @@ struct ccp_arm {
   double fl;            // flange offset along z7
   double sphi, cphi;    // sin/cos of the EE yaw (-pi/4)
   double shphi, chphi;  // half angle
+  // Joint 7 turns about the axis the flange offset and the EE yaw also use, so in the closed-chain code the yaw is
+  // folded into joint 7's angle (frame 7' = the EE frame turned back by nothing: Rz(theta7) Tz(fl) Rz(phi) =
+  // Tz(fl) Rz(theta7 + phi)) and the EE origin seen from frame 6 is a constant:
+  double hq7;           // link[6].hqoff + phi / 2
+  double r6[3];         // (0, 0, fl) pushed down link 7: (t_x, -sin(alpha) fl + t_y, cos(alpha) fl + t_z) of link[6]
 };
 
 struct ccp_pair_ref {
@@ -1407,7 +1412,7 @@ CCP_HD void ccp_residual(const ccp_fwd<K>& F, double* f, double* sv_out) {
 template <bool PANDA, int I, class SC, class XT>
 CCP_HD void ccp_fwd_link_quat(const ccp_arm& A, int a, const XT& x, double* q, SC& S) {
   const ccp_link& L = A.link[I];
-  double h = CCP_FMA(0.5, x[a * CCPC_DOF + I], L.hqoff);
+  double h = CCP_FMA(0.5, x[a * CCPC_DOF + I], (I == 6) ? A.hq7 : L.hqoff);  // joint 7 carries the EE yaw
   double sh, ch;
   ccp_sincos(h, &sh, &ch);
   ccp_qmul_link_rx<PANDA, I>(L, q);
@@ -1431,14 +1436,12 @@ CCP_HD void ccp_forward(const ccp_model& M, const XT& x, SC& S, ccp_fwd<K>& F) {
     ccp_fwd_link_quat<PANDA, 4>(A, a, x, q[a], S);
     ccp_fwd_link_quat<PANDA, 5>(A, a, x, q[a], S);
     ccp_fwd_link_quat<PANDA, 6>(A, a, x, q[a], S);
-    ccp_qmul_rz(q[a], A.chphi, A.shphi);
   }
-  // EE-0 origin: frame 7 of arm 0 -> base 0 -> world
-  double r[3] = {0.0, 0.0, M.arm[0].fl};
+  // EE-0 origin: (0, 0, fl) in frame 7' of arm 0 (on joint 7's axis: no lever arm there, and its image in frame 6
+  // is the constant r6) -> base 0 -> world
+  double r[3] = {M.arm[0].r6[0], M.arm[0].r6[1], M.arm[0].r6[2]};
   {
     const ccp_arm& A = M.arm[0];
-    S.rx(0, 6) = r[0]; S.ry(0, 6) = r[1];
-    ccp_down_pt<PANDA, 6>(A.link[6], S.s(0, 6), S.c(0, 6), r);
     S.rx(0, 5) = r[0]; S.ry(0, 5) = r[1];
     ccp_down_pt<PANDA, 5>(A.link[5], S.s(0, 5), S.c(0, 5), r);
     S.rx(0, 4) = r[0]; S.ry(0, 4) = r[1];
@@ -1481,8 +1484,7 @@ CCP_HD void ccp_forward(const ccp_model& M, const XT& x, SC& S, ccp_fwd<K>& F) {
     S.rx(a, 5) = v[0]; S.ry(a, 5) = v[1];
     ccp_up_pt<PANDA, 6>(A.link[6], S.s(a, 6), S.c(a, 6), v);
     S.rx(a, 6) = v[0]; S.ry(a, 6) = v[1];
-    v[2] -= A.fl;
-    ccp_rot2t(A.cphi, A.sphi, v[0], v[1]);
+    v[2] -= A.fl;  // frame 7' is the EE frame up to this shift along z
     double* tc = F.tc[a - 1];
     tc[0] = v[0]; tc[1] = v[1]; tc[2] = v[2];
     double* qc = F.qc[a - 1];
@@ -1570,11 +1572,15 @@ template <bool PANDA, int I, bool ARM0, class SC, class JT>
 CCP_HD void ccp_jac_link(const ccp_arm& A, int a, int p, const SC& S, double* w, double* m, JT& J) {
   // joint I sees (r, w, m) in frame I:  d f0 / d q = +-(r x w)_z,  d f1 / d q = +-m_z  (+ on arm 0);
   // r = lever arm to the EE-0 origin, left behind by the forward pass
-  const double cz = CCP_FMA(S.rx(a, I), w[1], -(S.ry(a, I) * w[0]));
-  if (ARM0) {
+  if (ARM0 && I == 6) {  // the EE-0 origin lies on joint 7's own axis
+    J.z(p, 0, I) = 0.0;
+    J.z(p, 1, I) = m[2];
+  } else if (ARM0) {
+    const double cz = CCP_FMA(S.rx(a, I), w[1], -(S.ry(a, I) * w[0]));
     J.z(p, 0, I) = cz;
     J.z(p, 1, I) = m[2];
   } else {
+    const double cz = CCP_FMA(S.rx(a, I), w[1], -(S.ry(a, I) * w[0]));
     J.a(p, 0, I) = cz;
     J.a(p, 1, I) = m[2];
   }
@@ -1602,24 +1608,22 @@ CCP_HD void ccp_jacobian(const ccp_model& M, const SC& S, const ccp_fwd<K>& F, J
     const int a = p + 1;
     const double* e = F.e[p];
     const double* d = F.d[p];
-    // arm a: frame EE_a -> frame 7 -> ... -> frame 1
+    // arm a: frame EE_a (= frame 7', the yaw rides on joint 7) -> ... -> frame 1
     {
       const ccp_arm& A = M.arm[a];
       double w[3] = {e[0], e[1], e[2]};
       double m[3] = {d[1], d[2], d[3]};
-      ccp_rot2(A.cphi, A.sphi, w[0], w[1]);
-      ccp_rot2(A.cphi, A.sphi, m[0], m[1]);
       ccp_jac_arm<PANDA, false>(A, a, p, S, w, m, J);
     }
-    // arm 0: e, vec d rotated into EE_0's frame by R_c^T, lever arm starts at the EE-0 origin
+    // arm 0: e rotated into EE_0's frame by R_c^T; vec d rotated the same way is the vector part of
+    // conj(q_c) d q_c = conj(q_ref) q_c (d = q_c conj(q_ref)): one product with a constant instead of a rotation
     {
       const ccp_arm& A = M.arm[0];
       double w[3] = {e[0], e[1], e[2]};
-      double m[3] = {d[1], d[2], d[3]};
       ccp_qrot_inv(F.qc[p], w);
-      ccp_qrot_inv(F.qc[p], m);
-      ccp_rot2(A.cphi, A.sphi, w[0], w[1]);
-      ccp_rot2(A.cphi, A.sphi, m[0], m[1]);
+      double dq[4];
+      ccp_qmul_conj_left(M.ref[p].q0, F.qc[p], dq);
+      double m[3] = {dq[1], dq[2], dq[3]};
       ccp_jac_arm<PANDA, true>(A, 0, p, S, w, m, J);
     }
   }

@@ -94,6 +94,10 @@ static inline int ccp_pack_model(const ccp_model_desc* d, ccp_model* M) {
     A.cphi = cos(s.ee_yaw);
     A.shphi = sin(0.5 * s.ee_yaw);
     A.chphi = cos(0.5 * s.ee_yaw);
+    A.hq7 = A.link[6].hqoff + 0.5 * s.ee_yaw;
+    A.r6[0] = A.link[6].tx;
+    A.r6[1] = -1.0 * A.link[6].sa * A.fl + A.link[6].ty;
+    A.r6[2] = A.link[6].ca * A.fl + A.link[6].tz;
   }
   for (int p = 0; p < CCPC_MAX_ARMS - 1; ++p) {
     M->ref[p].q0[0] = 1.0;
