@@ -68,6 +68,8 @@ struct ccp_arm {
   // Joint 7 turns about the axis the flange offset and the EE yaw also use, so in the closed-chain code the yaw is
   // folded into joint 7's angle (frame 7' = the EE frame turned back by nothing: Rz(theta7) Tz(fl) Rz(phi) =
   // Tz(fl) Rz(theta7 + phi)) and the EE origin seen from frame 6 is a constant:
+  // base of arm 0 seen from THIS arm's base (arms a >= 1): x_a = Rrel x_0 + prel, and q_rel = conj(qwb_a) qwb_0
+  double Rrel[9], prel[3], qrel[4];
   double hq7;           // link[6].hqoff + phi / 2
   double r6[3];         // (0, 0, fl) pushed down link 7: (t_x, -sin(alpha) fl + t_y, cos(alpha) fl + t_z) of link[6]
 };
@@ -1409,14 +1411,23 @@ CCP_HD void ccp_residual(const ccp_fwd<K>& F, double* f, double* sv_out) {
   }
 }
 
-template <bool PANDA, int I, class SC, class XT>
+// FROM_IDENTITY: the chain starts here from the identity quaternion (link 0 of an arm whose base rotation was folded
+// into the other arm's start): q = q_Rx(alpha_0) (x) q_Rz(theta/2) without a multiplication when alpha_0 = 0
+template <bool PANDA, int I, bool FROM_IDENTITY = false, class SC, class XT>
 CCP_HD void ccp_fwd_link_quat(const ccp_arm& A, int a, const XT& x, double* q, SC& S) {
   const ccp_link& L = A.link[I];
   double h = CCP_FMA(0.5, x[a * CCPC_DOF + I], (I == 6) ? A.hq7 : L.hqoff);  // joint 7 carries the EE yaw
   double sh, ch;
   ccp_sincos(h, &sh, &ch);
-  ccp_qmul_link_rx<PANDA, I>(L, q);
-  ccp_qmul_rz(q, ch, sh);
+  if (FROM_IDENTITY && PANDA && I == 0) {
+    q[0] = ch; q[1] = 0.0; q[2] = 0.0; q[3] = sh;
+  } else {
+    if (FROM_IDENTITY) {
+      q[0] = 1.0; q[1] = 0.0; q[2] = 0.0; q[3] = 0.0;
+    }
+    ccp_qmul_link_rx<PANDA, I>(L, q);
+    ccp_qmul_rz(q, ch, sh);
+  }
   double sh2 = sh + sh;
   S.s(a, I) = sh2 * ch;                // sin(theta)
   S.c(a, I) = CCP_FMA(-sh2, sh, 1.0);  // cos(theta)
@@ -1428,8 +1439,15 @@ CCP_HD void ccp_forward(const ccp_model& M, const XT& x, SC& S, ccp_fwd<K>& F) {
 #pragma unroll
   for (int a = 0; a < K; ++a) {
     const ccp_arm& A = M.arm[a];
-    q[a][0] = A.qwb[0]; q[a][1] = A.qwb[1]; q[a][2] = A.qwb[2]; q[a][3] = A.qwb[3];
-    ccp_fwd_link_quat<PANDA, 0>(A, a, x, q[a], S);
+    if (K == 2 && a == 1) {
+      // only the RELATIVE rotation conj(q_1) q_0 is used: arm 0's chain starts from conj(qwb_1) qwb_0 (below) and
+      // arm 1's from the identity, whose product with the first link quaternion is that quaternion itself
+      ccp_fwd_link_quat<PANDA, 0, true>(A, a, x, q[a], S);
+    } else {
+      const double* s0 = (K == 2) ? M.arm[1].qrel : A.qwb;
+      q[a][0] = s0[0]; q[a][1] = s0[1]; q[a][2] = s0[2]; q[a][3] = s0[3];
+      ccp_fwd_link_quat<PANDA, 0>(A, a, x, q[a], S);
+    }
     ccp_fwd_link_quat<PANDA, 1>(A, a, x, q[a], S);
     ccp_fwd_link_quat<PANDA, 2>(A, a, x, q[a], S);
     ccp_fwd_link_quat<PANDA, 3>(A, a, x, q[a], S);
@@ -1455,21 +1473,14 @@ CCP_HD void ccp_forward(const ccp_model& M, const XT& x, SC& S, ccp_fwd<K>& F) {
     S.rx(0, 0) = r[0]; S.ry(0, 0) = r[1];
     ccp_down_pt<PANDA, 0>(A.link[0], S.s(0, 0), S.c(0, 0), r);
   }
-  double p0[3];
-  {
-    const ccp_arm& A = M.arm[0];
-    p0[0] = CCP_FMA(A.Rwb[0], r[0], CCP_FMA(A.Rwb[1], r[1], CCP_FMA(A.Rwb[2], r[2], A.pwb[0])));
-    p0[1] = CCP_FMA(A.Rwb[3], r[0], CCP_FMA(A.Rwb[4], r[1], CCP_FMA(A.Rwb[5], r[2], A.pwb[1])));
-    p0[2] = CCP_FMA(A.Rwb[6], r[0], CCP_FMA(A.Rwb[7], r[1], CCP_FMA(A.Rwb[8], r[2], A.pwb[2])));
-  }
 #pragma unroll
   for (int a = 1; a < K; ++a) {
     const ccp_arm& A = M.arm[a];
-    double e0 = p0[0] - A.pwb[0], e1 = p0[1] - A.pwb[1], e2 = p0[2] - A.pwb[2];
+    // base 0 -> base a in one constant transform (t_wb_a^-1 t_wb_0, packed on the host)
     double v[3];
-    v[0] = CCP_FMA(A.Rwb[0], e0, CCP_FMA(A.Rwb[3], e1, A.Rwb[6] * e2));
-    v[1] = CCP_FMA(A.Rwb[1], e0, CCP_FMA(A.Rwb[4], e1, A.Rwb[7] * e2));
-    v[2] = CCP_FMA(A.Rwb[2], e0, CCP_FMA(A.Rwb[5], e1, A.Rwb[8] * e2));
+    v[0] = CCP_FMA(A.Rrel[0], r[0], CCP_FMA(A.Rrel[1], r[1], CCP_FMA(A.Rrel[2], r[2], A.prel[0])));
+    v[1] = CCP_FMA(A.Rrel[3], r[0], CCP_FMA(A.Rrel[4], r[1], CCP_FMA(A.Rrel[5], r[2], A.prel[1])));
+    v[2] = CCP_FMA(A.Rrel[6], r[0], CCP_FMA(A.Rrel[7], r[1], CCP_FMA(A.Rrel[8], r[2], A.prel[2])));
     ccp_up_pt<PANDA, 0>(A.link[0], S.s(a, 0), S.c(a, 0), v);
     S.rx(a, 0) = v[0]; S.ry(a, 0) = v[1];
     ccp_up_pt<PANDA, 1>(A.link[1], S.s(a, 1), S.c(a, 1), v);

@@ -99,6 +99,18 @@ static inline int ccp_pack_model(const ccp_model_desc* d, ccp_model* M) {
     A.r6[1] = -1.0 * A.link[6].sa * A.fl + A.link[6].ty;
     A.r6[2] = A.link[6].ca * A.fl + A.link[6].tz;
   }
+  // base 0 seen from base a:  Rrel = Rwb_a^T Rwb_0,  prel = Rwb_a^T (pwb_0 - pwb_a),  qrel = conj(qwb_a) qwb_0
+  for (int a = 1; a < d->n_arms; ++a) {
+    ccp_arm& A = M->arm[a];
+    const ccp_arm& Z = M->arm[0];
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c)
+        A.Rrel[3 * r + c] = A.Rwb[0 + r] * Z.Rwb[0 + c] + A.Rwb[3 + r] * Z.Rwb[3 + c] + A.Rwb[6 + r] * Z.Rwb[6 + c];
+      A.prel[r] = A.Rwb[0 + r] * (Z.pwb[0] - A.pwb[0]) + A.Rwb[3 + r] * (Z.pwb[1] - A.pwb[1]) +
+                  A.Rwb[6 + r] * (Z.pwb[2] - A.pwb[2]);
+    }
+    ccp_qmul_conj_left(A.qwb, Z.qwb, A.qrel);
+  }
   for (int p = 0; p < CCPC_MAX_ARMS - 1; ++p) {
     M->ref[p].q0[0] = 1.0;
   }
