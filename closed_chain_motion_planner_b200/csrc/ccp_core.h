@@ -70,6 +70,7 @@ struct ccp_arm {
   // Tz(fl) Rz(theta7 + phi)) and the EE origin seen from frame 6 is a constant:
   // base of arm 0 seen from THIS arm's base (arms a >= 1): x_a = Rrel x_0 + prel, and q_rel = conj(qwb_a) qwb_0
   double Rrel[9], prel[3], qrel[4];
+  double qrel_scaled[4];  // qrel / 64: the unscaled structured link quaternions (1, +-1, 0, 0) of two arms leave 2^6
   double hq7;           // link[6].hqoff + phi / 2
   double r6[3];         // (0, 0, fl) pushed down link 7: (t_x, -sin(alpha) fl + t_y, cos(alpha) fl + t_z) of link[6]
 };
@@ -1166,11 +1167,48 @@ static const double ccp_sc_table_host[1 << CCP_SC_TABLE_BITS][2] = {CCP_SC_TABLE
 static __device__ __align__(16) const double ccp_sc_table_dev[1 << CCP_SC_TABLE_BITS][2] = {CCP_SC_TABLE_ENTRIES};
 #endif
 
+// Constants of the elementary functions.  On the device they sit in the constant bank (pairs come in with one
+// LDCU.128); written as literals each of them costs two UMOVs per use site.
+#define CCP_ELEM_CONSTS                                                                                     \
+  {0x1.45f306dc9c883p+7,  /*  0 512 / pi                        */                                          \
+   0x1.921fb54400000p-8,  /*  1 pi/512, leading 33 bits         */                                          \
+   0x1.0b4611a626331p-42, /*  2 pi/512 - [1] to 53 bits         */                                          \
+   0x1.1111111111111p-7,  /*  3 1/5!                            */                                          \
+   -0x1.5555555555555p-3, /*  4 -1/3!                           */                                          \
+   0x1.5555555555555p-5,  /*  5 1/4!                            */                                          \
+   0x1.561b82ab7f990p-1,  /*  6 tan(3 pi/16)                    */                                          \
+   0x1.975f5e0553158p-3,  /*  7 tan(pi/16)                      */                                          \
+   0x1.a827999fcef32p-2,  /*  8 tan(pi/8)                       */                                          \
+   0x1.921fb54442d18p-1,  /*  9 pi/4                            */                                          \
+   0x1.921fb54442d18p-2,  /* 10 pi/8                            */                                          \
+   0x1.921fb54442d18p+0,  /* 11 pi/2                            */                                          \
+   -0x1.642c8590b2164p-5, /* 12 -1/23                           */                                          \
+   0x1.8618618618618p-5,  /* 13 1/21                            */                                          \
+   -0x1.af286bca1af28p-5, /* 14 -1/19                           */                                          \
+   0x1.e1e1e1e1e1e1ep-5,  /* 15 1/17                            */                                          \
+   -0x1.1111111111111p-4, /* 16 -1/15                           */                                          \
+   0x1.3b13b13b13b14p-4,  /* 17 1/13                            */                                          \
+   -0x1.745d1745d1746p-4, /* 18 -1/11                           */                                          \
+   0x1.c71c71c71c71cp-4,  /* 19 1/9                             */                                          \
+   -0x1.2492492492492p-3, /* 20 -1/7                            */                                          \
+   0x1.999999999999ap-3,  /* 21 1/5                             */                                          \
+   -0x1.5555555555555p-2, /* 22 -1/3                            */                                          \
+   0.0}
+static const double ccp_elem_host[24] = CCP_ELEM_CONSTS;
+#if defined(__CUDACC__)
+static __constant__ __align__(16) double ccp_elem_dev[24] = CCP_ELEM_CONSTS;
+#endif
+#if defined(__CUDA_ARCH__)
+#define CCP_EC(i) ccp_elem_dev[i]
+#else
+#define CCP_EC(i) ccp_elem_host[i]
+#endif
+
 CCP_HD void ccp_sincos(double x, double* s_out, double* c_out) {
-  const double SCALE = 0x1.45f306dc9c883p+7;            // 512 / pi
+  const double SCALE = CCP_EC(0);            // 512 / pi
   const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52: round-to-nearest-integer trick
-  const double P1 = 0x1.921fb54400000p-8;    // pi/512, leading 33 bits
-  const double P2 = 0x1.0b4611a626331p-42;   // pi/512 - P1 to 53 bits
+  const double P1 = CCP_EC(1);               // pi/512, leading 33 bits
+  const double P2 = CCP_EC(2);               // pi/512 - P1 to 53 bits
   const double t = CCP_FMA(x, SCALE, MAGIC);
   const uint32_t idx = (uint32_t)ccp_lo32(t) & ((1u << CCP_SC_TABLE_BITS) - 1u);
   const double k = t - MAGIC;
@@ -1183,9 +1221,9 @@ CCP_HD void ccp_sincos(double x, double* s_out, double* c_out) {
   const double S = ccp_sc_table_host[idx][0], C = ccp_sc_table_host[idx][1];
 #endif
   const double z = r * r;
-  const double ps = CCP_FMA(z, 0x1.1111111111111p-7, -0x1.5555555555555p-3);  // 1/5!, -1/3!
+  const double ps = CCP_FMA(z, CCP_EC(3), CCP_EC(4));                         // 1/5!, -1/3!
   const double sr = CCP_FMA(r * z, ps, r);                                    // sin r
-  const double pc = CCP_FMA(z, 0x1.5555555555555p-5, -0.5);                   // 1/4!, -1/2!
+  const double pc = CCP_FMA(z, CCP_EC(5), -0.5);                              // 1/4!, -1/2!
   const double cm1 = z * pc;                                                  // cos r - 1
   *s_out = CCP_FMA(C, sr, CCP_FMA(S, cm1, S));
   *c_out = CCP_FMA(-S, sr, CCP_FMA(C, cm1, C));
@@ -1199,24 +1237,24 @@ CCP_HD double ccp_atan2_pos(double y, double x) {
   const double den = inv ? y : x;
   // t = num/den in [0,1] is never formed: the region tests and the shifted argument
   // t' = (t - t0)/(1 + t t0) = (num - t0 den)/(den + t0 num) need ONE division in total
-  const bool hi = num > 0x1.561b82ab7f990p-1 * den;   // t > tan(3 pi/16)
-  const bool mid = num > 0x1.975f5e0553158p-3 * den;  // t > tan(pi/16)
-  const double t0 = hi ? 1.0 : (mid ? 0x1.a827999fcef32p-2 : 0.0);   // 1, tan(pi/8), 0
-  const double off = hi ? 0x1.921fb54442d18p-1 : (mid ? 0x1.921fb54442d18p-2 : 0.0);  // pi/4, pi/8, 0
+  const bool hi = num > CCP_EC(6) * den;   // t > tan(3 pi/16)
+  const bool mid = num > CCP_EC(7) * den;  // t > tan(pi/16)
+  const double t0 = hi ? 1.0 : (mid ? CCP_EC(8) : 0.0);          // 1, tan(pi/8), 0
+  const double off = hi ? CCP_EC(9) : (mid ? CCP_EC(10) : 0.0);  // pi/4, pi/8, 0
   double tr = (den > 0.0) ? CCP_FMA(-t0, den, num) / CCP_FMA(t0, num, den) : 0.0;
   double z = tr * tr;
-  double p = CCP_FMA(z, -0x1.642c8590b2164p-5, 0x1.8618618618618p-5);  // -1/23, 1/21
-  p = CCP_FMA(z, p, -0x1.af286bca1af28p-5);                            // -1/19
-  p = CCP_FMA(z, p, 0x1.e1e1e1e1e1e1ep-5);                             // 1/17
-  p = CCP_FMA(z, p, -0x1.1111111111111p-4);                            // -1/15
-  p = CCP_FMA(z, p, 0x1.3b13b13b13b14p-4);                             // 1/13
-  p = CCP_FMA(z, p, -0x1.745d1745d1746p-4);                            // -1/11
-  p = CCP_FMA(z, p, 0x1.c71c71c71c71cp-4);                             // 1/9
-  p = CCP_FMA(z, p, -0x1.2492492492492p-3);                            // -1/7
-  p = CCP_FMA(z, p, 0x1.999999999999ap-3);                             // 1/5
-  p = CCP_FMA(z, p, -0x1.5555555555555p-2);                            // -1/3
+  double p = CCP_FMA(z, CCP_EC(12), CCP_EC(13));  // -1/23, 1/21
+  p = CCP_FMA(z, p, CCP_EC(14));                  // -1/19
+  p = CCP_FMA(z, p, CCP_EC(15));                  // 1/17
+  p = CCP_FMA(z, p, CCP_EC(16));                  // -1/15
+  p = CCP_FMA(z, p, CCP_EC(17));                  // 1/13
+  p = CCP_FMA(z, p, CCP_EC(18));                  // -1/11
+  p = CCP_FMA(z, p, CCP_EC(19));                  // 1/9
+  p = CCP_FMA(z, p, CCP_EC(20));                  // -1/7
+  p = CCP_FMA(z, p, CCP_EC(21));                  // 1/5
+  p = CCP_FMA(z, p, CCP_EC(22));                  // -1/3
   double a = off + CCP_FMA(tr * z, p, tr);
-  return inv ? (0x1.921fb54442d18p+0 - a) : a;
+  return inv ? (CCP_EC(11) - a) : a;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1444,7 +1482,7 @@ CCP_HD void ccp_forward(const ccp_model& M, const XT& x, SC& S, ccp_fwd<K>& F) {
       // arm 1's from the identity, whose product with the first link quaternion is that quaternion itself
       ccp_fwd_link_quat<PANDA, 0, true>(A, a, x, q[a], S);
     } else {
-      const double* s0 = (K == 2) ? M.arm[1].qrel : A.qwb;
+      const double* s0 = (K == 2) ? (PANDA ? M.arm[1].qrel_scaled : M.arm[1].qrel) : A.qwb;
       q[a][0] = s0[0]; q[a][1] = s0[1]; q[a][2] = s0[2]; q[a][3] = s0[3];
       ccp_fwd_link_quat<PANDA, 0>(A, a, x, q[a], S);
     }
@@ -1500,7 +1538,7 @@ CCP_HD void ccp_forward(const ccp_model& M, const XT& x, SC& S, ccp_fwd<K>& F) {
     tc[0] = v[0]; tc[1] = v[1]; tc[2] = v[2];
     double* qc = F.qc[a - 1];
     ccp_qmul_conj_left(q[a], q[0], qc);
-    if (PANDA) {
+    if (PANDA && K != 2) {  // K == 2: the exact factor 1/64 is already in arm 0's start quaternion (qrel_scaled)
       qc[0] *= CCP_PANDA_QSCALE; qc[1] *= CCP_PANDA_QSCALE; qc[2] *= CCP_PANDA_QSCALE; qc[3] *= CCP_PANDA_QSCALE;
     }
     ccp_qmul_conj_right(qc, M.ref[a - 1].q0, F.d[a - 1]);

@@ -110,6 +110,7 @@ static inline int ccp_pack_model(const ccp_model_desc* d, ccp_model* M) {
                   A.Rwb[6 + r] * (Z.pwb[2] - A.pwb[2]);
     }
     ccp_qmul_conj_left(A.qwb, Z.qwb, A.qrel);
+    for (int k = 0; k < 4; ++k) A.qrel_scaled[k] = A.qrel[k] * CCP_PANDA_QSCALE;
   }
   for (int p = 0; p < CCPC_MAX_ARMS - 1; ++p) {
     M->ref[p].q0[0] = 1.0;
