@@ -272,16 +272,35 @@ def main():
         if exchange_kind == "fused":
             peer_pools[i % R].attach()
 
+    # The exchange of step s does not feed step s + 1, so it runs on a side stream behind an event: the ranks' skew
+    # at its barrier / collective is not waited for by the next projection launch.  A ring slot is reused only after
+    # its exchange has finished (event), and the timed region ends after the side stream has drained.
+    xstream = torch.cuda.Stream(device=dev) if world > 1 else None
+    xdone = [None] * R
+
     def exchange(i, o):
-        if exchange_kind == "fused":
-            cts = peer_pools[i % R].exchange_counts(o["n_ok"])
-            torch.maximum(max_counts, cts, out=max_counts)
-        elif exchange_kind == "nccl":
-            gather_converged(o["compact"], o["n_ok"], cap, None, pool, counts_all)
-            torch.maximum(max_counts, counts_all, out=max_counts)
+        if exchange_kind == "none":
+            return
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(xstream):
+            xstream.wait_event(ready)
+            if exchange_kind == "fused":
+                cts = peer_pools[i % R].exchange_counts(o["n_ok"])
+                torch.maximum(max_counts, cts, out=max_counts)
+            else:
+                gather_converged(o["compact"], o["n_ok"], cap, None, pool, counts_all)
+                torch.maximum(max_counts, counts_all, out=max_counts)
+            xdone[i % R] = torch.cuda.Event()
+            xdone[i % R].record()
+
+    def wait_slot(i):
+        if xdone[i % R] is not None:
+            torch.cuda.current_stream().wait_event(xdone[i % R])
 
     def step(i, ev0=None, ev1=None):
         o = outs[i % R]
+        wait_slot(i)
         o["n_ok"].zero_()
         pre_launch(i)
         if ev0 is not None:
@@ -297,6 +316,7 @@ def main():
 
     def flush(i, ev0=None, ev1=None):
         o = outs[i % R]
+        wait_slot(i)
         o["n_ok"].zero_()
         pre_launch(i)
         if ev0 is not None:
@@ -343,6 +363,8 @@ def main():
         o = flush(args.warmup + args.steps, *evs[args.steps])
         ok_counts.append(o["n_ok"].clone())
         iter_sums.append(prev["it"].sum(dtype=torch.int64))
+    if xstream is not None:
+        torch.cuda.current_stream().wait_stream(xstream)  # the exchanges are part of the timed region
     t_end.record()
     torch.cuda.synchronize()
     if world > 1:

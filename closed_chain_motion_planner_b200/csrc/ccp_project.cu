@@ -131,50 +131,46 @@ __device__ __forceinline__ void stage_chunk(ccp_warp_chunk* wc, int b, unsigned 
 
 // Lanes whose sample just finished take the next work numbers.  Returns the number (>= total: none left) and, in
 // `buf_sel`, which of the warp's two seed buffers belongs to the chunk the number came from.
+// Fast path: one shared-memory atomic on the warp's chunk cursor per lane.  Only the lanes that overflow the chunk
+// go on to claim a new one together (leader: global work counter, bulk copy of the seeds, new cursor).
 template <int K, bool SOA>
 __device__ __forceinline__ unsigned claim_chunked(ccp_warp_chunk* wc, double* stage, unsigned long long* mbar,
                                                    const ccp_project_args& A, const ccp_work& W, volatile int* s_tail,
                                                    int& buf_sel) {
   constexpr int n = CCPC_DOF * K;
-  const unsigned mask = __activemask();
+  // every lane of the event reads the chunk's end and sequence number BEFORE any of them may replace the chunk
+  const unsigned u0 = atomicAdd(&wc->next, 1u);
+  const unsigned end0 = *(volatile unsigned*)&wc->end;
+  const unsigned seq0 = *(volatile unsigned*)&wc->seq;
+  if (u0 < end0) {
+    buf_sel = (int)(seq0 & 1u);
+    return u0;
+  }
+  const unsigned mask = __activemask();  // the lanes that found the chunk empty
   const int lane = threadIdx.x & 31;
   const int leader = __ffs(mask) - 1;
   const unsigned need = __popc(mask);
   const unsigned rank = __popc(mask & ((1u << lane) - 1u));
-  unsigned base0 = 0, left = 0, base1 = W.total, seq = 0;
+  unsigned base1 = W.total;
   if (lane == leader) {
-    base0 = wc->next;
-    left = wc->end - base0;
-    seq = wc->seq;
-    if (left >= need) {
-      wc->next = base0 + need;
-      left = need;  // everybody is served from the current chunk
-    } else {
-      unsigned end1 = W.total;
-      if (!*s_tail) {
-        base1 = W.first_dynamic + atomicAdd((unsigned int*)A.counter, CCP_CLAIM_CHUNK);
-        if (base1 > W.total) base1 = W.total;
-        end1 = (W.total - base1 < CCP_CLAIM_CHUNK) ? W.total : base1 + CCP_CLAIM_CHUNK;
-        if (end1 - base1 < CCP_CLAIM_CHUNK) *s_tail = 1;  // the work has run dry: the block enters its tail
-      }
-      seq += 1u;
-      const int b = (int)(seq & 1u);
-      stage_chunk<K, SOA>(wc, b, base1, end1, stage + b * (int)CCP_CLAIM_CHUNK * n, mbar + b, A, W);
-      const unsigned take = need - left;  // <= 32 = CCP_CLAIM_CHUNK
-      wc->next = (end1 - base1 < take) ? end1 : base1 + take;
-      wc->end = end1;
-      wc->seq = seq;
+    unsigned end1 = W.total;
+    if (!*s_tail) {
+      base1 = W.first_dynamic + atomicAdd((unsigned int*)A.counter, CCP_CLAIM_CHUNK);
+      if (base1 > W.total) base1 = W.total;
+      end1 = (W.total - base1 < CCP_CLAIM_CHUNK) ? W.total : base1 + CCP_CLAIM_CHUNK;
+      if (end1 - base1 < CCP_CLAIM_CHUNK) *s_tail = 1;  // the work has run dry: the block enters its tail
     }
+    const unsigned seq = seq0 + 1u;
+    const int b = (int)(seq & 1u);
+    stage_chunk<K, SOA>(wc, b, base1, end1, stage + b * (int)CCP_CLAIM_CHUNK * n, mbar + b, A, W);
+    wc->end = end1;
+    wc->seq = seq;
+    wc->next = (end1 - base1 < need) ? end1 : base1 + need;  // need <= 32 = CCP_CLAIM_CHUNK
   }
-  base0 = __shfl_sync(mask, base0, leader);
-  left = __shfl_sync(mask, left, leader);
   base1 = __shfl_sync(mask, base1, leader);
-  seq = __shfl_sync(mask, seq, leader);
-  // lanes ranked below `left` are served from the chunk that was current on entry; if a new chunk was claimed
-  // (seq advanced) that is the previous buffer.  A number past the chunk's end is >= total: no work for the lane.
-  const bool from_old = rank < left;
-  buf_sel = (int)((from_old && left < need) ? ((seq - 1u) & 1u) : (seq & 1u));
-  return from_old ? base0 + rank : base1 + (rank - left);
+  buf_sel = (int)((seq0 + 1u) & 1u);
+  // a number past the chunk's end is >= total: no work for the lane
+  return base1 + rank;
 }
 
 // Work number u -> the lane's sample: state x, index within its launch, iteration count | launch slot << 16.
