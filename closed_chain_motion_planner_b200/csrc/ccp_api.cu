@@ -1059,6 +1059,7 @@ int ccp_project_batch_host(ccp_handle* h, const double* seeds_host, int64_t coun
   chunk = (chunk + 15) / 16 * 16;  // chunks never share a 128 B line of any output array
   parts = (int)((count + chunk - 1) / chunk);
   cudaStream_t sC = h->hstream[0], sK = h->hstream[1], sD = h->hstream[2];
+  if (parts == 1) sC = sD = sK;  // a small batch: one stream, no events — what a planner projecting state by state pays
   auto copy_out = [&](int c) -> int {
     const int64_t off = (int64_t)c * chunk;
     const int64_t cn = (count - off < chunk) ? (count - off) : chunk;
@@ -1075,8 +1076,10 @@ int ccp_project_batch_host(ccp_handle* h, const double* seeds_host, int64_t coun
     const int64_t off = (int64_t)c * chunk;
     const int64_t cn = (count - off < chunk) ? (count - off) : chunk;
     CCP_CUDA(cudaMemcpyAsync(dx + off * n, seeds_host + off * n, sizeof(double) * n * cn, cudaMemcpyHostToDevice, sC));
-    CCP_CUDA(cudaEventRecord(h->ev_chunk_in[c], sC));
-    CCP_CUDA(cudaStreamWaitEvent(sK, h->ev_chunk_in[c], 0));
+    if (parts > 1) {
+      CCP_CUDA(cudaEventRecord(h->ev_chunk_in[c], sC));
+      CCP_CUDA(cudaStreamWaitEvent(sK, h->ev_chunk_in[c], 0));
+    }
     ccp_project_args A;
     memset(&A, 0, sizeof A);
     A.seeds = dx + off * n;
@@ -1088,7 +1091,7 @@ int ccp_project_batch_host(ccp_handle* h, const double* seeds_host, int64_t coun
     A.count = cn;
     rc = launch_project(h, A, CCP_LAYOUT_AOS, sK, /*defer=*/parts > 1);
     if (rc) return rc;
-    CCP_CUDA(cudaEventRecord(h->ev_chunk_k[c], sK));
+    if (parts > 1) CCP_CUDA(cudaEventRecord(h->ev_chunk_k[c], sK));
     if (c > 0) {  // launch c completed chunk c - 1
       CCP_CUDA(cudaStreamWaitEvent(sD, h->ev_chunk_k[c], 0));
       rc = copy_out(c - 1);
@@ -1101,12 +1104,14 @@ int ccp_project_batch_host(ccp_handle* h, const double* seeds_host, int64_t coun
     rc = launch_project(h, F, CCP_LAYOUT_AOS, sK, false);
     if (rc) return rc;
   }
-  CCP_CUDA(cudaEventRecord(h->ev1, sK));
-  CCP_CUDA(cudaStreamWaitEvent(sD, h->ev1, 0));
+  if (parts > 1) {
+    CCP_CUDA(cudaEventRecord(h->ev1, sK));
+    CCP_CUDA(cudaStreamWaitEvent(sD, h->ev1, 0));
+  }
   rc = copy_out(parts - 1);
   if (rc) return rc;
   CCP_CUDA(cudaStreamSynchronize(sD));
-  CCP_CUDA(cudaStreamSynchronize(sK));
+  if (parts > 1) CCP_CUDA(cudaStreamSynchronize(sK));
   return CCP_OK;
 }
 
