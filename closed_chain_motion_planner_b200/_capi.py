@@ -43,8 +43,9 @@ class Options(C.Structure):
     _fields_ = [
         ("step", C.c_double),
         ("max_iter", C.c_int32),
-        ("reserved", C.c_int32),
+        ("clamp", C.c_int32),
         ("joint_margin", C.c_double),
+        ("damping", C.c_double),
     ]
 
 

@@ -247,9 +247,14 @@ class KinematicChainConstraint:
         no-op for drop-in compatibility; use setOptions(max_iter=...) to really change the cap."""
         self._ompl_max_iterations = int(n)
 
-    def setOptions(self, step: float = 0.30, max_iter: int = 250, joint_margin: float = 1e-3):
+    def setOptions(self, step: float = 0.30, max_iter: int = 250, joint_margin: float = 1e-3, damping: float = 0.0,
+                   clamp: bool = False):
+        """step / cap / margin of the reference (ConstraintFunction.h:71,26,45) plus two opt-in modes that the
+        reference does not have and parity runs keep off: `damping` = lambda^2 of a damped-least-squares step,
+        `clamp` = clamp every iterate to the joint limits."""
         self._need()
-        o = _capi.Options(step=step, max_iter=max_iter, reserved=0, joint_margin=joint_margin)
+        o = _capi.Options(step=step, max_iter=max_iter, clamp=1 if clamp else 0, joint_margin=joint_margin,
+                          damping=damping)
         _check(self._lib, self._h, self._lib.ccp_set_options(self._h, C.byref(o)))
 
     def function(self, x, out=None):

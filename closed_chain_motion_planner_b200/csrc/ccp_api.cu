@@ -538,10 +538,14 @@ int ccp_set_options(ccp_handle* h, const ccp_options* opt) {
   if (!h || !opt) return CCP_ERR_INVALID;
   if (!(opt->step > 0) || opt->max_iter < 0 || opt->max_iter > 65535 || !(opt->joint_margin >= 0))
     return set_err(h, CCP_ERR_INVALID, "%s", "bad options (step > 0, 0 <= max_iter <= 65535, joint_margin >= 0)");
+  if (!(opt->damping >= 0) || (opt->clamp != 0 && opt->clamp != 1))
+    return set_err(h, CCP_ERR_INVALID, "%s", "bad options (damping >= 0, clamp 0 or 1)");
   CCP_NO_OPEN_PIPELINE(h);
   h->model.step = opt->step;
   h->model.max_iter = opt->max_iter;
   ccp_model_set_margin(&h->model, opt->joint_margin);
+  h->model.damping = opt->damping;
+  h->model.clamp = opt->clamp;
   return CCP_OK;
 }
 
@@ -550,8 +554,9 @@ int ccp_get_options(const ccp_handle* h, ccp_options* opt, double* tol_position,
   if (opt) {
     opt->step = h->model.step;
     opt->max_iter = h->model.max_iter;
-    opt->reserved = 0;
+    opt->clamp = h->model.clamp;
     opt->joint_margin = h->model.margin;
+    opt->damping = h->model.damping;
   }
   if (tol_position) *tol_position = h->model.tol_p;
   if (tol_rotation) *tol_rotation = h->model.tol_r;

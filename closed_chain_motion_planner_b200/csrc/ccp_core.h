@@ -91,6 +91,10 @@ struct ccp_model {
   double tan2_r;        // tan^2(tol_r / 2): f1 > tol_r  <=>  |vec d|^2 > tan2_r d_w^2   (0 < tol_r < pi)
   double step;          // 0.30
   double margin;        // 1e-3
+  // opt-in modes of the north star's description, OFF in the reference and by default (parity):
+  double damping;       // lambda^2 added to the diagonal of the rows' Gram matrix (damped least squares); 0 = min-norm
+  int32_t clamp;        // 1: clamp every iterate to [lb, ub] (the reference only CHECKS the limits at the end)
+  int32_t reserved2;
   double lb[CCPC_DOF], ub[CCPC_DOF];
   double lbm[CCPC_DOF], ubm[CCPC_DOF];  // lb + margin, ub - margin (jointValid's thresholds, precomputed)
   ccp_arm arm[CCPC_MAX_ARMS];
@@ -1716,6 +1720,9 @@ CCP_HD void ccp_newton_step(const ccp_model& M, const ccp_fwd<K>& F, const JT& J
             for (int i = 1; i < CCPC_DOF; ++i) acca = CCP_FMA(J.a(p, ri, i), J.a(p, rj, i), acca);
             acc = acc + acca;
           }
+          // damped least squares J J^T + lambda^2 I, written for the unnormalised rows (J = D g):
+          // g g^T + lambda^2 D^-2 with D^-2 = diag(f0^2, |vec d|^2).  lambda^2 = 0 (the reference) leaves acc as is.
+          if (I == Jx) acc = CCP_FMA(M.damping, (ri == 0) ? F.e2[p] : F.sv2[p], acc);
           G[I][Jx] = acc;
         }
   double y[m];
@@ -1797,6 +1804,20 @@ CCP_HD void ccp_newton_step(const ccp_model& M, const ccp_fwd<K>& F, const JT& J
     }
 }
 
+// opt-in joint-limit clamping of an iterate (off in the reference: ConstraintFunction.h:57-82 never clamps)
+template <int K, class XT>
+CCP_HD void ccp_clamp_to_limits(const ccp_model& M, XT& x) {
+#pragma unroll
+  for (int a = 0; a < K; ++a)
+#pragma unroll
+    for (int i = 0; i < CCPC_DOF; ++i) {
+      double v = x[a * CCPC_DOF + i];
+      v = (v < M.lb[i]) ? M.lb[i] : v;
+      v = (v > M.ub[i]) ? M.ub[i] : v;
+      x[a * CCPC_DOF + i] = v;
+    }
+}
+
 // Dense m x n Jacobian (row-major), the layout jacobian() returns: J = D g with D = diag(1/f0, s/|vec d|)
 // (a row whose residual vanishes is 0), arm-a entries with their sign restored.
 template <int K>
@@ -1838,6 +1859,7 @@ CCP_HD void ccp_project_one(const ccp_model& M, double* x, double* f_out, int32_
     ++it;
     ccp_jacobian<K, PANDA>(M, S, F, J);
     ccp_newton_step<K>(M, F, J, x);
+    if (M.clamp) ccp_clamp_to_limits<K>(M, x);
     ccp_forward<K, PANDA>(M, x, S, F);
   }
   const bool conv = ccp_converged<K>(M, F);

@@ -84,6 +84,7 @@ ccp_geodesic_kernel(const __grid_constant__ ccp_model M, const __grid_constant__
       ++it;
       ccp_jacobian<K, PANDA>(M, S, F, J);
       ccp_newton_step<K>(M, F, J, x);
+      if (M.clamp) ccp_clamp_to_limits<K>(M, x);
     } else {
       // ---- the projection of this step finished: bookkeeping of the walk ----
       iters_sum += it;

@@ -396,6 +396,7 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
         ++it;
         ccp_jacobian<K, PANDA>(M, S, F, J);
         ccp_newton_step<K>(M, F, J, x);
+        if (M.clamp) ccp_clamp_to_limits<K>(M, x);
       } else {
         // ---- epilogue of this sample (ConstraintFunction.h:75-81), then refill the lane ----
         const bool cv = ccp_converged<K>(M, F);

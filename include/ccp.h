@@ -67,8 +67,10 @@ typedef struct ccp_model_desc {
 typedef struct ccp_options {
   double step;          /* 0.30  ConstraintFunction.h:71 */
   int32_t max_iter;     /* 250   ConstraintFunction.h:26,68 */
-  int32_t reserved;
+  int32_t clamp;        /* 0     1 = clamp every iterate to [lb, ub]; the reference never clamps (parity: keep 0) */
   double joint_margin;  /* 1e-3  ConstraintFunction.h:45 */
+  double damping;       /* 0     lambda^2 of a damped-least-squares step; the reference's step is the undamped
+                                 minimum-norm one, JacobiSVD::solve at ConstraintFunction.h:71 (parity: keep 0) */
 } ccp_options;
 
 typedef struct ccp_handle ccp_handle;

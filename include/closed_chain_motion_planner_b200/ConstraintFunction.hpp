@@ -100,8 +100,10 @@ class KinematicChainConstraint {
   // The reference's setMaxIterations(1000) (ConstrainedPlanningCommon.cpp:129) sets an OMPL base member the loop
   // never reads (the loop uses the private 250, ConstraintFunction.h:26): kept as a no-op.
   void setMaxIterations(unsigned int) {}
-  void setOptions(double step, int max_iter, double joint_margin) {
-    ccp_options o{step, max_iter, 0, joint_margin};
+  // damping (lambda^2 of a damped-least-squares step) and clamp (clamp every iterate to the limits) are opt-in modes
+  // the reference does not have; parity runs keep them at 0
+  void setOptions(double step, int max_iter, double joint_margin, double damping = 0.0, bool clamp = false) {
+    ccp_options o{step, max_iter, clamp ? 1 : 0, joint_margin, damping};
     check(ccp_set_options(need(), &o));
   }
 

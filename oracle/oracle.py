@@ -195,8 +195,9 @@ class OracleB:
     def set_tolerance(self, t1, t2):
         self.lib.ob_set_tolerance(self._buf, C.c_double(t1), C.c_double(t2))
 
-    def set_options(self, step=0.30, max_iter=250, margin=1e-3):
+    def set_options(self, step=0.30, max_iter=250, margin=1e-3, damping=0.0, clamp=False):
         self.lib.ob_set_options(self._buf, C.c_double(step), C.c_int(max_iter), C.c_double(margin))
+        self.lib.ob_set_modes(self._buf, C.c_double(damping), C.c_int(1 if clamp else 0))
 
     def function(self, x):
         x = _as_states(x, self.n)

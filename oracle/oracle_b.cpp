@@ -163,6 +163,7 @@ void ob_set_tolerance(ccp_model* M, double t1, double t2) { ccp_model_set_tolera
 void ob_set_options(ccp_model* M, double step, int max_iter, double margin) {
   M->step = step; M->max_iter = max_iter; ccp_model_set_margin(M, margin);
 }
+void ob_set_modes(ccp_model* M, double damping, int clamp) { M->damping = damping; M->clamp = clamp; }
 
 void ob_function_batch(const ccp_model* M, const double* x, int64_t count, double* f) {
 #define OB_CALL(K, P) function_batch<K, P>(M, x, count, f, nullptr)

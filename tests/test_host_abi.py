@@ -34,7 +34,7 @@ def test_struct_sizes_match_header():
     # ccp_arm_desc: 4*7 + 12 + 2 doubles; ccp_model_desc: 2 int32 + 3 arms + 14 doubles
     assert C.sizeof(_capi.ArmDesc) == 8 * (28 + 12 + 2)
     assert C.sizeof(_capi.ModelDesc) == 8 + 3 * C.sizeof(_capi.ArmDesc) + 8 * 14
-    assert C.sizeof(_capi.Options) == 24
+    assert C.sizeof(_capi.Options) == 32
 
 
 def test_default_model_matches_python_twin():
