@@ -109,6 +109,8 @@ SYMBOLS = {
     "ccp_geodesic_batch": (C.c_int, [_H, _P, _P, _I64, C.c_double, C.c_double, _I32, _P, _P, _P, _P, _P]),
     "ccp_enforce_bounds_batch": (C.c_int, [_H, _P, _I64, _I32, _P]),
     "ccp_project_batch_host": (C.c_int, [_H, _P, _I64, _P, _P, _P, _P, _P]),
+    "ccp_project_batch_host_submit": (C.c_int, [_H, _P, _I64, _P, _P, _P, _P, _P, C.POINTER(_I64)]),
+    "ccp_project_batch_host_wait": (C.c_int, [_H, _I64]),
     "ccp_function_batch_host": (C.c_int, [_H, _P, _I64, _P]),
     "ccp_sample_project_batch_host": (C.c_int, [_H, C.POINTER(SamplerArgs), _I64, _P, _P, _P, _P, _P]),
     "ccp_geodesic_batch_host": (C.c_int, [_H, _P, _P, _I64, C.c_double, C.c_double, _I32, _P, _P, _P, _P]),

@@ -351,6 +351,32 @@ class KinematicChainConstraint:
             rs.ctypes.data))
         return ProjectResult(xo, ok, cv, it, rs)
 
+    def submitHostBatch(self, X: np.ndarray, want_resid: bool = False):
+        """Streaming host path (ccp_project_batch_host_submit): enqueue a host batch and return (ticket, result); the
+        result arrays are complete after waitHostBatch(ticket).  Submit the next batch before waiting for this one and
+        the GPU never idles on a batch's stragglers nor on its copies.  X must stay alive until the wait."""
+        self._need()
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        if X.ndim != 2 or X.shape[1] != self.n_:
+            raise ValueError(f"states must have shape (count, {self.n_})")
+        count = X.shape[0]
+        xo = np.empty_like(X)
+        ok = np.zeros(count, np.uint8)
+        cv = np.zeros(count, np.uint8)
+        it = np.zeros(count, np.int32)
+        rs = np.zeros((count, self.getCoDimension())) if want_resid else None
+        t = C.c_int64(0)
+        _check(self._lib, self._h, self._lib.ccp_project_batch_host_submit(
+            self._h, X.ctypes.data, count, xo.ctypes.data, ok.ctypes.data, cv.ctypes.data, it.ctypes.data,
+            rs.ctypes.data if rs is not None else None, C.byref(t)))
+        res = ProjectResult(xo, ok, cv, it, rs)
+        res._keepalive = X
+        return int(t.value), res
+
+    def waitHostBatch(self, ticket: int):
+        self._need()
+        _check(self._lib, self._h, self._lib.ccp_project_batch_host_wait(self._h, int(ticket)))
+
     def flush(self, compact=None, n_ok=None, stream=None):
         """Completes the samples parked by pipelined projections (ccp_project_flush); async on the current stream."""
         self._need()

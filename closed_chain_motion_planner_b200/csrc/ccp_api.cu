@@ -39,6 +39,8 @@
 // handle
 // ------------------------------------------------------------------------------------------
 #define CCP_NUM_COUNTERS 64
+#define CCP_MAX_AGE 40          /* < CCP_NUM_DESC: a launch's descriptor slot outlives every sample it parked */
+#define CCP_HOST_LAG_DEFAULT 6
 #define CCP_HOST_MAX_CHUNKS 24  /* < CCP_NUM_DESC / 2: every chunk launch of a host call stays pipelined */
 
 // per-launch device record (ring of CCP_NUM_COUNTERS): zeroed by ONE stream-ordered memset before the launch
@@ -46,6 +48,28 @@ struct ccp_launch_rec {
   unsigned long long work;  // dynamic work counter of the projection / geodesic kernel
   unsigned parked;          // samples the (pipelined) launch parked
   unsigned pad;
+};
+
+// One submitted host batch of the streaming host path (ccp_project_batch_host_submit / _wait)
+struct ccp_host_call {
+  int64_t ticket;      // 0 = never used
+  bool finished;       // results are complete in the caller's host buffers (or the slot is free)
+  int64_t count, chunk;
+  int parts, copied;    // chunks of the batch / chunks whose D2H copies are enqueued
+  int64_t first_launch; // number (ccp_handle::host_launches) of the launch that projected chunk 0
+  double* x_out_host;
+  uint8_t* ok_host;
+  uint8_t* conv_host;
+  int32_t* iters_host;
+  double* resid_host;
+  void* stage;
+  size_t stage_bytes;
+  double* dx;
+  double* dres;
+  int32_t* dit;
+  uint8_t* dok;
+  uint8_t* dcv;
+  cudaEvent_t done;
 };
 
 struct ccp_handle {
@@ -74,6 +98,9 @@ struct ccp_handle {
   bool pipeline_open;      // parked samples exist
   int pipe_sig;            // layout | gen << 1 of the launches in the pipeline (same kernel instantiation)
   int pipe_launches;       // pipelined launches since the pipeline opened (slot ring safety)
+  ccp_host_call hcall[2];  // streaming host path: two batches in flight, each with its own device stage
+  int64_t next_ticket;
+  int64_t host_launches;   // chunk launches of the host path so far
   cudaMemPool_t pool;  // stream-ordered scratch of the sampler path; keeps its memory between calls
   // fused all-gather target (ccp_set_gather_peers)
   double* peer_pool[CCP_MAX_PEERS];
@@ -322,7 +349,6 @@ static int launch_project(ccp_handle* h, ccp_project_args& A, int layout, cudaSt
     if (rc) return rc;
   }
   if (A.count == 0 && !h->pipeline_open) return CCP_OK;
-  if (defer && h->pipe_launches >= CCP_NUM_DESC / 2) defer = false;  // a parked sample must find its launch's slot
   unsigned slot;
   {
     std::lock_guard<std::mutex> lk(h->mu);
@@ -331,6 +357,7 @@ static int launch_project(ccp_handle* h, ccp_project_args& A, int layout, cudaSt
   }
   A.counter = &h->d_counters[slot].work;
   A.slot = slot % CCP_NUM_DESC;
+  if (A.max_age == 0 || A.max_age > CCP_MAX_AGE) A.max_age = CCP_MAX_AGE;
   if (h->peer_world > 0 && A.n_ok) {
     A.peer_world = h->peer_world;
     A.peer_row0 = (long long)h->peer_rank * h->peer_cap;
@@ -432,6 +459,13 @@ int ccp_create(const ccp_model_desc* model, int32_t device, ccp_handle** out) {
   for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&nh->hstream[i], cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreate(&nh->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&nh->ev1);
+  nh->next_ticket = 1;
+  nh->host_launches = 0;
+  for (int i = 0; i < 2; ++i) {
+    memset(&nh->hcall[i], 0, sizeof nh->hcall[i]);
+    nh->hcall[i].finished = true;
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&nh->hcall[i].done, cudaEventDisableTiming);
+  }
   nh->pool = nullptr;
   if (e == cudaSuccess) {
     cudaMemPoolProps props;
@@ -465,6 +499,10 @@ void ccp_destroy(ccp_handle* h) {
   cudaDeviceSynchronize();
   if (h->d_counters) cudaFree(h->d_counters);
   if (h->d_stage) cudaFree(h->d_stage);
+  for (int i = 0; i < 2; ++i) {
+    if (h->hcall[i].stage) cudaFree(h->hcall[i].stage);
+    if (h->hcall[i].done) cudaEventDestroy(h->hcall[i].done);
+  }
   if (h->pool) cudaMemPoolDestroy(h->pool);
   if (h->d_park[0]) cudaFree(h->d_park[0]);
   if (h->d_park[1]) cudaFree(h->d_park[1]);
@@ -1026,28 +1064,125 @@ int ccp_enforce_bounds_batch(ccp_handle* h, double* x_dev, int64_t count, int32_
 // for the whole call however fine the chunks are, and chunk c's outputs are complete after launch c + 1).  Everything
 // is ordered by events; the host only waits at the end.  With pinned caller buffers the copies run at PCIe rate
 // behind the kernels; with pageable buffers CUDA stages them and the call is still correct.
-int ccp_project_batch_host(ccp_handle* h, const double* seeds_host, int64_t count, double* x_out_host,
-                           uint8_t* ok_host, uint8_t* converged_host, int32_t* iters_host, double* resid_host) {
-  int rc = check_common(h, seeds_host, count, CCP_LAYOUT_AOS);
+// ---- host path ----------------------------------------------------------------------------------------------------
+// A host batch is cut into chunks that flow through three private streams — H2D chunk c | pipelined projection launch c
+// | D2H of the chunk launch c has COMPLETED — ordered by events.  A pipelined launch parks what is still iterating when
+// its seed list runs dry and the next launch adopts it, so a sample may be carried through several launches; the
+// launches of the host path carry max_age = lag, so that launch c + lag finishes whatever chunk c still has in flight
+// and chunk c's outputs are copied behind launch c + lag.  Whatever is pending at the end is completed by one flush
+// launch.  ccp_project_batch_host_submit returns a ticket without waiting and ccp_project_batch_host_wait blocks until
+// that batch's results are in the caller's buffers: with two batches in flight the next batch's launches complete the
+// previous batch's last chunks, no launch tail is paid and the copies of one batch run behind the kernels of the other.
+static int host_lag() {
+  static int lag = -1;
+  if (lag < 0) {
+    const char* e = getenv("CCP_HOST_LAG");
+    lag = e ? atoi(e) : CCP_HOST_LAG_DEFAULT;
+    if (lag < 1) lag = 1;
+    if (lag > CCP_MAX_AGE) lag = CCP_MAX_AGE;
+  }
+  return lag;
+}
+
+static int host_copy_out(ccp_handle* h, const ccp_host_call& c, int chunk_index, cudaStream_t sD) {
+  const int n = CCPC_DOF * h->model.n_arms, m = 2 * (h->model.n_arms - 1);
+  const int64_t off = (int64_t)chunk_index * c.chunk;
+  const int64_t cn = (c.count - off < c.chunk) ? (c.count - off) : c.chunk;
+  if (c.x_out_host)
+    CCP_CUDA(cudaMemcpyAsync(c.x_out_host + off * n, c.dx + off * n, sizeof(double) * n * cn, cudaMemcpyDeviceToHost, sD));
+  if (c.ok_host) CCP_CUDA(cudaMemcpyAsync(c.ok_host + off, c.dok + off, (size_t)cn, cudaMemcpyDeviceToHost, sD));
+  if (c.conv_host) CCP_CUDA(cudaMemcpyAsync(c.conv_host + off, c.dcv + off, (size_t)cn, cudaMemcpyDeviceToHost, sD));
+  if (c.iters_host) CCP_CUDA(cudaMemcpyAsync(c.iters_host + off, c.dit + off, sizeof(int32_t) * cn, cudaMemcpyDeviceToHost, sD));
+  if (c.resid_host)
+    CCP_CUDA(cudaMemcpyAsync(c.resid_host + off * m, c.dres + off * m, sizeof(double) * m * cn, cudaMemcpyDeviceToHost, sD));
+  return CCP_OK;
+}
+
+// Copy out every chunk of q that the host-path launch numbered `g` (just enqueued, event `ev`) has completed.
+static int host_copy_ready(ccp_handle* h, ccp_host_call& q, int64_t g, cudaEvent_t ev, bool& waited) {
+  cudaStream_t sD = h->hstream[2];
+  while (q.copied < q.parts && q.first_launch + q.copied + host_lag() <= g) {
+    if (!waited) {
+      CCP_CUDA(cudaStreamWaitEvent(sD, ev, 0));
+      waited = true;
+    }
+    int rc = host_copy_out(h, q, q.copied, sD);
+    if (rc) return rc;
+    if (++q.copied == q.parts) CCP_CUDA(cudaEventRecord(q.done, sD));
+  }
+  return CCP_OK;
+}
+
+// Complete every submitted batch: one flush launch, then the chunks still on the device (older batch first).
+// The caller holds host_mu.
+static int host_drain_locked(ccp_handle* h) {
+  ccp_host_call* q[2] = {&h->hcall[0], &h->hcall[1]};
+  if (q[0]->ticket > q[1]->ticket) std::swap(q[0], q[1]);
+  if (q[0]->copied == q[0]->parts && q[1]->copied == q[1]->parts) return CCP_OK;
+  cudaStream_t sK = h->hstream[1], sD = h->hstream[2];
+  if (h->pipeline_open) {
+    ccp_project_args F;
+    memset(&F, 0, sizeof F);
+    int rc = launch_project(h, F, CCP_LAYOUT_AOS, sK, false);
+    if (rc) return rc;
+  }
+  CCP_CUDA(cudaEventRecord(h->ev1, sK));
+  CCP_CUDA(cudaStreamWaitEvent(sD, h->ev1, 0));
+  for (int i = 0; i < 2; ++i)
+    while (q[i]->copied < q[i]->parts) {
+      int rc = host_copy_out(h, *q[i], q[i]->copied, sD);
+      if (rc) return rc;
+      if (++q[i]->copied == q[i]->parts) CCP_CUDA(cudaEventRecord(q[i]->done, sD));
+    }
+  return CCP_OK;
+}
+
+static int host_wait_locked(ccp_handle* h, ccp_host_call& c) {
+  if (c.finished) return CCP_OK;
+  if (c.copied < c.parts) {
+    int rc = host_drain_locked(h);
+    if (rc) return rc;
+  }
+  CCP_CUDA(cudaEventSynchronize(c.done));
+  c.finished = true;
+  return CCP_OK;
+}
+
+// The caller holds host_mu and has checked the arguments.
+static int host_submit_locked(ccp_handle* h, const double* seeds_host, int64_t count, double* x_out_host, uint8_t* ok_host,
+                              uint8_t* converged_host, int32_t* iters_host, double* resid_host, int64_t* ticket_out) {
+  ccp_host_call& c = h->hcall[h->next_ticket & 1];
+  ccp_host_call& prev = h->hcall[(h->next_ticket & 1) ^ 1];
+  int rc = host_wait_locked(h, c);  // the batch that used this slot two submits ago
   if (rc) return rc;
-  if (!h->has_ref) return set_err(h, CCP_ERR_STATE, "%s", "project before ccp_set_reference (setInitialPosition)");
-  if (count == 0) return CCP_OK;
-  CCP_NO_OPEN_PIPELINE(h);  // this call runs its own pipeline on the handle's private streams
-  std::lock_guard<std::mutex> host_lock(h->host_mu);
-  device_guard g(h->device);
+  if (h->pipeline_open && prev.copied == prev.parts)
+    return set_err(h, CCP_ERR_STATE, "%s", "pipelined projections are in flight: call ccp_project_flush first");
   const int n = CCPC_DOF * h->model.n_arms, m = 2 * (h->model.n_arms - 1);
   const size_t per = sizeof(double) * n + sizeof(double) * m + 8 /* ok, conv, pad */ + sizeof(int32_t) + 4;
-  rc = ensure_stage(h, per * (size_t)count + 1024);
-  if (rc) return rc;
+  const size_t need = per * (size_t)count + 1024;
+  if (need > c.stage_bytes) {
+    if (c.stage) cudaFree(c.stage);
+    c.stage = nullptr;
+    c.stage_bytes = 0;
+    CCP_CUDA(cudaMalloc(&c.stage, need + need / 4));
+    c.stage_bytes = need + need / 4;
+  }
   // carve the stage: x [count][n] | resid [count][m] | iters | ok | conv
-  char* base = (char*)h->d_stage;
-  double* dx = (double*)base;
-  double* dres = (double*)(base + sizeof(double) * n * (size_t)count);
-  int32_t* dit = (int32_t*)((char*)dres + sizeof(double) * m * (size_t)count);
-  uint8_t* dok = (uint8_t*)((char*)dit + sizeof(int32_t) * (size_t)count);
-  uint8_t* dcv = dok + (size_t)count;
-  // chunking: a chunk a little larger than the resident lane count keeps every lane busy within a launch; the
-  // first H2D and the last D2H (the parts nothing hides) shrink with the chunk
+  char* base = (char*)c.stage;
+  c.dx = (double*)base;
+  c.dres = (double*)(base + sizeof(double) * n * (size_t)count);
+  c.dit = (int32_t*)((char*)c.dres + sizeof(double) * m * (size_t)count);
+  c.dok = (uint8_t*)((char*)c.dit + sizeof(int32_t) * (size_t)count);
+  c.dcv = c.dok + (size_t)count;
+  c.count = count;
+  c.x_out_host = x_out_host;
+  c.ok_host = ok_host;
+  c.conv_host = converged_host;
+  c.iters_host = iters_host;
+  c.resid_host = resid_host;
+  // chunking: a chunk ~1.45x the resident lane count keeps every lane busy within a launch and makes a launch long
+  // enough (~80 trips on uniform seeds) that a sample capped at 250 iterations is done within `lag` launches without
+  // being forced (tools/e2e_stream.py sweeps both); the first H2D (the part nothing hides) shrinks with the chunk
   int parts;
   {
     static int env_parts = -1;
@@ -1056,68 +1191,124 @@ int ccp_project_batch_host(ccp_handle* h, const double* seeds_host, int64_t coun
       env_parts = e ? atoi(e) : 0;
     }
     const int64_t lanes = (int64_t)h->sm_count * 384;
-    parts = env_parts > 0 ? env_parts : (int)(count / (lanes + lanes / 8));
+    parts = env_parts > 0 ? env_parts : (int)(count / (lanes + lanes * 9 / 20));
     if (parts > CCP_HOST_MAX_CHUNKS) parts = CCP_HOST_MAX_CHUNKS;
     if (parts < 1) parts = 1;
   }
   int64_t chunk = (count + parts - 1) / parts;
   chunk = (chunk + 15) / 16 * 16;  // chunks never share a 128 B line of any output array
   parts = (int)((count + chunk - 1) / chunk);
-  cudaStream_t sC = h->hstream[0], sK = h->hstream[1], sD = h->hstream[2];
-  if (parts == 1) sC = sD = sK;  // a small batch: one stream, no events — what a planner projecting state by state pays
-  auto copy_out = [&](int c) -> int {
-    const int64_t off = (int64_t)c * chunk;
+  c.chunk = chunk;
+  c.parts = parts;
+  c.copied = 0;
+  c.first_launch = h->host_launches;
+  c.finished = false;
+  c.ticket = h->next_ticket++;
+  cudaStream_t sC = h->hstream[0], sK = h->hstream[1];
+  for (int k = 0; k < parts; ++k) {
+    const int64_t off = (int64_t)k * chunk;
     const int64_t cn = (count - off < chunk) ? (count - off) : chunk;
-    if (x_out_host)
-      CCP_CUDA(cudaMemcpyAsync(x_out_host + off * n, dx + off * n, sizeof(double) * n * cn, cudaMemcpyDeviceToHost, sD));
-    if (ok_host) CCP_CUDA(cudaMemcpyAsync(ok_host + off, dok + off, (size_t)cn, cudaMemcpyDeviceToHost, sD));
-    if (converged_host) CCP_CUDA(cudaMemcpyAsync(converged_host + off, dcv + off, (size_t)cn, cudaMemcpyDeviceToHost, sD));
-    if (iters_host) CCP_CUDA(cudaMemcpyAsync(iters_host + off, dit + off, sizeof(int32_t) * cn, cudaMemcpyDeviceToHost, sD));
-    if (resid_host)
-      CCP_CUDA(cudaMemcpyAsync(resid_host + off * m, dres + off * m, sizeof(double) * m * cn, cudaMemcpyDeviceToHost, sD));
-    return CCP_OK;
-  };
-  for (int c = 0; c < parts; ++c) {
-    const int64_t off = (int64_t)c * chunk;
-    const int64_t cn = (count - off < chunk) ? (count - off) : chunk;
-    CCP_CUDA(cudaMemcpyAsync(dx + off * n, seeds_host + off * n, sizeof(double) * n * cn, cudaMemcpyHostToDevice, sC));
-    if (parts > 1) {
-      CCP_CUDA(cudaEventRecord(h->ev_chunk_in[c], sC));
-      CCP_CUDA(cudaStreamWaitEvent(sK, h->ev_chunk_in[c], 0));
-    }
+    CCP_CUDA(cudaMemcpyAsync(c.dx + off * n, seeds_host + off * n, sizeof(double) * n * cn, cudaMemcpyHostToDevice, sC));
+    CCP_CUDA(cudaEventRecord(h->ev_chunk_in[k], sC));
+    CCP_CUDA(cudaStreamWaitEvent(sK, h->ev_chunk_in[k], 0));
     ccp_project_args A;
     memset(&A, 0, sizeof A);
-    A.seeds = dx + off * n;
-    A.x_out = dx + off * n;
-    A.ok = dok + off;
-    A.conv = dcv + off;
-    A.iters = dit + off;
-    A.resid = resid_host ? dres + off * m : nullptr;
+    A.seeds = c.dx + off * n;
+    A.x_out = c.dx + off * n;
+    A.ok = c.dok + off;
+    A.conv = c.dcv + off;
+    A.iters = c.dit + off;
+    A.resid = resid_host ? c.dres + off * m : nullptr;
     A.count = cn;
-    rc = launch_project(h, A, CCP_LAYOUT_AOS, sK, /*defer=*/parts > 1);
+    A.max_age = (unsigned)host_lag();
+    rc = launch_project(h, A, CCP_LAYOUT_AOS, sK, /*defer=*/true);
     if (rc) return rc;
-    if (parts > 1) CCP_CUDA(cudaEventRecord(h->ev_chunk_k[c], sK));
-    if (c > 0) {  // launch c completed chunk c - 1
-      CCP_CUDA(cudaStreamWaitEvent(sD, h->ev_chunk_k[c], 0));
-      rc = copy_out(c - 1);
-      if (rc) return rc;
-    }
-  }
-  if (h->pipeline_open) {
-    ccp_project_args F;
-    memset(&F, 0, sizeof F);
-    rc = launch_project(h, F, CCP_LAYOUT_AOS, sK, false);
+    const int64_t g = h->host_launches++;
+    CCP_CUDA(cudaEventRecord(h->ev_chunk_k[k], sK));
+    bool waited = false;
+    rc = host_copy_ready(h, prev, g, h->ev_chunk_k[k], waited);
+    if (rc) return rc;
+    rc = host_copy_ready(h, c, g, h->ev_chunk_k[k], waited);
     if (rc) return rc;
   }
-  if (parts > 1) {
-    CCP_CUDA(cudaEventRecord(h->ev1, sK));
-    CCP_CUDA(cudaStreamWaitEvent(sD, h->ev1, 0));
-  }
-  rc = copy_out(parts - 1);
-  if (rc) return rc;
-  CCP_CUDA(cudaStreamSynchronize(sD));
-  if (parts > 1) CCP_CUDA(cudaStreamSynchronize(sK));
+  if (ticket_out) *ticket_out = c.ticket;
   return CCP_OK;
+}
+
+int ccp_project_batch_host(ccp_handle* h, const double* seeds_host, int64_t count, double* x_out_host,
+                           uint8_t* ok_host, uint8_t* converged_host, int32_t* iters_host, double* resid_host) {
+  int rc = check_common(h, seeds_host, count, CCP_LAYOUT_AOS);
+  if (rc) return rc;
+  if (!h->has_ref) return set_err(h, CCP_ERR_STATE, "%s", "project before ccp_set_reference (setInitialPosition)");
+  if (count == 0) return CCP_OK;
+  std::lock_guard<std::mutex> host_lock(h->host_mu);
+  device_guard g(h->device);
+  for (int i = 0; i < 2; ++i) {  // batches submitted through the streaming form complete first
+    rc = host_wait_locked(h, h->hcall[i]);
+    if (rc) return rc;
+  }
+  CCP_NO_OPEN_PIPELINE(h);  // this call runs its own pipeline on the handle's private streams
+  if (count >= 2 * ((int64_t)h->sm_count * 384 + (int64_t)h->sm_count * 48)) {
+    int64_t ticket = 0;
+    rc = host_submit_locked(h, seeds_host, count, x_out_host, ok_host, converged_host, iters_host, resid_host, &ticket);
+    if (rc) return rc;
+    return host_wait_locked(h, h->hcall[ticket & 1]);
+  }
+  // a batch too small to chunk: copy-in, one complete launch and copy-out on one stream, no events — what a planner
+  // projecting state by state pays
+  const int n = CCPC_DOF * h->model.n_arms, m = 2 * (h->model.n_arms - 1);
+  const size_t per = sizeof(double) * n + sizeof(double) * m + 8 /* ok, conv, pad */ + sizeof(int32_t) + 4;
+  rc = ensure_stage(h, per * (size_t)count + 1024);
+  if (rc) return rc;
+  char* base = (char*)h->d_stage;
+  double* dx = (double*)base;
+  double* dres = (double*)(base + sizeof(double) * n * (size_t)count);
+  int32_t* dit = (int32_t*)((char*)dres + sizeof(double) * m * (size_t)count);
+  uint8_t* dok = (uint8_t*)((char*)dit + sizeof(int32_t) * (size_t)count);
+  uint8_t* dcv = dok + (size_t)count;
+  cudaStream_t st = h->hstream[1];
+  CCP_CUDA(cudaMemcpyAsync(dx, seeds_host, sizeof(double) * n * count, cudaMemcpyHostToDevice, st));
+  ccp_project_args A;
+  memset(&A, 0, sizeof A);
+  A.seeds = dx;
+  A.x_out = dx;
+  A.ok = dok;
+  A.conv = dcv;
+  A.iters = dit;
+  A.resid = resid_host ? dres : nullptr;
+  A.count = count;
+  rc = launch_project(h, A, CCP_LAYOUT_AOS, st, false);
+  if (rc) return rc;
+  if (x_out_host) CCP_CUDA(cudaMemcpyAsync(x_out_host, dx, sizeof(double) * n * count, cudaMemcpyDeviceToHost, st));
+  if (ok_host) CCP_CUDA(cudaMemcpyAsync(ok_host, dok, (size_t)count, cudaMemcpyDeviceToHost, st));
+  if (converged_host) CCP_CUDA(cudaMemcpyAsync(converged_host, dcv, (size_t)count, cudaMemcpyDeviceToHost, st));
+  if (iters_host) CCP_CUDA(cudaMemcpyAsync(iters_host, dit, sizeof(int32_t) * count, cudaMemcpyDeviceToHost, st));
+  if (resid_host) CCP_CUDA(cudaMemcpyAsync(resid_host, dres, sizeof(double) * m * count, cudaMemcpyDeviceToHost, st));
+  CCP_CUDA(cudaStreamSynchronize(st));
+  return CCP_OK;
+}
+
+int ccp_project_batch_host_submit(ccp_handle* h, const double* seeds_host, int64_t count, double* x_out_host,
+                                  uint8_t* ok_host, uint8_t* converged_host, int32_t* iters_host, double* resid_host,
+                                  int64_t* ticket_out) {
+  int rc = check_common(h, seeds_host, count, CCP_LAYOUT_AOS);
+  if (rc) return rc;
+  if (!ticket_out) return set_err(h, CCP_ERR_INVALID, "%s", "null ticket");
+  if (count < 1) return set_err(h, CCP_ERR_INVALID, "%s", "submit needs at least one state");
+  if (!h->has_ref) return set_err(h, CCP_ERR_STATE, "%s", "project before ccp_set_reference (setInitialPosition)");
+  std::lock_guard<std::mutex> host_lock(h->host_mu);
+  device_guard g(h->device);
+  return host_submit_locked(h, seeds_host, count, x_out_host, ok_host, converged_host, iters_host, resid_host, ticket_out);
+}
+
+int ccp_project_batch_host_wait(ccp_handle* h, int64_t ticket) {
+  if (!h) return CCP_ERR_INVALID;
+  std::lock_guard<std::mutex> host_lock(h->host_mu);
+  if (ticket < 1 || ticket >= h->next_ticket) return set_err(h, CCP_ERR_INVALID, "%s", "unknown ticket");
+  device_guard g(h->device);
+  for (int i = 0; i < 2; ++i)
+    if (h->hcall[i].ticket == ticket) return host_wait_locked(h, h->hcall[i]);
+  return CCP_OK;  // an older ticket: its slot was recycled, which waited for it
 }
 
 // Host-buffer forms of the sampler, the geodesic walk and the IK sampler: what a C++ planner that never touches CUDA

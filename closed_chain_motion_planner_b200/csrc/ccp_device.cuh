@@ -81,6 +81,7 @@ struct ccp_project_args {
   unsigned* park_count;
   ccp_out_desc* desc_table;     // [CCP_NUM_DESC]
   unsigned slot;                // this launch's entry of desc_table
+  unsigned max_age;             // a sample adopted from a launch this many slots back is not parked again
 };
 
 // warp-aggregated claim of the next sample index by the lanes currently finishing

@@ -322,25 +322,36 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
         __syncwarp();
         const int park_at = (W.first_dynamic < W.total) ? 32 : 16;
         if (__popc(__ballot_sync(0xffffffffu, idx != CCP_NO_SAMPLE)) <= park_at) {
+          // A sample carried through A.max_age launches is not parked again: its lane finishes it here (the warp
+          // stays).  So launch c + max_age completes launch c's outputs (what the host path's D2H copies wait for),
+          // and a launch's slot in the 64-entry descriptor ring is never recycled under one of its samples.
           for (;;) {
             const bool live = idx != CCP_NO_SAMPLE;
-            const unsigned bal = __ballot_sync(0xffffffffu, live);
-            if (bal == 0u) break;
-            unsigned base = 0;
-            if (lane == 0) base = atomicAdd(A.park_count, (unsigned)__popc(bal));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (live) {
-              ccp_park_rec* r = A.park + base + __popc(bal & ((1u << lane) - 1u));
-              r->idx = idx;
-              r->it_slot = it;
+            const bool old = live && ((A.slot - ((unsigned)it >> 16)) & (CCP_NUM_DESC - 1u)) >= A.max_age;
+            const unsigned bal = __ballot_sync(0xffffffffu, live && !old);
+            if (bal != 0u) {
+              unsigned base = 0;
+              if (lane == 0) base = atomicAdd(A.park_count, (unsigned)__popc(bal));
+              base = __shfl_sync(0xffffffffu, base, 0);
+              if (live && !old) {
+                ccp_park_rec* r = A.park + base + __popc(bal & ((1u << lane) - 1u));
+                r->idx = idx;
+                r->it_slot = it;
 #pragma unroll
-              for (int j = 0; j < n; ++j) r->x[j] = x[j];
+                for (int j = 0; j < n; ++j) r->x[j] = x[j];
+                idx = CCP_NO_SAMPLE;
+              }
             }
-            int bsel;
-            const unsigned u = claim_chunked<K, SOA>(wc, stage, mbar, A, W, &s_tail, bsel);
-            load_sample<K, SOA>(M, A, W, u, wc, stage, mbar, bsel, x, idx, it);
+            if (idx == CCP_NO_SAMPLE) {  // the unstarted rest of the private chunk
+              int bsel;
+              const unsigned u = claim_chunked<K, SOA>(wc, stage, mbar, A, W, &s_tail, bsel);
+              load_sample<K, SOA>(M, A, W, u, wc, stage, mbar, bsel, x, idx, it);
+            }
+            __syncwarp();
+            const bool young = idx != CCP_NO_SAMPLE && ((A.slot - ((unsigned)it >> 16)) & (CCP_NUM_DESC - 1u)) < A.max_age;
+            if (__ballot_sync(0xffffffffu, young) == 0u) break;
           }
-          return;
+          if (__ballot_sync(0xffffffffu, idx != CCP_NO_SAMPLE) == 0u) return;
         }
       } else if (since == 0) {
         // ---- complete mode: tail rendezvous ----

@@ -275,6 +275,16 @@ int ccp_ik_sample_batch(ccp_handle* h, int32_t arm, const double* T_target_dev, 
 int ccp_project_batch_host(ccp_handle* h, const double* seeds_host, int64_t count,
                            double* x_out_host, uint8_t* ok_host, uint8_t* converged_host,
                            int32_t* iters_host, double* resid_host);
+/* Streaming form of ccp_project_batch_host for a caller with batch after batch of host states: submit enqueues the
+ * whole batch (copies and launches) and returns a ticket, wait blocks until that batch's results are in its buffers
+ * (which must stay valid, and pinned for the copies to overlap, until then).  Up to two batches are in flight; when
+ * batch k + 1 is submitted before batch k is waited for, k's stragglers finish inside k + 1's first launch — no launch
+ * tail, copies of one batch behind the kernels of the other.  Results are bit-identical to ccp_project_batch_host.
+ * Do not mix with other projection calls on the handle while a ticket is pending.                                 */
+int ccp_project_batch_host_submit(ccp_handle* h, const double* seeds_host, int64_t count, double* x_out_host,
+                                  uint8_t* ok_host, uint8_t* converged_host, int32_t* iters_host,
+                                  double* resid_host, int64_t* ticket_out);
+int ccp_project_batch_host_wait(ccp_handle* h, int64_t ticket);
 int ccp_function_batch_host(ccp_handle* h, const double* x_host, int64_t count, double* f_host);
 /* Host-buffer forms (AOS; synchronous) of ccp_sample_project_batch, ccp_geodesic_batch and ccp_ik_sample_batch, for a
  * C++ planner that never touches CUDA (include/closed_chain_motion_planner_b200/ProjectedStateSpace.hpp).  Any output

@@ -105,3 +105,60 @@ def test_many_small_pipelined_launches(setup):
     it = torch.cat([p.iters for p in parts])
     assert np.array_equal(_bits(full.x), _bits(x)) and torch.equal(full.iters, it)
     assert int(full.iters.max()) == 250
+
+
+def _np(v):
+    return v.cpu().numpy() if hasattr(v, "cpu") else np.asarray(v)
+
+
+def _same(r, g):
+    assert np.array_equal(_np(r.x).view(np.uint64), _np(g.x).view(np.uint64))
+    for name in ("ok", "converged", "iters"):
+        assert np.array_equal(_np(getattr(r, name)), _np(getattr(g, name))), name
+    assert np.array_equal(_np(r.resid).view(np.uint64), _np(g.resid).view(np.uint64))
+
+
+@pytest.mark.parametrize("count", [1_000_000, 200_000])
+def test_chunked_host_call_equals_device_launch(setup, count):
+    """ccp_project_batch_host on a batch large enough to be chunked: a sample is carried through several of the
+    call's launches, and every chunk's copy-out must wait for the launch that completes it.  A first call with other
+    seeds leaves different results in the stage, so a chunk copied early would show."""
+    pkg, c, A = setup
+    c.projectBatch(A.seeds_uniform(7, 0, count))
+    x = A.seeds_uniform(0, 12345, count)
+    got = c.projectBatch(x)  # numpy in: the host entry point
+    ref = c.projectBatch(torch.from_numpy(x).cuda())
+    torch.cuda.synchronize()
+    _same(ref, got)
+
+
+@pytest.mark.parametrize("count", [1_000_000, 70_000, 13])
+def test_streaming_host_submit_wait(setup, count):
+    """ccp_project_batch_host_submit / _wait: two host batches in flight; each result bit-identical to the complete
+    device launch's, whatever launch finished the stragglers."""
+    pkg, c, A = setup
+    batches = [A.seeds_uniform(0, b * count, count) for b in range(4)]
+    ref = [c.projectBatch(torch.from_numpy(x).cuda()) for x in batches]
+    torch.cuda.synchronize()
+    pending = []
+    got = []
+    for x in batches:
+        pending.append(c.submitHostBatch(x, want_resid=True))
+        if len(pending) == 2:
+            t, r = pending.pop(0)
+            c.waitHostBatch(t)
+            got.append(r)
+    while pending:
+        t, r = pending.pop(0)
+        c.waitHostBatch(t)
+        got.append(r)
+    assert not c.pipelineOpen()
+    for r, g in zip(ref, got):
+        _same(r, g)
+    # a ticket never issued is an error and leaves the handle usable; a synchronous call may follow a submit
+    with pytest.raises(Exception):
+        c.waitHostBatch(10_000_000)
+    t, r = c.submitHostBatch(batches[1])
+    _same(ref[0], c.projectBatch(batches[0]))
+    c.waitHostBatch(t)
+    assert np.array_equal(_np(ref[1].ok), r.ok)
