@@ -140,6 +140,15 @@ def _check(lib, h, rc):
         raise CcpError(f"ccp error {rc}: {msg.decode() if msg else ''}")
 
 
+def _host_array(shape, dtype, pinned: bool) -> np.ndarray:
+    """Zeroed host array; page-locked (through torch) when `pinned`."""
+    if not pinned:
+        return np.zeros(shape, dtype)
+    import torch
+
+    return torch.zeros(shape, dtype=getattr(torch, np.dtype(dtype).name)).pin_memory().numpy()
+
+
 @dataclass
 class ProjectResult:
     x: object  # projected states (same container type / layout as the input)
@@ -307,13 +316,15 @@ class KinematicChainConstraint:
         return count, torch.cuda.current_stream(X.device).cuda_stream
 
     def projectBatch(self, X, layout: int = CCP_LAYOUT_AOS, out=None, want_resid: bool = True,
-                     compact=None, n_ok=None, pipelined: bool = False) -> ProjectResult:
+                     compact=None, n_ok=None, pipelined: bool = False, pinned: bool = False) -> ProjectResult:
         """Batched project().  numpy (count, n) -> host path; torch CUDA tensor -> device path (async on the
         current stream).  `out` (device path) may alias X for in-place projection.  Device path only:
         `compact` ((>=count, n) float64) receives the ok states densely packed by the kernel epilogue and
         `n_ok` (int64[1], zeroed by the caller) their count.  `pipelined=True` (device path) parks the samples
         still iterating when the batch runs dry instead of idling the GPU on them: the result tensors are
-        complete only after the next non-pipelined projectBatch or flush() (ccp_project_batch_pipelined)."""
+        complete only after the next non-pipelined projectBatch or flush() (ccp_project_batch_pipelined).
+        `pinned=True` (host path) returns the results in page-locked arrays: the library then copies each chunk out the
+        moment its last sample has finished instead of a fixed number of launches later."""
         self._need()
         m = self.getCoDimension()
         if _is_torch(X):
@@ -341,17 +352,17 @@ class KinematicChainConstraint:
         if X.ndim != 2 or X.shape[1] != self.n_:
             raise ValueError(f"states must have shape (count, {self.n_})")
         count = X.shape[0]
-        xo = np.empty_like(X)
-        ok = np.zeros(count, np.uint8)
-        cv = np.zeros(count, np.uint8)
-        it = np.zeros(count, np.int32)
-        rs = np.zeros((count, m))
+        xo = _host_array((count, self.n_), np.float64, pinned)
+        ok = _host_array((count,), np.uint8, pinned)
+        cv = _host_array((count,), np.uint8, pinned)
+        it = _host_array((count,), np.int32, pinned)
+        rs = _host_array((count, m), np.float64, pinned)
         _check(self._lib, self._h, self._lib.ccp_project_batch_host(
             self._h, X.ctypes.data, count, xo.ctypes.data, ok.ctypes.data, cv.ctypes.data, it.ctypes.data,
             rs.ctypes.data))
         return ProjectResult(xo, ok, cv, it, rs)
 
-    def submitHostBatch(self, X: np.ndarray, want_resid: bool = False):
+    def submitHostBatch(self, X: np.ndarray, want_resid: bool = False, pinned: bool = False):
         """Streaming host path (ccp_project_batch_host_submit): enqueue a host batch and return (ticket, result); the
         result arrays are complete after waitHostBatch(ticket).  Submit the next batch before waiting for this one and
         the GPU never idles on a batch's stragglers nor on its copies.  X must stay alive until the wait."""
@@ -360,11 +371,11 @@ class KinematicChainConstraint:
         if X.ndim != 2 or X.shape[1] != self.n_:
             raise ValueError(f"states must have shape (count, {self.n_})")
         count = X.shape[0]
-        xo = np.empty_like(X)
-        ok = np.zeros(count, np.uint8)
-        cv = np.zeros(count, np.uint8)
-        it = np.zeros(count, np.int32)
-        rs = np.zeros((count, self.getCoDimension())) if want_resid else None
+        xo = _host_array((count, self.n_), np.float64, pinned)
+        ok = _host_array((count,), np.uint8, pinned)
+        cv = _host_array((count,), np.uint8, pinned)
+        it = _host_array((count,), np.int32, pinned)
+        rs = _host_array((count, self.getCoDimension()), np.float64, pinned) if want_resid else None
         t = C.c_int64(0)
         _check(self._lib, self._h, self._lib.ccp_project_batch_host_submit(
             self._h, X.ctypes.data, count, xo.ctypes.data, ok.ctypes.data, cv.ctypes.data, it.ctypes.data,

@@ -51,11 +51,17 @@ struct ccp_launch_rec {
 };
 
 // One submitted host batch of the streaming host path (ccp_project_batch_host_submit / _wait)
+// cuStreamWaitValue32(stream, device address, value, flags): flags 0 = wait until (int32)(*addr - value) >= 0
+typedef int (*ccp_wait32_fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+
 struct ccp_host_call {
   int64_t ticket;      // 0 = never used
   bool finished;       // results are complete in the caller's host buffers (or the slot is free)
   int64_t count, chunk;
   int parts, copied;    // chunks of the batch / chunks whose D2H copies are enqueued
+  bool use_wait;        // copies wait on the launch slots' completion counts (pinned outputs, cuStreamWaitValue32)
+  bool enqueued;        // use_wait: the waits and copies are on the D2H stream
+  unsigned slot[CCP_HOST_MAX_CHUNKS], expect[CCP_HOST_MAX_CHUNKS];  // per chunk: launch slot, completion count to wait for
   int64_t first_launch; // number (ccp_handle::host_launches) of the launch that projected chunk 0
   double* x_out_host;
   uint8_t* ok_host;
@@ -93,6 +99,10 @@ struct ccp_handle {
   ccp_park_rec* d_park[2];
   unsigned prev_slot;      // launch slot whose record counts the parked samples in d_park[park_cur]
   ccp_out_desc* d_desc;    // [CCP_NUM_DESC]
+  unsigned* d_done;        // [CCP_NUM_DESC] samples finished per launch slot (cumulative; ccp_project_args::done)
+  unsigned done_total[CCP_NUM_DESC];  // what d_done[slot] reads once every launch that used the slot is complete
+  unsigned last_slot;      // descriptor slot of the most recent projection launch
+  ccp_wait32_fn wait32;    // cuStreamWaitValue32, or nullptr (then the host path copies a chunk `lag` launches late)
   size_t park_capacity;    // records per buffer
   int park_cur;            // buffer holding the parked samples of the last pipelined launch
   bool pipeline_open;      // parked samples exist
@@ -313,6 +323,8 @@ static int ensure_pipeline(ccp_handle* h) {
   CCP_CUDA(cudaMalloc(&h->d_park[1], cap * sizeof(ccp_park_rec)));
   CCP_CUDA(cudaMalloc(&h->d_desc, CCP_NUM_DESC * sizeof(ccp_out_desc)));
   CCP_CUDA(cudaMemset(h->d_desc, 0, CCP_NUM_DESC * sizeof(ccp_out_desc)));
+  CCP_CUDA(cudaMalloc(&h->d_done, CCP_NUM_DESC * sizeof(unsigned)));
+  CCP_CUDA(cudaMemset(h->d_done, 0, CCP_NUM_DESC * sizeof(unsigned)));
   h->park_capacity = cap;
   return CCP_OK;
 }
@@ -357,6 +369,7 @@ static int launch_project(ccp_handle* h, ccp_project_args& A, int layout, cudaSt
   }
   A.counter = &h->d_counters[slot].work;
   A.slot = slot % CCP_NUM_DESC;
+  h->last_slot = A.slot;
   if (A.max_age == 0 || A.max_age > CCP_MAX_AGE) A.max_age = CCP_MAX_AGE;
   if (h->peer_world > 0 && A.n_ok) {
     A.peer_world = h->peer_world;
@@ -369,6 +382,8 @@ static int launch_project(ccp_handle* h, ccp_project_args& A, int layout, cudaSt
     int rc = ensure_pipeline(h);
     if (rc) return rc;
     A.desc_table = h->d_desc;
+    A.done = h->d_done;
+    h->done_total[A.slot] += (unsigned)A.count;
     if (h->pipeline_open) {
       A.adopt = h->d_park[h->park_cur];
       A.adopt_count = &h->d_counters[h->prev_slot].parked;
@@ -446,6 +461,20 @@ int ccp_create(const ccp_model_desc* model, int32_t device, ccp_handle** out) {
   nh->peer_rank = 0;
   nh->peer_cap = 0;
   nh->d_desc = nullptr;
+  nh->d_done = nullptr;
+  memset(nh->done_total, 0, sizeof nh->done_total);
+  nh->last_slot = 0;
+  nh->wait32 = nullptr;
+  {
+    const char* off = getenv("CCP_HOST_WAITVALUE");
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (!(off && atoi(off) == 0) &&
+        cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      nh->wait32 = (ccp_wait32_fn)fn;
+    cudaGetLastError();
+  }
   nh->park_capacity = 0;
   nh->park_cur = 0;
   nh->pipeline_open = false;
@@ -507,6 +536,7 @@ void ccp_destroy(ccp_handle* h) {
   if (h->d_park[0]) cudaFree(h->d_park[0]);
   if (h->d_park[1]) cudaFree(h->d_park[1]);
   if (h->d_desc) cudaFree(h->d_desc);
+  if (h->d_done) cudaFree(h->d_done);
   for (int i = 0; i < CCP_HOST_MAX_CHUNKS; ++i) {
     cudaEventDestroy(h->ev_chunk_in[i]);
     cudaEventDestroy(h->ev_chunk_k[i]);
@@ -1137,11 +1167,44 @@ static int host_drain_locked(ccp_handle* h) {
   return CCP_OK;
 }
 
+// use_wait scheme: put the batch's copies on the D2H stream, each behind a wait until the completion count of its
+// chunk's launch slot says every sample of the chunk has finished, in whichever launch that happened.  Called only when
+// the launches that make every one of these waits come true are already enqueued (see host_submit_locked), so nothing
+// that cannot complete by itself is ever left pending on the device.
+static int host_enqueue_copies(ccp_handle* h, ccp_host_call& c) {
+  cudaStream_t sD = h->hstream[2];
+  for (int k = 0; k < c.parts; ++k) {
+    if (h->wait32(sD, (unsigned long long)(uintptr_t)(h->d_done + c.slot[k]), c.expect[k], 0u) != 0)
+      return set_err(h, CCP_ERR_CUDA, "%s", "cuStreamWaitValue32 failed");
+    int rc = host_copy_out(h, c, k, sD);
+    if (rc) return rc;
+  }
+  CCP_CUDA(cudaEventRecord(c.done, sD));
+  c.copied = c.parts;
+  c.enqueued = true;
+  return CCP_OK;
+}
+
 static int host_wait_locked(ccp_handle* h, ccp_host_call& c) {
   if (c.finished) return CCP_OK;
-  if (c.copied < c.parts) {
-    int rc = host_drain_locked(h);
-    if (rc) return rc;
+  if (!c.use_wait) {
+    if (c.copied < c.parts) {
+      int rc = host_drain_locked(h);
+      if (rc) return rc;
+    }
+  } else {
+    const bool newest = c.first_launch + c.parts == h->host_launches;
+    if (newest && h->pipeline_open) {  // no later batch will finish what this one parked: flush
+      ccp_project_args F;
+      memset(&F, 0, sizeof F);
+      int rc = launch_project(h, F, CCP_LAYOUT_AOS, h->hstream[1], false);
+      if (rc) return rc;
+    }
+    // (not the newest: the later batch's last launch finishes whatever this one still had in flight)
+    if (!c.enqueued) {
+      int rc = host_enqueue_copies(h, c);
+      if (rc) return rc;
+    }
   }
   CCP_CUDA(cudaEventSynchronize(c.done));
   c.finished = true;
@@ -1155,12 +1218,35 @@ static int host_submit_locked(ccp_handle* h, const double* seeds_host, int64_t c
   ccp_host_call& prev = h->hcall[(h->next_ticket & 1) ^ 1];
   int rc = host_wait_locked(h, c);  // the batch that used this slot two submits ago
   if (rc) return rc;
-  if (h->pipeline_open && prev.copied == prev.parts)
+  // A D2H copy into pageable memory blocks the host until it has run, so it can only be issued once the launch that
+  // completes its chunk is enqueued (the `lag` scheme).  With pinned outputs the copy is enqueued at once behind a
+  // stream wait on the chunk's completion count.
+  bool use_wait = h->wait32 != nullptr;
+  {
+    const void* outs[5] = {x_out_host, ok_host, converged_host, iters_host, resid_host};
+    for (int i = 0; i < 5 && use_wait; ++i) {
+      if (!outs[i]) continue;
+      cudaPointerAttributes pa;
+      if (cudaPointerGetAttributes(&pa, outs[i]) != cudaSuccess || pa.type == cudaMemoryTypeUnregistered) use_wait = false;
+    }
+    cudaGetLastError();
+  }
+  if (!prev.finished && prev.use_wait != use_wait) {  // the two schemes do not share a pipeline
+    rc = host_wait_locked(h, prev);
+    if (rc) return rc;
+  }
+  c.use_wait = use_wait;
+  c.enqueued = false;
+  if (use_wait && !prev.finished && !prev.enqueued) {  // this batch's launches complete the previous one
+    rc = host_enqueue_copies(h, prev);
+    if (rc) return rc;
+  }
+  if (h->pipeline_open && (prev.finished || (!prev.use_wait && prev.copied == prev.parts)))
     return set_err(h, CCP_ERR_STATE, "%s", "pipelined projections are in flight: call ccp_project_flush first");
   const int n = CCPC_DOF * h->model.n_arms, m = 2 * (h->model.n_arms - 1);
   const size_t per = sizeof(double) * n + sizeof(double) * m + 8 /* ok, conv, pad */ + sizeof(int32_t) + 4;
   const size_t need = per * (size_t)count + 1024;
-  if (need > c.stage_bytes) {
+  if (need > c.stage_bytes) {  // (device-wide synchronisation: everything pending completes by itself)
     if (c.stage) cudaFree(c.stage);
     c.stage = nullptr;
     c.stage_bytes = 0;
@@ -1180,9 +1266,10 @@ static int host_submit_locked(ccp_handle* h, const double* seeds_host, int64_t c
   c.conv_host = converged_host;
   c.iters_host = iters_host;
   c.resid_host = resid_host;
-  // chunking: a chunk ~1.45x the resident lane count keeps every lane busy within a launch and makes a launch long
-  // enough (~80 trips on uniform seeds) that a sample capped at 250 iterations is done within `lag` launches without
-  // being forced (tools/e2e_stream.py sweeps both); the first H2D (the part nothing hides) shrinks with the chunk
+  // chunking: a chunk of ~2x the resident lane count keeps every lane busy within a launch and keeps the launch
+  // boundaries few (each costs a drain and a refill of the machine: 1 M seeds in 8 chunks 3.54 ms per batch streaming,
+  // in 12 chunks 3.66, in 24 chunks 4.08; tools/e2e_stream.py); the first H2D (the part nothing hides) shrinks with the
+  // chunk
   int parts;
   {
     static int env_parts = -1;
@@ -1191,7 +1278,7 @@ static int host_submit_locked(ccp_handle* h, const double* seeds_host, int64_t c
       env_parts = e ? atoi(e) : 0;
     }
     const int64_t lanes = (int64_t)h->sm_count * 384;
-    parts = env_parts > 0 ? env_parts : (int)(count / (lanes + lanes * 9 / 20));
+    parts = env_parts > 0 ? env_parts : (int)(count / (2 * lanes));
     if (parts > CCP_HOST_MAX_CHUNKS) parts = CCP_HOST_MAX_CHUNKS;
     if (parts < 1) parts = 1;
   }
@@ -1220,16 +1307,23 @@ static int host_submit_locked(ccp_handle* h, const double* seeds_host, int64_t c
     A.iters = c.dit + off;
     A.resid = resid_host ? c.dres + off * m : nullptr;
     A.count = cn;
-    A.max_age = (unsigned)host_lag();
+    // use_wait: the batch's LAST launch finishes every sample older than the batch (age >= parts), so that once a
+    // batch is submitted the one before it is complete without any further call; nothing else is ever forced.
+    A.max_age = !use_wait ? (unsigned)host_lag() : (k == parts - 1 ? (unsigned)parts : (unsigned)CCP_MAX_AGE);
     rc = launch_project(h, A, CCP_LAYOUT_AOS, sK, /*defer=*/true);
     if (rc) return rc;
     const int64_t g = h->host_launches++;
-    CCP_CUDA(cudaEventRecord(h->ev_chunk_k[k], sK));
-    bool waited = false;
-    rc = host_copy_ready(h, prev, g, h->ev_chunk_k[k], waited);
-    if (rc) return rc;
-    rc = host_copy_ready(h, c, g, h->ev_chunk_k[k], waited);
-    if (rc) return rc;
+    if (use_wait) {
+      c.slot[k] = h->last_slot;
+      c.expect[k] = h->done_total[h->last_slot];
+    } else {
+      CCP_CUDA(cudaEventRecord(h->ev_chunk_k[k], sK));
+      bool waited = false;
+      rc = host_copy_ready(h, prev, g, h->ev_chunk_k[k], waited);
+      if (rc) return rc;
+      rc = host_copy_ready(h, c, g, h->ev_chunk_k[k], waited);
+      if (rc) return rc;
+    }
   }
   if (ticket_out) *ticket_out = c.ticket;
   return CCP_OK;
@@ -1248,7 +1342,7 @@ int ccp_project_batch_host(ccp_handle* h, const double* seeds_host, int64_t coun
     if (rc) return rc;
   }
   CCP_NO_OPEN_PIPELINE(h);  // this call runs its own pipeline on the handle's private streams
-  if (count >= 2 * ((int64_t)h->sm_count * 384 + (int64_t)h->sm_count * 48)) {
+  if (count >= 4 * (int64_t)h->sm_count * 384) {  // at least two chunks
     int64_t ticket = 0;
     rc = host_submit_locked(h, seeds_host, count, x_out_host, ok_host, converged_host, iters_host, resid_host, &ticket);
     if (rc) return rc;

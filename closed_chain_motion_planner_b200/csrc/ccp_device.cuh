@@ -82,6 +82,8 @@ struct ccp_project_args {
   ccp_out_desc* desc_table;     // [CCP_NUM_DESC]
   unsigned slot;                // this launch's entry of desc_table
   unsigned max_age;             // a sample adopted from a launch this many slots back is not parked again
+  unsigned* done;               // [CCP_NUM_DESC] samples finished so far per launch slot, cumulative over the slot's
+                                // reuses (never reset); nullptr = do not count.  The host path's D2H stream waits on it.
 };
 
 // warp-aggregated claim of the next sample index by the lanes currently finishing

@@ -236,6 +236,8 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
   constexpr int NW = BLOCK / 32;
   extern __shared__ __align__(16) double ccp_smem[];
   __shared__ int s_tail;
+  __shared__ unsigned s_exited;              // pipelined mode: warps that have left
+  __shared__ unsigned s_done[CCP_NUM_DESC];  // samples this block finished since its last publication, by launch slot
   __shared__ int s_wcnt[NW];
   __shared__ ccp_warp_chunk s_chunk[NW];
   __shared__ __align__(8) unsigned long long s_mbar[NW][2];
@@ -265,7 +267,9 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
   // global counter hands out what lies beyond those gridDim.x * NW chunks.
   const unsigned static_chunks = gridDim.x * NW;
   W.first_dynamic = (W.total / CCP_CLAIM_CHUNK < static_chunks) ? W.total : static_chunks * CCP_CLAIM_CHUNK;
+  if (threadIdx.x < CCP_NUM_DESC) s_done[threadIdx.x] = 0u;
   if (threadIdx.x == 0) {
+    s_exited = 0u;
     s_tail = (W.first_dynamic >= W.total) ? 1 : 0;
     if (blockIdx.x == 0 && A.park) {  // successors find this launch's output arrays by slot
       ccp_out_desc d;
@@ -351,7 +355,24 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
             const bool young = idx != CCP_NO_SAMPLE && ((A.slot - ((unsigned)it >> 16)) & (CCP_NUM_DESC - 1u)) < A.max_age;
             if (__ballot_sync(0xffffffffu, young) == 0u) break;
           }
-          if (__ballot_sync(0xffffffffu, idx != CCP_NO_SAMPLE) == 0u) return;
+          if (__ballot_sync(0xffffffffu, idx != CCP_NO_SAMPLE) == 0u) {
+            if (A.done) {
+              // The last warp out publishes how many samples of each launch this block finished.  Fence, then
+              // count: whoever sees the count sees the results (the D2H stream waits on A.done[slot]).
+              __threadfence();
+              unsigned gone = 0;
+              if (lane == 0) gone = atomicAdd(&s_exited, 1u);
+              gone = __shfl_sync(0xffffffffu, gone, 0);
+              if (gone == NW - 1) {
+                __threadfence();
+                for (int sl = lane; sl < (int)CCP_NUM_DESC; sl += 32) {
+                  const unsigned c = *(volatile unsigned*)&s_done[sl];
+                  if (c) atomicAdd(A.done + sl, c);
+                }
+              }
+            }
+            return;
+          }
         }
       } else if (since == 0) {
         // ---- complete mode: tail rendezvous ----
@@ -362,7 +383,17 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
         }
         __syncwarp();
         const bool active = idx != CCP_NO_SAMPLE;
+        if (A.done) __threadfence();  // the results of the samples counted in s_done, before the count goes out
         const int total = __syncthreads_count(active);
+        unsigned fin = 0;
+        if (A.done && threadIdx.x < CCP_NUM_DESC) {  // no thread is inside an epilogue between these two barriers
+          fin = s_done[threadIdx.x];
+          s_done[threadIdx.x] = 0u;
+        }
+        if (fin) {
+          __threadfence();  // cumulative: everything the barrier made visible to this thread precedes the count
+          atomicAdd(A.done + threadIdx.x, fin);
+        }
         if (total == 0) break;
         const unsigned bal = __ballot_sync(0xffffffffu, active);
         if (lane == 0) s_wcnt[warp] = __popc(bal);
@@ -433,6 +464,7 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
         if (D.ok) D.ok[idx] = okk;
         if (D.conv) D.conv[idx] = cv;
         if (D.iters) D.iters[idx] = it & 0xffff;
+        if (A.done) atomicAdd(&s_done[(unsigned)it >> 16], 1u);
         if (D.resid) {
           double fv[m];
           ccp_residual<K>(F, fv, nullptr);

@@ -118,22 +118,24 @@ def _same(r, g):
     assert np.array_equal(_np(r.resid).view(np.uint64), _np(g.resid).view(np.uint64))
 
 
+@pytest.mark.parametrize("pinned", [False, True])
 @pytest.mark.parametrize("count", [1_000_000, 200_000])
-def test_chunked_host_call_equals_device_launch(setup, count):
+def test_chunked_host_call_equals_device_launch(setup, count, pinned):
     """ccp_project_batch_host on a batch large enough to be chunked: a sample is carried through several of the
     call's launches, and every chunk's copy-out must wait for the launch that completes it.  A first call with other
     seeds leaves different results in the stage, so a chunk copied early would show."""
     pkg, c, A = setup
-    c.projectBatch(A.seeds_uniform(7, 0, count))
+    c.projectBatch(A.seeds_uniform(7, 0, count), pinned=pinned)
     x = A.seeds_uniform(0, 12345, count)
-    got = c.projectBatch(x)  # numpy in: the host entry point
+    got = c.projectBatch(x, pinned=pinned)  # numpy in: the host entry point
     ref = c.projectBatch(torch.from_numpy(x).cuda())
     torch.cuda.synchronize()
     _same(ref, got)
 
 
+@pytest.mark.parametrize("pinned", [False, True])
 @pytest.mark.parametrize("count", [1_000_000, 70_000, 13])
-def test_streaming_host_submit_wait(setup, count):
+def test_streaming_host_submit_wait(setup, count, pinned):
     """ccp_project_batch_host_submit / _wait: two host batches in flight; each result bit-identical to the complete
     device launch's, whatever launch finished the stragglers."""
     pkg, c, A = setup
@@ -143,7 +145,7 @@ def test_streaming_host_submit_wait(setup, count):
     pending = []
     got = []
     for x in batches:
-        pending.append(c.submitHostBatch(x, want_resid=True))
+        pending.append(c.submitHostBatch(x, want_resid=True, pinned=pinned))
         if len(pending) == 2:
             t, r = pending.pop(0)
             c.waitHostBatch(t)
@@ -158,7 +160,9 @@ def test_streaming_host_submit_wait(setup, count):
     # a ticket never issued is an error and leaves the handle usable; a synchronous call may follow a submit
     with pytest.raises(Exception):
         c.waitHostBatch(10_000_000)
-    t, r = c.submitHostBatch(batches[1])
-    _same(ref[0], c.projectBatch(batches[0]))
+    t, r = c.submitHostBatch(batches[1], pinned=pinned)
+    if pinned:
+        torch.cuda.synchronize()  # a device-wide synchronisation between submit and wait is allowed
+    _same(ref[0], c.projectBatch(batches[0], pinned=not pinned))
     c.waitHostBatch(t)
     assert np.array_equal(_np(ref[1].ok), r.ok)
