@@ -277,10 +277,14 @@ int ccp_project_batch_host(ccp_handle* h, const double* seeds_host, int64_t coun
                            int32_t* iters_host, double* resid_host);
 /* Streaming form of ccp_project_batch_host for a caller with batch after batch of host states: submit enqueues the
  * whole batch (copies and launches) and returns a ticket, wait blocks until that batch's results are in its buffers
- * (which must stay valid, and pinned for the copies to overlap, until then).  Up to two batches are in flight; when
- * batch k + 1 is submitted before batch k is waited for, k's stragglers finish inside k + 1's first launch — no launch
- * tail, copies of one batch behind the kernels of the other.  Results are bit-identical to ccp_project_batch_host.
- * Do not mix with other projection calls on the handle while a ticket is pending.                                 */
+ * (which must stay valid until then).  Up to two batches are in flight (a third submit first waits for the oldest).
+ * When batch k + 1 is submitted before batch k is waited for, k + 1's launches finish k's stragglers — no launch tail —
+ * and the copies of one batch run behind the kernels of the other.  Results are bit-identical to
+ * ccp_project_batch_host.  With PAGE-LOCKED output buffers each chunk is copied out the moment its last sample has
+ * finished (a stream wait on the chunk's completion count); with pageable outputs a fixed number of launches later.
+ * Whatever is pending on the device after submit returns completes without a further call, so device-wide
+ * synchronisation between submit and wait is safe.  Do not issue other projection calls on the handle while a ticket
+ * is pending (the blocking ccp_project_batch_host may be called: it first completes the pending tickets).          */
 int ccp_project_batch_host_submit(ccp_handle* h, const double* seeds_host, int64_t count, double* x_out_host,
                                   uint8_t* ok_host, uint8_t* converged_host, int32_t* iters_host,
                                   double* resid_host, int64_t* ticket_out);
