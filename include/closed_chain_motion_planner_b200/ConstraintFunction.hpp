@@ -154,6 +154,16 @@ class KinematicChainConstraint {
                                  r.resid.data()));
     return r;
   }
+  // Streaming form for a caller with batch after batch of host states (caller-owned buffers, page-locked for full
+  // overlap; any output but x_out may be null): submit batch k + 1 before waiting for batch k and the GPU never idles
+  // on a batch's stragglers or copies.  At most two tickets are outstanding.
+  int64_t submitBatch(const double* states, int64_t count, double* x_out, uint8_t* ok, uint8_t* converged = nullptr,
+                      int32_t* iters = nullptr, double* resid = nullptr) const {
+    int64_t ticket = 0;
+    check(ccp_project_batch_host_submit(need(), states, count, x_out, ok, converged, iters, resid, &ticket));
+    return ticket;
+  }
+  void waitBatch(int64_t ticket) const { check(ccp_project_batch_host_wait(need(), ticket)); }
   // Device states, asynchronous on `stream` (cudaStream_t as void*); any output may be null.
   void projectBatchDevice(const double* seeds_dev, int64_t count, ccp_layout layout, double* x_out_dev, uint8_t* ok_dev,
                           uint8_t* converged_dev, int32_t* iters_dev, double* resid_dev, double* compact_dev,

@@ -3,6 +3,7 @@
 // project call (jy_ProjectedStateSpace.cpp:13).  usage: test_constraint seeds.bin out.bin  (built and checked by
 // tests/test_cpp_host_gpu.py, which compares out.bin with the CPU oracle bit for bit).
 #include <cstdio>
+#include <cstring>
 #include <cstdlib>
 #include <vector>
 
@@ -60,6 +61,21 @@ int main(int argc, char** argv) {
 
   // batched call
   ccp::ProjectBatchResult r = constraint->projectBatch(seeds.data(), count);
+
+  // streaming form: the two halves of the batch in flight together, same results
+  {
+    const int64_t half = count / 2, rest = count - half;
+    std::vector<double> sx((size_t)count * 14);
+    std::vector<uint8_t> sok(count);
+    std::vector<int32_t> sit(count);
+    int64_t t0 = constraint->submitBatch(seeds.data(), half, sx.data(), sok.data(), nullptr, sit.data());
+    int64_t t1 = constraint->submitBatch(seeds.data() + half * 14, rest, sx.data() + half * 14, sok.data() + half, nullptr,
+                                         sit.data() + half);
+    constraint->waitBatch(t0);
+    constraint->waitBatch(t1);
+    if (memcmp(sx.data(), r.x.data(), sizeof(double) * sx.size()) != 0) return 8;
+    if (memcmp(sok.data(), r.ok.data(), sok.size()) != 0 || memcmp(sit.data(), r.iters.data(), 4 * sit.size()) != 0) return 9;
+  }
 
   ccp::PandaModel pm;
   double q0[7] = {0, 0, 0, 0, 0, 0, 0};

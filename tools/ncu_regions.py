@@ -46,7 +46,11 @@ def func_map(path):
 import os
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 fm = {f: func_map(os.path.join(root, "closed_chain_motion_planner_b200", "csrc", f)) for f in ("ccp_core.h", "ccp_project.cu", "ccp_device.cuh")}
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+import os
+
+# NCU_IMPORT_ARGS="--launch-skip 1 --launch-count 1" picks a launch of the report other than the first
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + os.environ.get("NCU_IMPORT_ARGS", "").split(),
+                     capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr = rows[1]
 ci = {h: i for i, h in enumerate(hdr)}

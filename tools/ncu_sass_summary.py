@@ -10,7 +10,11 @@ import sys
 
 rep = sys.argv[1]
 warp_iters = float(sys.argv[2]) if len(sys.argv) > 2 else None  # total warp-iterations, to normalise
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+import os
+
+# NCU_IMPORT_ARGS="--launch-skip 1 --launch-count 1" picks a launch of the report other than the first
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + os.environ.get("NCU_IMPORT_ARGS", "").split(),
+                     capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr = rows[1]
 ci = {h: i for i, h in enumerate(hdr)}
