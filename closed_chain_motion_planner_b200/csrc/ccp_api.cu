@@ -41,6 +41,7 @@
 #define CCP_NUM_COUNTERS 64
 #define CCP_MAX_AGE 40          /* < CCP_NUM_DESC: a launch's descriptor slot outlives every sample it parked */
 #define CCP_HOST_LAG_DEFAULT 6
+#define CCP_ZERO_COPY_MAX 512   /* host batches up to this many states run in place in page-locked host memory */
 #define CCP_HOST_MAX_CHUNKS 24  /* < CCP_NUM_DESC / 2: every chunk launch of a host call stays pipelined */
 
 // per-launch device record (ring of CCP_NUM_COUNTERS): zeroed by ONE stream-ordered memset before the launch
@@ -91,6 +92,7 @@ struct ccp_handle {
   // grow-only device staging for the *_host entry points
   void* d_stage;
   size_t d_stage_bytes;
+  void* pin;               // page-locked host buffer of the zero-copy small-batch path
   cudaStream_t hstream[3];
   cudaEvent_t ev0, ev1;
   cudaEvent_t ev_chunk_in[CCP_HOST_MAX_CHUNKS], ev_chunk_k[CCP_HOST_MAX_CHUNKS];  // host path: chunk landed / projected
@@ -350,7 +352,7 @@ static int launch_project(ccp_handle* h, ccp_project_args& A, int layout, cudaSt
     return set_err(h, CCP_ERR_INVALID, "%s", "more than 2^31 - 65536 samples in one call: split the batch");
   const bool soa = layout == CCP_LAYOUT_SOA;
   const int sig = soa ? 1 : 0;
-  A.stage_seeds = (A.seeds && (((uintptr_t)A.seeds) & 15u) == 0) ? 1 : 0;
+  A.stage_seeds = (A.stage_seeds >= 0 && A.seeds && (((uintptr_t)A.seeds) & 15u) == 0) ? 1 : 0;
   if (A.seed_stride == 0) A.seed_stride = A.count;
   if (A.out_stride == 0) A.out_stride = A.count;
   if (h->pipeline_open && sig != h->pipe_sig) {
@@ -454,6 +456,7 @@ int ccp_create(const ccp_model_desc* model, int32_t device, ccp_handle** out) {
   nh->launch_seq = 0;
   nh->geo_seq = 0;
   nh->d_stage = nullptr;
+  nh->pin = nullptr;
   nh->d_stage_bytes = 0;
   nh->d_park[0] = nh->d_park[1] = nullptr;
   nh->prev_slot = 0;
@@ -528,6 +531,7 @@ void ccp_destroy(ccp_handle* h) {
   cudaDeviceSynchronize();
   if (h->d_counters) cudaFree(h->d_counters);
   if (h->d_stage) cudaFree(h->d_stage);
+  if (h->pin) cudaFreeHost(h->pin);
   for (int i = 0; i < 2; ++i) {
     if (h->hcall[i].stage) cudaFree(h->hcall[i].stage);
     if (h->hcall[i].done) cudaEventDestroy(h->hcall[i].done);
@@ -1103,6 +1107,15 @@ int ccp_enforce_bounds_batch(ccp_handle* h, double* x_dev, int64_t count, int32_
 // launch.  ccp_project_batch_host_submit returns a ticket without waiting and ccp_project_batch_host_wait blocks until
 // that batch's results are in the caller's buffers: with two batches in flight the next batch's launches complete the
 // previous batch's last chunks, no launch tail is paid and the copies of one batch run behind the kernels of the other.
+static bool zero_copy_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("CCP_HOST_ZERO_COPY");
+    on = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return on != 0;
+}
+
 static int host_lag() {
   static int lag = -1;
   if (lag < 0) {
@@ -1348,10 +1361,45 @@ int ccp_project_batch_host(ccp_handle* h, const double* seeds_host, int64_t coun
     if (rc) return rc;
     return host_wait_locked(h, h->hcall[ticket & 1]);
   }
-  // a batch too small to chunk: copy-in, one complete launch and copy-out on one stream, no events — what a planner
-  // projecting state by state pays
   const int n = CCPC_DOF * h->model.n_arms, m = 2 * (h->model.n_arms - 1);
   const size_t per = sizeof(double) * n + sizeof(double) * m + 8 /* ok, conv, pad */ + sizeof(int32_t) + 4;
+  if (count <= CCP_ZERO_COPY_MAX && zero_copy_enabled()) {
+    // A handful of states — what a planner projecting state by state sends: no copy operations at all.  The seeds are
+    // put into a page-locked buffer of the handle that the kernel reads and writes in place over PCIe (in place, as
+    // project() does); the only device work is the launch record's memset and the kernel.
+    if (!h->pin) {
+      CCP_CUDA(cudaHostAlloc(&h->pin, (size_t)CCP_ZERO_COPY_MAX * (sizeof(double) * (CCPC_DOF * CCPC_MAX_ARMS + 2 * CCPC_MAX_ARMS) + 16) + 256,
+                             cudaHostAllocDefault));
+    }
+    char* pb = (char*)h->pin;
+    double* px = (double*)pb;
+    double* pres = (double*)(pb + sizeof(double) * n * (size_t)count);
+    int32_t* pit = (int32_t*)((char*)pres + sizeof(double) * m * (size_t)count);
+    uint8_t* pok = (uint8_t*)((char*)pit + sizeof(int32_t) * (size_t)count);
+    uint8_t* pcv = pok + (size_t)count;
+    memcpy(px, seeds_host, sizeof(double) * n * (size_t)count);
+    cudaStream_t st = h->hstream[1];
+    ccp_project_args A;
+    memset(&A, 0, sizeof A);
+    A.seeds = px;
+    A.x_out = px;
+    A.ok = pok;
+    A.conv = converged_host ? pcv : nullptr;
+    A.iters = iters_host ? pit : nullptr;
+    A.resid = resid_host ? pres : nullptr;
+    A.count = count;
+    A.stage_seeds = -1;  // no bulk copies out of host memory: the lanes load their seeds directly
+    rc = launch_project(h, A, CCP_LAYOUT_AOS, st, false);
+    if (rc) return rc;
+    CCP_CUDA(cudaStreamSynchronize(st));
+    if (x_out_host) memcpy(x_out_host, px, sizeof(double) * n * (size_t)count);
+    if (ok_host) memcpy(ok_host, pok, (size_t)count);
+    if (converged_host) memcpy(converged_host, pcv, (size_t)count);
+    if (iters_host) memcpy(iters_host, pit, sizeof(int32_t) * (size_t)count);
+    if (resid_host) memcpy(resid_host, pres, sizeof(double) * m * (size_t)count);
+    return CCP_OK;
+  }
+  // a batch too small to chunk: copy-in, one complete launch and copy-out on one stream, no events
   rc = ensure_stage(h, per * (size_t)count + 1024);
   if (rc) return rc;
   char* base = (char*)h->d_stage;

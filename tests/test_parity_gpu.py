@@ -61,11 +61,12 @@ def test_project_bit_exact_vs_engine_arithmetic(constraints, name, layout):
     assert np.array_equal(_bits(rs), _bits(rb["resid"]))
 
 
+@pytest.mark.parametrize("count", [1, 37, 512, 513, 3001])  # <= 512: in place in page-locked host memory; odd counts
 @pytest.mark.parametrize("name", CONFIGS)
-def test_project_host_path_matches_device_path(constraints, name):
+def test_project_host_path_matches_device_path(constraints, name, count):
     cfg, A, B = make_oracles(name)
     c = constraints[name]
-    seeds = A.seeds_uniform(3, 100, 3001)  # odd count, not a multiple of the warp size
+    seeds = A.seeds_uniform(3, 100, count)
     rh = c.projectBatch(seeds)
     rd = c.projectBatch(torch.from_numpy(seeds).cuda())
     assert np.array_equal(_bits(rh.x), _bits(rd.x.cpu().numpy()))
