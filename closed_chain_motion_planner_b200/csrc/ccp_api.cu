@@ -418,6 +418,14 @@ static int check_common(ccp_handle* h, const void* p, int64_t count, int32_t lay
   return CCP_OK;
 }
 
+// page-locked host buffer of the copy-free small-call paths (the kernels read and write it in place over PCIe)
+#define CCP_PIN_BYTES ((size_t)CCP_ZERO_COPY_MAX * (sizeof(double) * (CCPC_DOF * CCPC_MAX_ARMS + 2 * CCPC_MAX_ARMS) + 16) + 256)
+static int ensure_pin(ccp_handle* h) {
+  if (h->pin) return CCP_OK;
+  CCP_CUDA(cudaHostAlloc(&h->pin, CCP_PIN_BYTES, cudaHostAllocDefault));
+  return CCP_OK;
+}
+
 static int ensure_stage(ccp_handle* h, size_t bytes) {
   if (bytes <= h->d_stage_bytes) return CCP_OK;
   if (h->d_stage) cudaFree(h->d_stage);
@@ -1367,10 +1375,8 @@ int ccp_project_batch_host(ccp_handle* h, const double* seeds_host, int64_t coun
     // A handful of states — what a planner projecting state by state sends: no copy operations at all.  The seeds are
     // put into a page-locked buffer of the handle that the kernel reads and writes in place over PCIe (in place, as
     // project() does); the only device work is the launch record's memset and the kernel.
-    if (!h->pin) {
-      CCP_CUDA(cudaHostAlloc(&h->pin, (size_t)CCP_ZERO_COPY_MAX * (sizeof(double) * (CCPC_DOF * CCPC_MAX_ARMS + 2 * CCPC_MAX_ARMS) + 16) + 256,
-                             cudaHostAllocDefault));
-    }
+    rc = ensure_pin(h);
+    if (rc) return rc;
     char* pb = (char*)h->pin;
     double* px = (double*)pb;
     double* pres = (double*)(pb + sizeof(double) * n * (size_t)count);
@@ -1579,24 +1585,61 @@ int ccp_ik_sample_batch_host(ccp_handle* h, int32_t arm, const double* T_target_
   return CCP_OK;
 }
 
+}  // extern "C"
+
+// Host-buffer form of the small evaluation kernels: in -> device kernel -> out.  Small calls (the single-state
+// function()/jacobian()/isSatisfied() of the reference's interface) run in place in the handle's page-locked buffer with
+// no copy operations; larger ones go through the device stage.  `run(in_dev, out_dev, stream)` enqueues the kernel.
+template <class Run>
+static int host_eval(ccp_handle* h, const void* in_host, size_t in_bytes, void* const* out_host, const size_t* out_bytes,
+                     int n_out, Run run) {
+  std::lock_guard<std::mutex> host_lock(h->host_mu);
+  device_guard g(h->device);
+  size_t total = (in_bytes + 15) & ~(size_t)15;
+  size_t off[4];
+  for (int i = 0; i < n_out; ++i) {
+    off[i] = total;
+    total += (out_bytes[i] + 15) & ~(size_t)15;
+  }
+  cudaStream_t st = h->hstream[0];
+  if (total <= CCP_PIN_BYTES && zero_copy_enabled()) {
+    int rc = ensure_pin(h);
+    if (rc) return rc;
+    char* pb = (char*)h->pin;
+    memcpy(pb, in_host, in_bytes);
+    rc = run(pb, pb, off, st);
+    if (rc) return rc;
+    CCP_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < n_out; ++i)
+      if (out_host[i]) memcpy(out_host[i], pb + off[i], out_bytes[i]);
+    return CCP_OK;
+  }
+  int rc = ensure_stage(h, total);
+  if (rc) return rc;
+  char* db = (char*)h->d_stage;
+  CCP_CUDA(cudaMemcpyAsync(db, in_host, in_bytes, cudaMemcpyHostToDevice, st));
+  rc = run(db, db, off, st);
+  if (rc) return rc;
+  for (int i = 0; i < n_out; ++i)
+    if (out_host[i]) CCP_CUDA(cudaMemcpyAsync(out_host[i], db + off[i], out_bytes[i], cudaMemcpyDeviceToHost, st));
+  CCP_CUDA(cudaStreamSynchronize(st));
+  return CCP_OK;
+}
+
+extern "C" {
+
 int ccp_function_batch_host(ccp_handle* h, const double* x_host, int64_t count, double* f_host) {
   int rc = check_common(h, x_host, count, CCP_LAYOUT_AOS);
   if (rc) return rc;
   if (count > 0 && !f_host) return set_err(h, CCP_ERR_INVALID, "%s", "null output");
   if (count == 0) return CCP_OK;
-  device_guard g(h->device);
   const int n = CCPC_DOF * h->model.n_arms, m = 2 * (h->model.n_arms - 1);
-  rc = ensure_stage(h, sizeof(double) * (n + m) * (size_t)count);
-  if (rc) return rc;
-  double* dx = (double*)h->d_stage;
-  double* df = dx + (size_t)n * count;
-  cudaStream_t st = h->hstream[0];
-  CCP_CUDA(cudaMemcpyAsync(dx, x_host, sizeof(double) * n * count, cudaMemcpyHostToDevice, st));
-  rc = ccp_function_batch(h, dx, count, CCP_LAYOUT_AOS, df, st);
-  if (rc) return rc;
-  CCP_CUDA(cudaMemcpyAsync(f_host, df, sizeof(double) * m * count, cudaMemcpyDeviceToHost, st));
-  CCP_CUDA(cudaStreamSynchronize(st));
-  return CCP_OK;
+  void* outs[1] = {f_host};
+  const size_t ob[1] = {sizeof(double) * m * (size_t)count};
+  return host_eval(h, x_host, sizeof(double) * n * (size_t)count, outs, ob, 1,
+                   [&](char* in, char* out, const size_t* off, cudaStream_t st) {
+                     return ccp_function_batch(h, (const double*)in, count, CCP_LAYOUT_AOS, (double*)(out + off[0]), st);
+                   });
 }
 
 int ccp_jacobian_batch_host(ccp_handle* h, const double* x_host, int64_t count, double* J_host) {
@@ -1604,19 +1647,13 @@ int ccp_jacobian_batch_host(ccp_handle* h, const double* x_host, int64_t count, 
   if (rc) return rc;
   if (count > 0 && !J_host) return set_err(h, CCP_ERR_INVALID, "%s", "null output");
   if (count == 0) return CCP_OK;
-  device_guard g(h->device);
   const int n = CCPC_DOF * h->model.n_arms, m = 2 * (h->model.n_arms - 1);
-  rc = ensure_stage(h, sizeof(double) * (n + (size_t)m * n) * (size_t)count);
-  if (rc) return rc;
-  double* dx = (double*)h->d_stage;
-  double* dJ = dx + (size_t)n * count;
-  cudaStream_t st = h->hstream[0];
-  CCP_CUDA(cudaMemcpyAsync(dx, x_host, sizeof(double) * n * count, cudaMemcpyHostToDevice, st));
-  rc = ccp_jacobian_batch(h, dx, count, CCP_LAYOUT_AOS, dJ, st);
-  if (rc) return rc;
-  CCP_CUDA(cudaMemcpyAsync(J_host, dJ, sizeof(double) * m * n * count, cudaMemcpyDeviceToHost, st));
-  CCP_CUDA(cudaStreamSynchronize(st));
-  return CCP_OK;
+  void* outs[1] = {J_host};
+  const size_t ob[1] = {sizeof(double) * m * n * (size_t)count};
+  return host_eval(h, x_host, sizeof(double) * n * (size_t)count, outs, ob, 1,
+                   [&](char* in, char* out, const size_t* off, cudaStream_t st) {
+                     return ccp_jacobian_batch(h, (const double*)in, count, CCP_LAYOUT_AOS, (double*)(out + off[0]), st);
+                   });
 }
 
 int ccp_arm_fk_batch_host(ccp_handle* h, int32_t arm, const double* q_host, int64_t count, double* T_host,
@@ -1624,20 +1661,14 @@ int ccp_arm_fk_batch_host(ccp_handle* h, int32_t arm, const double* q_host, int6
   int rc = check_common(h, q_host, count, CCP_LAYOUT_AOS);
   if (rc) return rc;
   if (count == 0) return CCP_OK;
-  device_guard g(h->device);
-  rc = ensure_stage(h, sizeof(double) * (7 + 12 + 42) * (size_t)count);
-  if (rc) return rc;
-  double* dq = (double*)h->d_stage;
-  double* dT = dq + 7 * (size_t)count;
-  double* dJ = dT + 12 * (size_t)count;
-  cudaStream_t st = h->hstream[0];
-  CCP_CUDA(cudaMemcpyAsync(dq, q_host, sizeof(double) * 7 * count, cudaMemcpyHostToDevice, st));
-  rc = arm_fk_impl(h, arm, dq, count, CCP_LAYOUT_AOS, T_host ? dT : nullptr, J_host ? dJ : nullptr, st);
-  if (rc) return rc;
-  if (T_host) CCP_CUDA(cudaMemcpyAsync(T_host, dT, sizeof(double) * 12 * count, cudaMemcpyDeviceToHost, st));
-  if (J_host) CCP_CUDA(cudaMemcpyAsync(J_host, dJ, sizeof(double) * 42 * count, cudaMemcpyDeviceToHost, st));
-  CCP_CUDA(cudaStreamSynchronize(st));
-  return CCP_OK;
+  void* outs[2] = {T_host, J_host};
+  const size_t ob[2] = {sizeof(double) * 12 * (size_t)count, sizeof(double) * 42 * (size_t)count};
+  return host_eval(h, q_host, sizeof(double) * 7 * (size_t)count, outs, ob, 2,
+                   [&](char* in, char* out, const size_t* off, cudaStream_t st) {
+                     return arm_fk_impl(h, arm, (const double*)in, count, CCP_LAYOUT_AOS,
+                                        T_host ? (double*)(out + off[0]) : nullptr,
+                                        J_host ? (double*)(out + off[1]) : nullptr, st);
+                   });
 }
 
 int ccp_fp64_peak_probe(ccp_handle* h, int32_t repeats, double* flops_per_s, double* ms_out) {

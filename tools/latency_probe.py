@@ -28,3 +28,10 @@ for name, S in (("uniform seeds", seeds), ("seeds 0.05 rad from the manifold", n
 t0 = time.perf_counter()
 r = A.project(near[:64], nthreads=1)
 print(f"oracle A, one thread: {1e6*(time.perf_counter()-t0)/64:.0f} us per projection (near-manifold seeds)")
+x1 = near[:1].copy()
+for name, fn in (("function()", lambda: c.function(x1[0])), ("jacobian()", lambda: c.jacobian(x1[0])), ("isSatisfied()", lambda: c.isSatisfied(x1[0]))):
+    fn()
+    t0 = time.perf_counter()
+    for _ in range(300):
+        fn()
+    print(f"single-state {name:14s}: {(time.perf_counter() - t0) / 300 * 1e6:6.1f} us per call")
