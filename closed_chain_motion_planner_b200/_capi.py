@@ -119,6 +119,8 @@ SYMBOLS = {
     "ccp_arm_fk_batch_host": (C.c_int, [_H, _I32, _P, _I64, _P, _P]),
     "ccp_fp64_peak_probe": (C.c_int, [_H, _I32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ccp_launch_count": (C.c_int64, [_H]),
+    "ccp_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "ccp_host_free": (None, [C.c_void_p]),
     "ccp_project_batch_timed": (C.c_int, [_H, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_float)]),
     "ccp_algorithmic_flops": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ccp_version": (C.c_char_p, []),

@@ -1671,6 +1671,22 @@ int ccp_arm_fk_batch_host(ccp_handle* h, int32_t arm, const double* q_host, int6
                    });
 }
 
+int ccp_host_alloc(void** out, size_t bytes) {
+  if (!out) return CCP_ERR_INVALID;
+  *out = nullptr;
+  if (bytes == 0) return CCP_OK;
+  cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+  if (e != cudaSuccess) {
+    *out = nullptr;
+    return set_err(nullptr, CCP_ERR_CUDA, "cudaHostAlloc: %s", cudaGetErrorString(e));
+  }
+  return CCP_OK;
+}
+
+void ccp_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 int ccp_fp64_peak_probe(ccp_handle* h, int32_t repeats, double* flops_per_s, double* ms_out) {
   if (!h) return CCP_ERR_INVALID;
   device_guard g(h->device);

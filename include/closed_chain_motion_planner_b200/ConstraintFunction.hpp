@@ -12,8 +12,10 @@
 #include <array>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <new>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -45,12 +47,44 @@ inline std::array<double, 12> base_frame(int index) {
   return t;
 }
 
+// std::allocator over page-locked host memory (ccp_host_alloc): buffers handed to the host-buffer entry points should
+// live in it, so that their copies overlap the kernels.  Pinning is slow — keep such vectors alive across calls.
+template <class T>
+struct PinnedAllocator {
+  using value_type = T;
+  PinnedAllocator() = default;
+  template <class U>
+  PinnedAllocator(const PinnedAllocator<U>&) {}
+  // small blocks stay pageable: pinning costs more than it saves below the size where the host path chunks a batch
+  static constexpr std::size_t kPinFrom = 1u << 20;
+  T* allocate(std::size_t count) {
+    void* p = nullptr;
+    if (count * sizeof(T) < kPinFrom) {
+      p = std::malloc(count ? count * sizeof(T) : 1);
+      if (!p) throw std::bad_alloc();
+    } else if (ccp_host_alloc(&p, count * sizeof(T)) != CCP_OK || !p) {
+      throw std::bad_alloc();
+    }
+    return static_cast<T*>(p);
+  }
+  void deallocate(T* p, std::size_t count) {
+    if (count * sizeof(T) < kPinFrom) std::free(p);
+    else ccp_host_free(p);
+  }
+  template <class U>
+  bool operator==(const PinnedAllocator<U>&) const { return true; }
+  template <class U>
+  bool operator!=(const PinnedAllocator<U>&) const { return false; }
+};
+template <class T>
+using PinnedVector = std::vector<T, PinnedAllocator<T>>;
+
 struct ProjectBatchResult {
-  std::vector<double> x;         // count x n, AOS
-  std::vector<uint8_t> ok;       // project()'s return value per state
-  std::vector<uint8_t> converged;
-  std::vector<int32_t> iters;
-  std::vector<double> resid;     // count x m
+  PinnedVector<double> x;         // count x n, AOS
+  PinnedVector<uint8_t> ok;       // project()'s return value per state
+  PinnedVector<uint8_t> converged;
+  PinnedVector<int32_t> iters;
+  PinnedVector<double> resid;     // count x m
 };
 
 class KinematicChainConstraint {
@@ -141,9 +175,14 @@ class KinematicChainConstraint {
   }
 
   // ---- batched entry points (north star) ----
-  // Host states (count x n, AOS): copies in, projects on the GPU, copies out.
+  // Host states (count x n, AOS): copies in, projects on the GPU, copies out.  The result lives in page-locked
+  // memory; a caller with batch after batch passes the previous result back in (second form) so it is pinned once.
   ProjectBatchResult projectBatch(const double* states, int64_t count) const {
     ProjectBatchResult r;
+    projectBatch(states, count, r);
+    return r;
+  }
+  void projectBatch(const double* states, int64_t count, ProjectBatchResult& r) const {
     const unsigned m = getCoDimension();
     r.x.resize((size_t)count * n_);
     r.ok.resize(count);
@@ -152,7 +191,6 @@ class KinematicChainConstraint {
     r.resid.resize((size_t)count * m);
     check(ccp_project_batch_host(need(), states, count, r.x.data(), r.ok.data(), r.converged.data(), r.iters.data(),
                                  r.resid.data()));
-    return r;
   }
   // Streaming form for a caller with batch after batch of host states (caller-owned buffers, page-locked for full
   // overlap; any output but x_out may be null): submit batch k + 1 before waiting for batch k and the GPU never idles

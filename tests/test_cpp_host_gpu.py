@@ -11,14 +11,14 @@ from conftest import ROOT, make_oracles
 pytestmark = pytest.mark.gpu
 
 
-def test_cpp_constraint_program(tmp_path):
+@pytest.mark.parametrize("count", [777, 300_000])  # 300 000: the chunked host path with page-locked results
+def test_cpp_constraint_program(tmp_path, count):
     cfg, A, B = make_oracles("dumbbell")
     exe = tmp_path / "test_constraint"
     lib_dir = os.path.join(ROOT, "closed_chain_motion_planner_b200", "csrc")
     subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"),
                            os.path.join(ROOT, "tests", "cpp", "test_constraint.cpp"), "-o", str(exe),
                            "-L", lib_dir, "-lccp", f"-Wl,-rpath,{lib_dir}"])
-    count = 777
     seeds = A.seeds_uniform(4, 0, count)
     with open(tmp_path / "in.bin", "wb") as f:
         f.write(np.int64(count).tobytes())
@@ -38,7 +38,7 @@ def test_cpp_constraint_program(tmp_path):
     fx, J, x0, flags = take(np.float64, 2), take(np.float64, 28).reshape(2, 14), take(np.float64, 14), take(np.uint8, 3)
     X, ok, iters = take(np.float64, count * 14).reshape(count, 14), take(np.uint8, count), take(np.int32, count)
     T, Jg = take(np.float64, 12).reshape(3, 4), take(np.float64, 42).reshape(6, 7)
-    rb = B.project(seeds, nthreads=4)
+    rb = B.project(seeds, nthreads=8)
     bits = lambda a: np.ascontiguousarray(a).view(np.uint64)
     assert np.array_equal(bits(fx), bits(B.function(seeds[0])[0]))
     assert np.array_equal(bits(J), bits(B.jacobian(seeds[0])[0]))

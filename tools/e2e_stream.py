@@ -1,6 +1,6 @@
 """Diagnostic: host-buffer projection throughput, synchronous call against the streaming submit/wait form.
 
-usage: python tools/e2e_stream.py [count] [batches]     (CCP_HOST_LAG / CCP_HOST_CHUNKS are read by the library)
+usage: python tools/e2e_stream.py [count] [batches] [--pageable]     (CCP_HOST_LAG / CCP_HOST_CHUNKS are read by the library)
 """
 import ctypes as C
 import os
@@ -14,19 +14,23 @@ import torch
 import closed_chain_motion_planner_b200 as pkg
 from closed_chain_motion_planner_b200 import _capi
 
-count = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
-nb = int(sys.argv[2]) if len(sys.argv) > 2 else 12
+pageable = "--pageable" in sys.argv
+argv = [a for a in sys.argv[1:] if not a.startswith("--")]
+count = int(argv[0]) if len(argv) > 0 else 1_000_000
+nb = int(argv[1]) if len(argv) > 1 else 12
 c = pkg.KinematicChainConstraint.from_config("dumbbell")
 lib, h = c._lib, c._h
 n = c.getAmbientDimension()
 d = torch.empty((count, n), dtype=torch.float64, device="cuda")
 a = _capi.SamplerArgs(rng_seed=0, first_index=0, mode=0, wrap_bounds=0, distance=0.0, near_host=None)
 assert lib.ccp_generate_seeds(h, C.byref(a), count, 0, d.data_ptr(), torch.cuda.current_stream().cuda_stream) == 0
-seeds = d.cpu().pin_memory()
+pin = (lambda t: t) if pageable else (lambda t: t.pin_memory())
+seeds = pin(d.cpu())
 R = 3
-xo = [torch.empty((count, n), dtype=torch.float64).pin_memory() for _ in range(R)]
-ok = [torch.empty(count, dtype=torch.uint8).pin_memory() for _ in range(R)]
-it = [torch.empty(count, dtype=torch.int32).pin_memory() for _ in range(R)]
+xo = [pin(torch.zeros((count, n), dtype=torch.float64)) for _ in range(R)]
+ok = [pin(torch.zeros(count, dtype=torch.uint8)) for _ in range(R)]
+it = [pin(torch.zeros(count, dtype=torch.int32)) for _ in range(R)]
+print("host buffers:", "pageable" if pageable else "page-locked")
 
 
 def sync_call(b):
