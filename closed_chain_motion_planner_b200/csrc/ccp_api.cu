@@ -1471,9 +1471,13 @@ int ccp_sample_project_batch_host(ccp_handle* h, const ccp_sampler_args* a, int6
     if (n_ok_host) *n_ok_host = 0;
     return CCP_OK;
   }
-  CCP_NO_OPEN_PIPELINE(h);
   std::lock_guard<std::mutex> host_lock(h->host_mu);
   device_guard g(h->device);
+  for (int i = 0; i < 2; ++i) {  // batches submitted through the streaming projection form complete first
+    int wrc = host_wait_locked(h, h->hcall[i]);
+    if (wrc) return wrc;
+  }
+  CCP_NO_OPEN_PIPELINE(h);
   const int n = CCPC_DOF * h->model.n_arms;
   cudaStream_t st = h->hstream[1];
   const size_t xb = sizeof(double) * n * (size_t)count;

@@ -18,6 +18,11 @@
  *     CCP_LAYOUT_SOA = joint-major, double[n][count] (coalesced, the engine's native layout).
  *   - All functions return CCP_OK (0) or a negative ccp_status; ccp_last_error() gives text.
  *   - There is no CPU fallback: without a CUDA device ccp_create fails with CCP_ERR_CUDA.
+ *   - Threads: host-pointer calls on one handle may come from several threads; they are serialised inside (the
+ *     reference serialises its callers with graphMutex_, stefanBiPRM.cpp:280,383,449).  Device-pointer projection
+ *     calls on one handle (ccp_project_batch*, ccp_sample_project_batch*, ccp_project_flush) share its launch pipeline
+ *     and must come from one thread at a time; use one handle per planner thread or stream otherwise.  Handles are
+ *     independent of one another.
  */
 #ifndef CCP_H_
 #define CCP_H_
