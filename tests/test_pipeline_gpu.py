@@ -166,3 +166,33 @@ def test_streaming_host_submit_wait(setup, count, pinned):
     _same(ref[0], c.projectBatch(batches[0], pinned=not pinned))
     c.waitHostBatch(t)
     assert np.array_equal(_np(ref[1].ok), r.ok)
+
+
+def test_streaming_host_random_sizes_and_buffer_kinds(setup):
+    """Batches of very different sizes, page-locked and pageable results mixed (the two copy schedules hand over to
+    each other), a blocking call and a device-wide synchronisation thrown in: every result equals the device launch's."""
+    pkg, c, A = setup
+    rng = np.random.default_rng(11)
+    sizes = [1, 100, 600, 5_000, 250_000, 500_000, 1_200_000]
+    pending = []
+    first = 0
+    for b in range(16):
+        count = int(rng.choice(sizes))
+        x = A.seeds_uniform(2, first, count)
+        first += count
+        ref = c.projectBatch(torch.from_numpy(x).cuda(), want_resid=False)
+        pinned = bool(rng.integers(2))
+        pending.append((c.submitHostBatch(x, pinned=pinned), ref))
+        if b == 5:
+            torch.cuda.synchronize()
+        if b == 9:
+            xs = A.seeds_uniform(5, 0, 3_000)
+            rs = c.projectBatch(xs)  # blocking host call: completes the pending tickets first
+            rd = c.projectBatch(torch.from_numpy(xs).cuda())
+            assert np.array_equal(_np(rd.x).view(np.uint64), rs.x.view(np.uint64))
+        while len(pending) > (0 if b == 15 else 1):
+            (t, r), ref = pending.pop(0)
+            c.waitHostBatch(t)
+            assert np.array_equal(_np(ref.x).view(np.uint64), r.x.view(np.uint64)), (b, count, pinned)
+            assert np.array_equal(_np(ref.ok), r.ok) and np.array_equal(_np(ref.iters), r.iters)
+    assert not c.pipelineOpen()
