@@ -1287,10 +1287,12 @@ static int host_submit_locked(ccp_handle* h, const double* seeds_host, int64_t c
   c.conv_host = converged_host;
   c.iters_host = iters_host;
   c.resid_host = resid_host;
-  // chunking: a chunk of ~2x the resident lane count keeps every lane busy within a launch and keeps the launch
-  // boundaries few (each costs a drain and a refill of the machine: 1 M seeds in 8 chunks 3.54 ms per batch streaming,
-  // in 12 chunks 3.66, in 24 chunks 4.08; tools/e2e_stream.py); the first H2D (the part nothing hides) shrinks with the
-  // chunk
+  // chunking.  A blocking call wants many chunks — its first H2D and the D2H of its last chunks are hidden by nothing
+  // and shrink with the chunk — but every launch boundary costs a drain and a refill of the machine: ~2x the resident
+  // lane count per chunk (1 M seeds: 8 chunks 4.74 ms, 4 chunks 5.34, 24 chunks 5.26).  With a previous batch still in
+  // flight (the streaming use) that batch hides this one's first copy and the next one its last, and fewer, larger
+  // chunks win: ~5x the lane count (1 M seeds per batch: 3 chunks 3.42 ms, 8 chunks 3.54, 2 chunks 4.00;
+  // tools/e2e_stream.py).
   int parts;
   {
     static int env_parts = -1;
@@ -1299,7 +1301,9 @@ static int host_submit_locked(ccp_handle* h, const double* seeds_host, int64_t c
       env_parts = e ? atoi(e) : 0;
     }
     const int64_t lanes = (int64_t)h->sm_count * 384;
-    parts = env_parts > 0 ? env_parts : (int)(count / (2 * lanes));
+    const bool streaming = !prev.finished;
+    parts = env_parts > 0 ? env_parts : (int)(count / ((streaming ? 5 : 2) * lanes));
+    if (streaming && env_parts <= 0 && parts < 3 && count >= 6 * lanes) parts = 3;
     if (parts > CCP_HOST_MAX_CHUNKS) parts = CCP_HOST_MAX_CHUNKS;
     if (parts < 1) parts = 1;
   }
