@@ -214,6 +214,61 @@ __device__ __forceinline__ void load_sample(const ccp_model& M, const ccp_projec
   for (int j = 0; j < n; ++j) x[j] = ld_elem<SOA>(A.seeds, idx, j, A.seed_stride, n);
 }
 
+// ---- epilogue of one sample (ConstraintFunction.h:75-81): flags, outputs, compaction, completion count ----
+// F needs only e2, sv2 and d[.][0] (what ccp_converged and ccp_residual read).
+template <int K, bool SOA, class XT>
+__device__ __forceinline__ void write_result(const ccp_model& M, const ccp_project_args& A, XT& x, unsigned idx, int it,
+                                             const ccp_fwd<K>& F, unsigned* s_done) {
+  constexpr int n = CCPC_DOF * K, m = 2 * (K - 1);
+  const bool cv = ccp_converged<K>(M, F);
+  const bool okk = cv && ccp_joint_valid<K>(M, x);
+  // the sample reports into the arrays of the launch it was submitted with
+  ccp_out_desc D;
+  if (((unsigned)it >> 16) == A.slot) {
+    D.x_out = A.x_out; D.ok = A.ok; D.conv = A.conv; D.iters = A.iters; D.resid = A.resid;
+    D.count = A.out_stride; D.wrap = A.wrap;
+  } else {
+    const ccp_out_desc* T = A.desc_table + ((unsigned)it >> 16);
+    D.x_out = T->x_out; D.ok = T->ok; D.conv = T->conv; D.iters = T->iters; D.resid = T->resid;
+    D.count = T->count; D.wrap = T->wrap;
+  }
+  if (D.wrap) {  // the sampler's enforceBounds (KinematicChain.h:118-130); one out-of-line copy of the fmod code
+#pragma unroll
+    for (int j = 0; j < n; ++j) x[j] = ccp_wrap_pi_call(x[j]);
+  }
+  if (D.x_out) {
+#pragma unroll
+    for (int j = 0; j < n; ++j) st_elem<SOA>(D.x_out, idx, j, D.count, n, x[j]);
+  }
+  if (D.ok) D.ok[idx] = okk;
+  if (D.conv) D.conv[idx] = cv;
+  if (D.iters) D.iters[idx] = it & 0xffff;
+  if (A.done) atomicAdd(&s_done[(unsigned)it >> 16], 1u);
+  if (D.resid) {
+    double fv[m];
+    ccp_residual<K>(F, fv, nullptr);
+#pragma unroll
+    for (int k = 0; k < m; ++k) st_elem<SOA>(D.resid, idx, k, D.count, m, fv[k]);
+  }
+  // the compacted stream is a stream: a state is appended to the buffer of the launch it finished in
+  if (A.n_ok && okk) {
+    const unsigned long long slot = atomicAdd(A.n_ok, 1ULL);
+    if (A.compact) {
+#pragma unroll
+      for (int j = 0; j < n; ++j) A.compact[slot * n + j] = x[j];
+    }
+    // fused all-gather: the state goes straight into this rank's rows of every peer's pool (NVLink P2P
+    // stores, fire and forget; visible to the peers when this kernel has completed)
+    if (A.peer_world > 0 && (long long)slot < A.peer_cap) {
+      for (int p = 0; p < A.peer_world; ++p) {
+        double* row = A.peer_pool[p] + (A.peer_row0 + (long long)slot) * n;
+#pragma unroll
+        for (int j = 0; j < n; ++j) row[j] = x[j];
+      }
+    }
+  }
+}
+
 // PANDA: structured stock-Panda link code (ccp_core.h).  SM: which per-sample arrays are staged in
 // shared memory (CCP_SM_* bits) instead of registers.
 //
@@ -310,7 +365,11 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
   bool tail = false;
   int since = 0;
   for (;;) {
-    if (!tail) tail = *(volatile int*)&s_tail != 0;
+    // Every lane of the warp meets here (lanes never leave the loop on their own).  `tail` must be the same for all of
+    // them — the tail handling below is warp-collective — so it is agreed on by a vote, not read lane by lane: a lane
+    // coming out of the epilogue branch may itself have just set s_tail.
+    __syncwarp();
+    if (!tail) tail = __any_sync(0xffffffffu, *(volatile int*)&s_tail != 0);
     if (tail) {
       if (A.park) {
         // ---- pipelined mode: once few enough of the warp's lanes still carry a sample, park what the warp
@@ -440,54 +499,8 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
         ccp_newton_step<K>(M, F, J, x);
         if (M.clamp) ccp_clamp_to_limits<K>(M, x);
       } else {
-        // ---- epilogue of this sample (ConstraintFunction.h:75-81), then refill the lane ----
-        const bool cv = ccp_converged<K>(M, F);
-        const bool okk = cv && ccp_joint_valid<K>(M, x);
-        // the sample reports into the arrays of the launch it was submitted with
-        ccp_out_desc D;
-        if (((unsigned)it >> 16) == A.slot) {
-          D.x_out = A.x_out; D.ok = A.ok; D.conv = A.conv; D.iters = A.iters; D.resid = A.resid;
-          D.count = A.out_stride; D.wrap = A.wrap;
-        } else {
-          const ccp_out_desc* T = A.desc_table + ((unsigned)it >> 16);
-          D.x_out = T->x_out; D.ok = T->ok; D.conv = T->conv; D.iters = T->iters; D.resid = T->resid;
-          D.count = T->count; D.wrap = T->wrap;
-        }
-        if (D.wrap) {  // the sampler's enforceBounds (KinematicChain.h:118-130); one out-of-line copy of the fmod code
-#pragma unroll
-          for (int j = 0; j < n; ++j) x[j] = ccp_wrap_pi_call(x[j]);
-        }
-        if (D.x_out) {
-#pragma unroll
-          for (int j = 0; j < n; ++j) st_elem<SOA>(D.x_out, idx, j, D.count, n, x[j]);
-        }
-        if (D.ok) D.ok[idx] = okk;
-        if (D.conv) D.conv[idx] = cv;
-        if (D.iters) D.iters[idx] = it & 0xffff;
-        if (A.done) atomicAdd(&s_done[(unsigned)it >> 16], 1u);
-        if (D.resid) {
-          double fv[m];
-          ccp_residual<K>(F, fv, nullptr);
-#pragma unroll
-          for (int k = 0; k < m; ++k) st_elem<SOA>(D.resid, idx, k, D.count, m, fv[k]);
-        }
-        // the compacted stream is a stream: a state is appended to the buffer of the launch it finished in
-        if (A.n_ok && okk) {
-          const unsigned long long slot = atomicAdd(A.n_ok, 1ULL);
-          if (A.compact) {
-#pragma unroll
-            for (int j = 0; j < n; ++j) A.compact[slot * n + j] = x[j];
-          }
-          // fused all-gather: the state goes straight into this rank's rows of every peer's pool (NVLink P2P
-          // stores, fire and forget; visible to the peers when this kernel has completed)
-          if (A.peer_world > 0 && (long long)slot < A.peer_cap) {
-            for (int p = 0; p < A.peer_world; ++p) {
-              double* row = A.peer_pool[p] + (A.peer_row0 + (long long)slot) * n;
-#pragma unroll
-              for (int j = 0; j < n; ++j) row[j] = x[j];
-            }
-          }
-        }
+        // ---- the sample is finished (ConstraintFunction.h:75-81): results out, then refill the lane ----
+        write_result<K, SOA>(M, A, x, idx, it, F, s_done);
         // Has the global counter run dry?  Private chunks keep a warp supplied for ~50 more trips, so without
         // this look a block would notice the end of the work long after the blocks around it, and a pipelined
         // launch would wait on it with SMs idle.  (Complete launches pack their tail anyway and skip the look.)
