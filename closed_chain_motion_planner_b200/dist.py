@@ -16,7 +16,7 @@ torch.distributed is the plumbing (NCCL over NVLink/NVSwitch on GPUs; gloo in th
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Tuple
 
 
 def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:

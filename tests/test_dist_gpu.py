@@ -1,6 +1,5 @@
 """Multi-GPU path on real devices: sharded sample->project->compact and the NCCL gather of converged states.
 Needs >= 2 GPUs (skipped on a single-GPU box; the host logic is covered on CPU by tests/test_dist_cpu.py)."""
-import os
 import socket
 import subprocess
 import sys

@@ -4,7 +4,6 @@ import sys
 import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
 import torch
 
 import closed_chain_motion_planner_b200 as pkg
