@@ -297,6 +297,44 @@ def test_three_arm_projection(constraints):
     assert c.jacobianBatch(xs[:5]).shape == (5, 4, 21)
 
 
+def test_three_arm_host_paths():
+    """21-DoF states through every host path (in place in page-locked memory, one launch, chunked, streaming):
+    bit-identical to the device launch."""
+    import closed_chain_motion_planner_b200 as pkg
+    from oracle.oracle import OracleA
+
+    gp = pkg.grasping_point()
+    arms = [pkg.ArmModel("panda_left", 0, gp.t_wb[0]), pkg.ArmModel("panda_right", 1, gp.t_wb[1]),
+            pkg.ArmModel("panda_top", 2, gp.t_wb[2])]
+    c = pkg.KinematicChainConstraint(21)
+    c.setArmModels(*arms)
+    q = np.array([-0.16661368, -0.7661184, -0.03369873, -2.37254935, -0.09888003, 1.6927669, 0.17440837] * 3)
+    q[7:14] += 0.05
+    q[14:] -= 0.07
+    c.setInitialPosition(q)
+    A = OracleA([0, 1, 2])
+    rng = np.random.default_rng(3)
+    big = np.concatenate([q[None, :] + 0.08 * rng.standard_normal((200_000, 21)), A.seeds_uniform(0, 0, 50_000)])
+    ref = c.projectBatch(torch.from_numpy(big).cuda())
+    torch.cuda.synchronize()
+
+    def same(r, lo, hi):
+        assert np.array_equal(_bits(ref.x[lo:hi].cpu().numpy()), _bits(r.x))
+        assert np.array_equal(ref.ok[lo:hi].cpu().numpy(), r.ok) and np.array_equal(ref.iters[lo:hi].cpu().numpy(), r.iters)
+        assert np.array_equal(_bits(ref.resid[lo:hi].cpu().numpy()), _bits(r.resid))
+
+    for count in (1, 300, 5_000):
+        same(c.projectBatch(big[:count]), 0, count)
+    same(c.projectBatch(big, pinned=True), 0, len(big))
+    half = len(big) // 2
+    t0, r0 = c.submitHostBatch(big[:half], want_resid=True, pinned=True)
+    t1, r1 = c.submitHostBatch(big[half:], want_resid=True, pinned=True)
+    c.waitHostBatch(t0)
+    c.waitHostBatch(t1)
+    same(r0, 0, half)
+    same(r1, half, len(big))
+
+
 def test_panda_model_api(constraints):
     """RobotModel virtuals (panda_rbdl.h:13-23) through the GPU batch kernels."""
     import closed_chain_motion_planner_b200 as pkg
