@@ -121,6 +121,8 @@ SYMBOLS = {
     "ccp_launch_count": (C.c_int64, [_H]),
     "ccp_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "ccp_host_free": (None, [C.c_void_p]),
+    "ccp_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "ccp_host_unregister": (C.c_int, [C.c_void_p]),
     "ccp_project_batch_timed": (C.c_int, [_H, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_float)]),
     "ccp_algorithmic_flops": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ccp_version": (C.c_char_p, []),

@@ -1695,6 +1695,20 @@ void ccp_host_free(void* p) {
   if (p) cudaFreeHost(p);
 }
 
+int ccp_host_register(void* p, size_t bytes) {
+  if (!p || bytes == 0) return CCP_ERR_INVALID;
+  cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+  if (e != cudaSuccess) return set_err(nullptr, CCP_ERR_CUDA, "cudaHostRegister: %s", cudaGetErrorString(e));
+  return CCP_OK;
+}
+
+int ccp_host_unregister(void* p) {
+  if (!p) return CCP_ERR_INVALID;
+  cudaError_t e = cudaHostUnregister(p);
+  if (e != cudaSuccess) return set_err(nullptr, CCP_ERR_CUDA, "cudaHostUnregister: %s", cudaGetErrorString(e));
+  return CCP_OK;
+}
+
 int ccp_fp64_peak_probe(ccp_handle* h, int32_t repeats, double* flops_per_s, double* ms_out) {
   if (!h) return CCP_ERR_INVALID;
   device_guard g(h->device);

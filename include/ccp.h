@@ -318,6 +318,10 @@ int ccp_arm_fk_batch_host(ccp_handle* h, int32_t arm, const double* q_host, int6
  * against 18.7 ms with pageable buffers).  Allocation is slow (it pins pages): allocate once, reuse across calls.  */
 int ccp_host_alloc(void** out, size_t bytes);
 void ccp_host_free(void* p);
+/* Page-lock memory the caller already owns (a long-lived std::vector's storage, a numpy array) and release it again
+ * before that memory is freed.  Same effect on the host path as ccp_host_alloc; also slow, do it once per buffer.  */
+int ccp_host_register(void* p, size_t bytes);
+int ccp_host_unregister(void* p);
 
 /* ---- measurement helpers ---------------------------------------------------------------- */
 /* Register-only DFMA chains on every SM: returns achieved FP64 FLOP/s (FMA = 2) and the

@@ -196,3 +196,36 @@ def test_streaming_host_random_sizes_and_buffer_kinds(setup):
             assert np.array_equal(_np(ref.x).view(np.uint64), r.x.view(np.uint64)), (b, count, pinned)
             assert np.array_equal(_np(ref.ok), r.ok) and np.array_equal(_np(ref.iters), r.iters)
     assert not c.pipelineOpen()
+
+
+def test_registered_caller_buffers(setup):
+    """ccp_host_register: memory the caller already owns is page-locked in place and the chunked host call then takes
+    the completion-count schedule; ccp_host_alloc memory likewise.  Results equal the device launch's."""
+    import ctypes as C
+
+    pkg, c, A = setup
+    lib, h = c._lib, c._h
+    count, n = 300_000, 14
+    x = A.seeds_uniform(9, 0, count)
+    ref = c.projectBatch(torch.from_numpy(x).cuda(), want_resid=False)
+    torch.cuda.synchronize()
+    xo = np.zeros((count, n))
+    ok = np.zeros(count, np.uint8)
+    it = np.zeros(count, np.int32)
+    for a in (x, xo, ok, it):
+        assert lib.ccp_host_register(a.ctypes.data, a.nbytes) == 0
+    try:
+        assert lib.ccp_project_batch_host(h, x.ctypes.data, count, xo.ctypes.data, ok.ctypes.data, None, it.ctypes.data, None) == 0
+    finally:
+        for a in (x, xo, ok, it):
+            assert lib.ccp_host_unregister(a.ctypes.data) == 0
+    assert np.array_equal(_np(ref.x).view(np.uint64), xo.view(np.uint64))
+    assert np.array_equal(_np(ref.ok), ok) and np.array_equal(_np(ref.iters), it)
+    p = C.c_void_p()
+    assert lib.ccp_host_alloc(C.byref(p), xo.nbytes) == 0 and p.value
+    try:
+        xa = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(count, n))
+        assert lib.ccp_project_batch_host(h, x.ctypes.data, count, p, None, None, None, None) == 0
+        assert np.array_equal(_np(ref.x).view(np.uint64), xa.view(np.uint64))
+    finally:
+        lib.ccp_host_free(p)
