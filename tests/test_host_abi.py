@@ -115,3 +115,17 @@ def test_constraint_argument_checks_without_gpu():
     assert pkg.KinematicChainConstraint(21).getCoDimension() == 4
     with pytest.raises(ValueError):
         c.setArmModels(pkg.ArmModel("a", 0))
+
+
+def test_null_arguments_are_refused_not_dereferenced():
+    """Entry points that can be reached without a handle return CCP_ERR_INVALID instead of crashing."""
+    lib = _capi.load_library()
+    t = C.c_int64(0)
+    assert lib.ccp_project_batch_host_wait(None, 1) == -1
+    assert lib.ccp_project_batch_host_submit(None, None, 1, None, None, None, None, None, C.byref(t)) == -1
+    assert lib.ccp_project_batch_host(None, None, 1, None, None, None, None, None) == -1
+    assert lib.ccp_host_alloc(None, 64) == -1
+    assert lib.ccp_host_register(None, 64) == -1 and lib.ccp_host_unregister(None) == -1
+    lib.ccp_host_free(None)  # a no-op
+    p = C.c_void_p()
+    assert lib.ccp_host_alloc(C.byref(p), 0) == 0 and not p.value
