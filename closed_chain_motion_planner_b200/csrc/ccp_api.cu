@@ -541,7 +541,7 @@ void ccp_destroy(ccp_handle* h) {
   if (h->d_stage) cudaFree(h->d_stage);
   if (h->pin) cudaFreeHost(h->pin);
   for (int i = 0; i < 2; ++i) {
-    if (h->hcall[i].stage) cudaFree(h->hcall[i].stage);
+    if (h->hcall[i].stage) cudaFreeAsync(h->hcall[i].stage, h->hstream[0]);
     if (h->hcall[i].done) cudaEventDestroy(h->hcall[i].done);
   }
   if (h->pool) cudaMemPoolDestroy(h->pool);
@@ -568,6 +568,18 @@ int64_t ccp_launch_count(const ccp_handle* h) { return h ? h->launches : 0; }
   do {                                                                                                             \
     if ((h)->pipeline_open)                                                                                        \
       return set_err((h), CCP_ERR_STATE, "%s", "pipelined projections are in flight: call ccp_project_flush first"); \
+  } while (0)
+
+
+// Device-pointer projection calls share the handle's launch pipeline with the streaming host path, whose launches run on
+// the handle's private (non-blocking) streams: a device launch on the caller's stream would adopt the host batch's
+// parked samples with nothing ordering it after them.  So they are refused while a host ticket is unfinished
+// (ccp.h: "do not issue other projection calls on the handle while a ticket is pending").
+#define CCP_NO_PENDING_TICKETS(h)                                                                                  \
+  do {                                                                                                              \
+    if (!(h)->hcall[0].finished || !(h)->hcall[1].finished)                                                         \
+      return set_err((h), CCP_ERR_STATE, "%s",                                                                      \
+                     "a host batch is pending (ccp_project_batch_host_submit): wait for its ticket first");         \
   } while (0)
 
 int ccp_set_reference(ccp_handle* h, const double* q_start_host) {
@@ -764,6 +776,7 @@ int ccp_project_batch(ccp_handle* h, const double* seeds_dev, int64_t count, int
   int rc = check_common(h, seeds_dev, count, layout);
   if (rc) return rc;
   if (compact_dev && !n_ok_dev) return set_err(h, CCP_ERR_INVALID, "%s", "compact output needs n_ok");
+  CCP_NO_PENDING_TICKETS(h);
   device_guard g(h->device);
   ccp_project_args A;
   memset(&A, 0, sizeof A);
@@ -787,6 +800,7 @@ int ccp_project_batch_pipelined(ccp_handle* h, const double* seeds_dev, int64_t 
   int rc = check_common(h, seeds_dev, count, layout);
   if (rc) return rc;
   if (compact_dev && !n_ok_dev) return set_err(h, CCP_ERR_INVALID, "%s", "compact output needs n_ok");
+  CCP_NO_PENDING_TICKETS(h);
   device_guard g(h->device);
   ccp_project_args A;
   memset(&A, 0, sizeof A);
@@ -809,12 +823,15 @@ static int sample_project_impl(ccp_handle* h, const ccp_sampler_args* a, int64_t
 int ccp_sample_project_batch_pipelined(ccp_handle* h, const ccp_sampler_args* a, int64_t count, int32_t layout,
                                        double* x_out_dev, uint8_t* ok_dev, int32_t* iters_dev, double* compact_dev,
                                        int64_t* n_ok_dev, void* stream) {
+  if (!h) return CCP_ERR_INVALID;
+  CCP_NO_PENDING_TICKETS(h);
   return sample_project_impl(h, a, count, layout, x_out_dev, ok_dev, iters_dev, compact_dev, n_ok_dev, stream, true);
 }
 
 int ccp_project_flush(ccp_handle* h, double* compact_dev, int64_t* n_ok_dev, void* stream) {
   if (!h) return CCP_ERR_INVALID;
   if (compact_dev && !n_ok_dev) return set_err(h, CCP_ERR_INVALID, "%s", "compact output needs n_ok");
+  CCP_NO_PENDING_TICKETS(h);
   if (!h->pipeline_open) return CCP_OK;
   device_guard g(h->device);
   ccp_project_args A;
@@ -991,6 +1008,8 @@ static int sample_project_impl(ccp_handle* h, const ccp_sampler_args* a, int64_t
 int ccp_sample_project_batch(ccp_handle* h, const ccp_sampler_args* a, int64_t count, int32_t layout,
                              double* x_out_dev, uint8_t* ok_dev, int32_t* iters_dev, double* compact_dev,
                              int64_t* n_ok_dev, void* stream) {
+  if (!h) return CCP_ERR_INVALID;
+  CCP_NO_PENDING_TICKETS(h);
   return sample_project_impl(h, a, count, layout, x_out_dev, ok_dev, iters_dev, compact_dev, n_ok_dev, stream, false);
 }
 
@@ -1256,24 +1275,27 @@ static int host_submit_locked(ccp_handle* h, const double* seeds_host, int64_t c
     rc = host_wait_locked(h, prev);
     if (rc) return rc;
   }
-  c.use_wait = use_wait;
-  c.enqueued = false;
-  if (use_wait && !prev.finished && !prev.enqueued) {  // this batch's launches complete the previous one
-    rc = host_enqueue_copies(h, prev);
-    if (rc) return rc;
-  }
   if (h->pipeline_open && (prev.finished || (!prev.use_wait && prev.copied == prev.parts)))
     return set_err(h, CCP_ERR_STATE, "%s", "pipelined projections are in flight: call ccp_project_flush first");
   const int n = CCPC_DOF * h->model.n_arms, m = 2 * (h->model.n_arms - 1);
   const size_t per = sizeof(double) * n + sizeof(double) * m + 8 /* ok, conv, pad */ + sizeof(int32_t) + 4;
   const size_t need = per * (size_t)count + 1024;
-  if (need > c.stage_bytes) {  // (device-wide synchronisation: everything pending completes by itself)
-    if (c.stage) cudaFree(c.stage);
+  cudaStream_t sC = h->hstream[0], sK = h->hstream[1];
+  if (need > c.stage_bytes) {
+    // Stream-ordered, from the handle's pool: no device-wide synchronisation.  (cudaFree would wait for everything
+    // pending on the device — and the previous batch's last chunks are only finished by THIS batch's launches.)  The
+    // old stage was last touched by the batch two submits back, which host_wait_locked above has seen complete.
+    if (c.stage) CCP_CUDA(cudaFreeAsync(c.stage, sC));
     c.stage = nullptr;
     c.stage_bytes = 0;
-    CCP_CUDA(cudaMalloc(&c.stage, need + need / 4));
+    CCP_CUDA(cudaMallocFromPoolAsync(&c.stage, need + need / 4, h->pool, sC));
     c.stage_bytes = need + need / 4;
   }
+  // Every fallible host-side check is behind us.  The previous batch's copies (use_wait scheme) go on the D2H stream
+  // only AFTER this batch's launches are enqueued (below): their stream waits are satisfied by these launches, and a
+  // wait whose launches never came would block the D2H stream — and ccp_destroy's synchronisation — for ever.
+  c.use_wait = use_wait;
+  c.enqueued = false;
   // carve the stage: x [count][n] | resid [count][m] | iters | ok | conv
   char* base = (char*)c.stage;
   c.dx = (double*)base;
@@ -1316,7 +1338,6 @@ static int host_submit_locked(ccp_handle* h, const double* seeds_host, int64_t c
   c.first_launch = h->host_launches;
   c.finished = false;
   c.ticket = h->next_ticket++;
-  cudaStream_t sC = h->hstream[0], sK = h->hstream[1];
   for (int k = 0; k < parts; ++k) {
     const int64_t off = (int64_t)k * chunk;
     const int64_t cn = (count - off < chunk) ? (count - off) : chunk;
@@ -1349,6 +1370,10 @@ static int host_submit_locked(ccp_handle* h, const double* seeds_host, int64_t c
       rc = host_copy_ready(h, c, g, h->ev_chunk_k[k], waited);
       if (rc) return rc;
     }
+  }
+  if (use_wait && !prev.finished && !prev.enqueued) {  // this batch's launches complete the previous one
+    rc = host_enqueue_copies(h, prev);
+    if (rc) return rc;
   }
   if (ticket_out) *ticket_out = c.ticket;
   return CCP_OK;

@@ -5,6 +5,7 @@
 // Replaces KinematicChainConstraint::project (ConstraintFunction.h:57-82) for a whole batch.
 #include <stdlib.h>
 
+#include <atomic>
 #include <type_traits>
 
 #include "ccp_device.cuh"
@@ -66,6 +67,7 @@ constexpr size_t ccp_proj_smem_bytes() {
 // memory: [next, end)).  Lanes whose sample just finished take the next numbers from it; only when it runs dry
 // does the warp's leader touch the global work counter (one atomic per CCP_CLAIM_CHUNK samples instead of one
 // per refill) and start the bulk copy of the new chunk's seeds into shared memory.
+#define CCP_MAX_DEVICES 64
 #define CCP_CLAIM_CHUNK 32u
 
 // how many trips pass between two tail rendezvous of the block
@@ -532,11 +534,16 @@ static cudaError_t launch_project_v(int sm_count, const ccp_model& M, const ccp_
   if (grid < 1) grid = 1;
   constexpr size_t smem = ccp_proj_smem_bytes<K, BLOCK, SM>();
   auto kern = ccp_project_kernel<K, PANDA, SOA, BLOCK, MINB, SM>;
-  static bool attr_done = false;  // per instantiation
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // Function attributes are per DEVICE: one flag per (instantiation, device), so that handles on several GPUs of one
+  // process each raise the dynamic shared-memory limit on their own device.  (Relaxed atomics: setting it twice is harmless.)
+  static std::atomic<unsigned char> attr_done[CCP_MAX_DEVICES];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= CCP_MAX_DEVICES || !attr_done[dev].load(std::memory_order_relaxed)) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr_done = true;
+    if (dev >= 0 && dev < CCP_MAX_DEVICES) attr_done[dev].store(1, std::memory_order_relaxed);
   }
   kern<<<grid, BLOCK, smem, st>>>(M, A);
   return cudaGetLastError();

@@ -174,6 +174,7 @@ class jy_ProjectedStateSampler:
         self.rng_seed = int(rng_seed)
         self.wrap_bounds = bool(wrap_bounds)
         self.group = group
+        self._sharded = None
         self._next_index = 0  # position in the counter-based stream
         self._pool = np.zeros((0, self.constraint_.getAmbientDimension()))
         self._pos = 0
@@ -207,9 +208,11 @@ class jy_ProjectedStateSampler:
     def sampleUniformBatch(self, count: int):
         """`count` uniform seeds -> the projected states that succeeded (torch (k, n), k <= count)."""
         if self.group is not None:
-            from .dist import ShardedSampleProjector
+            if self._sharded is None:  # created once: its symmetric-memory pool is kept across refills
+                from .dist import ShardedSampleProjector
 
-            states, _ = ShardedSampleProjector(self.constraint_, self.group).sample_project(
+                self._sharded = ShardedSampleProjector(self.constraint_, self.group)
+            states, _ = self._sharded.sample_project(
                 self.rng_seed, self._next_index, count, wrap_bounds=self.wrap_bounds)
             self._next_index += count
             self.launches += 1

@@ -101,7 +101,14 @@ def test_project_flags_vs_reference_faithful_oracle(constraints, name):
     frac_uni = np.mean(d[both & ~near] <= 1e-6)
     print(f"\n[{name}] ok-flag agreement {agree_ok:.4f}; |x_gpu - x_refA| <= 1e-6: near-manifold {frac_near:.3f}, "
           f"uniform {frac_uni:.3f}; median {np.median(d[both]):.2e}, max {d[both].max():.2e}")
-    assert frac_near >= (0.6 if name == "dumbbell" else 0.8)
+    # The gate is BASELINE.md's 0.8 unless the reference-faithful oracle itself cannot reach it: its agreement with
+    # ITSELF on the same seeds moved by one ulp is the ceiling (dumbbell's near-planar start: ~0.67), and the engine
+    # must sit at that ceiling.  tests/test_parity_full_gpu.py repeats this at 10 000 seeds per regime.
+    r2 = A.project(np.nextafter(seeds[1500:], np.inf), nthreads=A.max_threads)
+    both2 = (ra["ok"][1500:] == 1) & (r2["ok"] == 1)
+    ceiling = np.mean(np.max(np.abs(ra["x"][1500:] - r2["x"]), axis=1)[both2] <= 1e-6)
+    print(f"[{name}] near-manifold ceiling (oracle A vs itself, 1 ulp apart): {ceiling:.3f}")
+    assert frac_near >= min(0.8, ceiling - 0.05), (frac_near, ceiling)
     assert d[both].max() < 5e-3
 
 

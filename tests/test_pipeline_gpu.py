@@ -172,6 +172,7 @@ def test_streaming_host_random_sizes_and_buffer_kinds(setup):
     """Batches of very different sizes, page-locked and pageable results mixed (the two copy schedules hand over to
     each other), a blocking call and a device-wide synchronisation thrown in: every result equals the device launch's."""
     pkg, c, A = setup
+    c_ref = pkg.KinematicChainConstraint.from_config("dumbbell", device=0)
     rng = np.random.default_rng(11)
     sizes = [1, 100, 600, 5_000, 250_000, 500_000, 1_200_000]
     pending = []
@@ -180,7 +181,9 @@ def test_streaming_host_random_sizes_and_buffer_kinds(setup):
         count = int(rng.choice(sizes))
         x = A.seeds_uniform(2, first, count)
         first += count
-        ref = c.projectBatch(torch.from_numpy(x).cuda(), want_resid=False)
+        # reference results from a SECOND handle: device-pointer projections on `c` are refused while one of its host
+        # tickets is pending (and every submit now really hands over to the previous batch: no launch in between)
+        ref = c_ref.projectBatch(torch.from_numpy(x).cuda(), want_resid=False)
         pinned = bool(rng.integers(2))
         pending.append((c.submitHostBatch(x, pinned=pinned), ref))
         if b == 5:
@@ -188,7 +191,7 @@ def test_streaming_host_random_sizes_and_buffer_kinds(setup):
         if b == 9:
             xs = A.seeds_uniform(5, 0, 3_000)
             rs = c.projectBatch(xs)  # blocking host call: completes the pending tickets first
-            rd = c.projectBatch(torch.from_numpy(xs).cuda())
+            rd = c_ref.projectBatch(torch.from_numpy(xs).cuda())
             assert np.array_equal(_np(rd.x).view(np.uint64), rs.x.view(np.uint64))
         while len(pending) > (0 if b == 15 else 1):
             (t, r), ref = pending.pop(0)
@@ -229,3 +232,75 @@ def test_registered_caller_buffers(setup):
         assert np.array_equal(_np(ref.x).view(np.uint64), xa.view(np.uint64))
     finally:
         lib.ccp_host_free(p)
+
+
+def test_device_calls_refused_while_host_ticket_pending(setup):
+    """ccp.h: no other projection call on the handle while a ticket is pending.  The library enforces it
+    (CCP_ERR_STATE) instead of letting a device launch on the caller's stream adopt the host batch's parked samples."""
+    pkg, c, A = setup
+    x = A.seeds_uniform(4, 0, 400_000)
+    xd = torch.from_numpy(x[:1000]).cuda()
+    ref = c.projectBatch(torch.from_numpy(x).cuda(), want_resid=False)
+    torch.cuda.synchronize()
+    t, r = c.submitHostBatch(x, pinned=True)
+    with pytest.raises(pkg.CcpError, match="host batch is pending"):
+        c.projectBatch(xd)
+    with pytest.raises(pkg.CcpError, match="host batch is pending"):
+        c.projectBatch(xd, pipelined=True)
+    with pytest.raises(pkg.CcpError, match="host batch is pending"):
+        c.flush()
+    c.waitHostBatch(t)
+    assert np.array_equal(_np(ref.x).view(np.uint64), r.x.view(np.uint64)) and np.array_equal(_np(ref.ok), r.ok)
+    r2 = c.projectBatch(xd)  # usable again
+    torch.cuda.synchronize()
+    assert np.array_equal(_np(r2.x).view(np.uint64), r.x[:1000].view(np.uint64))
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+def test_streaming_host_growing_batches_back_to_back(pinned):
+    """Batches of growing size submitted back to back with nothing in between: every submit outgrows its slot's device
+    stage while the previous batch still has chunks in flight that only THIS batch's launches finish.  (The stage used to
+    be regrown with cudaFree/cudaMalloc — a device-wide synchronisation — after the previous batch's stream waits were
+    already enqueued: a hang.)  A fresh handle, so that no stage exists beforehand."""
+    import closed_chain_motion_planner_b200 as pkg
+    from conftest import make_oracles as mk
+
+    cfg, A, B = mk("dumbbell")
+    c = pkg.KinematicChainConstraint.from_config("dumbbell", device=0)
+    c_ref = pkg.KinematicChainConstraint.from_config("dumbbell", device=0)
+    sizes = [240_000, 320_000, 420_000, 560_000, 740_000, 1_000_000]
+    pending, first = [], 0
+    for count in sizes:
+        x = A.seeds_uniform(6, first, count)
+        first += count
+        ref = c_ref.projectBatch(torch.from_numpy(x).cuda(), want_resid=False)
+        pending.append((c.submitHostBatch(x, pinned=pinned), ref))
+        if len(pending) == 2:
+            (t, r), rf = pending.pop(0)
+            c.waitHostBatch(t)
+            assert np.array_equal(_np(rf.x).view(np.uint64), r.x.view(np.uint64)), count
+            assert np.array_equal(_np(rf.ok), r.ok) and np.array_equal(_np(rf.iters), r.iters)
+    (t, r), rf = pending.pop(0)
+    c.waitHostBatch(t)
+    assert np.array_equal(_np(rf.x).view(np.uint64), r.x.view(np.uint64))
+    assert not c.pipelineOpen()
+    del c  # ccp_destroy synchronises the device: must not hang on a leftover stream wait
+
+
+def test_handles_on_two_devices_in_one_process():
+    """cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: a second handle on another GPU of the same process
+    must raise the limit there too (it used to be done once per process)."""
+    import closed_chain_motion_planner_b200 as pkg
+    from conftest import make_oracles as mk
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one process")
+    cfg, A, B = mk("dumbbell")
+    x = A.seeds_uniform(1, 0, 20_000)
+    out = []
+    for dev in (0, 1):
+        c = pkg.KinematicChainConstraint.from_config("dumbbell", device=dev)
+        r = c.projectBatch(torch.from_numpy(x).to(f"cuda:{dev}"))
+        torch.cuda.synchronize(dev)
+        out.append((r.x.cpu().numpy(), r.ok.cpu().numpy()))
+    assert np.array_equal(out[0][0].view(np.uint64), out[1][0].view(np.uint64)) and np.array_equal(out[0][1], out[1][1])
