@@ -68,9 +68,10 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.perf_counter(), ln.strip()))
 
-    def stop(self):
+    def stop(self, windows=None):
+        """windows: [(t0, t1)] perf_counter intervals of continuous GPU load; only samples inside one are kept."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -79,9 +80,15 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except subprocess.TimeoutExpired:
             self.proc.kill()
+        return self.summarise(self.lines, windows)
+
+    @staticmethod
+    def summarise(lines, windows=None):
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ts, ln in lines:
+            if windows is not None and not any(a + 0.05 <= ts <= b for a, b in windows):
+                continue
             p = [t.strip() for t in ln.split(",")]
             if len(p) < 9:
                 continue
@@ -99,6 +106,39 @@ class ClockSampler:
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
                 "reasons": sorted(reasons)}
+
+
+def _parse_cpulist(txt):
+    cpus = set()
+    for part in txt.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa(torch, local):
+    """Pin this rank's threads (and so, by first touch, its page-locked buffers) to the NUMA node its GPU hangs off.
+    Returns what was found for the JSON line; a single-node box (or a VM that hides the topology) is left alone."""
+    info = {"cpus_visible": os.cpu_count(), "numa_nodes": None, "gpu_numa_node": None, "bound": False}
+    try:
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        info["numa_nodes"] = len(nodes)
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        info["gpu_numa_node"] = node
+        if len(nodes) > 1 and node >= 0:
+            cpus = _parse_cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read())
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                info["bound"] = True
+        info["affinity"] = len(os.sched_getaffinity(0))
+    except (OSError, ValueError, AttributeError) as e:
+        info["note"] = repr(e)
+    return info
 
 
 def cpu_baseline(config: str, sample: int, threads: int, with_engine_arithmetic: bool = False):
@@ -135,6 +175,176 @@ def cpu_baseline(config: str, sample: int, threads: int, with_engine_arithmetic:
         dtb = time.perf_counter() - t0
         out["engine_arithmetic_on_cpu"] = {"projections_per_s": sample / dtb, "converged_per_s": float(rb["ok"].sum()) / dtb,
                                            "seconds": dtb, "threads": threads}
+    return out
+
+
+NOMINAL_FP64_TFLOPS = 37.2  # 148 SMs x 64 DFMA lanes x 2 FLOP x 1.965 GHz (no driver-measured FP64 peak exists)
+
+
+def sampler_leg(c, count, first_index, reps, peak_flops, warm=True, peer=None, world=1, dist=None, windows=None):
+    """One timed leg on the sampler path of constraint `c`: `count` device-generated Seeds-U starting at counter
+    `first_index` (ccp_sample_project_batch: seed kernel + pipelined projection launches of 2 M seeds + the completing
+    launch), per-seed ok + iteration outputs, CUDA events on the launching stream.  peer: PeerPool — the kernel's fused
+    gather of the converged states plus the count exchange are inside the timed region.  Returns the record and the
+    tensors a check needs."""
+    import ctypes as C
+
+    import torch
+
+    from closed_chain_motion_planner_b200 import _capi
+
+    lib, h = c._lib, c._h
+    dev = torch.device("cuda", c.device)
+    ok = torch.empty(count, dtype=torch.uint8, device=dev)
+    it = torch.empty(count, dtype=torch.int32, device=dev)
+    n_ok = torch.zeros(1, dtype=torch.int64, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    fl_iter, fl_tail = c.algorithmicFlops()
+    times, counts = [], None
+    launches0 = c.launchCount()
+    t_open = None
+    for r in range(reps + (1 if warm else 0)):
+        if t_open is None and (r > 0 or not warm):
+            t_open = time.perf_counter()
+        a = _capi.SamplerArgs(rng_seed=0, first_index=first_index, mode=0, wrap_bounds=0, distance=0.0, near_host=None)
+        n_ok.zero_()
+        if peer is not None:
+            dist.barrier()  # nobody still reads the pool of the previous repetition
+            peer.attach()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = lib.ccp_sample_project_batch(h, C.byref(a), count, 0, None, ok.data_ptr(), it.data_ptr(), None, n_ok.data_ptr(), st)
+        assert rc == 0, lib.ccp_last_error(h)
+        if peer is not None:
+            counts = peer.exchange_counts(n_ok)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        if peer is not None:
+            peer.detach()
+        if r > 0 or not warm:
+            times.append(e0.elapsed_time(e1))
+    if windows is not None and t_open is not None:
+        windows.append((t_open, time.perf_counter()))  # continuous load: the clock sampler keeps these samples
+    ms = sum(times) / len(times)
+    iters = int(it.sum(dtype=torch.int64))
+    nk = int(n_ok.item())
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    w = torch.tensor([float(count), float(nk), float(iters)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+    ms = t.item()
+    cnt_all, ok_all, it_all = w.tolist()
+    flops = it_all * fl_iter + cnt_all * fl_tail
+    rec = {"seeds": int(cnt_all), "seeds_per_gpu": count, "ms": ms, "reps": len(times),
+           "projections_per_s": cnt_all / ms * 1e3, "converged_per_s": ok_all / ms * 1e3, "ok_fraction": ok_all / cnt_all,
+           "mean_iters": it_all / cnt_all,
+           "roofline": {"bound": "fp64", "achieved": flops / world / ms / 1e9, "peak": peak_flops / 1e12, "unit": "TFLOP/s",
+                        "frac": flops / world / (ms * 1e-3) / peak_flops,
+                        "frac_of_nominal": flops / world / (ms * 1e-3) / (NOMINAL_FP64_TFLOPS * 1e12)},
+           "gpu_launches": (c.launchCount() - launches0) // (reps + (1 if warm else 0))}
+    return rec, ok, n_ok, counts
+
+
+def gather_check(peer, ok, n_ok, counts, world, rank, dist, dev):
+    """N > 1: every rank's copy of the gathered pool must be identical (a wrapping int64 sum over the bit patterns of
+    each source rank's rows, compared across ranks), and the exchanged per-rank counts must equal the ranks' own
+    recount of their ok flags."""
+    import torch
+
+    cl = [int(v) for v in counts.tolist()]
+    sums = torch.stack([peer.pool[r, :cl[r]].view(torch.int64).sum() for r in range(world)])
+    all_sums = torch.empty((world, world), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_sums, sums)
+    recount = torch.tensor([int(ok.sum(dtype=torch.int64))], dtype=torch.int64, device=dev)
+    all_recount = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_recount, recount)
+    same_pools = bool((all_sums == all_sums[0:1]).all())
+    counts_ok = [int(v) for v in all_recount.tolist()] == cl and cl[rank] == int(n_ok.item())
+    return {"pools_identical_across_ranks": same_pools, "counts_equal_local_recount": counts_ok, "counts": cl,
+            "checksum_rank0_rows": int(all_sums[0, 0].item())}
+
+
+def extra_configs(args, pkg, rank, world, local, dist, peak_flops, windows):
+    """BASELINE configs[0], [2], [3] measured in the same process, after the headline region:
+      C1  stefan, 10 000 Seeds-U on the reference-faithful CPU oracle (all host cores), the GPU on the same seeds beside it
+      C3  Wine_Bottle (joint limits bite: its start sits 7.5e-3 rad from one), 10 M seeds: strong (10 M sharded over
+          the N ranks) and weak (10 M per GPU); at N > 1 the fused gather + count exchange inside, with a gather check
+      C4  stefan three-arm (21 DoF), 1e3 .. 1e8 seeds on one GPU (N = 1 runs only)"""
+    import numpy as np
+    import torch
+
+    from closed_chain_motion_planner_b200.dist import PeerPool, gather_capacity, shard_range
+
+    dev = torch.device("cuda", local)
+    out = {}
+    # ---- C3 ----
+    cw = pkg.KinematicChainConstraint.from_config("Wine_Bottle", device=local)
+    total = args.c3_seeds
+    c3 = {"workload": f"Wine_Bottle (configs/Wine_Bottle.yaml) projection with joint limits, {total} Seeds-U, sampler path "
+                      "(device-generated seeds, ok + iteration outputs)"}
+    for mode in ("strong", "weak"):
+        first, count = shard_range(total, rank, world) if mode == "strong" else (rank * total, total)
+        peer = None
+        if world > 1:
+            try:
+                peer = PeerPool(cw, gather_capacity(max(shard_range(total, 0, world)[1], 1) if mode == "strong" else total))
+            except Exception as e:  # noqa: BLE001 - every rank fails alike
+                c3["peer_memory_error"] = repr(e)
+        # the weak leg also feeds the clock record: >= ~1.2 s of continuous load (fixed repetition count, the same on
+        # every rank: the fused exchange is a collective)
+        reps = 3 if mode == "strong" else max(3, min(60, int(1200.0 / (0.0021 * total / 1000.0)) + 1))
+        rec, ok, n_ok, counts = sampler_leg(cw, count, first, reps, peak_flops, peer=peer, world=world, dist=dist,
+                                            windows=windows if mode == "weak" else None)
+        rec["scaling"] = mode
+        if peer is not None:
+            rec["exchange"] = "fused peer stores + count exchange inside the timed region"
+            rec["gather_check"] = gather_check(peer, ok, n_ok, counts, world, rank, dist, dev)
+            assert rec["gather_check"]["pools_identical_across_ranks"] and rec["gather_check"]["counts_equal_local_recount"]
+        c3[mode] = rec
+        del peer, ok
+
+    out["C3"] = c3
+    del cw
+    if world > 1:
+        return out
+    # ---- C4 ----
+    c4 = {"workload": "stefan three-arm closed chain (configs/stefan_three_arm.yaml, 21 DoF, co-dimension 4), Seeds-U, "
+                      "sampler path, one GPU", "sweep": []}
+    ck = pkg.KinematicChainConstraint.from_config("stefan_three_arm", device=local)
+    for e in range(3, args.c4_max_exp + 1):
+        cnt = 10 ** e
+        rec, _, _, _ = sampler_leg(ck, cnt, 0, 3 if e <= 6 else (2 if e == 7 else 1), peak_flops, warm=e <= 7)
+        c4["sweep"].append(rec)
+    out["C4"] = c4
+    # ---- C1 ----
+    from closed_chain_motion_planner_b200 import grasping_point
+    from oracle.oracle import OracleA
+
+    cs = pkg.KinematicChainConstraint.from_config("stefan", device=local)
+    cfg = grasping_point().loadConfig("stefan")
+    A = OracleA(cfg.arm_indices)
+    A.set_initial_position(cfg.start)
+    seeds = A.seeds_uniform(0, 0, 10_000)
+    threads = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    ra = A.project(seeds, fd=True, nthreads=threads)
+    dt = time.perf_counter() - t0
+    cs.projectBatch(seeds)  # warm the host path
+    t0 = time.perf_counter()
+    rg = cs.projectBatch(seeds)
+    dg = time.perf_counter() - t0
+    okm = rg.ok == 1
+    f = A.function(rg.x[okm], nthreads=threads)
+    out["C1"] = {"workload": "stefan (configs/stefan.yaml) dual-arm closed-chain projection of 10 000 Seeds-U",
+                 "cpu": {"kind": "port", "impl": "oracle A (reference-faithful FD Jacobian + SVD solve)", "cores": threads,
+                         "seconds": dt, "projections_per_s": 10_000 / dt, "converged_per_s": float(ra["ok"].sum()) / dt,
+                         "ok_fraction": float(ra["ok"].mean()), "mean_iters": float(ra["iters"].mean())},
+                 "gpu_host_call": {"api": "ccp_project_batch_host (pageable numpy in, all outputs back)", "seconds": dg,
+                                   "projections_per_s": 10_000 / dg, "converged_per_s": float(rg.ok.sum()) / dg},
+                 "parity": {"ok_flag_agreement": float(np.mean(rg.ok == ra["ok"])),
+                            "converged_flag_agreement": float(np.mean(rg.converged == ra["converged"])),
+                            "max_residual_of_ok_states_by_oracle": [float(f[:, 0].max()), float(f[:, 1].max())]}}
     return out
 
 
@@ -184,6 +394,9 @@ def main():
     ap.add_argument("--layout", default="aos", choices=["aos", "soa"])
     ap.add_argument("--nccl-gather", action="store_true",
                     help="N > 1: collect the converged states with NCCL all-gathers instead of the kernel's fused peer stores")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C1 / C3 / C4 records (BASELINE configs[0], [2], [3])")
+    ap.add_argument("--c3-seeds", type=int, default=10_000_000)
+    ap.add_argument("--c4-max-exp", type=int, default=8, help="the 21-DoF sweep runs 1e3 .. 1e<this> seeds")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="every launch runs its own stragglers to completion (ccp_project_batch) instead of parking them "
                          "for the next launch (ccp_project_batch_pipelined + one ccp_project_flush)")
@@ -209,6 +422,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
+    host_info = bind_to_gpu_numa(torch, local)
     c = pkg.KinematicChainConstraint.from_config(args.config, device=local)
     lib, h = c._lib, c._h
     n, m = c.getAmbientDimension(), c.getCoDimension()
@@ -217,8 +431,16 @@ def main():
     shape = (count, n) if layout == pkg.CCP_LAYOUT_AOS else (n, count)
     stream = torch.cuda.current_stream().cuda_stream
 
-    # measured FP64 peak of this GPU (register-only DFMA chains), before the timed region
-    peak_flops, _ = c.fp64PeakProbe(5)
+    # measured FP64 peak of this GPU (register-only DFMA chains), before the timed region; the clock sampler runs from
+    # here on and its samples are kept per window of continuous load (probe / headline region / C3 weak leg)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    c.fp64PeakProbe(2)
+    t_probe = time.perf_counter()
+    peak_flops, _ = c.fp64PeakProbe(40)
+    probe_window = [(t_probe, time.perf_counter())]
+    load_windows = []
 
     # synthetic seeds, resident in HBM: a different slice of the counter stream per step and per rank
     n_batches = min(args.warmup + args.steps, 8)
@@ -337,10 +559,8 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = c.launchCount()
+    t_region = time.perf_counter()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps + 1)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     total_ok = 0
@@ -371,8 +591,8 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     launches = c.launchCount() - launches0
+    load_windows.append((t_region - 0.05, time.perf_counter()))
     assert int(max_counts.max().item()) <= cap, "gather capacity overflow"
-    clocks = sampler.stop() if rank == 0 else None
 
     ms_total = t_begin.elapsed_time(t_end)
     n_timed_launches = args.steps + (1 if pipelined else 0)
@@ -450,16 +670,111 @@ def main():
                 dist.all_reduce(oe, op=dist.ReduceOp.SUM)
             return oe.item(), te.item()
 
+        # ---- compact-output forms (ccp_host_batch_submit / _wait): only the ok states come back, packed, with their
+        # seed indices + the per-seed ok / iteration arrays; (a) host seeds in, (b) sampler arguments in (the seeds are
+        # generated on the device: the pool refill of jy_ProjectedStateSampler — no H2D at all)
+        ccap = int(count * 0.4) + 64
+        cst = [torch.empty((ccap, n), dtype=torch.float64).pin_memory() for _ in range(2)]
+        cix = [torch.empty(ccap, dtype=torch.int32).pin_memory() for _ in range(2)]
+        d2h_compact = [0]
+
+        def make_compact_runner(seeded):
+            def run(steps):
+                ok = 0
+                tick = C.c_int64(0)
+                nk = C.c_int64(0)
+                pending = []
+                keep = []
+                for k in range(steps + 1):
+                    if k < steps:
+                        r = k & 1
+                        b = _capi.HostBatch()
+                        b.count = count
+                        if seeded:
+                            sa = _capi.SamplerArgs(rng_seed=0, first_index=(rank * 64 + (k % 8)) * count, mode=0, wrap_bounds=0,
+                                                   distance=0.0, near_host=None)
+                            keep.append(sa)
+                            b.sampler = C.pointer(sa)
+                        else:
+                            b.seeds_host = hs[r].data_ptr()
+                        b.ok_host = hok[r].data_ptr()
+                        b.iters_host = hit[r].data_ptr()
+                        b.compact_host = cst[r].data_ptr()
+                        b.compact_index_host = cix[r].data_ptr()
+                        b.compact_capacity = ccap
+                        assert lib.ccp_host_batch_submit(h, C.byref(b), C.byref(tick)) == 0, lib.ccp_last_error(h)
+                        pending.append((tick.value, r))
+                    if len(pending) == 2 or (k == steps and pending):
+                        t, r = pending.pop(0)
+                        assert lib.ccp_host_batch_wait(h, t, C.byref(nk)) == 0
+                        assert 0 <= nk.value <= ccap
+                        ok += nk.value  # the step's result: the number of packed rows (checked against the flags below)
+                        d2h_compact[0] = count * 5 + nk.value * (n * 8 + 4) + 8
+                return ok
+            return run
+
         ok_sync, t_sync = timed_host(run_sync)
         ok_str, t_str = timed_host(run_streaming)
+        ok_cmp, t_cmp = timed_host(make_compact_runner(False))
+        assert int(np.count_nonzero(hok_np[(e_steps - 1) & 1])) > 0
+        d2h_cmp = d2h_compact[0]
+        ok_sed, t_sed = timed_host(make_compact_runner(True))
+        d2h_sed = d2h_compact[0]
+
+        # ---- host ceiling: nothing but the copies of the full-output form, on every rank at once (what the box's host
+        # side can move through pinned memory; the full-output e2e cannot beat count / this time)
+        s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        dstage = torch.empty((count, n), dtype=torch.float64, device=dev)
+        dflags = torch.empty(count * 5, dtype=torch.uint8, device=dev)
+        hflags = torch.empty(count * 5, dtype=torch.uint8).pin_memory()
+
+        def run_copies(steps):
+            for k in range(steps):
+                with torch.cuda.stream(s_in):
+                    dstage.copy_(hs[k & 1], non_blocking=True)
+                with torch.cuda.stream(s_out):
+                    hx[k & 1].copy_(dstage, non_blocking=True)
+                    hflags.copy_(dflags, non_blocking=True)
+            s_in.synchronize()
+            s_out.synchronize()
+            return 0
+
+        _, t_cpy = timed_host(run_copies)
+        bytes_step = count * n * 8 + count * (n * 8 + 5)
+        ceiling_pps = world * count * e_steps / t_cpy
         e2e = {"value": ok_str / t_str, "unit": UNIT, "h2d_bytes_per_step": count * n * 8,
                "d2h_bytes_per_step": count * (n * 8 + 1 + 4), "steps": e_steps,
                "projections_per_s": world * count * e_steps / t_str,
+               "host_ceiling": {"what": "the same pinned H2D (states) + D2H (states, ok, iters) copies alone, all ranks at once, "
+                                        "two streams per rank, no kernels",
+                                "aggregate_gb_per_s": world * bytes_step * e_steps / t_cpy / 1e9,
+                                "projections_per_s": ceiling_pps,
+                                "e2e_fraction_of_ceiling": (world * count * e_steps / t_str) / ceiling_pps,
+                                "device_rate_projections_per_s": world * count * args.steps / (ms_total_max * 1e-3)},
+               "compact_outputs": {"value": ok_cmp / t_cmp, "projections_per_s": world * count * e_steps / t_cmp,
+                                   "h2d_bytes_per_step": count * n * 8, "d2h_bytes_per_step": d2h_cmp,
+                                   "api": "ccp_host_batch_submit / _wait: pinned host states in; ok + iters per seed and the ok "
+                                          "states packed (with seed indices) out"},
+               "seeded": {"value": ok_sed / t_sed, "projections_per_s": world * count * e_steps / t_sed,
+                          "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h_sed,
+                          "api": "ccp_host_batch_submit / _wait with sampler arguments (the batched jy_ProjectedStateSampler "
+                                 "refill): seeds generated on the device from the counter stream, packed ok states + ok/iters "
+                                 "out; not an e2e number in the contract's sense (no inputs cross PCIe), reported beside it"},
+               "host": host_info,
                "synchronous_call": {"value": ok_sync / t_sync, "projections_per_s": world * count * e_steps / t_sync,
                                     "api": "ccp_project_batch_host, one blocking call per step"},
                "api": "ccp_project_batch_host_submit / _wait, two batches in flight: pinned host AOS states in, states + ok "
                       "+ iters out; chunked H2D | pipelined projection launches | D2H of completed chunks on three streams; "
                       "every step's submit, wait and host-side read of its ok flags inside the timed region"}
+
+    configs = None
+    if not args.no_configs:
+        configs = extra_configs(args, pkg, rank, world, local, dist if world > 1 else None, peak_flops, load_windows)
+    clocks = None
+    if rank == 0:
+        clocks = sampler.stop(load_windows)
+        clocks["windows"] = "headline timed region + the C3 weak leg (continuous load)"
+        clocks["fp64_probe"] = ClockSampler.summarise(sampler.lines, probe_window)
 
     if rank != 0:
         if world > 1:
@@ -504,8 +819,11 @@ def main():
         "ok_fraction": ok_all / (world * count * args.steps),
         "mean_iters": iters_all / (world * count * args.steps),
         "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": peak_flops / 1e12, "unit": "TFLOP/s",
-                     "frac": achieved / peak_flops, "traffic": traffic,
-                     "peak_source": "measured in this run: ccp_fp64_peak_probe (register-only DFMA chains, best of 5)",
+                     "frac": achieved / peak_flops, "frac_of_nominal": achieved / (NOMINAL_FP64_TFLOPS * 1e12),
+                     "nominal_peak": NOMINAL_FP64_TFLOPS, "traffic": traffic,
+                     "peak_source": "measured in this run: ccp_fp64_peak_probe (register-only DFMA chains, best of 40; SM clock during "
+                                    "the probe in clocks.fp64_probe); MEASURED_PEAKS.json has no FP64 entry; nominal = 148 SM x 64 "
+                                    "lanes x 2 x 1.965 GHz",
                      "flops_per_iteration": fl_iter, "flops_per_tail": fl_tail,
                      # second figure: the transcendental calls the headline count leaves out, expanded at
                      # a stated cost of 50 FLOP per sincos and 60 per atan2 (7K sincos + (K-1) atan2 per evaluation)
@@ -520,6 +838,8 @@ def main():
     }
     if e2e:
         line["e2e"] = e2e
+    if configs:
+        line["configs"] = configs
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         cb = cpu_baseline(args.config, args.cpu_sample, threads, with_engine_arithmetic=True)

@@ -71,6 +71,24 @@ class SamplerArgs(C.Structure):
     ]
 
 
+class HostBatch(C.Structure):
+    """ccp_host_batch (include/ccp.h): one batch of the streaming host path."""
+
+    _fields_ = [
+        ("seeds_host", C.c_void_p),
+        ("sampler", C.POINTER(SamplerArgs)),
+        ("count", C.c_int64),
+        ("x_out_host", C.c_void_p),
+        ("ok_host", C.c_void_p),
+        ("converged_host", C.c_void_p),
+        ("iters_host", C.c_void_p),
+        ("resid_host", C.c_void_p),
+        ("compact_host", C.c_void_p),
+        ("compact_index_host", C.c_void_p),
+        ("compact_capacity", C.c_int64),
+    ]
+
+
 # every symbol include/ccp.h declares: name -> (restype, argtypes)
 _H = C.c_void_p
 _P = C.c_void_p
@@ -111,6 +129,8 @@ SYMBOLS = {
     "ccp_project_batch_host": (C.c_int, [_H, _P, _I64, _P, _P, _P, _P, _P]),
     "ccp_project_batch_host_submit": (C.c_int, [_H, _P, _I64, _P, _P, _P, _P, _P, C.POINTER(_I64)]),
     "ccp_project_batch_host_wait": (C.c_int, [_H, _I64]),
+    "ccp_host_batch_submit": (C.c_int, [_H, C.POINTER(HostBatch), C.POINTER(_I64)]),
+    "ccp_host_batch_wait": (C.c_int, [_H, _I64, C.POINTER(_I64)]),
     "ccp_function_batch_host": (C.c_int, [_H, _P, _I64, _P]),
     "ccp_sample_project_batch_host": (C.c_int, [_H, C.POINTER(SamplerArgs), _I64, _P, _P, _P, _P, _P]),
     "ccp_geodesic_batch_host": (C.c_int, [_H, _P, _P, _I64, C.c_double, C.c_double, _I32, _P, _P, _P, _P]),

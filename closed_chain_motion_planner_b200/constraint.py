@@ -158,6 +158,15 @@ class ProjectResult:
     resid: object
 
 
+@dataclass
+class CompactResult:
+    states: np.ndarray  # (capacity, n): the first min(n_ok, capacity) rows are the batch's ok states, order unspecified
+    index: Optional[np.ndarray]  # (capacity,) int32: seed index of each packed row
+    ok: Optional[np.ndarray]
+    iters: Optional[np.ndarray]
+    n_ok: int = -1  # set by waitCompactBatch
+
+
 # ------------------------------------------------------------------------------------------------
 # the constraint
 # ------------------------------------------------------------------------------------------------
@@ -387,6 +396,54 @@ class KinematicChainConstraint:
     def waitHostBatch(self, ticket: int):
         self._need()
         _check(self._lib, self._h, self._lib.ccp_project_batch_host_wait(self._h, int(ticket)))
+
+    def submitCompactBatch(self, X: Optional[np.ndarray] = None, *, sampler=None, count: Optional[int] = None,
+                           capacity: Optional[int] = None, want_index: bool = True, want_flags: bool = False,
+                           pinned: bool = True):
+        """General streaming host batch (ccp_host_batch_submit) with COMPACT outputs: only the states with
+        project() == true come back, densely packed, plus (optionally) the seed index of each packed row and the per-seed
+        ok / iteration arrays.  Either X (host states, (count, n)) or `sampler` (_capi.SamplerArgs: the seeds are generated
+        on the device, nothing is copied in) with `count`.  Returns (ticket, CompactResult); call waitCompactBatch(ticket,
+        result) to complete it: result.n_ok rows of result.states / result.index are then valid."""
+        self._need()
+        b = _capi.HostBatch()
+        keep = []
+        if (X is None) == (sampler is None):
+            raise ValueError("give either X or sampler")
+        if X is not None:
+            X = np.ascontiguousarray(X, dtype=np.float64)
+            if X.ndim != 2 or X.shape[1] != self.n_:
+                raise ValueError(f"states must have shape (count, {self.n_})")
+            count = X.shape[0]
+            b.seeds_host = X.ctypes.data
+            keep.append(X)
+        else:
+            if count is None:
+                raise ValueError("count is required with sampler arguments")
+            b.sampler = C.pointer(sampler)
+            keep.append(sampler)
+        cap = int(count if capacity is None else capacity)
+        res = CompactResult(states=_host_array((cap, self.n_), np.float64, pinned),
+                            index=_host_array((cap,), np.int32, pinned) if want_index else None,
+                            ok=_host_array((count,), np.uint8, pinned) if want_flags else None,
+                            iters=_host_array((count,), np.int32, pinned) if want_flags else None)
+        b.count = int(count)
+        b.compact_host = res.states.ctypes.data
+        b.compact_index_host = res.index.ctypes.data if want_index else None
+        b.compact_capacity = cap
+        b.ok_host = res.ok.ctypes.data if want_flags else None
+        b.iters_host = res.iters.ctypes.data if want_flags else None
+        t = C.c_int64(0)
+        _check(self._lib, self._h, self._lib.ccp_host_batch_submit(self._h, C.byref(b), C.byref(t)))
+        res._keepalive = keep
+        return int(t.value), res
+
+    def waitCompactBatch(self, ticket: int, result: "CompactResult") -> int:
+        self._need()
+        nk = C.c_int64(-1)
+        _check(self._lib, self._h, self._lib.ccp_host_batch_wait(self._h, int(ticket), C.byref(nk)))
+        result.n_ok = int(nk.value)
+        return result.n_ok
 
     def flush(self, compact=None, n_ok=None, stream=None):
         """Completes the samples parked by pipelined projections (ccp_project_flush); async on the current stream."""

@@ -69,6 +69,17 @@ struct ccp_host_call {
   uint8_t* conv_host;
   int32_t* iters_host;
   double* resid_host;
+  // compact outputs (ccp_host_batch::compact_host): the ok states of the batch packed by the kernels' epilogues; their
+  // count is copied to `pin_nok` behind the last chunk, the rows themselves are copied by the wait (sized by the count)
+  bool compact;
+  double* compact_host;
+  int32_t* cidx_host;
+  int64_t ccap;          // rows the caller's buffers hold
+  int64_t n_ok;          // valid after the wait
+  double* dcompact;
+  int32_t* dcidx;
+  unsigned long long* dnok;
+  long long* pin_nok;    // page-locked, one per slot
   void* stage;
   size_t stage_bytes;
   double* dx;
@@ -505,6 +516,7 @@ int ccp_create(const ccp_model_desc* model, int32_t device, ccp_handle** out) {
     memset(&nh->hcall[i], 0, sizeof nh->hcall[i]);
     nh->hcall[i].finished = true;
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&nh->hcall[i].done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&nh->hcall[i].pin_nok, 64, cudaHostAllocDefault);
   }
   nh->pool = nullptr;
   if (e == cudaSuccess) {
@@ -543,6 +555,7 @@ void ccp_destroy(ccp_handle* h) {
   for (int i = 0; i < 2; ++i) {
     if (h->hcall[i].stage) cudaFreeAsync(h->hcall[i].stage, h->hstream[0]);
     if (h->hcall[i].done) cudaEventDestroy(h->hcall[i].done);
+    if (h->hcall[i].pin_nok) cudaFreeHost(h->hcall[i].pin_nok);
   }
   if (h->pool) cudaMemPoolDestroy(h->pool);
   if (h->d_park[0]) cudaFree(h->d_park[0]);
@@ -1168,6 +1181,14 @@ static int host_copy_out(ccp_handle* h, const ccp_host_call& c, int chunk_index,
   return CCP_OK;
 }
 
+// Behind a batch's last chunk copy: the number of packed ok rows (compact outputs), then the batch's `done` event.
+static int host_finish_copies(ccp_handle* h, ccp_host_call& q, cudaStream_t sD) {
+  if (q.compact)
+    CCP_CUDA(cudaMemcpyAsync(q.pin_nok, q.dnok, sizeof(long long), cudaMemcpyDeviceToHost, sD));
+  CCP_CUDA(cudaEventRecord(q.done, sD));
+  return CCP_OK;
+}
+
 // Copy out every chunk of q that the host-path launch numbered `g` (just enqueued, event `ev`) has completed.
 static int host_copy_ready(ccp_handle* h, ccp_host_call& q, int64_t g, cudaEvent_t ev, bool& waited) {
   cudaStream_t sD = h->hstream[2];
@@ -1178,7 +1199,10 @@ static int host_copy_ready(ccp_handle* h, ccp_host_call& q, int64_t g, cudaEvent
     }
     int rc = host_copy_out(h, q, q.copied, sD);
     if (rc) return rc;
-    if (++q.copied == q.parts) CCP_CUDA(cudaEventRecord(q.done, sD));
+    if (++q.copied == q.parts) {
+      rc = host_finish_copies(h, q, sD);
+      if (rc) return rc;
+    }
   }
   return CCP_OK;
 }
@@ -1202,7 +1226,10 @@ static int host_drain_locked(ccp_handle* h) {
     while (q[i]->copied < q[i]->parts) {
       int rc = host_copy_out(h, *q[i], q[i]->copied, sD);
       if (rc) return rc;
-      if (++q[i]->copied == q[i]->parts) CCP_CUDA(cudaEventRecord(q[i]->done, sD));
+      if (++q[i]->copied == q[i]->parts) {
+        rc = host_finish_copies(h, *q[i], sD);
+        if (rc) return rc;
+      }
     }
   return CCP_OK;
 }
@@ -1219,7 +1246,8 @@ static int host_enqueue_copies(ccp_handle* h, ccp_host_call& c) {
     int rc = host_copy_out(h, c, k, sD);
     if (rc) return rc;
   }
-  CCP_CUDA(cudaEventRecord(c.done, sD));
+  int rc = host_finish_copies(h, c, sD);
+  if (rc) return rc;
   c.copied = c.parts;
   c.enqueued = true;
   return CCP_OK;
@@ -1247,13 +1275,40 @@ static int host_wait_locked(ccp_handle* h, ccp_host_call& c) {
     }
   }
   CCP_CUDA(cudaEventSynchronize(c.done));
+  if (c.compact) {
+    // the packed rows, sized by the count that just arrived; the device is already busy with the next batch
+    const int n = CCPC_DOF * h->model.n_arms;
+    c.n_ok = *c.pin_nok;
+    const int64_t rows = c.n_ok < c.ccap ? c.n_ok : c.ccap;
+    cudaStream_t sD = h->hstream[2];
+    if (rows > 0) {
+      if (c.compact_host)
+        CCP_CUDA(cudaMemcpyAsync(c.compact_host, c.dcompact, sizeof(double) * n * (size_t)rows, cudaMemcpyDeviceToHost, sD));
+      if (c.cidx_host)
+        CCP_CUDA(cudaMemcpyAsync(c.cidx_host, c.dcidx, sizeof(int32_t) * (size_t)rows, cudaMemcpyDeviceToHost, sD));
+      CCP_CUDA(cudaEventRecord(c.done, sD));
+      CCP_CUDA(cudaEventSynchronize(c.done));
+    }
+  }
   c.finished = true;
   return CCP_OK;
 }
 
 // The caller holds host_mu and has checked the arguments.
-static int host_submit_locked(ccp_handle* h, const double* seeds_host, int64_t count, double* x_out_host, uint8_t* ok_host,
-                              uint8_t* converged_host, int32_t* iters_host, double* resid_host, int64_t* ticket_out) {
+static int host_submit_locked(ccp_handle* h, const ccp_host_batch& B, int64_t* ticket_out) {
+  const double* seeds_host = B.seeds_host;
+  const int64_t count = B.count;
+  double* x_out_host = B.x_out_host;
+  uint8_t* ok_host = B.ok_host;
+  uint8_t* converged_host = B.converged_host;
+  int32_t* iters_host = B.iters_host;
+  double* resid_host = B.resid_host;
+  const bool compact = B.compact_host != nullptr || B.compact_index_host != nullptr || B.compact_capacity > 0;
+  ccp_project_args S;  // seeds generated on the device
+  if (B.sampler) {
+    int src = fill_sampler_args(h, B.sampler, count, &S);
+    if (src) return src;
+  }
   ccp_host_call& c = h->hcall[h->next_ticket & 1];
   ccp_host_call& prev = h->hcall[(h->next_ticket & 1) ^ 1];
   int rc = host_wait_locked(h, c);  // the batch that used this slot two submits ago
@@ -1263,8 +1318,8 @@ static int host_submit_locked(ccp_handle* h, const double* seeds_host, int64_t c
   // stream wait on the chunk's completion count.
   bool use_wait = h->wait32 != nullptr;
   {
-    const void* outs[5] = {x_out_host, ok_host, converged_host, iters_host, resid_host};
-    for (int i = 0; i < 5 && use_wait; ++i) {
+    const void* outs[7] = {x_out_host, ok_host, converged_host, iters_host, resid_host, B.compact_host, B.compact_index_host};
+    for (int i = 0; i < 7 && use_wait; ++i) {
       if (!outs[i]) continue;
       cudaPointerAttributes pa;
       if (cudaPointerGetAttributes(&pa, outs[i]) != cudaSuccess || pa.type == cudaMemoryTypeUnregistered) use_wait = false;
@@ -1279,7 +1334,10 @@ static int host_submit_locked(ccp_handle* h, const double* seeds_host, int64_t c
     return set_err(h, CCP_ERR_STATE, "%s", "pipelined projections are in flight: call ccp_project_flush first");
   const int n = CCPC_DOF * h->model.n_arms, m = 2 * (h->model.n_arms - 1);
   const size_t per = sizeof(double) * n + sizeof(double) * m + 8 /* ok, conv, pad */ + sizeof(int32_t) + 4;
-  const size_t need = per * (size_t)count + 1024;
+  // packed rows: as many as the caller's buffers hold, never more than the batch
+  const int64_t ccap = compact ? (B.compact_capacity < count ? B.compact_capacity : count) : 0;
+  const size_t cbytes = compact ? (sizeof(double) * n + sizeof(int32_t)) * (size_t)ccap + 64 : 0;
+  const size_t need = per * (size_t)count + 1024 + cbytes;
   cudaStream_t sC = h->hstream[0], sK = h->hstream[1];
   if (need > c.stage_bytes) {
     // Stream-ordered, from the handle's pool: no device-wide synchronisation.  (cudaFree would wait for everything
@@ -1303,6 +1361,18 @@ static int host_submit_locked(ccp_handle* h, const double* seeds_host, int64_t c
   c.dit = (int32_t*)((char*)c.dres + sizeof(double) * m * (size_t)count);
   c.dok = (uint8_t*)((char*)c.dit + sizeof(int32_t) * (size_t)count);
   c.dcv = c.dok + (size_t)count;
+  c.compact = compact;
+  c.compact_host = B.compact_host;
+  c.cidx_host = B.compact_index_host;
+  c.ccap = ccap;
+  c.n_ok = 0;
+  if (compact) {
+    char* cb = base + ((per * (size_t)count + 1024 - 64) & ~(size_t)63);
+    c.dnok = (unsigned long long*)cb;
+    c.dcompact = (double*)(cb + 64);
+    c.dcidx = (int32_t*)(cb + 64 + sizeof(double) * n * (size_t)ccap);
+    CCP_CUDA(cudaMemsetAsync(c.dnok, 0, 64, sC));  // on the copy stream: behind the stage's allocation, ahead of the first chunk event
+  }
   c.count = count;
   c.x_out_host = x_out_host;
   c.ok_host = ok_host;
@@ -1341,17 +1411,38 @@ static int host_submit_locked(ccp_handle* h, const double* seeds_host, int64_t c
   for (int k = 0; k < parts; ++k) {
     const int64_t off = (int64_t)k * chunk;
     const int64_t cn = (count - off < chunk) ? (count - off) : chunk;
-    CCP_CUDA(cudaMemcpyAsync(c.dx + off * n, seeds_host + off * n, sizeof(double) * n * cn, cudaMemcpyHostToDevice, sC));
-    CCP_CUDA(cudaEventRecord(h->ev_chunk_in[k], sC));
-    CCP_CUDA(cudaStreamWaitEvent(sK, h->ev_chunk_in[k], 0));
+    if (B.sampler) {
+      // the chunk's seeds come from the counter-based seed kernel on the projection stream: nothing crosses PCIe
+      if (k == 0) {  // the stage (re)allocation on the copy stream precedes the first kernel that touches it
+        CCP_CUDA(cudaEventRecord(h->ev_chunk_in[0], sC));
+        CCP_CUDA(cudaStreamWaitEvent(sK, h->ev_chunk_in[0], 0));
+      }
+      S.count = cn;
+      S.first_index = B.sampler->first_index + off;
+      if (h->model.n_arms == 2) launch_seed_kernel<2, false>(h, S, c.dx + off * n, sK);
+      else launch_seed_kernel<3, false>(h, S, c.dx + off * n, sK);
+      h->launches++;
+    } else {
+      CCP_CUDA(cudaMemcpyAsync(c.dx + off * n, seeds_host + off * n, sizeof(double) * n * cn, cudaMemcpyHostToDevice, sC));
+      CCP_CUDA(cudaEventRecord(h->ev_chunk_in[k], sC));
+      CCP_CUDA(cudaStreamWaitEvent(sK, h->ev_chunk_in[k], 0));
+    }
     ccp_project_args A;
     memset(&A, 0, sizeof A);
     A.seeds = c.dx + off * n;
-    A.x_out = c.dx + off * n;
-    A.ok = c.dok + off;
-    A.conv = c.dcv + off;
-    A.iters = c.dit + off;
+    A.x_out = x_out_host ? c.dx + off * n : nullptr;
+    A.ok = ok_host ? c.dok + off : nullptr;
+    A.conv = converged_host ? c.dcv + off : nullptr;
+    A.iters = iters_host ? c.dit + off : nullptr;
     A.resid = resid_host ? c.dres + off * m : nullptr;
+    A.wrap = B.sampler ? B.sampler->wrap_bounds : 0;
+    if (compact) {
+      A.own_n_ok = c.dnok;
+      A.own_compact = B.compact_host ? c.dcompact : nullptr;
+      A.own_compact_idx = B.compact_index_host ? c.dcidx : nullptr;
+      A.own_compact_cap = ccap;
+      A.idx_base = (unsigned)off;
+    }
     A.count = cn;
     // use_wait: the batch's LAST launch finishes every sample older than the batch (age >= parts), so that once a
     // batch is submitted the one before it is complete without any further call; nothing else is ever forced.
@@ -1394,7 +1485,16 @@ int ccp_project_batch_host(ccp_handle* h, const double* seeds_host, int64_t coun
   CCP_NO_OPEN_PIPELINE(h);  // this call runs its own pipeline on the handle's private streams
   if (count >= 4 * (int64_t)h->sm_count * 384) {  // at least two chunks
     int64_t ticket = 0;
-    rc = host_submit_locked(h, seeds_host, count, x_out_host, ok_host, converged_host, iters_host, resid_host, &ticket);
+    ccp_host_batch B;
+    memset(&B, 0, sizeof B);
+    B.seeds_host = seeds_host;
+    B.count = count;
+    B.x_out_host = x_out_host;
+    B.ok_host = ok_host;
+    B.converged_host = converged_host;
+    B.iters_host = iters_host;
+    B.resid_host = resid_host;
+    rc = host_submit_locked(h, B, &ticket);
     if (rc) return rc;
     return host_wait_locked(h, h->hcall[ticket & 1]);
   }
@@ -1473,9 +1573,49 @@ int ccp_project_batch_host_submit(ccp_handle* h, const double* seeds_host, int64
   if (!ticket_out) return set_err(h, CCP_ERR_INVALID, "%s", "null ticket");
   if (count < 1) return set_err(h, CCP_ERR_INVALID, "%s", "submit needs at least one state");
   if (!h->has_ref) return set_err(h, CCP_ERR_STATE, "%s", "project before ccp_set_reference (setInitialPosition)");
+  ccp_host_batch B;
+  memset(&B, 0, sizeof B);
+  B.seeds_host = seeds_host;
+  B.count = count;
+  B.x_out_host = x_out_host;
+  B.ok_host = ok_host;
+  B.converged_host = converged_host;
+  B.iters_host = iters_host;
+  B.resid_host = resid_host;
   std::lock_guard<std::mutex> host_lock(h->host_mu);
   device_guard g(h->device);
-  return host_submit_locked(h, seeds_host, count, x_out_host, ok_host, converged_host, iters_host, resid_host, ticket_out);
+  return host_submit_locked(h, B, ticket_out);
+}
+
+int ccp_host_batch_submit(ccp_handle* h, const ccp_host_batch* b, int64_t* ticket_out) {
+  if (!h) return CCP_ERR_INVALID;
+  if (!b || !ticket_out) return set_err(h, CCP_ERR_INVALID, "%s", "null batch / ticket");
+  if (b->count < 1) return set_err(h, CCP_ERR_INVALID, "%s", "submit needs at least one state");
+  if ((b->seeds_host != nullptr) == (b->sampler != nullptr))
+    return set_err(h, CCP_ERR_INVALID, "%s", "a host batch has either seeds_host or sampler arguments");
+  if (b->count > 0x7fff0000LL) return set_err(h, CCP_ERR_INVALID, "%s", "more than 2^31 - 65536 samples in one batch");
+  if ((b->compact_host || b->compact_index_host) && b->compact_capacity < 1)
+    return set_err(h, CCP_ERR_INVALID, "%s", "compact outputs need compact_capacity >= 1");
+  if (b->compact_capacity < 0) return set_err(h, CCP_ERR_INVALID, "%s", "negative compact_capacity");
+  if (!h->has_ref) return set_err(h, CCP_ERR_STATE, "%s", "project before ccp_set_reference (setInitialPosition)");
+  std::lock_guard<std::mutex> host_lock(h->host_mu);
+  device_guard g(h->device);
+  return host_submit_locked(h, *b, ticket_out);
+}
+
+int ccp_host_batch_wait(ccp_handle* h, int64_t ticket, int64_t* n_ok_out) {
+  if (!h) return CCP_ERR_INVALID;
+  std::lock_guard<std::mutex> host_lock(h->host_mu);
+  if (ticket < 1 || ticket >= h->next_ticket) return set_err(h, CCP_ERR_INVALID, "%s", "unknown ticket");
+  device_guard g(h->device);
+  for (int i = 0; i < 2; ++i)
+    if (h->hcall[i].ticket == ticket) {
+      int rc = host_wait_locked(h, h->hcall[i]);
+      if (rc) return rc;
+      if (n_ok_out) *n_ok_out = h->hcall[i].compact ? h->hcall[i].n_ok : -1;
+      return CCP_OK;
+    }
+  return set_err(h, CCP_ERR_INVALID, "%s", "ticket already retired (its slot was reused by a later submit)");
 }
 
 int ccp_project_batch_host_wait(ccp_handle* h, int64_t ticket) {

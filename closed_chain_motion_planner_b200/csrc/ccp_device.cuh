@@ -33,7 +33,13 @@ struct ccp_out_desc {
   double* resid;
   long long count;  // SOA stride of those arrays
   int wrap;
-  int pad;
+  unsigned idx_base;            // index of the launch's first seed within its host batch
+  // per-BATCH compaction (host path): the ok states of the batch this launch belongs to, whichever launch finishes
+  // them.  n_ok == nullptr: the launch's own stream-compaction arguments apply (ccp_project_args::compact / n_ok).
+  double* compact;              // AOS [cap][n]
+  unsigned long long* n_ok;
+  int32_t* compact_idx;         // [cap] seed index (within the batch) of each packed row, or nullptr
+  long long compact_cap;
 };
 #define CCP_NUM_DESC 64
 #define CCP_MAX_PEERS 8
@@ -84,6 +90,12 @@ struct ccp_project_args {
   unsigned max_age;             // a sample adopted from a launch this many slots back is not parked again
   unsigned* done;               // [CCP_NUM_DESC] samples finished so far per launch slot, cumulative over the slot's
                                 // reuses (never reset); nullptr = do not count.  The host path's D2H stream waits on it.
+  // per-batch compaction of the host path (see ccp_out_desc): travels with the launch's descriptor
+  double* own_compact;
+  unsigned long long* own_n_ok;
+  int32_t* own_compact_idx;
+  long long own_compact_cap;
+  unsigned idx_base;
 };
 
 // warp-aggregated claim of the next sample index by the lanes currently finishing

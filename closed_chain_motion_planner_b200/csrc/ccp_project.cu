@@ -229,10 +229,14 @@ __device__ __forceinline__ void write_result(const ccp_model& M, const ccp_proje
   if (((unsigned)it >> 16) == A.slot) {
     D.x_out = A.x_out; D.ok = A.ok; D.conv = A.conv; D.iters = A.iters; D.resid = A.resid;
     D.count = A.out_stride; D.wrap = A.wrap;
+    D.n_ok = A.own_n_ok; D.compact = A.own_compact; D.compact_idx = A.own_compact_idx;
+    D.compact_cap = A.own_compact_cap; D.idx_base = A.idx_base;
   } else {
     const ccp_out_desc* T = A.desc_table + ((unsigned)it >> 16);
     D.x_out = T->x_out; D.ok = T->ok; D.conv = T->conv; D.iters = T->iters; D.resid = T->resid;
     D.count = T->count; D.wrap = T->wrap;
+    D.n_ok = T->n_ok; D.compact = T->compact; D.compact_idx = T->compact_idx;
+    D.compact_cap = T->compact_cap; D.idx_base = T->idx_base;
   }
   if (D.wrap) {  // the sampler's enforceBounds (KinematicChain.h:118-130); one out-of-line copy of the fmod code
 #pragma unroll
@@ -251,6 +255,20 @@ __device__ __forceinline__ void write_result(const ccp_model& M, const ccp_proje
     ccp_residual<K>(F, fv, nullptr);
 #pragma unroll
     for (int k = 0; k < m; ++k) st_elem<SOA>(D.resid, idx, k, D.count, m, fv[k]);
+  }
+  if (D.n_ok) {
+    // per-batch compaction (host path): the state joins the packed rows of the batch it was submitted with
+    if (okk) {
+      const unsigned long long slot = atomicAdd(D.n_ok, 1ULL);
+      if ((long long)slot < D.compact_cap) {
+        if (D.compact) {
+#pragma unroll
+          for (int j = 0; j < n; ++j) D.compact[slot * n + j] = x[j];
+        }
+        if (D.compact_idx) D.compact_idx[slot] = (int32_t)(D.idx_base + idx);
+      }
+    }
+    return;
   }
   // the compacted stream is a stream: a state is appended to the buffer of the launch it finished in
   if (A.n_ok && okk) {
@@ -331,7 +349,8 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
     if (blockIdx.x == 0 && A.park) {  // successors find this launch's output arrays by slot
       ccp_out_desc d;
       d.x_out = A.x_out; d.ok = A.ok; d.conv = A.conv; d.iters = A.iters; d.resid = A.resid;
-      d.count = A.out_stride; d.wrap = A.wrap; d.pad = 0;
+      d.count = A.out_stride; d.wrap = A.wrap; d.idx_base = A.idx_base;
+      d.compact = A.own_compact; d.n_ok = A.own_n_ok; d.compact_idx = A.own_compact_idx; d.compact_cap = A.own_compact_cap;
       A.desc_table[A.slot] = d;
     }
   }

@@ -295,6 +295,35 @@ int ccp_project_batch_host_submit(ccp_handle* h, const double* seeds_host, int64
                                   uint8_t* ok_host, uint8_t* converged_host, int32_t* iters_host,
                                   double* resid_host, int64_t* ticket_out);
 int ccp_project_batch_host_wait(ccp_handle* h, int64_t ticket);
+/* General form of the streaming host path: one batch = either host states (seeds_host) or counter-based sampler
+ * arguments (sampler: the seeds are generated on the device, nothing is copied in — jy_ProjectedStateSampler::
+ * sampleUniform/Near/Gaussian, jy_ProjectedStateSpace.cpp:10-29, for a whole pool refill), and any subset of outputs:
+ *   per-seed   x_out_host [count][n], ok_host, converged_host, iters_host, resid_host [count][m]   (NULL = not wanted:
+ *              neither computed-and-copied nor, for x_out, written at all)
+ *   compact    compact_host [compact_capacity][n]: the states with ok == 1 of THIS batch densely packed (order
+ *              unspecified; whichever launch finishes a straggler, it joins its own batch's rows);
+ *              compact_index_host [compact_capacity]: the seed index (0 .. count-1) of each packed row.
+ *              The reference's sampler hands the planner one projected state per call and the planner drops the failed
+ *              ones; a pool refill only needs the ok rows: 112 B x ~21 % instead of 112 B per seed back over PCIe.
+ * ccp_host_batch_wait returns in *n_ok_out the number of ok states of the batch (-1 when no compact output was asked
+ * for); min(n_ok, compact_capacity) rows are valid.  The packed rows are copied by the wait itself (sized by the count,
+ * while the device already works on the next batch).  sampler->wrap_bounds applies enforceBounds to every result.
+ * Ticket and ordering rules are those of ccp_project_batch_host_submit / _wait, with which tickets are shared.        */
+typedef struct ccp_host_batch {
+  const double* seeds_host;
+  const ccp_sampler_args* sampler;
+  int64_t count;
+  double* x_out_host;
+  uint8_t* ok_host;
+  uint8_t* converged_host;
+  int32_t* iters_host;
+  double* resid_host;
+  double* compact_host;
+  int32_t* compact_index_host;
+  int64_t compact_capacity;
+} ccp_host_batch;
+int ccp_host_batch_submit(ccp_handle* h, const ccp_host_batch* batch, int64_t* ticket_out);
+int ccp_host_batch_wait(ccp_handle* h, int64_t ticket, int64_t* n_ok_out);
 int ccp_function_batch_host(ccp_handle* h, const double* x_host, int64_t count, double* f_host);
 /* Host-buffer forms (AOS; synchronous) of ccp_sample_project_batch, ccp_geodesic_batch and ccp_ik_sample_batch, for a
  * C++ planner that never touches CUDA (include/closed_chain_motion_planner_b200/ProjectedStateSpace.hpp).  Any output

@@ -304,3 +304,81 @@ def test_handles_on_two_devices_in_one_process():
         torch.cuda.synchronize(dev)
         out.append((r.x.cpu().numpy(), r.ok.cpu().numpy()))
     assert np.array_equal(out[0][0].view(np.uint64), out[1][0].view(np.uint64)) and np.array_equal(out[0][1], out[1][1])
+
+
+def _compact_rows_equal(ref_x, ref_ok, res, n_ok):
+    """packed rows == the reference launch's ok rows, matched through the packed seed indices"""
+    okm = _np(ref_ok).astype(bool)
+    assert n_ok == int(okm.sum())
+    idx = res.index[:n_ok]
+    assert np.array_equal(np.sort(idx), np.nonzero(okm)[0])  # every ok seed exactly once
+    assert np.array_equal(res.states[:n_ok].view(np.uint64), _np(ref_x)[idx].view(np.uint64))
+
+
+@pytest.mark.parametrize("count", [1_000_000, 70_000, 13])
+def test_compact_host_batches_streaming(setup, count):
+    """ccp_host_batch_submit with compact outputs: only the ok states come back, packed per batch (a straggler finished
+    by the NEXT batch's launch still lands in its own batch's rows), with the seed index of every row."""
+    pkg, c, A = setup
+    c_ref = pkg.KinematicChainConstraint.from_config("dumbbell", device=0)
+    batches = [A.seeds_uniform(0, b * count, count) for b in range(4)]
+    refs = [c_ref.projectBatch(torch.from_numpy(x).cuda(), want_resid=False) for x in batches]
+    torch.cuda.synchronize()
+    pending, got = [], []
+    for x in batches:
+        pending.append(c.submitCompactBatch(x, want_flags=True))
+        if len(pending) == 2:
+            t, r = pending.pop(0)
+            got.append((r, c.waitCompactBatch(t, r)))
+    while pending:
+        t, r = pending.pop(0)
+        got.append((r, c.waitCompactBatch(t, r)))
+    assert not c.pipelineOpen()
+    for rf, (r, nk) in zip(refs, got):
+        _compact_rows_equal(rf.x, rf.ok, r, nk)
+        assert np.array_equal(_np(rf.ok), r.ok) and np.array_equal(_np(rf.iters), r.iters)
+    # a capacity smaller than the number of ok states: the count is still exact, the rows that fit are valid ok states
+    t, r = c.submitCompactBatch(batches[0], capacity=5)
+    nk = c.waitCompactBatch(t, r)
+    assert nk == int(_np(refs[0].ok).sum())
+    k = min(nk, 5)
+    okrows = _np(refs[0].x)[_np(refs[0].ok).astype(bool)]
+    assert np.all(_np(refs[0].ok)[r.index[:k]] == 1)
+    assert np.array_equal(r.states[:k].view(np.uint64), _np(refs[0].x)[r.index[:k]].view(np.uint64))
+    assert okrows.shape[0] == nk
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_seeded_compact_host_batches_equal_sampler(setup, mode):
+    """Sampler arguments instead of host states: the seeds are generated on the device (no H2D), the packed ok states
+    equal those of ccp_sample_project_batch on the same counter range, wrap included."""
+    import ctypes as C
+
+    from closed_chain_motion_planner_b200 import _capi
+
+    pkg, c, A = setup
+    count = 300_000
+    near = c.config.start.copy()
+    nearp = near.ctypes.data_as(C.POINTER(C.c_double))
+    outs = []
+    for b in range(3):
+        a = _capi.SamplerArgs(rng_seed=5, first_index=b * count, mode=mode, wrap_bounds=1, distance=0.4, near_host=nearp)
+        x = torch.empty((count, 14), dtype=torch.float64, device="cuda")
+        ok = torch.empty(count, dtype=torch.uint8, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        assert c._lib.ccp_sample_project_batch(c._h, C.byref(a), count, 0, x.data_ptr(), ok.data_ptr(), None, None, None, st) == 0
+        torch.cuda.synchronize()
+        outs.append((x.cpu().numpy(), ok.cpu().numpy()))
+    pending, got = [], []
+    for b in range(3):
+        a = _capi.SamplerArgs(rng_seed=5, first_index=b * count, mode=mode, wrap_bounds=1, distance=0.4, near_host=nearp)
+        pending.append(c.submitCompactBatch(sampler=a, count=count))
+        if len(pending) == 2:
+            t, r = pending.pop(0)
+            got.append((r, c.waitCompactBatch(t, r)))
+    while pending:
+        t, r = pending.pop(0)
+        got.append((r, c.waitCompactBatch(t, r)))
+    for (x, ok), (r, nk) in zip(outs, got):
+        _compact_rows_equal(x, ok, r, nk)
+    assert not c.pipelineOpen()
