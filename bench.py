@@ -749,8 +749,10 @@ def main():
                                         "two streams per rank, no kernels",
                                 "aggregate_gb_per_s": world * bytes_step * e_steps / t_cpy / 1e9,
                                 "projections_per_s": ceiling_pps,
-                                "e2e_fraction_of_ceiling": (world * count * e_steps / t_str) / ceiling_pps,
-                                "device_rate_projections_per_s": world * count * args.steps / (ms_total_max * 1e-3)},
+                                "device_rate_projections_per_s": world * count * args.steps / (ms_total_max * 1e-3),
+                                # the full-output e2e is bounded by the slower of the two: the host's copies, the kernels
+                                "e2e_fraction_of_bound": (world * count * e_steps / t_str)
+                                / min(ceiling_pps, world * count * args.steps / (ms_total_max * 1e-3))},
                "compact_outputs": {"value": ok_cmp / t_cmp, "projections_per_s": world * count * e_steps / t_cmp,
                                    "h2d_bytes_per_step": count * n * 8, "d2h_bytes_per_step": d2h_cmp,
                                    "api": "ccp_host_batch_submit / _wait: pinned host states in; ok + iters per seed and the ok "

@@ -99,6 +99,7 @@ SYMBOLS = {
     "ccp_create": (C.c_int, [C.POINTER(ModelDesc), _I32, C.POINTER(_H)]),
     "ccp_destroy": (None, [_H]),
     "ccp_last_error": (C.c_char_p, [_H]),
+    "ccp_device_count": (C.c_int, []),
     "ccp_n_arms": (C.c_int, [_H]),
     "ccp_device": (C.c_int, [_H]),
     "ccp_set_reference": (C.c_int, [_H, _P]),
@@ -114,7 +115,16 @@ SYMBOLS = {
     "ccp_project_pipeline_open": (C.c_int, [_H]),
     "ccp_sample_project_batch_pipelined": (C.c_int, [_H, C.POINTER(SamplerArgs), _I64, _I32, _P, _P, _P, _P, _P, _P]),
     "ccp_set_gather_peers": (C.c_int, [_H, _I32, _I32, C.POINTER(C.c_uint64), _I64]),
+    "ccp_set_gather_multicast": (C.c_int, [_H, C.c_uint64]),
     "ccp_publish_count": (C.c_int, [_H, _P, _I32, _I32, C.POINTER(C.c_uint64), _P]),
+    "ccp_peer_group_create": (C.c_int, [C.POINTER(_H), _I32, _I64, C.POINTER(_H)]),
+    "ccp_peer_group_destroy": (None, [_H]),
+    "ccp_peer_group_world": (_I32, [_H]),
+    "ccp_peer_group_last_error": (C.c_char_p, [_H]),
+    "ccp_peer_group_sample_project": (C.c_int, [_H, C.POINTER(SamplerArgs), _I64, C.POINTER(_I64)]),
+    "ccp_peer_group_pool": (C.c_int, [_H, _I32, C.POINTER(_P), C.POINTER(_P), C.POINTER(_I64)]),
+    "ccp_peer_group_gather_host": (C.c_int, [_H, _I32, _P, _I64, C.POINTER(_I64), C.POINTER(_I64)]),
+    "ccp_allgather_converged": (C.c_int, [_H, _P, _I32, _P, _P, _I64, _P, _P, _P]),
     "ccp_is_satisfied_batch": (C.c_int, [_H, _P, _I64, _I32, _P, _P]),
     "ccp_joint_valid_batch": (C.c_int, [_H, _P, _I64, _I32, _P, _P]),
     "ccp_fk_batch": (C.c_int, [_H, _I32, _P, _I64, _I32, _P, _P]),

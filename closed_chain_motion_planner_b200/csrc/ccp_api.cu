@@ -127,6 +127,7 @@ struct ccp_handle {
   cudaMemPool_t pool;  // stream-ordered scratch of the sampler path; keeps its memory between calls
   // fused all-gather target (ccp_set_gather_peers)
   double* peer_pool[CCP_MAX_PEERS];
+  double* peer_mc;
   int peer_world, peer_rank;
   long long peer_cap;
   std::mutex mu;
@@ -388,6 +389,7 @@ static int launch_project(ccp_handle* h, ccp_project_args& A, int layout, cudaSt
     A.peer_world = h->peer_world;
     A.peer_row0 = (long long)h->peer_rank * h->peer_cap;
     A.peer_cap = h->peer_cap;
+    A.peer_mc = h->peer_mc;
     for (int p = 0; p < h->peer_world; ++p) A.peer_pool[p] = h->peer_pool[p];
   }
   CCP_CUDA(cudaMemsetAsync(h->d_counters + slot, 0, sizeof(ccp_launch_rec), st));
@@ -480,6 +482,7 @@ int ccp_create(const ccp_model_desc* model, int32_t device, ccp_handle** out) {
   nh->d_park[0] = nh->d_park[1] = nullptr;
   nh->prev_slot = 0;
   nh->peer_world = 0;
+  nh->peer_mc = nullptr;
   nh->peer_rank = 0;
   nh->peer_cap = 0;
   nh->d_desc = nullptr;
@@ -573,6 +576,14 @@ void ccp_destroy(ccp_handle* h) {
 }
 
 const char* ccp_last_error(const ccp_handle* h) { return h ? h->err : g_create_err; }
+int ccp_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
 int ccp_n_arms(const ccp_handle* h) { return h ? h->model.n_arms : CCP_ERR_INVALID; }
 int ccp_device(const ccp_handle* h) { return h ? h->device : CCP_ERR_INVALID; }
 int64_t ccp_launch_count(const ccp_handle* h) { return h ? h->launches : 0; }
@@ -856,6 +867,7 @@ int ccp_project_flush(ccp_handle* h, double* compact_dev, int64_t* n_ok_dev, voi
 
 int ccp_set_gather_peers(ccp_handle* h, int32_t world, int32_t rank, const uint64_t* pool_dev_ptrs, int64_t capacity) {
   if (!h) return CCP_ERR_INVALID;
+  h->peer_mc = nullptr;
   if (world == 0) {
     h->peer_world = 0;
     return CCP_OK;
@@ -864,11 +876,21 @@ int ccp_set_gather_peers(ccp_handle* h, int32_t world, int32_t rank, const uint6
     return set_err(h, CCP_ERR_INVALID, "%s", "gather peers: 1 <= world <= 8, 0 <= rank < world, capacity >= 1");
   for (int p = 0; p < world; ++p) {
     if (!pool_dev_ptrs[p]) return set_err(h, CCP_ERR_INVALID, "%s", "gather peers: null pool pointer");
+    if (pool_dev_ptrs[p] & 15u) return set_err(h, CCP_ERR_INVALID, "%s", "gather peers: pools must be 16-byte aligned");
     h->peer_pool[p] = (double*)(uintptr_t)pool_dev_ptrs[p];
   }
   h->peer_world = world;
   h->peer_rank = rank;
   h->peer_cap = capacity;
+  return CCP_OK;
+}
+
+int ccp_set_gather_multicast(ccp_handle* h, uint64_t pool_multicast_dev_ptr) {
+  if (!h) return CCP_ERR_INVALID;
+  if (pool_multicast_dev_ptr && h->peer_world < 1)
+    return set_err(h, CCP_ERR_STATE, "%s", "gather multicast: call ccp_set_gather_peers first");
+  if (pool_multicast_dev_ptr & 15u) return set_err(h, CCP_ERR_INVALID, "%s", "gather multicast: the mapping must be 16-byte aligned");
+  h->peer_mc = (double*)(uintptr_t)pool_multicast_dev_ptr;
   return CCP_OK;
 }
 

@@ -76,6 +76,7 @@ struct ccp_project_args {
   // fused all-gather of the converged states (ccp_set_gather_peers): the epilogue also stores an ok state into row
   // peer_row0 + slot of EVERY rank's pool (peer-mapped device memory: P2P stores over NVLink)
   double* peer_pool[CCP_MAX_PEERS];
+  double* peer_mc;              // multicast mapping of the pool (one store reaches every rank's pool), or nullptr
   int peer_world;               // 0 = off
   long long peer_row0;          // rank * capacity
   long long peer_cap;           // rows per rank in a pool

@@ -280,10 +280,32 @@ __device__ __forceinline__ void write_result(const ccp_model& M, const ccp_proje
     // fused all-gather: the state goes straight into this rank's rows of every peer's pool (NVLink P2P
     // stores, fire and forget; visible to the peers when this kernel has completed)
     if (A.peer_world > 0 && (long long)slot < A.peer_cap) {
-      for (int p = 0; p < A.peer_world; ++p) {
-        double* row = A.peer_pool[p] + (A.peer_row0 + (long long)slot) * n;
+      const long long row_off = (A.peer_row0 + (long long)slot) * n;
+      if (A.peer_mc) {
+        // ONE store per 16 bytes into the pool's MULTICAST mapping: the NVSwitch fans it out to every rank's pool
+        // (n / 2 stores per state whatever the world size, instead of n per peer)
+        double* row = A.peer_mc + row_off;
+        if constexpr ((n & 1) == 0) {
 #pragma unroll
-        for (int j = 0; j < n; ++j) row[j] = x[j];
+          for (int j = 0; j < n; j += 2)
+            asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + j), "r"(__double2loint(x[j])),
+                         "r"(__double2hiint(x[j])), "r"(__double2loint(x[j + 1])), "r"(__double2hiint(x[j + 1]))
+                         : "memory");
+        } else {  // 21 doubles: rows are only 8-byte aligned
+#pragma unroll
+          for (int j = 0; j < n; ++j) asm volatile("multimem.st.weak.global.f64 [%0], %1;" ::"l"(row + j), "d"(x[j]) : "memory");
+        }
+      } else {
+        for (int p = 0; p < A.peer_world; ++p) {
+          double* row = A.peer_pool[p] + row_off;
+          if constexpr ((n & 1) == 0) {  // 112-byte rows of a 16-byte aligned pool: 16-byte stores
+#pragma unroll
+            for (int j = 0; j < n; j += 2) *reinterpret_cast<double2*>(row + j) = make_double2(x[j], x[j + 1]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < n; ++j) row[j] = x[j];
+          }
+        }
       }
     }
   }

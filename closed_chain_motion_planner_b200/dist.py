@@ -83,12 +83,26 @@ class PeerPool:
         dev = torch.device("cuda", constraint.device)
         self.pool = symm.empty((self.world, self.capacity, self.n), dtype=torch.float64, device=dev)
         self.handle = symm.rendezvous(self.pool, self.group)
-        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        # buffer_ptrs are the ranks' allocation bases: add the tensor's offset inside its allocation (0 unless torch
+        # carved it out of a symmetric-memory pool)
+        off = int(self.pool.data_ptr()) - int(self.handle.buffer_ptrs[self.rank])
+        self.ptrs = [int(p) + off for p in self.handle.buffer_ptrs]
+        # NVLS: a multicast mapping of the pool, when the fabric offers one (0 otherwise): one store reaches every rank
+        import os
+
+        self.multicast_ptr = 0
+        if os.environ.get("CCP_GATHER_MULTICAST", "1") != "0":
+            try:
+                mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+                self.multicast_ptr = mc + off if mc else 0
+            except Exception:  # noqa: BLE001 - older torch: no multicast support
+                self.multicast_ptr = 0
         # the per-rank counts live in symmetric memory too: every rank stores its own count into all of them
         self.counts = symm.empty((self.world,), dtype=torch.int64, device=dev)
         self.counts.zero_()
         self.counts_handle = symm.rendezvous(self.counts, self.group)
-        self.count_ptrs = [int(p) for p in self.counts_handle.buffer_ptrs]
+        coff = int(self.counts.data_ptr()) - int(self.counts_handle.buffer_ptrs[self.rank])
+        self.count_ptrs = [int(p) + coff for p in self.counts_handle.buffer_ptrs]
         self.use_nccl_counts = False
 
     def attach(self):
@@ -97,6 +111,8 @@ class PeerPool:
 
         arr = (C.c_uint64 * self.world)(*self.ptrs)
         rc = self.c._lib.ccp_set_gather_peers(self.c._h, self.world, self.rank, arr, self.capacity)
+        if rc == 0 and self.multicast_ptr:
+            rc = self.c._lib.ccp_set_gather_multicast(self.c._h, self.multicast_ptr)
         if rc != 0:
             raise RuntimeError(self.c._lib.ccp_last_error(self.c._h).decode())
 

@@ -92,6 +92,8 @@ int ccp_default_model(int32_t n_arms, const int32_t* arm_index, ccp_model_desc* 
 int ccp_create(const ccp_model_desc* model, int32_t device, ccp_handle** out);
 void ccp_destroy(ccp_handle* h);
 const char* ccp_last_error(const ccp_handle* h); /* h may be NULL: error of the last failed ccp_create */
+/* CUDA devices visible to the process (0 without a driver): for a host that does not link CUDA itself. */
+int ccp_device_count(void);
 int ccp_n_arms(const ccp_handle* h);
 int ccp_device(const ccp_handle* h);
 
@@ -168,6 +170,12 @@ int ccp_project_pipeline_open(const ccp_handle* h);
  * A peer may read this rank's rows once the projection kernel has completed (e.g. after the count exchange that
  * follows it on the same stream).  world = 0 switches the mode off.                                           */
 int ccp_set_gather_peers(ccp_handle* h, int32_t world, int32_t rank, const uint64_t* pool_dev_ptrs, int64_t capacity);
+/* Optional, after ccp_set_gather_peers: the address on this device of a MULTICAST mapping of the same pool (CUDA
+ * multicast object over all ranks' pools: NVLS; torch symmetric memory's multicast_ptr).  The epilogue then issues one
+ * multimem store per 16 bytes and the NVSwitch replicates it into every rank's pool — n/2 stores per converged state
+ * whatever the world size, instead of n stores per peer.  0 switches back to per-peer stores; ccp_set_gather_peers
+ * resets it.                                                                                                      */
+int ccp_set_gather_multicast(ccp_handle* h, uint64_t pool_multicast_dev_ptr);
 /* Stores *n_ok_dev into slot `rank` of every rank's int64[world] count array (counts_dev_ptrs[p] = rank p's array,
  * peer-mapped), stream-ordered after the projection launches that counted into n_ok_dev: with a barrier of the
  * symmetric-memory group afterwards no collective library call is needed to exchange the counts.                */
@@ -224,6 +232,37 @@ int ccp_sample_project_batch_pipelined(ccp_handle* h, const ccp_sampler_args* a,
                                        double* compact_dev, int64_t* n_ok_dev, void* stream);
 /* ≙ KinematicChainSpace::enforceBounds (KinematicChain.h:118-130), in place.                */
 int ccp_enforce_bounds_batch(ccp_handle* h, double* x_dev, int64_t count, int32_t layout, void* stream);
+
+/* ---- multi-GPU for a C++ host (the reference planner is one C++ process, src/main.cpp:27-63) ----------------------
+ * (a) ONE PROCESS, one handle per GPU: a peer group gives every device a pool double[world][capacity][n] + int64
+ *     counts[world] that its peers can write (cudaDeviceEnablePeerAccess between all pairs).
+ *     ccp_peer_group_sample_project shards `total` counter-stream seeds over the handles (rank r projects a contiguous
+ *     slice starting at a->first_index + its offset), every projection kernel stores its converged states into EVERY
+ *     device's pool from its epilogue and publishes its count the same way; the call returns when all devices are done,
+ *     and then pool[r][q][0 .. counts[q]) on every device r holds rank q's converged states — the all-gather of SURVEY
+ *     §8e without a collective library.  counts_host (int64[world], may be NULL) receives the counts; more converged
+ *     states than `capacity` on a rank is an error (CCP_ERR_INVALID).  ccp_peer_group_gather_host copies device `rank`'s
+ *     gathered pool to the host, padding dropped, rank-major, and reports the rows.  The handles stay usable on their
+ *     own between calls; they must outlive the group.                                                              */
+typedef struct ccp_peer_group ccp_peer_group;
+int ccp_peer_group_create(ccp_handle* const* handles, int32_t world, int64_t capacity, ccp_peer_group** out);
+void ccp_peer_group_destroy(ccp_peer_group* g);
+int32_t ccp_peer_group_world(const ccp_peer_group* g);
+const char* ccp_peer_group_last_error(const ccp_peer_group* g); /* g may be NULL: error of the last failed create */
+int ccp_peer_group_sample_project(ccp_peer_group* g, const ccp_sampler_args* a, int64_t total, int64_t* counts_host);
+int ccp_peer_group_pool(const ccp_peer_group* g, int32_t rank, const double** pool_dev, const int64_t** counts_dev,
+                        int64_t* capacity);
+int ccp_peer_group_gather_host(ccp_peer_group* g, int32_t rank, double* states_host, int64_t max_rows,
+                               int64_t* counts_host, int64_t* rows_out);
+/* (b) ONE PROCESS PER GPU with an NCCL communicator the host owns (nccl_comm = its ncclComm_t): all-gather of the
+ *     converged counts (counts_dev int64[world]) and of the compacted states padded to `capacity` rows (compact_dev
+ *     double[>=capacity][n] from ccp_project_batch / ccp_sample_project_batch, pool_dev double[world][capacity][n]),
+ *     asynchronous on `stream`.  NCCL is looked up at run time — first in the process image, so that the communicator
+ *     and the calls belong to the same library, then libnccl.so.2 — libccp.so does not link it; CCP_ERR_NCCL when it
+ *     cannot be found or a call fails.  Inside one thread driving several devices, bracket the per-device calls with the
+ *     host's own ncclGroupStart/ncclGroupEnd as NCCL requires.                                                     */
+int ccp_allgather_converged(ccp_handle* h, void* nccl_comm, int32_t world, const double* compact_dev,
+                            const int64_t* n_ok_dev, int64_t capacity, double* pool_dev, int64_t* counts_dev, void* stream);
 
 /* ---- batched manifold traversal --------------------------------------------------------- */
 /* ≙ jy_ProjectedStateSpace::discreteGeodesic(from, to, interpolate = true, &geodesic)

@@ -94,13 +94,20 @@ class jy_ProjectedStateSpace;
 // ccp_sample_project_batch call refills (seed kernel -> projection -> enforceBounds wrap -> compaction).  The
 // reference ignores project()'s return value (.cpp:13) and hands failed projections to the planner; the pool only
 // holds states with project() == true.
+//   setReturnFailed(true) reproduces the reference's distribution instead: every projected seed is returned, failed
+//   projections included (their last iterate, wrapped), for planners that rely on rejecting them later.
+//   setPrefetch(true): the NEXT pool is projected on the GPU while the planner consumes the current one
+//   (ccp_host_batch_submit with sampler arguments: seeds generated on the device, only the ok states come back).
 class jy_ProjectedStateSampler {
  public:
   jy_ProjectedStateSampler(const jy_ProjectedStateSpace* space, int64_t pool_size, uint64_t rng_seed);
+  ~jy_ProjectedStateSampler();
   void sampleUniform(double* state) {  // .cpp:10-15
     while (pos_ >= count_) refill();
     std::memcpy(state, &pool_[(size_t)pos_++ * n_], sizeof(double) * n_);
   }
+  void setReturnFailed(bool on) { return_failed_ = on; }
+  void setPrefetch(bool on) { prefetch_ = on; }
   // .cpp:17-22 / :24-29: a small batch around `near`; the lowest-numbered draw that projected wins, else the wrapped
   // last iterate of the first draw (what the reference would have returned).  Returns whether a draw projected.
   bool sampleUniformNear(double* state, const double* near, double distance, int tries = 32) {
@@ -113,12 +120,16 @@ class jy_ProjectedStateSampler {
 
  private:
   void refill();
+  void submit_next();
   bool first_success(int mode, const double* center, double spread, double* state, int tries);
   const jy_ProjectedStateSpace* space_;
   unsigned int n_;
   int64_t pool_size_, count_ = 0, pos_ = 0, next_index_ = 0, refills_ = 0;
   uint64_t rng_seed_;
   std::vector<double> pool_;
+  bool return_failed_ = false, prefetch_ = false;
+  double* next_pool_ = nullptr;  // page-locked (ccp_host_alloc): the pool being projected ahead
+  int64_t next_ticket_ = 0;
 };
 typedef std::shared_ptr<jy_ProjectedStateSampler> jy_ProjectedStateSamplerPtr;
 
@@ -194,7 +205,52 @@ inline jy_ProjectedStateSampler::jy_ProjectedStateSampler(const jy_ProjectedStat
   pool_.resize((size_t)pool_size * n_);
 }
 
+inline jy_ProjectedStateSampler::~jy_ProjectedStateSampler() {
+  if (next_ticket_) ccp_host_batch_wait(space_->getConstraint()->handle(), next_ticket_, nullptr);
+  ccp_host_free(next_pool_);
+}
+
+// prefetch: enqueue the projection of the next pool_size_ seeds of the stream; returns at once
+inline void jy_ProjectedStateSampler::submit_next() {
+  ccp_handle* h = space_->getConstraint()->handle();
+  if (!next_pool_ && ccp_host_alloc((void**)&next_pool_, sizeof(double) * (size_t)pool_size_ * n_) != CCP_OK)
+    throw Exception("jy_ProjectedStateSampler: ccp_host_alloc failed");
+  ccp_sampler_args a;
+  a.rng_seed = rng_seed_;
+  a.first_index = next_index_;
+  a.mode = 0;
+  a.wrap_bounds = 1;
+  a.distance = 0.0;
+  a.near_host = nullptr;
+  next_index_ += pool_size_;
+  ccp_host_batch b;
+  std::memset(&b, 0, sizeof b);
+  b.sampler = &a;
+  b.count = pool_size_;
+  if (return_failed_) b.x_out_host = next_pool_;
+  else {
+    b.compact_host = next_pool_;
+    b.compact_capacity = pool_size_;
+  }
+  if (ccp_host_batch_submit(h, &b, &next_ticket_) != CCP_OK)
+    throw Exception(std::string("jy_ProjectedStateSampler: ") + ccp_last_error(h));
+}
+
 inline void jy_ProjectedStateSampler::refill() {
+  ccp_handle* h = space_->getConstraint()->handle();
+  if (prefetch_) {
+    if (!next_ticket_) submit_next();
+    int64_t n_ok = -1;
+    if (ccp_host_batch_wait(h, next_ticket_, &n_ok) != CCP_OK)
+      throw Exception(std::string("jy_ProjectedStateSampler: ") + ccp_last_error(h));
+    next_ticket_ = 0;
+    count_ = return_failed_ ? pool_size_ : n_ok;
+    std::memcpy(pool_.data(), next_pool_, sizeof(double) * (size_t)count_ * n_);
+    pos_ = 0;
+    ++refills_;
+    submit_next();  // the GPU works on the next pool while the planner consumes this one
+    return;
+  }
   ccp_sampler_args a;
   a.rng_seed = rng_seed_;
   a.first_index = next_index_;
@@ -204,10 +260,11 @@ inline void jy_ProjectedStateSampler::refill() {
   a.near_host = nullptr;
   next_index_ += pool_size_;
   int64_t n_ok = 0;
-  ccp_handle* h = space_->getConstraint()->handle();
-  if (ccp_sample_project_batch_host(h, &a, pool_size_, nullptr, nullptr, nullptr, pool_.data(), &n_ok) != CCP_OK)
-    throw Exception(std::string("jy_ProjectedStateSampler: ") + ccp_last_error(h));
-  count_ = n_ok;
+  const int rc = return_failed_
+                     ? ccp_sample_project_batch_host(h, &a, pool_size_, pool_.data(), nullptr, nullptr, nullptr, nullptr)
+                     : ccp_sample_project_batch_host(h, &a, pool_size_, nullptr, nullptr, nullptr, pool_.data(), &n_ok);
+  if (rc != CCP_OK) throw Exception(std::string("jy_ProjectedStateSampler: ") + ccp_last_error(h));
+  count_ = return_failed_ ? pool_size_ : n_ok;
   pos_ = 0;
   ++refills_;
 }
@@ -237,6 +294,60 @@ inline bool jy_ProjectedStateSampler::first_success(int mode, const double* cent
   std::memcpy(state, &x[(size_t)first * n_], sizeof(double) * n_);
   return any;
 }
+
+// Pool refill over EVERY GPU of the box from one C++ process (the reference planner is one process, main.cpp:27-63):
+// one constraint per device with the same model, a peer group over their handles; sample(total) shards the seed stream
+// over the devices, the projection kernels gather the converged states into every device's pool over NVLink, and the
+// rows come back from device 0.  Returns the number of projected (ok, wrapped) states appended to `out`.
+class MultiGpuProjectedSampler {
+ public:
+  MultiGpuProjectedSampler(const std::vector<ChainConstraintPtr>& constraints, int64_t seeds_per_refill, uint64_t rng_seed)
+      : constraints_(constraints), total_(seeds_per_refill), rng_seed_(rng_seed) {
+    if (constraints.empty()) throw Exception("MultiGpuProjectedSampler: no constraints");
+    std::vector<ccp_handle*> hs;
+    for (auto& c : constraints) hs.push_back(c->handle());
+    n_ = constraints[0]->getAmbientDimension();
+    const int64_t per_rank = (total_ + (int64_t)hs.size() - 1) / (int64_t)hs.size();
+    capacity_ = per_rank * 2 / 5 + 64;  // uniform seeds succeed on ~21-23 %; overflow is reported, not silent
+    if (capacity_ > per_rank) capacity_ = per_rank;
+    if (ccp_peer_group_create(hs.data(), (int32_t)hs.size(), capacity_, &group_) != CCP_OK)
+      throw Exception(std::string("MultiGpuProjectedSampler: ") + ccp_peer_group_last_error(nullptr));
+  }
+  ~MultiGpuProjectedSampler() { ccp_peer_group_destroy(group_); }
+  MultiGpuProjectedSampler(const MultiGpuProjectedSampler&) = delete;
+  MultiGpuProjectedSampler& operator=(const MultiGpuProjectedSampler&) = delete;
+  int world() const { return ccp_peer_group_world(group_); }
+  int64_t sample(std::vector<double>* out, std::vector<int64_t>* counts = nullptr) {
+    ccp_sampler_args a;
+    a.rng_seed = rng_seed_;
+    a.first_index = next_index_;
+    a.mode = 0;
+    a.wrap_bounds = 1;
+    a.distance = 0.0;
+    a.near_host = nullptr;
+    next_index_ += total_;
+    std::vector<int64_t> cnt(world());
+    if (ccp_peer_group_sample_project(group_, &a, total_, cnt.data()) != CCP_OK)
+      throw Exception(std::string("MultiGpuProjectedSampler: ") + ccp_peer_group_last_error(group_));
+    int64_t rows = 0;
+    for (int64_t v : cnt) rows += v;
+    const size_t at = out->size();
+    out->resize(at + (size_t)rows * n_);
+    int64_t got = 0;
+    if (ccp_peer_group_gather_host(group_, 0, out->data() + at, rows, cnt.data(), &got) != CCP_OK)
+      throw Exception(std::string("MultiGpuProjectedSampler: ") + ccp_peer_group_last_error(group_));
+    if (counts) *counts = cnt;
+    return got;
+  }
+  ccp_peer_group* group() const { return group_; }
+
+ private:
+  std::vector<ChainConstraintPtr> constraints_;
+  ccp_peer_group* group_ = nullptr;
+  unsigned int n_ = 0;
+  int64_t total_, capacity_ = 0, next_index_ = 0;
+  uint64_t rng_seed_;
+};
 
 // The goal sampler's per-arm IK loop (jy_ConstrainedValidStateSampler.h:63-189) for a batch of targets: `restarts`
 // solves per target (restart 0 from q_ref if given, the rest from N(mid-range, 0.3) clipped to the limits); the seeded

@@ -77,8 +77,28 @@ int main(int argc, char** argv) {
   ikc.setArmModels(std::make_shared<ccp::ArmModel>(), std::make_shared<ccp::ArmModel>());
   ccp::ikSampleBatch(ikc, 0, targets.data(), NT, 15, 5, qref.data(), qbest.data(), ikok.data(), iksucc.data());
 
+  // ---- the same stream through a PREFETCHING sampler (the next pool is projected while this one is consumed) and
+  // through one that returns failed projections too, as the reference's sampler does (jy_ProjectedStateSpace.cpp:13) ----
+  auto ahead = space->allocStateSampler(2000, /*rng_seed*/ 11);
+  ahead->setPrefetch(true);
+  const int SA = 700;  // spans more than one pool
+  std::vector<double> ahead_samples((size_t)SA * 14);
+  for (int i = 0; i < SA; ++i) {
+    ahead->sampleUniform(&ahead_samples[(size_t)i * 14]);
+    if (i == 100) constraint->isSatisfied(&ahead_samples[0]);  // other calls on the handle while a pool is in flight
+  }
+  int64_t ahead_refills = ahead->refills();
+  auto all_states = space->allocStateSampler(500, /*rng_seed*/ 11);
+  all_states->setReturnFailed(true);
+  const int SF = 120;
+  std::vector<double> failed_too((size_t)SF * 14);
+  for (int i = 0; i < SF; ++i) all_states->sampleUniform(&failed_too[(size_t)i * 14]);
+
   FILE* o = fopen(argv[2], "wb");
   if (!o) return 7;
+  fwrite(ahead_samples.data(), sizeof(double), ahead_samples.size(), o);
+  fwrite(&ahead_refills, sizeof ahead_refills, 1, o);
+  fwrite(failed_too.data(), sizeof(double), failed_too.size(), o);
   fwrite(samples.data(), sizeof(double), samples.size(), o);
   fwrite(sat.data(), 1, S, o);
   fwrite(jv.data(), 1, S, o);

@@ -34,6 +34,9 @@ def test_cpp_state_space_program(tmp_path):
         return a
 
     S, E, MS, NT = 300, 64, 48, 32
+    ahead = take(np.float64, 700 * 14).reshape(700, 14)
+    ahead_refills = int(take(np.int64, 1)[0])
+    failed_too = take(np.float64, 120 * 14).reshape(120, 14)
     samples = take(np.float64, S * 14).reshape(S, 14)
     sat, jv = take(np.uint8, S), take(np.uint8, S)
     refills = int(take(np.int64, 1)[0])
@@ -68,6 +71,19 @@ def test_cpp_state_space_program(tmp_path):
     first = samples[: min(S, len(want))]
     keyset = {row.tobytes() for row in want}
     assert all(row.tobytes() in keyset for row in first)
+    # the prefetching sampler walks the same stream pool by pool: its first pool is the same set, the second the ok
+    # states of seeds 2000 .. 3999
+    k1 = len(want)
+    assert ahead_refills >= 2 and k1 < 700
+    assert {r_.tobytes() for r_ in ahead[:k1]} == keyset
+    rb2 = B.project(A.seeds_uniform(11, 2000, 2000), nthreads=4)
+    want2 = B.enforce_bounds(rb2["x"][rb2["ok"].astype(bool)]).reshape(-1, 14)
+    keyset2 = {row.tobytes() for row in want2}
+    assert all(r_.tobytes() in keyset2 for r_ in ahead[k1:min(700, k1 + len(want2))])
+    # returnFailed: every seed's wrapped last iterate, in stream order (what the reference's sampler hands out)
+    rb3 = B.project(A.seeds_uniform(11, 0, 120), nthreads=4)
+    assert np.array_equal(failed_too.view(np.uint64), B.enforce_bounds(rb3["x"]).reshape(-1, 14).view(np.uint64))
+    assert 0 < rb3["ok"].mean() < 1
     # near / gaussian draws around the start project back onto the manifold
     assert near_ok and gauss_ok
     for s_ in (near_state, gauss_state):
