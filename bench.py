@@ -298,7 +298,8 @@ def extra_configs(args, pkg, rank, world, local, dist, peak_flops, windows):
                                             windows=windows if mode == "weak" else None)
         rec["scaling"] = mode
         if peer is not None:
-            rec["exchange"] = "fused peer stores + count exchange inside the timed region"
+            rec["exchange"] = ("fused peer stores (%s) + count exchange inside the timed region"
+                               % ("one multicast store per 16 B, NVSwitch fan-out" if peer.multicast_ptr else "16-byte stores per peer"))
             rec["gather_check"] = gather_check(peer, ok, n_ok, counts, world, rank, dist, dev)
             assert rec["gather_check"]["pools_identical_across_ranks"] and rec["gather_check"]["counts_equal_local_recount"]
         c3[mode] = rec
@@ -836,6 +837,7 @@ def main():
                              "frac": alg_bytes / (ksecs / args.steps) / 1e9 / hbm_peak,
                              "algorithmic_bytes_per_projection": 2 * n * 8 + 6,
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
+        "gather_multicast": bool(peer_pools and peer_pools[0].multicast_ptr),
         "gpu_launches": launches, "clocks": clocks,
     }
     if e2e:

@@ -167,13 +167,16 @@ class jy_ProjectedStateSampler:
     """
 
     def __init__(self, space: jy_ProjectedStateSpace, pool_size: int = 65536, rng_seed: int = 0, wrap_bounds: bool = True,
-                 group=None):
+                 group=None, return_failed: bool = False):
         self.space_ = space
         self.constraint_ = space.getConstraint()
         self.pool_size = int(pool_size)
         self.rng_seed = int(rng_seed)
         self.wrap_bounds = bool(wrap_bounds)
         self.group = group
+        # True reproduces the reference's distribution: jy_ProjectedStateSpace.cpp:13 ignores project()'s return value, so
+        # failed projections (their wrapped last iterate) reach the planner too, in stream order
+        self.return_failed = bool(return_failed)
         self._sharded = None
         self._next_index = 0  # position in the counter-based stream
         self._pool = np.zeros((0, self.constraint_.getAmbientDimension()))
@@ -229,7 +232,10 @@ class jy_ProjectedStateSampler:
     def sampleUniform(self, state: Optional[np.ndarray] = None) -> np.ndarray:
         """jy_ProjectedStateSpace.cpp:10-15."""
         while self._pos >= len(self._pool):
-            self._pool = self.sampleUniformBatch(self.pool_size).cpu().numpy()
+            if self.return_failed:
+                self._pool = self._sample_project(self.pool_size, 0, want_all=True)[1].cpu().numpy()
+            else:
+                self._pool = self.sampleUniformBatch(self.pool_size).cpu().numpy()
             self._pos = 0
         s = self._pool[self._pos]
         self._pos += 1

@@ -113,3 +113,20 @@ def test_sample_near_and_gaussian(con):
     # mode without a near state is rejected
     a = _args(mode=1, distance=0.25)
     assert con._lib.ccp_generate_seeds(con._h, C.byref(a), n, 0, s.data_ptr(), st) == -1
+
+
+def test_python_sampler_return_failed_switch(con):
+    """return_failed=True reproduces the reference's sampler (jy_ProjectedStateSpace.cpp:13 ignores project()'s return
+    value): every seed's wrapped last iterate in stream order; the default pool holds only states with project()==true."""
+    import closed_chain_motion_planner_b200 as pkg
+
+    cfg, A, B = make_oracles("stefan")
+    space = pkg.jy_ProjectedStateSpace(pkg.KinematicChainSpace(14), con)
+    s_all = pkg.jy_ProjectedStateSampler(space, pool_size=256, rng_seed=9, return_failed=True)
+    got = np.stack([s_all.sampleUniform() for _ in range(300)])  # spans two refills
+    rb = B.project(A.seeds_uniform(9, 0, 512), nthreads=4)
+    want = B.enforce_bounds(rb["x"]).reshape(-1, 14)
+    assert np.array_equal(_bits(got), _bits(want[:300])) and 0 < rb["ok"][:300].mean() < 1
+    s_ok = pkg.jy_ProjectedStateSampler(space, pool_size=256, rng_seed=9)
+    first = s_ok.sampleUniform()
+    assert first.tobytes() in {r.tobytes() for r in want[:256][rb["ok"][:256].astype(bool)]}
