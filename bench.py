@@ -265,6 +265,82 @@ def gather_check(peer, ok, n_ok, counts, world, rank, dist, dev):
             "checksum_rank0_rows": int(all_sums[0, 0].item())}
 
 
+def aux_kernels(pkg, local, peak_flops):
+    """The SURVEY §8(f) kernels beside the projection (N = 1 runs): 100 000 discreteGeodesic edges between projected
+    states (ccp_geodesic_kernel), 1 M single-arm IK solves (ccp_ik_kernel) and 100 000 goal-sampler targets with 15
+    restarts each (ccp_ik_sample_kernel), each with its FP64 roofline fraction on the frozen counts of csrc/ccp_flops.h
+    and the kernel's own iteration counters.  CUDA events on the launching stream, best of 3 after a warm-up."""
+    import ctypes as C
+
+    import numpy as np
+    import torch
+
+    dev = torch.device("cuda", local)
+
+    def best_ms(fn, reps=3):
+        fn()
+        torch.cuda.synchronize(dev)
+        best, out = 1e30, None
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            best = min(best, e0.elapsed_time(e1))
+        return best, out
+
+    def roof(flops, ms):
+        return {"bound": "fp64", "achieved": flops / ms / 1e9, "peak": peak_flops / 1e12, "unit": "TFLOP/s",
+                "frac": flops / (ms * 1e-3) / peak_flops, "frac_of_nominal": flops / (ms * 1e-3) / (NOMINAL_FP64_TFLOPS * 1e12)}
+
+    out = {}
+    # ---- discreteGeodesic: edges between projected states of the dumbbell manifold ----
+    c = pkg.KinematicChainConstraint.from_config("dumbbell", device=local)
+    space = pkg.jy_ProjectedStateSpace(pkg.KinematicChainSpace(14), c)
+    smp = space.allocStateSampler(pool_size=1 << 20, rng_seed=3)
+    V = smp.sampleUniformBatch(1_200_000)
+    E = 100_000
+    g = torch.Generator(device=dev).manual_seed(1)
+    V = V[torch.randperm(V.shape[0], device=dev, generator=g)][: 2 * E]
+    frm, to = V[:E].contiguous(), V[E:2 * E].contiguous()
+    ms, r = best_ms(lambda: space.discreteGeodesicBatch(frm, to, max_states=40))
+    fl_iter, fl_tail = c.algorithmicFlops()
+    iters, nproj = int(r.iters.sum(dtype=torch.int64)), int(r.n_states.sum(dtype=torch.int64))
+    out["geodesic"] = {"workload": "100 000 discreteGeodesic edges between random projected dumbbell states (delta 0.25, lambda 2)",
+                       "kernel": "ccp_geodesic_kernel", "ms": ms, "edges_per_s": E / ms * 1e3,
+                       "projections_per_s": nproj / ms * 1e3, "reached_fraction": float(r.reached.float().mean()),
+                       "mean_states_per_edge": nproj / E, "newton_iterations": iters,
+                       "roofline": roof(iters * fl_iter + nproj * fl_tail, ms)}
+    # ---- pose IK ----
+    pm = pkg.PandaModel(device=local)
+    lb, ub = pm.getJointLimit().T
+    rng = np.random.default_rng(0)
+    n = 1_000_000
+    q_true = lb + (ub - lb) * rng.uniform(0.08, 0.92, (n, 7))
+    qd = torch.from_numpy(q_true).to(dev)
+    T = torch.empty((n, 12), dtype=torch.float64, device=dev)
+    cc = pm._c
+    assert cc._lib.ccp_fk_batch(cc._h, 0, qd.data_ptr(), n, 0, T.data_ptr(), torch.cuda.current_stream(dev).cuda_stream) == 0
+    T = T.view(n, 3, 4)
+    seeds = torch.from_numpy(np.clip(q_true + 0.4 * rng.standard_normal(q_true.shape), lb, ub)).to(dev)
+    a_it, a_tail = C.c_double(), C.c_double()
+    cc._lib.ccp_algorithmic_flops_ik(C.byref(a_it), C.byref(a_tail))
+    ms, r = best_ms(lambda: pm.ikBatch(T, seeds))
+    iters = int(r["iters"].sum(dtype=torch.int64))
+    out["ik"] = {"workload": "1 000 000 single-arm pose IK solves, seed 0.4 rad (sigma) from a solution, eps 1e-5",
+                 "kernel": "ccp_ik_kernel", "ms": ms, "solves_per_s": n / ms * 1e3,
+                 "success_fraction": float(r["ok"].float().mean()), "mean_iters": iters / n,
+                 "roofline": roof(iters * a_it.value + n * a_tail.value, ms)}
+    nt = 100_000
+    ms, r = best_ms(lambda: pm.ikSampleBatch(T[:nt].contiguous(), restarts=15, rng_seed=1))
+    out["ik_sample"] = {"workload": "100 000 goal-sampler targets x 15 restarts (N(mid-range, 0.3) seeds), nearest success wins",
+                        "kernel": "ccp_ik_sample_kernel", "ms": ms, "targets_per_s": nt / ms * 1e3,
+                        "success_fraction": float(r["ok"].float().mean()),
+                        "mean_successful_restarts": float(r["n_success"].float().mean())}
+    return out
+
+
 def extra_configs(args, pkg, rank, world, local, dist, peak_flops, windows):
     """BASELINE configs[0], [2], [3] measured in the same process, after the headline region:
       C1  stefan, 10 000 Seeds-U on the reference-faithful CPU oracle (all host cores), the GPU on the same seeds beside it
@@ -844,6 +920,8 @@ def main():
         line["e2e"] = e2e
     if configs:
         line["configs"] = configs
+    if world == 1 and not args.no_configs:
+        line["aux_kernels"] = aux_kernels(pkg, local, peak_flops)
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         cb = cpu_baseline(args.config, args.cpu_sample, threads, with_engine_arithmetic=True)

@@ -106,6 +106,7 @@ SYMBOLS = {
     "ccp_get_reference": (C.c_int, [_H, _I32, _P, _P]),
     "ccp_set_tolerance": (C.c_int, [_H, C.c_double, C.c_double]),
     "ccp_set_options": (C.c_int, [_H, C.POINTER(Options)]),
+    "ccp_set_coop_threshold": (C.c_int, [_H, _I64]),
     "ccp_get_options": (C.c_int, [_H, C.POINTER(Options), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ccp_function_batch": (C.c_int, [_H, _P, _I64, _I32, _P, _P]),
     "ccp_jacobian_batch": (C.c_int, [_H, _P, _I64, _I32, _P, _P]),
@@ -155,6 +156,7 @@ SYMBOLS = {
     "ccp_host_unregister": (C.c_int, [C.c_void_p]),
     "ccp_project_batch_timed": (C.c_int, [_H, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_float)]),
     "ccp_algorithmic_flops": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "ccp_algorithmic_flops_ik": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ccp_version": (C.c_char_p, []),
 }
 

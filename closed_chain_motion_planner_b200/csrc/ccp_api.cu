@@ -42,6 +42,7 @@
 #define CCP_MAX_AGE 40          /* < CCP_NUM_DESC: a launch's descriptor slot outlives every sample it parked */
 #define CCP_HOST_LAG_DEFAULT 6
 #define CCP_ZERO_COPY_MAX 512   /* host batches up to this many states run in place in page-locked host memory */
+#define CCP_COOP_MAX_DEFAULT 24000 /* batch size up to which the two-lanes-per-sample kernel is the faster one (measured) */
 #define CCP_HOST_MAX_CHUNKS 24  /* < CCP_NUM_DESC / 2: every chunk launch of a host call stays pipelined */
 
 // per-launch device record (ring of CCP_NUM_COUNTERS): zeroed by ONE stream-ordered memset before the launch
@@ -130,6 +131,7 @@ struct ccp_handle {
   double* peer_mc;
   int peer_world, peer_rank;
   long long peer_cap;
+  long long coop_max;  // complete launches of at most this many samples take the cooperative kernel (K = 2)
   std::mutex mu;
   std::mutex host_mu;  // the *_host entry points share the stage buffer and the private streams: one at a time
   char err[512];
@@ -408,7 +410,14 @@ static int launch_project(ccp_handle* h, ccp_project_args& A, int layout, cudaSt
       A.park_count = &h->d_counters[slot].parked;
     }
   }
-  int rc = dispatch_project(h, A, soa, st);
+  int rc;
+  if (!defer && !A.adopt && !A.done && h->model.n_arms == 2 && A.count <= h->coop_max && A.peer_world == 0 && !A.own_n_ok) {
+    // a small complete launch: latency, not throughput, is what it costs — two lanes per sample (ccp_coop.cu)
+    cudaError_t e = ccp_launch_project_coop(h->sm_count, h->model, A, soa, st);
+    rc = (e == cudaSuccess) ? CCP_OK : set_err(h, CCP_ERR_CUDA, "cooperative project kernel launch: %s", cudaGetErrorString(e));
+  } else {
+    rc = dispatch_project(h, A, soa, st);
+  }
   if (rc) return rc;
   if (defer) {
     h->pipeline_open = true;
@@ -481,6 +490,10 @@ int ccp_create(const ccp_model_desc* model, int32_t device, ccp_handle** out) {
   nh->d_stage_bytes = 0;
   nh->d_park[0] = nh->d_park[1] = nullptr;
   nh->prev_slot = 0;
+  {
+    const char* e = getenv("CCP_COOP_MAX");
+    nh->coop_max = e ? atoll(e) : CCP_COOP_MAX_DEFAULT;
+  }
   nh->peer_world = 0;
   nh->peer_mc = nullptr;
   nh->peer_rank = 0;
@@ -665,6 +678,12 @@ int ccp_set_options(ccp_handle* h, const ccp_options* opt) {
   return CCP_OK;
 }
 
+int ccp_set_coop_threshold(ccp_handle* h, int64_t max_count) {
+  if (!h) return CCP_ERR_INVALID;
+  h->coop_max = max_count < 0 ? CCP_COOP_MAX_DEFAULT : max_count;
+  return CCP_OK;
+}
+
 int ccp_get_options(const ccp_handle* h, ccp_options* opt, double* tol_position, double* tol_rotation) {
   if (!h) return CCP_ERR_INVALID;
   if (opt) {
@@ -684,6 +703,12 @@ int ccp_algorithmic_flops(const ccp_handle* h, double* per_iteration, double* pe
   const bool k2 = h->model.n_arms == 2;
   if (per_iteration) *per_iteration = k2 ? CCP_FLOPS_ITER_K2 : CCP_FLOPS_ITER_K3;
   if (per_tail) *per_tail = k2 ? CCP_FLOPS_TAIL_K2 : CCP_FLOPS_TAIL_K3;
+  return CCP_OK;
+}
+
+int ccp_algorithmic_flops_ik(double* per_iteration, double* per_tail) {
+  if (per_iteration) *per_iteration = CCP_FLOPS_IK_ITER;
+  if (per_tail) *per_tail = CCP_FLOPS_IK_TAIL;
   return CCP_OK;
 }
 
@@ -1112,8 +1137,14 @@ int ccp_ik_batch(ccp_handle* h, int32_t arm, const double* T_target_dev, const d
   if (rc) return rc;
   if (count == 0) return CCP_OK;
   device_guard g(h->device);
+  unsigned slot;
+  {  // the geodesic ring of launch records doubles as the IK kernels' work counters
+    std::lock_guard<std::mutex> lk(h->mu);
+    slot = CCP_NUM_COUNTERS + h->geo_seq++ % CCP_NUM_COUNTERS;
+  }
+  CCP_CUDA(cudaMemsetAsync(h->d_counters + slot, 0, sizeof(ccp_launch_rec), (cudaStream_t)stream));
   cudaError_t e = ccp_launch_ik(h->sm_count, h->model, arm, T_target_dev, q_seed_dev, count, O, q_out_dev, ok_dev, iters_dev,
-                                err_dev, (cudaStream_t)stream);
+                                err_dev, &h->d_counters[slot].work, (cudaStream_t)stream);
   h->launches++;
   if (e != cudaSuccess) return set_err(h, CCP_ERR_CUDA, "IK kernel launch: %s", cudaGetErrorString(e));
   return CCP_OK;
@@ -1132,10 +1163,22 @@ int ccp_ik_sample_batch(ccp_handle* h, int32_t arm, const double* T_target_dev, 
   int rc = ik_options(h, opt, &O);
   if (rc) return rc;
   if (n_targets == 0) return CCP_OK;
+  if (n_targets > CCP_IK_SAMPLE_CHUNK * CCP_IK_SAMPLE_MAX_LAUNCHES)
+    return set_err(h, CCP_ERR_INVALID, "%s", "more than 16 M IK targets in one call: split the batch");
   device_guard g(h->device);
-  cudaError_t e = ccp_launch_ik_sample(h->sm_count, h->model, arm, T_target_dev, q_ref_dev, n_targets, restarts, rng_seed,
-                                       sigma, O, q_best_dev, ok_dev, n_success_dev, (cudaStream_t)stream);
-  h->launches++;
+  cudaStream_t st = (cudaStream_t)stream;
+  // scratch (selection keys + candidate solutions + per-target done counts) and the chunk launches' work counters
+  const size_t sbytes = (ccp_ik_sample_scratch_bytes(n_targets, restarts) + 255) & ~(size_t)255;
+  const size_t cbytes = sizeof(unsigned long long) * CCP_IK_SAMPLE_MAX_LAUNCHES;
+  char* scratch = nullptr;
+  CCP_CUDA(cudaMallocFromPoolAsync((void**)&scratch, sbytes + cbytes, h->pool, st));
+  unsigned long long* counters = (unsigned long long*)(scratch + sbytes);
+  cudaError_t e = cudaMemsetAsync(counters, 0, cbytes, st);
+  if (e == cudaSuccess)
+    e = ccp_launch_ik_sample(h->sm_count, h->model, arm, T_target_dev, q_ref_dev, n_targets, restarts, rng_seed, sigma, O,
+                             q_best_dev, ok_dev, n_success_dev, scratch, counters, st);
+  h->launches += (n_targets + CCP_IK_SAMPLE_CHUNK - 1) / CCP_IK_SAMPLE_CHUNK;
+  cudaFreeAsync(scratch, st);
   if (e != cudaSuccess) return set_err(h, CCP_ERR_CUDA, "IK sample kernel launch: %s", cudaGetErrorString(e));
   return CCP_OK;
 }

@@ -430,6 +430,7 @@ CCP_HD void ccp_residual(const ccp_fwd<K>& F, double* f, double* sv_out) {
 
 // FROM_IDENTITY: the chain starts here from the identity quaternion (link 0 of an arm whose base rotation was folded
 // into the other arm's start): q = q_Rx(alpha_0) (x) q_Rz(theta/2) without a multiplication when alpha_0 = 0
+// `a` only indexes x and S (the cooperative kernel passes a lane's own 7 joints with a = 0); A is the arm's constants.
 template <bool PANDA, int I, bool FROM_IDENTITY = false, class SC, class XT>
 CCP_HD void ccp_fwd_link_quat(const ccp_arm& A, int a, const XT& x, double* q, SC& S) {
   const ccp_link& L = A.link[I];
@@ -450,6 +451,76 @@ CCP_HD void ccp_fwd_link_quat(const ccp_arm& A, int a, const XT& x, double* q, S
   S.c(a, I) = CCP_FMA(-sh2, sh, 1.0);  // cos(theta)
 }
 
+// ---- the pieces of the forward evaluation, one arm at a time (ccp_forward composes them; the cooperative kernel runs
+// them on the lane that owns the arm) ----
+// links 1..6 of an arm's quaternion chain (link 0 differs between the arms: see ccp_forward)
+template <bool PANDA, class SC, class XT>
+CCP_HD void ccp_fwd_quat_links_1_6(const ccp_arm& A, int a, const XT& x, double* q, SC& S) {
+  ccp_fwd_link_quat<PANDA, 1>(A, a, x, q, S);
+  ccp_fwd_link_quat<PANDA, 2>(A, a, x, q, S);
+  ccp_fwd_link_quat<PANDA, 3>(A, a, x, q, S);
+  ccp_fwd_link_quat<PANDA, 4>(A, a, x, q, S);
+  ccp_fwd_link_quat<PANDA, 5>(A, a, x, q, S);
+  ccp_fwd_link_quat<PANDA, 6>(A, a, x, q, S);
+}
+// EE-0 origin: (0, 0, fl) in frame 7' of arm 0 (on joint 7's axis: no lever arm there, and its image in frame 6
+// is the constant r6) -> base 0.  Leaves the lever arms (rx, ry) of joints 5..0.  a = index of arm 0 in S.
+template <bool PANDA, class SC>
+CCP_HD void ccp_fwd_down_arm0(const ccp_arm& A, int a, SC& S, double* r) {
+  r[0] = A.r6[0]; r[1] = A.r6[1]; r[2] = A.r6[2];
+  S.rx(a, 5) = r[0]; S.ry(a, 5) = r[1];
+  ccp_down_pt<PANDA, 5>(A.link[5], S.s(a, 5), S.c(a, 5), r);
+  S.rx(a, 4) = r[0]; S.ry(a, 4) = r[1];
+  ccp_down_pt<PANDA, 4>(A.link[4], S.s(a, 4), S.c(a, 4), r);
+  S.rx(a, 3) = r[0]; S.ry(a, 3) = r[1];
+  ccp_down_pt<PANDA, 3>(A.link[3], S.s(a, 3), S.c(a, 3), r);
+  S.rx(a, 2) = r[0]; S.ry(a, 2) = r[1];
+  ccp_down_pt<PANDA, 2>(A.link[2], S.s(a, 2), S.c(a, 2), r);
+  S.rx(a, 1) = r[0]; S.ry(a, 1) = r[1];
+  ccp_down_pt<PANDA, 1>(A.link[1], S.s(a, 1), S.c(a, 1), r);
+  S.rx(a, 0) = r[0]; S.ry(a, 0) = r[1];
+  ccp_down_pt<PANDA, 0>(A.link[0], S.s(a, 0), S.c(a, 0), r);
+}
+// arm a >= 1: base 0 -> base a in one constant transform (t_wb_a^-1 t_wb_0, packed on the host), then up the arm to
+// frame 7' (= the EE frame up to the flange shift along z).  r: the EE-0 origin in base 0; v: tc = R_a^T (p_0 - p_a).
+template <bool PANDA, class SC>
+CCP_HD void ccp_fwd_up_arm(const ccp_arm& A, int a, SC& S, const double* r, double* v) {
+  v[0] = CCP_FMA(A.Rrel[0], r[0], CCP_FMA(A.Rrel[1], r[1], CCP_FMA(A.Rrel[2], r[2], A.prel[0])));
+  v[1] = CCP_FMA(A.Rrel[3], r[0], CCP_FMA(A.Rrel[4], r[1], CCP_FMA(A.Rrel[5], r[2], A.prel[1])));
+  v[2] = CCP_FMA(A.Rrel[6], r[0], CCP_FMA(A.Rrel[7], r[1], CCP_FMA(A.Rrel[8], r[2], A.prel[2])));
+  ccp_up_pt<PANDA, 0>(A.link[0], S.s(a, 0), S.c(a, 0), v);
+  S.rx(a, 0) = v[0]; S.ry(a, 0) = v[1];
+  ccp_up_pt<PANDA, 1>(A.link[1], S.s(a, 1), S.c(a, 1), v);
+  S.rx(a, 1) = v[0]; S.ry(a, 1) = v[1];
+  ccp_up_pt<PANDA, 2>(A.link[2], S.s(a, 2), S.c(a, 2), v);
+  S.rx(a, 2) = v[0]; S.ry(a, 2) = v[1];
+  ccp_up_pt<PANDA, 3>(A.link[3], S.s(a, 3), S.c(a, 3), v);
+  S.rx(a, 3) = v[0]; S.ry(a, 3) = v[1];
+  ccp_up_pt<PANDA, 4>(A.link[4], S.s(a, 4), S.c(a, 4), v);
+  S.rx(a, 4) = v[0]; S.ry(a, 4) = v[1];
+  ccp_up_pt<PANDA, 5>(A.link[5], S.s(a, 5), S.c(a, 5), v);
+  S.rx(a, 5) = v[0]; S.ry(a, 5) = v[1];
+  ccp_up_pt<PANDA, 6>(A.link[6], S.s(a, 6), S.c(a, 6), v);
+  S.rx(a, 6) = v[0]; S.ry(a, 6) = v[1];
+  v[2] -= A.fl;  // frame 7' is the EE frame up to this shift along z
+}
+// residual of pair p (arm p + 1 against arm 0) from tc = v and the two chain quaternions
+template <int K, bool PANDA>
+CCP_HD void ccp_fwd_pair(const ccp_pair_ref& ref, const double* v, const double* qa, const double* q0, double* tc, double* qc,
+                         double* d, double* e, double& e2, double& sv2) {
+  tc[0] = v[0]; tc[1] = v[1]; tc[2] = v[2];
+  ccp_qmul_conj_left(qa, q0, qc);
+  if (PANDA && K != 2) {  // K == 2: the exact factor 1/64 is already in arm 0's start quaternion (qrel_scaled)
+    qc[0] *= CCP_PANDA_QSCALE; qc[1] *= CCP_PANDA_QSCALE; qc[2] *= CCP_PANDA_QSCALE; qc[3] *= CCP_PANDA_QSCALE;
+  }
+  ccp_qmul_conj_right(qc, ref.q0, d);
+  const double* t0 = ref.t0;
+  const double ex = tc[0] - t0[0], ey = tc[1] - t0[1], ez = tc[2] - t0[2];
+  e[0] = ex; e[1] = ey; e[2] = ez;
+  e2 = CCP_FMA(ex, ex, CCP_FMA(ey, ey, ez * ez));
+  sv2 = CCP_FMA(d[1], d[1], CCP_FMA(d[2], d[2], d[3] * d[3]));
+}
+
 template <int K, bool PANDA, class SC, class XT>
 CCP_HD void ccp_forward(const ccp_model& M, const XT& x, SC& S, ccp_fwd<K>& F) {
   double q[K][4];
@@ -465,68 +536,16 @@ CCP_HD void ccp_forward(const ccp_model& M, const XT& x, SC& S, ccp_fwd<K>& F) {
       q[a][0] = s0[0]; q[a][1] = s0[1]; q[a][2] = s0[2]; q[a][3] = s0[3];
       ccp_fwd_link_quat<PANDA, 0>(A, a, x, q[a], S);
     }
-    ccp_fwd_link_quat<PANDA, 1>(A, a, x, q[a], S);
-    ccp_fwd_link_quat<PANDA, 2>(A, a, x, q[a], S);
-    ccp_fwd_link_quat<PANDA, 3>(A, a, x, q[a], S);
-    ccp_fwd_link_quat<PANDA, 4>(A, a, x, q[a], S);
-    ccp_fwd_link_quat<PANDA, 5>(A, a, x, q[a], S);
-    ccp_fwd_link_quat<PANDA, 6>(A, a, x, q[a], S);
+    ccp_fwd_quat_links_1_6<PANDA>(A, a, x, q[a], S);
   }
-  // EE-0 origin: (0, 0, fl) in frame 7' of arm 0 (on joint 7's axis: no lever arm there, and its image in frame 6
-  // is the constant r6) -> base 0 -> world
-  double r[3] = {M.arm[0].r6[0], M.arm[0].r6[1], M.arm[0].r6[2]};
-  {
-    const ccp_arm& A = M.arm[0];
-    S.rx(0, 5) = r[0]; S.ry(0, 5) = r[1];
-    ccp_down_pt<PANDA, 5>(A.link[5], S.s(0, 5), S.c(0, 5), r);
-    S.rx(0, 4) = r[0]; S.ry(0, 4) = r[1];
-    ccp_down_pt<PANDA, 4>(A.link[4], S.s(0, 4), S.c(0, 4), r);
-    S.rx(0, 3) = r[0]; S.ry(0, 3) = r[1];
-    ccp_down_pt<PANDA, 3>(A.link[3], S.s(0, 3), S.c(0, 3), r);
-    S.rx(0, 2) = r[0]; S.ry(0, 2) = r[1];
-    ccp_down_pt<PANDA, 2>(A.link[2], S.s(0, 2), S.c(0, 2), r);
-    S.rx(0, 1) = r[0]; S.ry(0, 1) = r[1];
-    ccp_down_pt<PANDA, 1>(A.link[1], S.s(0, 1), S.c(0, 1), r);
-    S.rx(0, 0) = r[0]; S.ry(0, 0) = r[1];
-    ccp_down_pt<PANDA, 0>(A.link[0], S.s(0, 0), S.c(0, 0), r);
-  }
+  double r[3];
+  ccp_fwd_down_arm0<PANDA>(M.arm[0], 0, S, r);
 #pragma unroll
   for (int a = 1; a < K; ++a) {
-    const ccp_arm& A = M.arm[a];
-    // base 0 -> base a in one constant transform (t_wb_a^-1 t_wb_0, packed on the host)
     double v[3];
-    v[0] = CCP_FMA(A.Rrel[0], r[0], CCP_FMA(A.Rrel[1], r[1], CCP_FMA(A.Rrel[2], r[2], A.prel[0])));
-    v[1] = CCP_FMA(A.Rrel[3], r[0], CCP_FMA(A.Rrel[4], r[1], CCP_FMA(A.Rrel[5], r[2], A.prel[1])));
-    v[2] = CCP_FMA(A.Rrel[6], r[0], CCP_FMA(A.Rrel[7], r[1], CCP_FMA(A.Rrel[8], r[2], A.prel[2])));
-    ccp_up_pt<PANDA, 0>(A.link[0], S.s(a, 0), S.c(a, 0), v);
-    S.rx(a, 0) = v[0]; S.ry(a, 0) = v[1];
-    ccp_up_pt<PANDA, 1>(A.link[1], S.s(a, 1), S.c(a, 1), v);
-    S.rx(a, 1) = v[0]; S.ry(a, 1) = v[1];
-    ccp_up_pt<PANDA, 2>(A.link[2], S.s(a, 2), S.c(a, 2), v);
-    S.rx(a, 2) = v[0]; S.ry(a, 2) = v[1];
-    ccp_up_pt<PANDA, 3>(A.link[3], S.s(a, 3), S.c(a, 3), v);
-    S.rx(a, 3) = v[0]; S.ry(a, 3) = v[1];
-    ccp_up_pt<PANDA, 4>(A.link[4], S.s(a, 4), S.c(a, 4), v);
-    S.rx(a, 4) = v[0]; S.ry(a, 4) = v[1];
-    ccp_up_pt<PANDA, 5>(A.link[5], S.s(a, 5), S.c(a, 5), v);
-    S.rx(a, 5) = v[0]; S.ry(a, 5) = v[1];
-    ccp_up_pt<PANDA, 6>(A.link[6], S.s(a, 6), S.c(a, 6), v);
-    S.rx(a, 6) = v[0]; S.ry(a, 6) = v[1];
-    v[2] -= A.fl;  // frame 7' is the EE frame up to this shift along z
-    double* tc = F.tc[a - 1];
-    tc[0] = v[0]; tc[1] = v[1]; tc[2] = v[2];
-    double* qc = F.qc[a - 1];
-    ccp_qmul_conj_left(q[a], q[0], qc);
-    if (PANDA && K != 2) {  // K == 2: the exact factor 1/64 is already in arm 0's start quaternion (qrel_scaled)
-      qc[0] *= CCP_PANDA_QSCALE; qc[1] *= CCP_PANDA_QSCALE; qc[2] *= CCP_PANDA_QSCALE; qc[3] *= CCP_PANDA_QSCALE;
-    }
-    ccp_qmul_conj_right(qc, M.ref[a - 1].q0, F.d[a - 1]);
-    const double* d = F.d[a - 1];
-    const double* t0 = M.ref[a - 1].t0;
-    const double ex = tc[0] - t0[0], ey = tc[1] - t0[1], ez = tc[2] - t0[2];
-    F.e[a - 1][0] = ex; F.e[a - 1][1] = ey; F.e[a - 1][2] = ez;
-    F.e2[a - 1] = CCP_FMA(ex, ex, CCP_FMA(ey, ey, ez * ez));
-    F.sv2[a - 1] = CCP_FMA(d[1], d[1], CCP_FMA(d[2], d[2], d[3] * d[3]));
+    ccp_fwd_up_arm<PANDA>(M.arm[a], a, S, r, v);
+    ccp_fwd_pair<K, PANDA>(M.ref[a - 1], v, q[a], q[0], F.tc[a - 1], F.qc[a - 1], F.d[a - 1], F.e[a - 1], F.e2[a - 1],
+                           F.sv2[a - 1]);
   }
 }
 
@@ -660,19 +679,48 @@ CCP_HD void ccp_jacobian(const ccp_model& M, const SC& S, const ccp_fwd<K>& F, J
 // ------------------------------------------------------------------------------------------
 // Newton step: x <- x - step * J^T (J J^T)^-1 f         (ConstraintFunction.h:71)
 // ------------------------------------------------------------------------------------------
+// right-hand side D^-1 f = (f0^2, s |vec d| f1) of one pair: the only place sqrt and atan2 are needed
+CCP_HD void ccp_step_rhs(double e2, double sv2, double d0, double* rhs) {
+  const double sv = sqrt(sv2);
+  const double atn = ccp_atan2_pos(sv, fabs(d0));
+  const double h = sv * (atn + atn);
+  rhs[0] = e2;
+  rhs[1] = (d0 < 0.0) ? -h : h;
+}
+// 2x2: Cramer's rule, one division.  A vanished row (g_kk = 0) or dependent rows (det <= 0) drop row 1 / the
+// vanished row, exactly what the L D L^T path of ccp_newton_step does.
+CCP_HD void ccp_solve_2x2(double g00, double g01, double g11, const double* rhs, double* y) {
+  const double det = CCP_FMA(g00, g11, -(g01 * g01));
+  const bool k0 = g00 > 0.0, k1 = g11 > 0.0;
+  if (k0 && k1 && det > 0.0) {
+    const double inv = 1.0 / det;
+    y[0] = CCP_FMA(g11, rhs[0], -(g01 * rhs[1])) * inv;
+    y[1] = CCP_FMA(g00, rhs[1], -(g01 * rhs[0])) * inv;
+  } else if (k0) {
+    y[0] = rhs[0] / g00;
+    y[1] = 0.0;
+  } else if (k1) {
+    y[0] = 0.0;
+    y[1] = rhs[1] / g11;
+  } else {
+    y[0] = 0.0;
+    y[1] = 0.0;
+  }
+}
+// one arm's share of the Gram entry of two gradient rows (7 columns), the accumulation order of ccp_newton_step
+CCP_HD double ccp_row_dot7(const double* a, const double* b) {
+  double acc = a[0] * b[0];
+#pragma unroll
+  for (int i = 1; i < CCPC_DOF; ++i) acc = CCP_FMA(a[i], b[i], acc);
+  return acc;
+}
+
 template <int K, class JT, class XT>
 CCP_HD void ccp_newton_step(const ccp_model& M, const ccp_fwd<K>& F, const JT& J, XT& x) {
   constexpr int m = 2 * (K - 1);
-  // right-hand side D^-1 f = (f0^2, s |vec d| f1) per pair: the only place sqrt and atan2 are needed
   double rhs[m];
 #pragma unroll
-  for (int p = 0; p < K - 1; ++p) {
-    const double sv = sqrt(F.sv2[p]);
-    const double atn = ccp_atan2_pos(sv, fabs(F.d[p][0]));
-    const double h = sv * (atn + atn);
-    rhs[2 * p] = F.e2[p];
-    rhs[2 * p + 1] = (F.d[p][0] < 0.0) ? -h : h;
-  }
+  for (int p = 0; p < K - 1; ++p) ccp_step_rhs(F.e2[p], F.sv2[p], F.d[p][0], rhs + 2 * p);
   double G[m][m];
   // Gram matrix of the rows, lower triangle.  Rows of the same pair share both arms' columns; rows of
   // different pairs only share arm 0's columns.  The two arms' partial sums are independent chains.
@@ -702,25 +750,7 @@ CCP_HD void ccp_newton_step(const ccp_model& M, const ccp_fwd<K>& F, const JT& J
         }
   double y[m];
   if (m == 2) {
-    // 2x2: Cramer's rule, one division.  A vanished row (g_kk = 0) or dependent rows (det <= 0) drop row 1 / the
-    // vanished row, exactly what the L D L^T path below does.
-    const double g00 = G[0][0], g01 = G[1][0], g11 = G[1][1];
-    const double det = CCP_FMA(g00, g11, -(g01 * g01));
-    const bool k0 = g00 > 0.0, k1 = g11 > 0.0;
-    if (k0 && k1 && det > 0.0) {
-      const double inv = 1.0 / det;
-      y[0] = CCP_FMA(g11, rhs[0], -(g01 * rhs[1])) * inv;
-      y[1] = CCP_FMA(g00, rhs[1], -(g01 * rhs[0])) * inv;
-    } else if (k0) {
-      y[0] = rhs[0] / g00;
-      y[1] = 0.0;
-    } else if (k1) {
-      y[0] = 0.0;
-      y[1] = rhs[1] / g11;
-    } else {
-      y[0] = 0.0;
-      y[1] = 0.0;
-    }
+    ccp_solve_2x2(G[0][0], G[1][0], G[1][1], rhs, y);
   } else {
   // L D L^T with row dropping.  Lm is unit lower triangular, D the pivots.
   double D[m], invD[m];

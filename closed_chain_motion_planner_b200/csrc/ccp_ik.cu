@@ -4,138 +4,191 @@
 #include "ccp_ik.h"
 #include "ccp_internal.h"
 
-// explicit seeds: thread per (target, seed) pair
+// `arm` is uniform; the switch keeps the model in the constant bank
+__device__ __forceinline__ bool ik_trip(const ccp_model& M, int arm, const double* T, double* q, const ccp_ik_opt& O, int32_t& it,
+                                        bool& conv, double& ep, double& er) {
+  switch (arm) {
+    case 0: return ccp_ik_trip(M.arm[0], M.lb, M.ub, T, q, O, it, conv, ep, er);
+    case 1: return ccp_ik_trip(M.arm[1], M.lb, M.ub, T, q, O, it, conv, ep, er);
+    default: return ccp_ik_trip(M.arm[2], M.lb, M.ub, T, q, O, it, conv, ep, er);
+  }
+}
+
+// Explicit seeds: one lane owns one (target, seed) pair at a time.  Iteration counts spread 0 .. max_iter (a solve
+// that fails runs all 200 while the average success takes ~30), so this is a persistent LANE-REFILL loop like the
+// projection kernel: one loop pass = one Newton trip of the lane's current solve, and a lane whose solve finished
+// writes it out and takes the next pair (first pair static and interleaved over the blocks, the rest from a global
+// counter, one warp-aggregated atomic per refill event).  Measured before: 4.8 of 32 lanes active per instruction.
 __global__ void __launch_bounds__(128)
 ccp_ik_kernel(const __grid_constant__ ccp_model M, int arm, const double* __restrict__ Tt, const double* __restrict__ qseed,
               long long count, const __grid_constant__ ccp_ik_opt O, double* __restrict__ qout, uint8_t* __restrict__ ok,
-              int32_t* __restrict__ iters, double* __restrict__ err) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
-    double T[12], q[CCPC_DOF], e[2];
+              int32_t* __restrict__ iters, double* __restrict__ err, unsigned long long* __restrict__ counter) {
+  double T[12], q[CCPC_DOF];
+  int32_t it = 0;
+  const long long static_items = (long long)gridDim.x * blockDim.x;
+  long long i = ((long long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32 + (threadIdx.x & 31);
+  bool load = true;
+  for (;;) {
+    if (load) {
+      if (i >= count) break;
 #pragma unroll
-    for (int k = 0; k < 12; ++k) T[k] = __ldg(Tt + i * 12 + k);
+      for (int k = 0; k < 12; ++k) T[k] = __ldg(Tt + i * 12 + k);
 #pragma unroll
-    for (int k = 0; k < CCPC_DOF; ++k) q[k] = __ldg(qseed + i * CCPC_DOF + k);
-    int32_t it;
-    bool okk;
-    switch (arm) {  // `arm` is uniform; the switch keeps the model in the constant bank
-      case 0: ccp_ik_solve_one(M.arm[0], M.lb, M.ub, T, q, O, &it, &okk, e); break;
-      case 1: ccp_ik_solve_one(M.arm[1], M.lb, M.ub, T, q, O, &it, &okk, e); break;
-      default: ccp_ik_solve_one(M.arm[2], M.lb, M.ub, T, q, O, &it, &okk, e); break;
+      for (int k = 0; k < CCPC_DOF; ++k) q[k] = __ldg(qseed + i * CCPC_DOF + k);
+      it = 0;
+      load = false;
     }
+    bool conv;
+    double ep, er;
+    if (ik_trip(M, arm, T, q, O, it, conv, ep, er)) {
 #pragma unroll
-    for (int k = 0; k < CCPC_DOF; ++k) qout[i * CCPC_DOF + k] = q[k];
-    if (ok) ok[i] = okk;
-    if (iters) iters[i] = it;
-    if (err) {
-      err[2 * i] = e[0];
-      err[2 * i + 1] = e[1];
+      for (int k = 0; k < CCPC_DOF; ++k) qout[i * CCPC_DOF + k] = q[k];
+      if (ok) ok[i] = ccp_ik_accept(M.lb, M.ub, q, O, conv);
+      if (iters) iters[i] = it;
+      if (err) {
+        err[2 * i] = ep;
+        err[2 * i + 1] = er;
+      }
+      i = static_items + claim_next(counter);
+      load = true;
     }
   }
 }
 
-// Goal sampling: a group of G = 2^g lanes (G >= restarts) owns one target.  Lane 0 of the group starts from the
-// reference configuration (the seeded solve of sampleCalibGoal), lanes 1.. from N(nominal, sigma) draws clipped to the
-// limits (getRandomConfig); the group then picks, with shuffles, the seeded solution if it succeeded, else the
-// successful restart nearest to the reference (sampleCalibGoal) — or, without a reference, the lowest-numbered
-// successful restart.
-template <int G>
+// Goal sampling: every (target, restart) pair is one work item of the same lane-refill loop (a restart that fails runs
+// all max_iter trips, one that succeeds ~30: with a lane group per target and no refill 11 of 32 lanes were active).
+// Restart 0 starts from the reference configuration when there is one (the seeded solve of sampleCalibGoal), the others
+// from N(nominal, sigma) draws clipped to the limits (getRandomConfig).  A finished restart leaves its selection key
+// (and, when it succeeded, its solution) in scratch memory and counts itself done; whichever lane finishes a target's
+// LAST restart picks the winner: the seeded solution if it succeeded, else the successful restart nearest to the
+// reference (sampleCalibGoal) — or, without a reference, the lowest-numbered successful restart.  Ties go to the lower
+// restart number, so the result does not depend on which lane ran what.
+struct ccp_ik_sample_scratch {
+  double* key;        // [n_targets][restarts] selection key, 1e300 = failed
+  double* q;          // [n_targets][restarts][7] solutions of the successful restarts
+  unsigned* done;     // [n_targets] restarts finished (zeroed before the launch)
+};
+
 __global__ void __launch_bounds__(128)
 ccp_ik_sample_kernel(const __grid_constant__ ccp_model M, int arm, const double* __restrict__ Tt,
                      const double* __restrict__ qref, long long n_targets, int restarts, unsigned long long rng_seed,
-                     double sigma, const __grid_constant__ ccp_ik_opt O, double* __restrict__ qbest,
-                     uint8_t* __restrict__ ok, int32_t* __restrict__ n_success) {
-  const int lane_in_group = threadIdx.x % G;
-  const long long groups_per_block = blockDim.x / G;
-  for (long long t0 = blockIdx.x * groups_per_block; t0 < n_targets; t0 += (long long)gridDim.x * groups_per_block) {
-    const long long t = t0 + threadIdx.x / G;
-    const bool have_target = t < n_targets;
-    const bool active = have_target && lane_in_group < restarts;
-    double T[12], q[CCPC_DOF], ref[CCPC_DOF];
-    bool okk = false;
-    double dist2 = 0.0;
-    if (have_target) {
-#pragma unroll
-      for (int k = 0; k < CCPC_DOF; ++k) ref[k] = qref ? __ldg(qref + t * CCPC_DOF + k) : 0.5 * (M.lb[k] + M.ub[k]);
-    }
-    if (active) {
+                     long long first_target, double sigma, const __grid_constant__ ccp_ik_opt O,
+                     const __grid_constant__ ccp_ik_sample_scratch W, double* __restrict__ qbest, uint8_t* __restrict__ ok,
+                     int32_t* __restrict__ n_success, unsigned long long* __restrict__ counter) {
+  double T[12], q[CCPC_DOF], ref[CCPC_DOF];
+  int32_t it = 0;
+  const long long items = n_targets * restarts;
+  const long long static_items = (long long)gridDim.x * blockDim.x;
+  long long w = ((long long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32 + (threadIdx.x & 31);
+  long long t = 0;
+  int r = 0;
+  bool load = true;
+  for (;;) {
+    if (load) {
+      if (w >= items) break;
+      t = w / restarts;
+      r = (int)(w - t * restarts);
 #pragma unroll
       for (int k = 0; k < 12; ++k) T[k] = __ldg(Tt + t * 12 + k);
-      if (lane_in_group == 0 && qref) {
+#pragma unroll
+      for (int k = 0; k < CCPC_DOF; ++k) ref[k] = qref ? __ldg(qref + t * CCPC_DOF + k) : 0.5 * (M.lb[k] + M.ub[k]);
+      if (r == 0 && qref) {
 #pragma unroll
         for (int k = 0; k < CCPC_DOF; ++k) q[k] = ref[k];
       } else {
 #pragma unroll
         for (int k = 0; k < CCPC_DOF; ++k)
           q[k] = ccp_ik_random_joint(M.lb[k], M.ub[k], sigma,
-                                     gauss01(rng_seed, (unsigned long long)t * 64ull + (unsigned)lane_in_group, (unsigned)k));
+                                     gauss01(rng_seed, (unsigned long long)(first_target + t) * 64ull + (unsigned)r, (unsigned)k));
       }
-      int32_t it;
-      switch (arm) {
-        case 0: ccp_ik_solve_one(M.arm[0], M.lb, M.ub, T, q, O, &it, &okk, nullptr); break;
-        case 1: ccp_ik_solve_one(M.arm[1], M.lb, M.ub, T, q, O, &it, &okk, nullptr); break;
-        default: ccp_ik_solve_one(M.arm[2], M.lb, M.ub, T, q, O, &it, &okk, nullptr); break;
-      }
+      it = 0;
+      load = false;
+    }
+    bool conv;
+    double ep, er;
+    if (ik_trip(M, arm, T, q, O, it, conv, ep, er)) {
+      const bool okk = ccp_ik_accept(M.lb, M.ub, q, O, conv);
+      double dist2 = 0.0;
 #pragma unroll
       for (int k = 0; k < CCPC_DOF; ++k) {
         const double d = q[k] - ref[k];
         dist2 = CCP_FMA(d, d, dist2);
       }
-    }
-    // selection key: seeded success wins outright, then distance to the reference (or the restart number)
-    double key = okk ? ((lane_in_group == 0 && qref) ? -1.0 : (qref ? dist2 : (double)lane_in_group)) : 1e300;
-    int who = lane_in_group;
-    int cnt = okk ? 1 : 0;
+      // selection key: seeded success wins outright, then distance to the reference (or the restart number)
+      const double key = okk ? ((r == 0 && qref) ? -1.0 : (qref ? dist2 : (double)r)) : 1e300;
+      W.key[w] = key;
+      if (okk) {
 #pragma unroll
-    for (int off = G / 2; off > 0; off >>= 1) {
-      const double k2 = __shfl_xor_sync(0xffffffffu, key, off, G);
-      const int w2 = __shfl_xor_sync(0xffffffffu, who, off, G);
-      cnt += __shfl_xor_sync(0xffffffffu, cnt, off, G);
-      if (k2 < key || (k2 == key && w2 < who)) {
-        key = k2;
-        who = w2;
+        for (int k = 0; k < CCPC_DOF; ++k) W.q[w * CCPC_DOF + k] = q[k];
       }
-    }
-    if (have_target) {
-      const bool any = key < 1e300;
-      if (lane_in_group == who && any) {
+      __threadfence();  // key and solution before the count
+      if (atomicAdd(W.done + t, 1u) == (unsigned)restarts - 1u) {
+        __threadfence();
+        double best = 1e300;
+        int who = 0, cnt = 0;
+        for (int rr = 0; rr < restarts; ++rr) {
+          const double k2 = __ldcg(W.key + t * restarts + rr);
+          cnt += k2 < 1e300;
+          if (k2 < best) {
+            best = k2;
+            who = rr;
+          }
+        }
+        const bool any = best < 1e300;
+        if (any) {
 #pragma unroll
-        for (int k = 0; k < CCPC_DOF; ++k) qbest[t * CCPC_DOF + k] = q[k];
-      }
-      if (lane_in_group == 0) {
+          for (int k = 0; k < CCPC_DOF; ++k) qbest[t * CCPC_DOF + k] = __ldcg(W.q + (t * restarts + who) * CCPC_DOF + k);
+        }
         ok[t] = any;
         if (n_success) n_success[t] = cnt;
       }
+      w = static_items + claim_next(counter);
+      load = true;
     }
   }
 }
 
 cudaError_t ccp_launch_ik(int sm_count, const ccp_model& M, int arm, const double* Tt, const double* qseed, long long count,
-                          const ccp_ik_opt& O, double* qout, uint8_t* ok, int32_t* iters, double* err, cudaStream_t st) {
-  long long need = (count + 127) / 128, cap = (long long)sm_count * 8;
+                          const ccp_ik_opt& O, double* qout, uint8_t* ok, int32_t* iters, double* err,
+                          unsigned long long* counter, cudaStream_t st) {
+  // persistent grid: 2 blocks of 128 per SM at ~250 registers; a small batch is spread one warp's worth per block
+  long long need = (count + 31) / 32, cap = (long long)sm_count * 2;
   const int grid = (int)(need < cap ? (need < 1 ? 1 : need) : cap);
-  ccp_ik_kernel<<<grid, 128, 0, st>>>(M, arm, Tt, qseed, count, O, qout, ok, iters, err);
+  ccp_ik_kernel<<<grid, 128, 0, st>>>(M, arm, Tt, qseed, count, O, qout, ok, iters, err, counter);
   return cudaGetLastError();
+}
+
+size_t ccp_ik_sample_scratch_bytes(long long n_targets, int restarts) {
+  const long long chunk = n_targets < CCP_IK_SAMPLE_CHUNK ? n_targets : CCP_IK_SAMPLE_CHUNK;
+  return (size_t)chunk * ((size_t)restarts * (8 + 8 * CCPC_DOF) + 4) + 256;
 }
 
 cudaError_t ccp_launch_ik_sample(int sm_count, const ccp_model& M, int arm, const double* Tt, const double* qref,
                                  long long n_targets, int restarts, unsigned long long rng_seed, double sigma,
-                                 const ccp_ik_opt& O, double* qbest, uint8_t* ok, int32_t* n_success, cudaStream_t st) {
-  int G = 1;
-  while (G < restarts) G <<= 1;
-  const long long per_block = 128 / G;
-  long long need = (n_targets + per_block - 1) / per_block, cap = (long long)sm_count * 8;
-  const int grid = (int)(need < cap ? (need < 1 ? 1 : need) : cap);
-#define CCP_IK_CASE(GG) \
-  case GG: ccp_ik_sample_kernel<GG><<<grid, 128, 0, st>>>(M, arm, Tt, qref, n_targets, restarts, rng_seed, sigma, O, qbest, ok, n_success); break
-  switch (G) {
-    CCP_IK_CASE(1);
-    CCP_IK_CASE(2);
-    CCP_IK_CASE(4);
-    CCP_IK_CASE(8);
-    CCP_IK_CASE(16);
-    CCP_IK_CASE(32);
-    default: return cudaErrorInvalidValue;
+                                 const ccp_ik_opt& O, double* qbest, uint8_t* ok, int32_t* n_success, void* scratch,
+                                 unsigned long long* counters, cudaStream_t st) {
+  // targets go through in chunks so that the scratch stays bounded; every chunk has its own work counter
+  int launch = 0;
+  for (long long first = 0; first < n_targets; first += CCP_IK_SAMPLE_CHUNK, ++launch) {
+    const long long nt = (n_targets - first < CCP_IK_SAMPLE_CHUNK) ? (n_targets - first) : CCP_IK_SAMPLE_CHUNK;
+    ccp_ik_sample_scratch W;
+    char* p = (char*)scratch;
+    W.key = (double*)p;
+    p += sizeof(double) * (size_t)nt * restarts;
+    W.q = (double*)p;
+    p += sizeof(double) * CCPC_DOF * (size_t)nt * restarts;
+    W.done = (unsigned*)p;
+    cudaError_t e = cudaMemsetAsync(W.done, 0, sizeof(unsigned) * (size_t)nt, st);
+    if (e != cudaSuccess) return e;
+    if (launch >= CCP_IK_SAMPLE_MAX_LAUNCHES) return cudaErrorInvalidValue;
+    const long long items = nt * restarts;
+    long long need = (items + 31) / 32, cap = (long long)sm_count * 2;
+    const int grid = (int)(need < cap ? (need < 1 ? 1 : need) : cap);
+    ccp_ik_sample_kernel<<<grid, 128, 0, st>>>(M, arm, Tt + first * 12, qref ? qref + first * CCPC_DOF : nullptr, nt, restarts,
+                                                rng_seed, first, sigma, O, W, qbest + first * CCPC_DOF, ok + first,
+                                                n_success ? n_success + first : nullptr, counters + launch);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
   }
-#undef CCP_IK_CASE
-  return cudaGetLastError();
+  return cudaSuccess;
 }

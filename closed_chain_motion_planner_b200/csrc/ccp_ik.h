@@ -68,19 +68,18 @@ CCP_HD void ccp_rot_error(const double* Rt, const double* R, double* er) {
   er[2] = sg * z;
 }
 
-// One solve.  Tt: target EE pose in the arm's base frame, row-major 3x4 [R|p] (the frame getTransform returns).
-// q: seed in, last iterate out.  err[0] = |p_t - p|_inf, err[1] = |e_rot|_inf at exit.
-CCP_HD void ccp_ik_solve_one(const ccp_arm& A, const double* lb, const double* ub, const double* Tt, double* q,
-                             const ccp_ik_opt& O, int32_t* iters, bool* ok, double* err) {
+// One TRIP of a solve: evaluate the pose error at q; if it is under the tolerance or the iteration budget is spent the
+// solve is finished (returns true, q untouched); otherwise take one damped Newton step, clamp, count it, return false.
+// The kernels run one trip per loop pass (lane refill); ccp_ik_solve_one below is the same trips in a plain loop.
+// Tt: target EE pose in the arm's base frame, row-major 3x4 [R|p] (the frame getTransform returns).
+CCP_HD bool ccp_ik_trip(const ccp_arm& A, const double* lb, const double* ub, const double* Tt, double* q,
+                        const ccp_ik_opt& O, int32_t& it, bool& conv, double& ep_inf, double& er_inf) {
   double Rt[9];
 #pragma unroll
   for (int r = 0; r < 3; ++r)
 #pragma unroll
     for (int c = 0; c < 3; ++c) Rt[3 * r + c] = Tt[4 * r + c];
-  int32_t it = 0;
-  bool conv = false;
-  double ep_inf = 0.0, er_inf = 0.0;
-  for (;;) {
+  {
     double T[12], J[42];
     ccp_arm_fk(A, q, T, J);
     double R[9], e[6];
@@ -94,7 +93,7 @@ CCP_HD void ccp_ik_solve_one(const ccp_arm& A, const double* lb, const double* u
     ep_inf = fmax(fabs(e[0]), fmax(fabs(e[1]), fabs(e[2])));
     er_inf = fmax(fabs(e[3]), fmax(fabs(e[4]), fabs(e[5])));
     conv = (ep_inf <= O.eps_p) && (er_inf <= O.eps_r);
-    if (conv || it >= O.max_iter) break;
+    if (conv || it >= O.max_iter) return true;
     ++it;
     // G = J J^T + lambda^2 I (lower triangle), Cholesky G = L L^T, solve G y = e
     double L[6][6];
@@ -150,11 +149,27 @@ CCP_HD void ccp_ik_solve_one(const ccp_arm& A, const double* lb, const double* u
       q[k] = v;
     }
   }
+  return false;
+}
+
+// success test of a finished solve: converged, and inside the limits by the margin (TrackIKAdaptor::isValid)
+CCP_HD bool ccp_ik_accept(const double* lb, const double* ub, const double* q, const ccp_ik_opt& O, bool conv) {
   bool inside = true;
 #pragma unroll
   for (int k = 0; k < CCPC_DOF; ++k) inside = inside && !(q[k] < lb[k] + O.margin) && !(q[k] > ub[k] - O.margin);
+  return conv && inside;
+}
+
+// One solve.  q: seed in, last iterate out.  err[0] = |p_t - p|_inf, err[1] = |e_rot|_inf at exit.
+CCP_HD void ccp_ik_solve_one(const ccp_arm& A, const double* lb, const double* ub, const double* Tt, double* q,
+                             const ccp_ik_opt& O, int32_t* iters, bool* ok, double* err) {
+  int32_t it = 0;
+  bool conv = false;
+  double ep_inf = 0.0, er_inf = 0.0;
+  while (!ccp_ik_trip(A, lb, ub, Tt, q, O, it, conv, ep_inf, er_inf)) {
+  }
   *iters = it;
-  *ok = conv && inside;
+  *ok = ccp_ik_accept(lb, ub, q, O, conv);
   if (err) {
     err[0] = ep_inf;
     err[1] = er_inf;

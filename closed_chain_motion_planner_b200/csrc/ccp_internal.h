@@ -10,13 +10,23 @@ cudaError_t ccp_launch_project_K2_P1(int sm_count, const ccp_model& M, const ccp
 cudaError_t ccp_launch_project_K3_P0(int sm_count, const ccp_model& M, const ccp_project_args& A, bool soa, cudaStream_t st);
 cudaError_t ccp_launch_project_K3_P1(int sm_count, const ccp_model& M, const ccp_project_args& A, bool soa, cudaStream_t st);
 
+// cooperative kernel (two lanes per sample, K = 2, complete launches without pipelining / peers): ccp_coop.cu
+cudaError_t ccp_launch_project_coop(int sm_count, const ccp_model& M, const ccp_project_args& A, bool soa, cudaStream_t st);
+
 cudaError_t ccp_launch_geodesic(int sm_count, const ccp_model& M, const double* from, const double* to, long long edges,
                                 double delta, double lambda, int max_states, double* states, int32_t* n_states,
                                 uint8_t* reached, int32_t* total_iters, unsigned long long* counter, cudaStream_t st);
 
 struct ccp_ik_opt;
 cudaError_t ccp_launch_ik(int sm_count, const ccp_model& M, int arm, const double* Tt, const double* qseed, long long count,
-                          const ccp_ik_opt& O, double* qout, uint8_t* ok, int32_t* iters, double* err, cudaStream_t st);
+                          const ccp_ik_opt& O, double* qout, uint8_t* ok, int32_t* iters, double* err,
+                          unsigned long long* counter, cudaStream_t st);
+// goal sampling: targets run in chunks of CCP_IK_SAMPLE_CHUNK (bounded scratch); `counters` has one zeroed work counter
+// per chunk launch (at most CCP_IK_SAMPLE_MAX_LAUNCHES), `scratch` ccp_ik_sample_scratch_bytes() of device memory
+#define CCP_IK_SAMPLE_CHUNK 262144LL
+#define CCP_IK_SAMPLE_MAX_LAUNCHES 64
+size_t ccp_ik_sample_scratch_bytes(long long n_targets, int restarts);
 cudaError_t ccp_launch_ik_sample(int sm_count, const ccp_model& M, int arm, const double* Tt, const double* qref,
                                  long long n_targets, int restarts, unsigned long long rng_seed, double sigma,
-                                 const ccp_ik_opt& O, double* qbest, uint8_t* ok, int32_t* n_success, cudaStream_t st);
+                                 const ccp_ik_opt& O, double* qbest, uint8_t* ok, int32_t* n_success, void* scratch,
+                                 unsigned long long* counters, cudaStream_t st);

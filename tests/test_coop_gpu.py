@@ -1,0 +1,130 @@
+"""The cooperative projection kernel (csrc/ccp_coop.cu: two lanes per sample, one arm each) against the
+thread-per-sample kernel: BIT-IDENTICAL states, flags, iteration counts, residuals, compaction — so the launcher may
+pick either by batch size (ccp_set_coop_threshold).  Also against the host build of the engine arithmetic."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import CONFIGS, make_oracles, near_manifold_seeds
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+FORCE, NEVER = 1 << 30, 0
+
+
+def _bits(t):
+    return t.cpu().numpy().view(np.uint64)
+
+
+def _both(c, fn):
+    """fn() with the thread-per-sample kernel, then with the cooperative one"""
+    out = []
+    for thr in (NEVER, FORCE):
+        assert c._lib.ccp_set_coop_threshold(c._h, thr) == 0
+        out.append(fn())
+        torch.cuda.synchronize()
+    assert c._lib.ccp_set_coop_threshold(c._h, -1) == 0
+    return out
+
+
+@pytest.mark.parametrize("layout", ["aos", "soa"])
+@pytest.mark.parametrize("name", CONFIGS)
+def test_coop_equals_thread_per_sample(name, layout):
+    import closed_chain_motion_planner_b200 as pkg
+
+    cfg, A, B = make_oracles(name)
+    c = pkg.KinematicChainConstraint.from_config(name, device=0)
+    lay = pkg.CCP_LAYOUT_AOS if layout == "aos" else pkg.CCP_LAYOUT_SOA
+    for count in (1, 2, 15, 16, 17, 37, 1000, 20_001):
+        seeds = np.concatenate([A.seeds_uniform(1, 0, count), near_manifold_seeds(cfg, count, seed=3)])[:max(count, 1)]
+        xs = torch.from_numpy(seeds if layout == "aos" else np.ascontiguousarray(seeds.T)).cuda()
+
+        def run():
+            compact = torch.zeros((len(seeds), 14), dtype=torch.float64, device="cuda")
+            n_ok = torch.zeros(1, dtype=torch.int64, device="cuda")
+            r = c.projectBatch(xs, layout=lay, compact=compact, n_ok=n_ok)
+            return r, compact, n_ok
+
+        (r0, c0, n0), (r1, c1, n1) = _both(c, run)
+        assert np.array_equal(_bits(r0.x), _bits(r1.x)), (name, layout, count)
+        assert torch.equal(r0.ok, r1.ok) and torch.equal(r0.converged, r1.converged) and torch.equal(r0.iters, r1.iters)
+        assert np.array_equal(_bits(r0.resid), _bits(r1.resid))
+        k = int(n0.item())
+        assert k == int(n1.item()) == int(r0.ok.sum())
+        srt = lambda m: m[np.lexsort(m.T[::-1])]
+        assert np.array_equal(srt(c0[:k].cpu().numpy()).view(np.uint64), srt(c1[:k].cpu().numpy()).view(np.uint64))
+        if count == 1000:  # and against the host twin
+            rb = B.project(seeds, nthreads=8)
+            x1 = r1.x.cpu().numpy() if layout == "aos" else r1.x.cpu().numpy().T
+            assert np.array_equal(x1.view(np.uint64), rb["x"].view(np.uint64)) and np.array_equal(r1.iters.cpu().numpy(), rb["iters"])
+
+
+def test_coop_edge_cases_options_and_calibrated_model():
+    import closed_chain_motion_planner_b200 as pkg
+
+    cfg, A, B = make_oracles("Wine_Bottle")
+    c = pkg.KinematicChainConstraint.from_config("Wine_Bottle", device=0)
+    seeds = A.seeds_uniform(9, 0, 300)
+    seeds[5, 3] = np.nan
+    seeds[40, 0] = np.inf
+    seeds[41, :] = 1e300
+    xs = torch.from_numpy(seeds).cuda()
+    for opts in (dict(), dict(max_iter=0), dict(max_iter=3), dict(damping=1e-4, clamp=True), dict(step=0.5, joint_margin=0.0)):
+        c.setOptions(**opts)
+        r0, r1 = _both(c, lambda: c.projectBatch(xs))
+        assert np.array_equal(_bits(r0.x), _bits(r1.x)), opts
+        assert torch.equal(r0.ok, r1.ok) and torch.equal(r0.iters, r1.iters) and np.array_equal(_bits(r0.resid), _bits(r1.resid))
+    c.setOptions()
+    c.setTolerance(1e-2, 5e-2)
+    r0, r1 = _both(c, lambda: c.projectBatch(xs))
+    assert np.array_equal(_bits(r0.x), _bits(r1.x)) and torch.equal(r0.iters, r1.iters)
+    # host entry points (in place in page-locked memory, one launch) take the same kernel choice
+    assert c._lib.ccp_set_coop_threshold(c._h, FORCE) == 0
+    rh = c.projectBatch(seeds)
+    assert np.array_equal(rh.x.view(np.uint64), r1.x.cpu().numpy().view(np.uint64)) and np.array_equal(rh.ok, r1.ok.cpu().numpy())
+    # calibrated (alpha-offset) arms: the generic link code
+    gp = pkg.grasping_point()
+    dh = 1e-2 * np.random.default_rng(4).standard_normal((2, 7, 4))
+    arms = [pkg.ArmModel("l", 0, gp.t_wb[0], dh_offsets=dh[0]), pkg.ArmModel("t", 2, gp.t_wb[2], dh_offsets=dh[1])]
+    cc = pkg.KinematicChainConstraint(14)
+    cc.setArmModels(*arms)
+    cc.setInitialPosition(cfg.start)
+    s2 = torch.from_numpy(A.seeds_uniform(2, 0, 700)).cuda()
+    r0, r1 = _both(cc, lambda: cc.projectBatch(s2))
+    assert np.array_equal(_bits(r0.x), _bits(r1.x)) and torch.equal(r0.ok, r1.ok) and torch.equal(r0.iters, r1.iters)
+
+
+def test_coop_sampler_wrap_and_golden_rows():
+    """the sampler path (seed kernel -> projection with the enforceBounds wrap and compaction) and the reference's dumped
+    path rows through the cooperative kernel"""
+    import closed_chain_motion_planner_b200 as pkg
+    from closed_chain_motion_planner_b200 import _capi
+    from conftest import load_path
+
+    c = pkg.KinematicChainConstraint.from_config("dumbbell", device=0)
+    n = 5000
+
+    def run():
+        a = _capi.SamplerArgs(rng_seed=3, first_index=77, mode=0, wrap_bounds=1, distance=0.0, near_host=None)
+        x = torch.empty((n, 14), dtype=torch.float64, device="cuda")
+        ok = torch.empty(n, dtype=torch.uint8, device="cuda")
+        it = torch.empty(n, dtype=torch.int32, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        assert c._lib.ccp_sample_project_batch(c._h, C.byref(a), n, 0, x.data_ptr(), ok.data_ptr(), it.data_ptr(), None, None, st) == 0
+        return x, ok, it
+
+    (x0, ok0, it0), (x1, ok1, it1) = _both(c, run)
+    assert np.array_equal(_bits(x0), _bits(x1)) and torch.equal(ok0, ok1) and torch.equal(it0, it1)
+    assert float(x1.abs().max()) <= np.pi
+    P = load_path("dumbbell")
+    keep = np.ones(len(P), bool)
+    keep[-1] = False
+    for i in range(len(P) - 1):
+        if np.array_equal(P[i], P[i + 1]):
+            keep[i] = keep[i + 1] = False
+    rows = torch.from_numpy(P[keep]).cuda()
+    assert c._lib.ccp_set_coop_threshold(c._h, FORCE) == 0
+    r = c.projectBatch(rows)
+    assert bool((r.ok == 1).all()) and int(r.iters.max()) <= 1 and float((r.x - rows).abs().max()) < 5e-4
