@@ -14,7 +14,7 @@ CCP_LAYOUT_AOS = 0
 CCP_LAYOUT_SOA = 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libccp.so")
+LIB_PATH = os.environ.get("CCP_LIB") or os.path.join(_HERE, "csrc", "libccp.so")  # CCP_LIB: a tuning build of the same ABI
 
 
 class ArmDesc(C.Structure):

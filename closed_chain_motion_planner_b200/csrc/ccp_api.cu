@@ -42,7 +42,9 @@
 #define CCP_MAX_AGE 40          /* < CCP_NUM_DESC: a launch's descriptor slot outlives every sample it parked */
 #define CCP_HOST_LAG_DEFAULT 6
 #define CCP_ZERO_COPY_MAX 512   /* host batches up to this many states run in place in page-locked host memory */
-#define CCP_COOP_MAX_DEFAULT 24000 /* batch size up to which the two-lanes-per-sample kernel is the faster one (measured) */
+/* batch size up to which the two-lanes-per-sample kernel is the faster one: one cooperative warp (16 samples) per
+ * scheduler, 3/4 full — measured crossover on B200 between 4 000 and 10 000 samples (tools/coop_probe.py) */
+#define CCP_COOP_MAX_PER_SM 48
 #define CCP_HOST_MAX_CHUNKS 24  /* < CCP_NUM_DESC / 2: every chunk launch of a host call stays pipelined */
 
 // per-launch device record (ring of CCP_NUM_COUNTERS): zeroed by ONE stream-ordered memset before the launch
@@ -243,11 +245,15 @@ template <int K, bool SOA>
 __global__ void __launch_bounds__(128)
 ccp_seed_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ ccp_project_args A,
                 double* __restrict__ out) {
+  // one thread per ELEMENT (sample, joint): every element of the counter-based stream is an independent hash of
+  // (seed, sample, joint), and element order = memory order in both layouts, so the stores are fully coalesced (a
+  // thread per sample wrote 14 doubles at a 112-byte stride: 0.76 TB/s, 6 % of a Wine_Bottle pool refill)
   constexpr int n = CCPC_DOF * K;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < A.count;
-       idx += (long long)gridDim.x * blockDim.x) {
-#pragma unroll
-    for (int j = 0; j < n; ++j) st_elem<SOA>(out, idx, j, A.count, n, make_seed<K>(M, A, idx, j));
+  const long long total = A.count * n;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long idx = SOA ? e % A.count : e / n;
+    const int j = (int)(SOA ? e / A.count : e % n);
+    out[e] = make_seed<K>(M, A, idx, j);
   }
 }
 
@@ -492,7 +498,7 @@ int ccp_create(const ccp_model_desc* model, int32_t device, ccp_handle** out) {
   nh->prev_slot = 0;
   {
     const char* e = getenv("CCP_COOP_MAX");
-    nh->coop_max = e ? atoll(e) : CCP_COOP_MAX_DEFAULT;
+    nh->coop_max = e ? atoll(e) : -1;  // -1: default, resolved once the SM count is known
   }
   nh->peer_world = 0;
   nh->peer_mc = nullptr;
@@ -522,6 +528,7 @@ int ccp_create(const ccp_model_desc* model, int32_t device, ccp_handle** out) {
   device_guard g(device);
   cudaError_t e = g.ok ? cudaSuccess : cudaErrorInvalidDevice;
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&nh->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (e == cudaSuccess && nh->coop_max < 0) nh->coop_max = (long long)nh->sm_count * CCP_COOP_MAX_PER_SM;
   if (e == cudaSuccess) e = cudaMalloc(&nh->d_counters, 2 * CCP_NUM_COUNTERS * sizeof(ccp_launch_rec));
   for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&nh->hstream[i], cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreate(&nh->ev0);
@@ -680,7 +687,7 @@ int ccp_set_options(ccp_handle* h, const ccp_options* opt) {
 
 int ccp_set_coop_threshold(ccp_handle* h, int64_t max_count) {
   if (!h) return CCP_ERR_INVALID;
-  h->coop_max = max_count < 0 ? CCP_COOP_MAX_DEFAULT : max_count;
+  h->coop_max = max_count < 0 ? (long long)h->sm_count * CCP_COOP_MAX_PER_SM : max_count;
   return CCP_OK;
 }
 
@@ -979,7 +986,7 @@ int ccp_generate_seeds(ccp_handle* h, const ccp_sampler_args* a, int64_t count, 
   if (count == 0) return CCP_OK;
   device_guard g(h->device);
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = grid_for(h, count, 128, 8);
+  const int grid = grid_for(h, count * CCPC_DOF * h->model.n_arms, 128, 16);
   const bool soa = layout == CCP_LAYOUT_SOA;
   if (h->model.n_arms == 2) {
     if (soa) ccp_seed_kernel<2, true><<<grid, 128, 0, st>>>(h->model, A, seeds_dev);
@@ -996,7 +1003,7 @@ int ccp_generate_seeds(ccp_handle* h, const ccp_sampler_args* a, int64_t count, 
 }  // extern "C"
 template <int K, bool SOA>
 static void launch_seed_kernel(const ccp_handle* h, const ccp_project_args& A, double* out, cudaStream_t st) {
-  const int grid = grid_for(h, A.count, 128, 8);
+  const int grid = grid_for(h, A.count * CCPC_DOF * K, 128, 16);
   ccp_seed_kernel<K, SOA><<<grid, 128, 0, st>>>(h->model, A, out);
 }
 extern "C" {

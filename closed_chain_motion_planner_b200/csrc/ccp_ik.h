@@ -37,29 +37,34 @@ CCP_HD void ccp_rot_error(const double* Rt, const double* R, double* er) {
   // Shepperd: pick the largest of (trace, E00, E11, E22) as pivot
   const double tr = E[0] + E[4] + E[8];
   double w, x, y, z;
+  // (one reciprocal per branch and three products: an FP64 division is ~14 instructions)
   if (tr > 0.0) {
     const double s = sqrt(tr + 1.0) * 2.0;  // 4 w
+    const double is = 1.0 / s;
     w = 0.25 * s;
-    x = (E[7] - E[5]) / s;
-    y = (E[2] - E[6]) / s;
-    z = (E[3] - E[1]) / s;
+    x = (E[7] - E[5]) * is;
+    y = (E[2] - E[6]) * is;
+    z = (E[3] - E[1]) * is;
   } else if (E[0] > E[4] && E[0] > E[8]) {
     const double s = sqrt(1.0 + E[0] - E[4] - E[8]) * 2.0;  // 4 x
-    w = (E[7] - E[5]) / s;
+    const double is = 1.0 / s;
+    w = (E[7] - E[5]) * is;
     x = 0.25 * s;
-    y = (E[1] + E[3]) / s;
-    z = (E[2] + E[6]) / s;
+    y = (E[1] + E[3]) * is;
+    z = (E[2] + E[6]) * is;
   } else if (E[4] > E[8]) {
     const double s = sqrt(1.0 + E[4] - E[0] - E[8]) * 2.0;  // 4 y
-    w = (E[2] - E[6]) / s;
-    x = (E[1] + E[3]) / s;
+    const double is = 1.0 / s;
+    w = (E[2] - E[6]) * is;
+    x = (E[1] + E[3]) * is;
     y = 0.25 * s;
-    z = (E[5] + E[7]) / s;
+    z = (E[5] + E[7]) * is;
   } else {
     const double s = sqrt(1.0 + E[8] - E[0] - E[4]) * 2.0;  // 4 z
-    w = (E[3] - E[1]) / s;
-    x = (E[2] + E[6]) / s;
-    y = (E[5] + E[7]) / s;
+    const double is = 1.0 / s;
+    w = (E[3] - E[1]) * is;
+    x = (E[2] + E[6]) * is;
+    y = (E[5] + E[7]) * is;
     z = 0.25 * s;
   }
   const double sg = (w < 0.0) ? -2.0 : 2.0;
@@ -96,7 +101,7 @@ CCP_HD bool ccp_ik_trip(const ccp_arm& A, const double* lb, const double* ub, co
     if (conv || it >= O.max_iter) return true;
     ++it;
     // G = J J^T + lambda^2 I (lower triangle), Cholesky G = L L^T, solve G y = e
-    double L[6][6];
+    double L[6][6], invd[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i)
 #pragma unroll
@@ -113,6 +118,7 @@ CCP_HD bool ccp_ik_trip(const ccp_arm& A, const double* lb, const double* ub, co
       for (int k = 0; k < j; ++k) d = CCP_FMA(-L[j][k], L[j][k], d);
       d = sqrt(fmax(d, 1e-300));
       const double inv = 1.0 / d;
+      invd[j] = inv;  // the triangular solves multiply by it instead of dividing by the pivot twelve more times
       L[j][j] = d;
 #pragma unroll
       for (int i = j + 1; i < 6; ++i) {
@@ -128,14 +134,14 @@ CCP_HD bool ccp_ik_trip(const ccp_arm& A, const double* lb, const double* ub, co
       double v = e[i];
 #pragma unroll
       for (int k = 0; k < i; ++k) v = CCP_FMA(-L[i][k], y[k], v);
-      y[i] = v / L[i][i];
+      y[i] = v * invd[i];
     }
 #pragma unroll
     for (int i = 5; i >= 0; --i) {
       double v = y[i];
 #pragma unroll
       for (int k = i + 1; k < 6; ++k) v = CCP_FMA(-L[k][i], y[k], v);
-      y[i] = v / L[i][i];
+      y[i] = v * invd[i];
     }
     // q <- clamp(q + J^T y)      (KDL ChainIkSolverPos_NR_JL clamps to the limits after every step)
 #pragma unroll
