@@ -27,6 +27,22 @@ struct ccp_sc_smem {
   __device__ __forceinline__ double ry(int a, int i) const { return at(a, i, 3); }
 };
 
+// hybrid: (sin, cos) stay in registers, only the lever arms (rx, ry) — written once by the forward pass, read once by
+// the gradient pass — go to shared memory ([slot][thread], conflict-free): 28 doubles less per thread for K = 2
+template <int K, int BLOCK>
+struct ccp_sc_hybrid {
+  double v[K][CCPC_DOF][2];
+  double* base;  // &smem[threadIdx.x]
+  __device__ __forceinline__ double& s(int a, int i) { return v[a][i][0]; }
+  __device__ __forceinline__ double& c(int a, int i) { return v[a][i][1]; }
+  __device__ __forceinline__ double& rx(int a, int i) { return base[((a * CCPC_DOF + i) * 2 + 0) * BLOCK]; }
+  __device__ __forceinline__ double& ry(int a, int i) { return base[((a * CCPC_DOF + i) * 2 + 1) * BLOCK]; }
+  __device__ __forceinline__ double s(int a, int i) const { return v[a][i][0]; }
+  __device__ __forceinline__ double c(int a, int i) const { return v[a][i][1]; }
+  __device__ __forceinline__ double rx(int a, int i) const { return base[((a * CCPC_DOF + i) * 2 + 0) * BLOCK]; }
+  __device__ __forceinline__ double ry(int a, int i) const { return base[((a * CCPC_DOF + i) * 2 + 1) * BLOCK]; }
+};
+
 // the Jacobian rows (28 (K-1) doubles) and the state x (7K doubles) can live there too
 template <int K, int BLOCK>
 struct ccp_jac_smem {
@@ -46,17 +62,21 @@ struct ccp_x_smem {
 #define CCP_SM_SC 1
 #define CCP_SM_J 2
 #define CCP_SM_X 4
+#define CCP_SM_NOSTAGE 8   // no seed staging buffers (lanes load their seeds directly)
+#define CCP_SM_RXY 16      // lever arms in shared memory, (sin, cos) in registers (ccp_sc_hybrid)
 // doubles in front of the seed staging area: max(staging arrays, tail exchange) + state x
 template <int K, int BLOCK, int SM>
 __host__ __device__ constexpr int ccp_proj_stage_offset() {
-  constexpr int stage = ((SM & CCP_SM_SC) ? 4 * CCPC_DOF * K : 0) + ((SM & CCP_SM_J) ? 4 * CCPC_DOF * (K - 1) : 0);
+  constexpr int stage = ((SM & CCP_SM_SC) ? 4 * CCPC_DOF * K : 0) + ((SM & CCP_SM_J) ? 4 * CCPC_DOF * (K - 1) : 0) +
+                        ((SM & CCP_SM_RXY) ? 2 * CCPC_DOF * K : 0);
   constexpr int exch = CCPC_DOF * K + 1;
   return BLOCK * ((stage > exch ? stage : exch) + ((SM & CCP_SM_X) ? CCPC_DOF * K : 0));
 }
 template <int K, int BLOCK, int SM>
 constexpr size_t ccp_proj_smem_bytes() {
   // + per warp two seed buffers of one claim chunk (32 states) each
-  return sizeof(double) * ((size_t)ccp_proj_stage_offset<K, BLOCK, SM>() + (size_t)(BLOCK / 32) * 2 * 32 * CCPC_DOF * K);
+  return sizeof(double) * ((size_t)ccp_proj_stage_offset<K, BLOCK, SM>() +
+                           ((SM & CCP_SM_NOSTAGE) ? 0 : (size_t)(BLOCK / 32) * 2 * 32 * CCPC_DOF * K));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -102,7 +122,7 @@ __device__ __forceinline__ void stage_chunk(ccp_warp_chunk* wc, int b, unsigned 
   constexpr int n = CCPC_DOF * K;
   wc->base[b] = base;
   wc->staged[b] = 0u;
-  if (!A.stage_seeds || end <= base || base < W.n_adopt) return;
+  if (!A.stage_seeds || buf == nullptr || end <= base || base < W.n_adopt) return;
   const unsigned i0 = base - W.n_adopt, cnt = end - base;
   const unsigned dst = smem_u32(buf), bar = smem_u32(mbar);
   if (!SOA) {
@@ -339,10 +359,14 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
   __shared__ ccp_warp_chunk s_chunk[NW];
   __shared__ __align__(8) unsigned long long s_mbar[NW][2];
   double* sm_next = ccp_smem + threadIdx.x;
-  typename std::conditional<(SM & CCP_SM_SC) != 0, ccp_sc_smem<K, BLOCK>, ccp_sc_local<K>>::type S;
+  typename std::conditional<(SM & CCP_SM_SC) != 0, ccp_sc_smem<K, BLOCK>,
+                            typename std::conditional<(SM & CCP_SM_RXY) != 0, ccp_sc_hybrid<K, BLOCK>, ccp_sc_local<K>>::type>::type S;
   if constexpr ((SM & CCP_SM_SC) != 0) {
     S.base = sm_next;
     sm_next += 4 * CCPC_DOF * K * BLOCK;
+  } else if constexpr ((SM & CCP_SM_RXY) != 0) {
+    S.base = sm_next;
+    sm_next += 2 * CCPC_DOF * K * BLOCK;
   }
   typename std::conditional<(SM & CCP_SM_J) != 0, ccp_jac_smem<K, BLOCK>, ccp_jac<K>>::type J;
   if constexpr ((SM & CCP_SM_J) != 0) {
@@ -586,7 +610,13 @@ static cudaError_t launch_project_v(int sm_count, const ccp_model& M, const ccp_
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < CCP_MAX_DEVICES) attr_done[dev].store(1, std::memory_order_relaxed);
   }
-  kern<<<grid, BLOCK, smem, st>>>(M, A);
+  if constexpr ((SM & CCP_SM_NOSTAGE) != 0) {
+    ccp_project_args A2 = A;
+    A2.stage_seeds = 0;  // no staging buffers in this configuration: the lanes load their seeds directly
+    kern<<<grid, BLOCK, smem, st>>>(M, A2);
+  } else {
+    kern<<<grid, BLOCK, smem, st>>>(M, A);
+  }
   return cudaGetLastError();
 }
 
@@ -609,6 +639,11 @@ static cudaError_t launch_project_g(int sm_count, const ccp_model& M, const ccp_
       case 3: return launch_project_v<K, PANDA, SOA, 256, 1, 0>(sm_count, M, A, st);
       case 4: return launch_project_v<K, PANDA, SOA, 384, 1, CCP_SM_X>(sm_count, M, A, st);
       case 5: return launch_project_v<K, PANDA, SOA, 448, 1, CCP_SM_X>(sm_count, M, A, st);
+      case 6: return launch_project_v<K, PANDA, SOA, 512, 1, CCP_SM_RXY | CCP_SM_NOSTAGE>(sm_count, M, A, st);
+      case 7: return launch_project_v<K, PANDA, SOA, 448, 1, CCP_SM_RXY | CCP_SM_NOSTAGE>(sm_count, M, A, st);
+      case 8: return launch_project_v<K, PANDA, SOA, 448, 1, CCP_SM_RXY>(sm_count, M, A, st);
+      case 9: return launch_project_v<K, PANDA, SOA, 416, 1, CCP_SM_RXY>(sm_count, M, A, st);
+      case 10: return launch_project_v<K, PANDA, SOA, 384, 1, CCP_SM_RXY>(sm_count, M, A, st);
       default: break;
     }
   } else {
@@ -619,6 +654,9 @@ static cudaError_t launch_project_g(int sm_count, const ccp_model& M, const ccp_
       case 4: return launch_project_v<K, PANDA, SOA, 256, 1, CCP_SM_SC>(sm_count, M, A, st);
       case 5: return launch_project_v<K, PANDA, SOA, 288, 1, 0>(sm_count, M, A, st);
       case 6: return launch_project_v<K, PANDA, SOA, 320, 1, 0>(sm_count, M, A, st);
+      case 7: return launch_project_v<K, PANDA, SOA, 320, 1, CCP_SM_RXY>(sm_count, M, A, st);
+      case 8: return launch_project_v<K, PANDA, SOA, 384, 1, CCP_SM_RXY | CCP_SM_NOSTAGE>(sm_count, M, A, st);
+      case 9: return launch_project_v<K, PANDA, SOA, 288, 1, CCP_SM_RXY>(sm_count, M, A, st);
       default: break;
     }
   }

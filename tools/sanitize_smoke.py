@@ -16,8 +16,15 @@ for cfgname in ("dumbbell", "stefan_three_arm"):
     s = A.seeds_uniform(0, 0, 9001)
     xa = torch.from_numpy(s).cuda()
     xs = torch.from_numpy(np.ascontiguousarray(s.T)).cuda()
+    c._lib.ccp_set_coop_threshold(c._h, 0)  # the thread-per-sample kernel ...
     r = c.projectBatch(xa)
     r2 = c.projectBatch(xs, layout=pkg.CCP_LAYOUT_SOA)
+    c._lib.ccp_set_coop_threshold(c._h, 1 << 30)  # ... and the cooperative one (two arms only; three arms fall through)
+    rc = c.projectBatch(xa)
+    rc2 = c.projectBatch(xs, layout=pkg.CCP_LAYOUT_SOA)
+    torch.cuda.synchronize()
+    assert torch.equal(rc.x, r.x) and torch.equal(rc2.x, r2.x) and torch.equal(rc.iters, r.iters)
+    c._lib.ccp_set_coop_threshold(c._h, -1)
     compact = torch.zeros((3 * 9001, n), dtype=torch.float64, device="cuda")
     n_ok = torch.zeros(1, dtype=torch.int64, device="cuda")
     ps = [c.projectBatch(xa[i * 3000:(i + 1) * 3000].contiguous(), compact=compact, n_ok=n_ok, pipelined=True) for i in range(3)]
@@ -42,3 +49,17 @@ ik = pm.ikSampleBatch(T, restarts=15, rng_seed=2)
 ik1 = pm.ikBatch(T, q)
 torch.cuda.synchronize()
 print("geodesic/ik ok", float(ik["ok"].mean()))
+# streaming host batches: full outputs, compact outputs, device-generated seeds
+from closed_chain_motion_planner_b200 import _capi
+
+A = OracleA(c.config.arm_indices)
+hb = [A.seeds_uniform(3, b * 250_000, 250_000) for b in range(3)]
+pend = [c.submitHostBatch(x, pinned=True) for x in hb[:2]]
+c.waitHostBatch(pend[0][0])
+pend.append(c.submitCompactBatch(hb[2], want_flags=True))
+c.waitHostBatch(pend[1][0])
+nk = c.waitCompactBatch(*pend[2])
+sa = _capi.SamplerArgs(rng_seed=5, first_index=0, mode=0, wrap_bounds=1, distance=0.0, near_host=None)
+t, r = c.submitCompactBatch(sampler=sa, count=120_000)
+nk2 = c.waitCompactBatch(t, r)
+print("host batches ok", nk, nk2)
