@@ -298,16 +298,21 @@ def aux_kernels(pkg, local, peak_flops):
     # ---- discreteGeodesic: edges between projected states of the dumbbell manifold ----
     c = pkg.KinematicChainConstraint.from_config("dumbbell", device=local)
     space = pkg.jy_ProjectedStateSpace(pkg.KinematicChainSpace(14), c)
-    smp = space.allocStateSampler(pool_size=1 << 20, rng_seed=3)
-    V = smp.sampleUniformBatch(1_200_000)
-    E = 100_000
-    g = torch.Generator(device=dev).manual_seed(1)
-    V = V[torch.randperm(V.shape[0], device=dev, generator=g)][: 2 * E]
-    frm, to = V[:E].contiguous(), V[E:2 * E].contiguous()
+    # the planner's edges (stefanBiPRM.cpp:278-318): every new vertex against its k = 5 nearest roadmap vertices
+    smp = space.allocStateSampler(pool_size=1 << 17, rng_seed=3)
+    nv, knn = 20_000, 5
+    V = smp.sampleUniformBatch(120_000)[:nv].contiguous()
+    dm = torch.cdist(V, V)
+    dm.fill_diagonal_(float("inf"))
+    nbr = dm.topk(knn, largest=False).indices
+    del dm
+    E = nv * knn
+    frm, to = V.repeat_interleave(knn, dim=0).contiguous(), V[nbr.reshape(-1)].contiguous()
     ms, r = best_ms(lambda: space.discreteGeodesicBatch(frm, to, max_states=40))
     fl_iter, fl_tail = c.algorithmicFlops()
     iters, nproj = int(r.iters.sum(dtype=torch.int64)), int(r.n_states.sum(dtype=torch.int64))
-    out["geodesic"] = {"workload": "100 000 discreteGeodesic edges between random projected dumbbell states (delta 0.25, lambda 2)",
+    out["geodesic"] = {"workload": "100 000 discreteGeodesic edges: 20 000 projected dumbbell states, each to its 5 nearest neighbours "
+                                   "(delta 0.25, lambda 2)",
                        "kernel": "ccp_geodesic_kernel", "ms": ms, "edges_per_s": E / ms * 1e3,
                        "projections_per_s": nproj / ms * 1e3, "reached_fraction": float(r.reached.float().mean()),
                        "mean_states_per_edge": nproj / E, "newton_iterations": iters,
