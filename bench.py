@@ -675,6 +675,22 @@ def main():
     launches = c.launchCount() - launches0
     load_windows.append((t_region - 0.05, time.perf_counter()))
     assert int(max_counts.max().item()) <= cap, "gather capacity overflow"
+    # N > 1: the pool the LAST full step gathered (its ring slot is untouched since) must be bit-identical on every rank,
+    # and the exchanged counts must equal every rank's own count of the states that finished in that launch
+    headline_gather_check = None
+    if exchange_kind == "fused":
+        last = args.warmup + args.steps - 1
+        pp, oo = peer_pools[last % R], outs[last % R]
+        cl = [int(v) for v in pp.counts.tolist()]
+        sums = torch.stack([pp.pool[r, :cl[r]].view(torch.int64).sum() for r in range(world)])
+        all_sums = torch.empty((world, world), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(all_sums, sums)
+        mine = torch.tensor([int(oo["n_ok"].item())], dtype=torch.int64, device=dev)
+        all_mine = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(all_mine, mine)
+        headline_gather_check = {"pools_identical_across_ranks": bool((all_sums == all_sums[0:1]).all()),
+                                 "counts_equal_ranks_own_counts": [int(v) for v in all_mine.tolist()] == cl, "counts": cl}
+        assert headline_gather_check["pools_identical_across_ranks"] and headline_gather_check["counts_equal_ranks_own_counts"]
 
     ms_total = t_begin.elapsed_time(t_end)
     n_timed_launches = args.steps + (1 if pipelined else 0)
@@ -919,6 +935,7 @@ def main():
                              "algorithmic_bytes_per_projection": 2 * n * 8 + 6,
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
         "gather_multicast": bool(peer_pools and peer_pools[0].multicast_ptr),
+        "gather_check": headline_gather_check,
         "gpu_launches": launches, "clocks": clocks,
     }
     if e2e:

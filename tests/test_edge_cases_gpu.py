@@ -137,3 +137,81 @@ def test_opt_in_damping_and_clamping(setup):
     c.setOptions()
     again = c.projectBatch(torch.from_numpy(seeds).cuda())
     assert np.array_equal(_bits(again.x), _bits(base.x)) and torch.equal(again.ok, base.ok)
+
+
+def test_round2_entry_points_reject_bad_arguments(setup):
+    """Argument checking of the entry points added in round 2 (error codes, no crash, handle usable afterwards)."""
+    import ctypes as C
+
+    import closed_chain_motion_planner_b200 as pkg
+    from closed_chain_motion_planner_b200 import _capi
+
+    _, c, A, B = setup
+    lib, h = c._lib, c._h
+    INVALID, STATE = -1, -3
+    x = np.ascontiguousarray(A.seeds_uniform(0, 0, 64))
+    xo = np.zeros_like(x)
+    t = C.c_int64(0)
+    nk = C.c_int64(0)
+    # ccp_host_batch_submit: exactly one source of seeds, a capacity with compact outputs, a positive count
+    b = _capi.HostBatch()
+    b.count = 64
+    assert lib.ccp_host_batch_submit(h, C.byref(b), C.byref(t)) == INVALID  # neither seeds nor sampler
+    sa = _capi.SamplerArgs(rng_seed=0, first_index=0, mode=0, wrap_bounds=0, distance=0.0, near_host=None)
+    b.seeds_host = x.ctypes.data
+    b.sampler = C.pointer(sa)
+    assert lib.ccp_host_batch_submit(h, C.byref(b), C.byref(t)) == INVALID  # both
+    b.sampler = None
+    b.compact_host = xo.ctypes.data
+    assert lib.ccp_host_batch_submit(h, C.byref(b), C.byref(t)) == INVALID  # compact output without a capacity
+    b.compact_capacity = 64
+    b.count = 0
+    assert lib.ccp_host_batch_submit(h, C.byref(b), C.byref(t)) == INVALID
+    assert lib.ccp_host_batch_submit(h, None, C.byref(t)) == INVALID and lib.ccp_host_batch_submit(h, C.byref(b), None) == INVALID
+    bad_mode = _capi.SamplerArgs(rng_seed=0, first_index=0, mode=7, wrap_bounds=0, distance=0.0, near_host=None)
+    b2 = _capi.HostBatch()
+    b2.count = 64
+    b2.sampler = C.pointer(bad_mode)
+    b2.compact_host = xo.ctypes.data
+    b2.compact_capacity = 64
+    assert lib.ccp_host_batch_submit(h, C.byref(b2), C.byref(t)) == INVALID  # sampler mode out of range
+    assert lib.ccp_host_batch_wait(h, 123456789, C.byref(nk)) == INVALID  # a ticket never issued
+    # a good batch still goes through, and waiting twice for it is harmless
+    b.count = 64
+    assert lib.ccp_host_batch_submit(h, C.byref(b), C.byref(t)) == 0
+    assert lib.ccp_host_batch_wait(h, t.value, C.byref(nk)) == 0 and 0 <= nk.value <= 64
+    assert lib.ccp_host_batch_wait(h, t.value, C.byref(nk)) == 0
+    rb = B.project(x)
+    assert nk.value == int(rb["ok"].sum())
+    # multicast needs peers first; peers need aligned pools
+    assert lib.ccp_set_gather_multicast(h, 0x1000) == STATE
+    pools = (C.c_uint64 * 1)(0x1008)
+    assert lib.ccp_set_gather_peers(h, 1, 0, pools, 16) == INVALID  # not 16-byte aligned
+    assert lib.ccp_set_gather_peers(h, 0, 0, None, 0) == 0
+    # peer groups and the NCCL gather
+    g = C.c_void_p()
+    assert lib.ccp_peer_group_create(None, 1, 16, C.byref(g)) == INVALID
+    hs = (C.c_void_p * 1)(h)
+    assert lib.ccp_peer_group_create(hs, 0, 16, C.byref(g)) == INVALID and lib.ccp_peer_group_create(hs, 9, 16, C.byref(g)) == INVALID
+    assert lib.ccp_peer_group_create(hs, 1, 0, C.byref(g)) == INVALID and b"capacity" in lib.ccp_peer_group_last_error(None)
+    assert lib.ccp_peer_group_create(hs, 1, 4096, C.byref(g)) == 0 and lib.ccp_peer_group_world(g) == 1
+    cnt = (C.c_int64 * 1)()
+    assert lib.ccp_peer_group_sample_project(g, None, 100, cnt) == INVALID
+    assert lib.ccp_peer_group_sample_project(g, C.byref(sa), 2000, cnt) == 0 and 0 < cnt[0] < 2000  # a group of one works
+    rows = np.zeros((4096, 14))
+    got = C.c_int64(0)
+    assert lib.ccp_peer_group_gather_host(g, 0, rows.ctypes.data, 4096, cnt, C.byref(got)) == 0 and got.value == cnt[0]
+    assert lib.ccp_peer_group_gather_host(g, 0, rows.ctypes.data, 3, cnt, C.byref(got)) == INVALID  # host buffer too small
+    assert lib.ccp_peer_group_gather_host(g, 5, rows.ctypes.data, 4096, cnt, C.byref(got)) == INVALID
+    f = A.function(rows[:got.value])
+    assert np.all(f[:, 0] <= 1e-3 * (1 + 1e-9)) and np.all(f[:, 1] < 5e-3)
+    lib.ccp_peer_group_destroy(g)
+    lib.ccp_peer_group_destroy(None)
+    assert lib.ccp_allgather_converged(h, None, 2, None, None, 16, None, None, None) == INVALID
+    assert lib.ccp_set_coop_threshold(None, 5) == INVALID and lib.ccp_set_coop_threshold(h, -1) == 0
+    assert lib.ccp_device_count() >= 1
+    it, tl = C.c_double(), C.c_double()
+    assert lib.ccp_algorithmic_flops_ik(C.byref(it), C.byref(tl)) == 0 and it.value == 1070.0 and tl.value == 540.0
+    # the handle is still fine
+    r = c.projectBatch(x)
+    assert np.array_equal(r.x.view(np.uint64), rb["x"].view(np.uint64))
