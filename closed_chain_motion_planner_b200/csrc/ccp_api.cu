@@ -400,7 +400,14 @@ static int launch_project(ccp_handle* h, ccp_project_args& A, int layout, cudaSt
     A.peer_mc = h->peer_mc;
     for (int p = 0; p < h->peer_world; ++p) A.peer_pool[p] = h->peer_pool[p];
   }
-  CCP_CUDA(cudaMemsetAsync(h->d_counters + slot, 0, sizeof(ccp_launch_rec), st));
+  // a small complete launch: latency, not throughput, is what it costs — two lanes per sample (ccp_coop.cu).  When every
+  // sample has its static place in the grid (always, below the default threshold) the work counter is never touched and
+  // its stream-ordered zeroing — one more operation on the path of a single project() call — is skipped.
+  const bool coop = !defer && !h->pipeline_open && h->model.n_arms == 2 && A.count <= h->coop_max && A.peer_world == 0 &&
+                    !A.own_n_ok;
+  const bool coop_static = coop && A.count <= 64LL * ((A.count + 15) / 16 < 3LL * h->sm_count ? (A.count + 15) / 16 : 3LL * h->sm_count);
+  if (coop_static) A.counter = nullptr;
+  else CCP_CUDA(cudaMemsetAsync(h->d_counters + slot, 0, sizeof(ccp_launch_rec), st));
   if (defer || h->pipeline_open) {
     int rc = ensure_pipeline(h);
     if (rc) return rc;
@@ -417,8 +424,7 @@ static int launch_project(ccp_handle* h, ccp_project_args& A, int layout, cudaSt
     }
   }
   int rc;
-  if (!defer && !A.adopt && !A.done && h->model.n_arms == 2 && A.count <= h->coop_max && A.peer_world == 0 && !A.own_n_ok) {
-    // a small complete launch: latency, not throughput, is what it costs — two lanes per sample (ccp_coop.cu)
+  if (coop) {
     cudaError_t e = ccp_launch_project_coop(h->sm_count, h->model, A, soa, st);
     rc = (e == cudaSuccess) ? CCP_OK : set_err(h, CCP_ERR_CUDA, "cooperative project kernel launch: %s", cudaGetErrorString(e));
   } else {

@@ -192,7 +192,8 @@ ccp_project_coop_kernel(const __grid_constant__ ccp_model M, const __grid_consta
           st_elem<SOA>(A.resid, idx, 1, A.out_stride, 2, fv[1]);
         }
         if (A.n_ok && okk) slot = atomicAdd(A.n_ok, 1ULL);
-        u = static_samples + atomicAdd((unsigned*)A.counter, 1u);  // the pair's next sample
+        // the pair's next sample (no counter: every sample had its static place, nothing is left)
+        u = A.counter ? static_samples + atomicAdd((unsigned*)A.counter, 1u) : total;
       }
       packed = A.n_ok && okk && A.compact;
       idx = CCP_NO_SAMPLE;
