@@ -382,3 +382,39 @@ def test_seeded_compact_host_batches_equal_sampler(setup, mode):
     for (x, ok), (r, nk) in zip(outs, got):
         _compact_rows_equal(x, ok, r, nk)
     assert not c.pipelineOpen()
+
+
+def test_three_arm_compact_and_seeded_host_batches():
+    """21-DoF states through the compact-output and device-seeded forms of the streaming host path."""
+    import closed_chain_motion_planner_b200 as pkg
+    from closed_chain_motion_planner_b200 import _capi
+
+    c = pkg.KinematicChainConstraint.from_config("stefan_three_arm", device=0)
+    c_ref = pkg.KinematicChainConstraint.from_config("stefan_three_arm", device=0)
+    rng = np.random.default_rng(5)
+    count = 260_000
+    x = c.config.start[None, :] + 0.08 * rng.standard_normal((count, 21))
+    ref = c_ref.projectBatch(torch.from_numpy(x).cuda(), want_resid=False)
+    torch.cuda.synchronize()
+    t0, r0 = c.submitCompactBatch(x[: count // 2], want_flags=True)
+    t1, r1 = c.submitCompactBatch(x[count // 2:], want_flags=True)
+    n0 = c.waitCompactBatch(t0, r0)
+    n1 = c.waitCompactBatch(t1, r1)
+    okm = _np(ref.ok).astype(bool)
+    h = count // 2
+    assert n0 == int(okm[:h].sum()) and n1 == int(okm[h:].sum()) and n0 > 0
+    assert np.array_equal(r0.states[:n0].view(np.uint64), _np(ref.x)[:h][r0.index[:n0]].view(np.uint64))
+    assert np.array_equal(r1.states[:n1].view(np.uint64), _np(ref.x)[h:][r1.index[:n1]].view(np.uint64))
+    assert np.array_equal(np.sort(r1.index[:n1]), np.nonzero(okm[h:])[0])
+    # device-generated seeds: the packed rows equal those of the device sampler call on the same counter range
+    import ctypes as C
+
+    a = _capi.SamplerArgs(rng_seed=2, first_index=10, mode=0, wrap_bounds=0, distance=0.0, near_host=None)
+    xs = torch.empty((50_000, 21), dtype=torch.float64, device="cuda")
+    oks = torch.empty(50_000, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    assert c_ref._lib.ccp_sample_project_batch(c_ref._h, C.byref(a), 50_000, 0, xs.data_ptr(), oks.data_ptr(), None, None, None, st) == 0
+    torch.cuda.synchronize()
+    t, r = c.submitCompactBatch(sampler=a, count=50_000)
+    nk = c.waitCompactBatch(t, r)
+    _compact_rows_equal(xs, oks, r, nk)
