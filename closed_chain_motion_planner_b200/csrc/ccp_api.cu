@@ -1107,7 +1107,8 @@ int ccp_geodesic_batch(ccp_handle* h, const double* from_dev, const double* to_d
   unsigned long long* counter = &h->d_counters[slot].work;
   CCP_CUDA(cudaMemsetAsync(h->d_counters + slot, 0, sizeof(ccp_launch_rec), st));
   cudaError_t e = ccp_launch_geodesic(h->sm_count, h->model, from_dev, to_dev, edges, delta, lambda, max_states, states_dev,
-                                      n_states_dev, reached_dev, iters_dev, counter, st);
+                                      n_states_dev, reached_dev, iters_dev, counter,
+                                      4 * h->coop_max /* a walk is long: two lanes per edge win up to ~4x the projection's threshold */, st);
   if (e != cudaSuccess) return set_err(h, CCP_ERR_CUDA, "geodesic kernel launch: %s", cudaGetErrorString(e));
   return CCP_OK;
 }

@@ -5,6 +5,7 @@
 // loop whose trip is ONE Newton iteration, so edges of different length and projections of different difficulty
 // do not idle the warp.  The state validity check (MoveIt collision, jy_ProjectedStateSpace.cpp:66) is a host
 // concern: this is the `interpolate = true` walk; callers validate the returned states lazily.
+#include "ccp_coop.cuh"
 #include "ccp_device.cuh"
 #include "ccp_internal.h"
 
@@ -125,9 +126,127 @@ ccp_geodesic_kernel(const __grid_constant__ ccp_model M, const __grid_constant__
   }
 }
 
+// ---- the same walk with TWO lanes per edge (lane a owns arm a; ccp_coop.cuh) ---------------------------------------------
+// A batch of edges is bounded by its longest edge — a serial chain of projections — so for the planner's
+// batch sizes (the k = 5 edges of a new vertex, stefanBiPRM.cpp:315; a few thousand at most) what matters is the time of
+// one Newton trip of a lone warp, which the cooperative mapping shortens.  Pairs run independently (pair-masked
+// shuffles); distances are accumulated across the pair in joint order, so every number equals the one-thread walk's.
+template <bool PANDA>
+__global__ void __launch_bounds__(128, 2)
+ccp_geodesic_coop_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ ccp_geodesic_args A) {
+  constexpr int n = 2 * CCPC_DOF, H = CCPC_DOF;
+  const ccp_pair P = ccp_make_pair();
+  const int a = P.a;
+  double x[H], prev[H], tov[H];
+  ccp_geo_state g;
+  g.dist = g.total = g.max = 0.0;
+  int it = 0, ns = 0, iters_sum = 0;
+  // the first edge of every pair is static and interleaved over the blocks; the counter hands out the rest
+  const long long static_edges = (long long)gridDim.x * (blockDim.x / 2);
+  long long e = ((long long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 16 + ((threadIdx.x & 31) >> 1);
+  bool need_edge = true, first = true;
+  for (;;) {
+    if (need_edge) {
+      if (!first) {
+        unsigned long long c = 0;
+        if (a == 0) c = atomicAdd(A.counter, 1ULL);
+        const unsigned lo = __shfl_sync(P.mask, (unsigned)c, P.lane0), hi = __shfl_sync(P.mask, (unsigned)(c >> 32), P.lane0);
+        e = static_edges + (long long)(((unsigned long long)hi << 32) | lo);
+      }
+      first = false;
+      if (e >= A.edges) break;
+      const double* fr = A.from + e * n + a * H;
+      const double* to = A.to + e * n + a * H;
+      double* out = A.states + (e * A.max_states) * n + a * H;
+#pragma unroll
+      for (int j = 0; j < H; ++j) {
+        prev[j] = __ldg(fr + j);
+        tov[j] = __ldg(to + j);
+        out[j] = prev[j];
+        x[j] = prev[j];
+      }
+      g.dist = ccp_pair_distance(P, prev, tov);
+      g.total = 0.0;
+      g.max = g.dist * A.lambda;
+      ns = 1;
+      iters_sum = 0;
+      if (g.dist <= A.delta) {  // already there
+        if (a == 0) {
+          A.n_states[e] = 1;
+          A.reached[e] = 1;
+          if (A.total_iters) A.total_iters[e] = 0;
+        }
+        continue;
+      }
+      const double t = A.delta / g.dist;
+#pragma unroll
+      for (int j = 0; j < H; ++j) x[j] = ccp_interpolate_joint(x[j], tov[j], t);
+      it = 0;
+      need_edge = false;
+    }
+    ccp_sc_local<1> S;
+    double w[3], m[3], e2, sv2, d0;
+    ccp_pair_forward<PANDA>(M, P, x, S, w, m, e2, sv2, d0);
+    const double dw2 = M.tan2_r * (d0 * d0);
+    const bool cont = ((e2 > M.tol_p2) || (sv2 > dw2)) && it < M.max_iter;
+    if (cont) {
+      ++it;
+      ccp_pair_step<PANDA>(M, P, S, w, m, e2, sv2, d0, x);
+    } else {
+      // ---- the projection of this step finished: bookkeeping of the walk (ccp_geodesic_advance, term by term) ----
+      iters_sum += it;
+      const bool cv = (e2 <= M.tol_p2) && (sv2 < dw2);
+      const bool okk = ccp_pair_joint_valid(M, P, x) && cv;
+      int code = 2;
+      if (okk) {
+        const double step = ccp_pair_distance(P, prev, x);
+        if (!(step > A.lambda * A.delta)) {
+          g.total += step;
+          if (!(g.total > g.max)) {
+            const double newDist = ccp_pair_distance(P, x, tov);
+            if (!(newDist >= g.dist)) {
+              g.dist = newDist;
+              code = (g.dist >= A.delta) ? 0 : 1;
+            }
+          }
+        }
+      }
+      bool overflow = false;
+      if (code != 2) {
+        if (ns < A.max_states) {
+          double* out = A.states + (e * A.max_states + ns) * n + a * H;
+#pragma unroll
+          for (int j = 0; j < H; ++j) {
+            out[j] = x[j];
+            prev[j] = x[j];
+          }
+          ++ns;
+        } else {
+          code = 2;  // out of room: report as not reached
+          overflow = true;
+        }
+      }
+      if (code == 0) {
+        const double t = A.delta / g.dist;
+#pragma unroll
+        for (int j = 0; j < H; ++j) x[j] = ccp_interpolate_joint(x[j], tov[j], t);
+        it = 0;
+      } else {
+        if (a == 0) {
+          A.n_states[e] = ns;
+          A.reached[e] = (!overflow && g.dist <= A.delta) ? 1 : 0;
+          if (A.total_iters) A.total_iters[e] = iters_sum;
+        }
+        need_edge = true;
+      }
+    }
+  }
+}
+
 cudaError_t ccp_launch_geodesic(int sm_count, const ccp_model& M, const double* from, const double* to, long long edges,
                                 double delta, double lambda, int max_states, double* states, int32_t* n_states,
-                                uint8_t* reached, int32_t* total_iters, unsigned long long* counter, cudaStream_t st) {
+                                uint8_t* reached, int32_t* total_iters, unsigned long long* counter, long long coop_max,
+                                cudaStream_t st) {
   ccp_geodesic_args A;
   A.from = from;
   A.to = to;
@@ -140,6 +259,16 @@ cudaError_t ccp_launch_geodesic(int sm_count, const ccp_model& M, const double* 
   A.max_states = max_states;
   A.delta = delta;
   A.lambda = lambda;
+  if (M.n_arms == 2 && edges <= coop_max) {
+    // few edges: two lanes per edge, one cooperative warp (16 edges) per block before any block gets a second one
+    long long needc = (edges + 15) / 16;
+    const long long capc = (long long)sm_count * 2;
+    int gridc = (int)(needc < capc ? needc : capc);
+    if (gridc < 1) gridc = 1;
+    if (M.panda_alpha) ccp_geodesic_coop_kernel<true><<<gridc, 128, 0, st>>>(M, A);
+    else ccp_geodesic_coop_kernel<false><<<gridc, 128, 0, st>>>(M, A);
+    return cudaGetLastError();
+  }
   long long need = (edges + 31) / 32;  // one warp's worth of edges per block before any block gets more
   long long cap = (long long)sm_count * 3;
   int grid = (int)(need < cap ? need : cap);

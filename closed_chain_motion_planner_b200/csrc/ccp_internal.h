@@ -15,7 +15,8 @@ cudaError_t ccp_launch_project_coop(int sm_count, const ccp_model& M, const ccp_
 
 cudaError_t ccp_launch_geodesic(int sm_count, const ccp_model& M, const double* from, const double* to, long long edges,
                                 double delta, double lambda, int max_states, double* states, int32_t* n_states,
-                                uint8_t* reached, int32_t* total_iters, unsigned long long* counter, cudaStream_t st);
+                                uint8_t* reached, int32_t* total_iters, unsigned long long* counter, long long coop_max,
+                                cudaStream_t st);
 
 struct ccp_ik_opt;
 cudaError_t ccp_launch_ik(int sm_count, const ccp_model& M, int arm, const double* Tt, const double* qseed, long long count,

@@ -128,3 +128,31 @@ def test_coop_sampler_wrap_and_golden_rows():
     assert c._lib.ccp_set_coop_threshold(c._h, FORCE) == 0
     r = c.projectBatch(rows)
     assert bool((r.ok == 1).all()) and int(r.iters.max()) <= 1 and float((r.x - rows).abs().max()) < 5e-4
+
+
+@pytest.mark.parametrize("name", ["stefan", "Wine_Bottle"])
+def test_coop_geodesic_equals_thread_per_edge(name):
+    """discreteGeodesic with two lanes per edge (ccp_geodesic_coop_kernel) against the one-thread walk and the host twin:
+    the same states, state counts, reached flags and iteration totals, bit for bit."""
+    import closed_chain_motion_planner_b200 as pkg
+
+    cfg, A, B = make_oracles(name)
+    c = pkg.KinematicChainConstraint.from_config(name, device=0)
+    space = pkg.jy_ProjectedStateSpace(pkg.KinematicChainSpace(14), c)
+    smp = space.allocStateSampler(pool_size=8192, rng_seed=5)
+    V = smp.sampleUniformBatch(8000)
+    for E in (1, 5, 17, 700):
+        frm = torch.cat([torch.from_numpy(cfg.start[None, :]).cuda().repeat(E // 2 + 1, 1), V[:E]])[:E].contiguous()
+        to = V[E:2 * E].contiguous()
+        if E == 5:
+            to[0] = frm[0]  # an edge that is "already there"
+        r0, r1 = _both(c, lambda: space.discreteGeodesicBatch(frm, to, max_states=24))
+        assert torch.equal(r0.reached, r1.reached) and torch.equal(r0.n_states, r1.n_states) and torch.equal(r0.iters, r1.iters)
+        for e in range(E):
+            k = int(r0.n_states[e])
+            assert np.array_equal(_bits(r0.states[e, :k]), _bits(r1.states[e, :k])), (name, E, e)
+        rc_b, ns_b, st_b, it_b = B.discrete_geodesic(frm.cpu().numpy(), to.cpu().numpy(), delta=0.25, lam=2.0, max_states=24)
+        assert np.array_equal(r1.reached.cpu().numpy(), rc_b) and np.array_equal(r1.n_states.cpu().numpy(), ns_b)
+        assert np.array_equal(r1.iters.cpu().numpy(), it_b)
+        for e in range(E):
+            assert np.array_equal(_bits(r1.states[e, :ns_b[e]]), st_b[e, :ns_b[e]].view(np.uint64))

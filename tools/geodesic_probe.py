@@ -14,7 +14,11 @@ smp = space.allocStateSampler(pool_size=1_200_000, rng_seed=1)
 pts = smp.sampleUniformBatch(1_200_000)
 E = min(100_000, pts.shape[0] // 2)
 frm, to = pts[:E].contiguous(), pts[E:2 * E].contiguous()
-for edges in (5, 100, 1000, 5000, 20000, E):
+import itertools
+
+for edges, thr in itertools.product((5, 100, 1000, 5000, 20000, E), (0, 1 << 30)):
+    c._lib.ccp_set_coop_threshold(c._h, thr)
+    print("two lanes per edge " if thr else "one thread per edge", end=" ")
     best = 1e9
     for _ in range(3):
         torch.cuda.synchronize()
