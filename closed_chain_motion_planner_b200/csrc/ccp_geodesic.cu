@@ -25,8 +25,11 @@ struct ccp_geodesic_args {
 #ifndef CCP_GEO_BLOCKS_K3
 #define CCP_GEO_BLOCKS_K3 2  // three arms: 255 registers and 144 B of spill; 3 blocks (168 registers, 680 B) measured 1.3-1.6x slower
 #endif
+#ifndef CCP_GEO_BLOCKS_K2
+#define CCP_GEO_BLOCKS_K2 3
+#endif
 template <int K, bool PANDA>
-__global__ void __launch_bounds__(128, K == 2 ? 3 : CCP_GEO_BLOCKS_K3)
+__global__ void __launch_bounds__(128, K == 2 ? CCP_GEO_BLOCKS_K2 : CCP_GEO_BLOCKS_K3)
 ccp_geodesic_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ ccp_geodesic_args A) {
   constexpr int n = CCPC_DOF * K;
   double x[n];
@@ -273,7 +276,7 @@ cudaError_t ccp_launch_geodesic(int sm_count, const ccp_model& M, const double* 
     return cudaGetLastError();
   }
   long long need = (edges + 31) / 32;  // one warp's worth of edges per block before any block gets more
-  long long cap = (long long)sm_count * (M.n_arms == 2 ? 3 : CCP_GEO_BLOCKS_K3);
+  long long cap = (long long)sm_count * (M.n_arms == 2 ? CCP_GEO_BLOCKS_K2 : CCP_GEO_BLOCKS_K3);
   int grid = (int)(need < cap ? need : cap);
   if (grid < 1) grid = 1;
   if (M.n_arms == 2) {

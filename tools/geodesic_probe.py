@@ -12,6 +12,14 @@ c = pkg.KinematicChainConstraint.from_config("dumbbell")
 space = pkg.jy_ProjectedStateSpace(pkg.KinematicChainSpace(14), c)
 smp = space.allocStateSampler(pool_size=1_200_000, rng_seed=1)
 pts = smp.sampleUniformBatch(1_200_000)
+# the pool's row order is whatever the compaction atomics made it: sort it, then shuffle with a fixed seed, so that two
+# runs (two builds) walk the SAME edges
+import numpy as np
+
+pn = pts.cpu().numpy()
+pn = pn[np.lexsort(pn.T[::-1])]
+pn = pn[np.random.default_rng(0).permutation(len(pn))]
+pts = torch.from_numpy(pn).cuda()
 E = min(100_000, pts.shape[0] // 2)
 frm, to = pts[:E].contiguous(), pts[E:2 * E].contiguous()
 import itertools
