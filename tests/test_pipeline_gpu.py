@@ -315,8 +315,9 @@ def _compact_rows_equal(ref_x, ref_ok, res, n_ok):
     assert np.array_equal(res.states[:n_ok].view(np.uint64), _np(ref_x)[idx].view(np.uint64))
 
 
+@pytest.mark.parametrize("pinned", [True, False])
 @pytest.mark.parametrize("count", [1_000_000, 70_000, 13])
-def test_compact_host_batches_streaming(setup, count):
+def test_compact_host_batches_streaming(setup, count, pinned):
     """ccp_host_batch_submit with compact outputs: only the ok states come back, packed per batch (a straggler finished
     by the NEXT batch's launch still lands in its own batch's rows), with the seed index of every row."""
     pkg, c, A = setup
@@ -326,7 +327,7 @@ def test_compact_host_batches_streaming(setup, count):
     torch.cuda.synchronize()
     pending, got = [], []
     for x in batches:
-        pending.append(c.submitCompactBatch(x, want_flags=True))
+        pending.append(c.submitCompactBatch(x, want_flags=True, pinned=pinned))  # pageable: the launch-lag copy schedule
         if len(pending) == 2:
             t, r = pending.pop(0)
             got.append((r, c.waitCompactBatch(t, r)))
