@@ -215,3 +215,39 @@ def test_round2_entry_points_reject_bad_arguments(setup):
     # the handle is still fine
     r = c.projectBatch(x)
     assert np.array_equal(r.x.view(np.uint64), rb["x"].view(np.uint64))
+
+
+def test_host_entry_points_from_several_threads(setup):
+    """ccp.h: host-pointer calls on one handle may come from several threads (serialised inside, as the reference's
+    graphMutex_ serialises its callers); handles are independent of one another.  ctypes drops the GIL during the calls."""
+    import threading
+
+    import closed_chain_motion_planner_b200 as pkg
+
+    _, c, A, B = setup
+    c2 = pkg.KinematicChainConstraint.from_config("Wine_Bottle", device=0)
+    sets = [A.seeds_uniform(20 + t, 0, n) for t, n in enumerate((1, 300, 5_000, 40_000, 260_000, 7))]
+    want = [B.project(s, nthreads=4) for s in sets]
+    errors = []
+
+    def worker(tid, handle):
+        try:
+            for rep in range(3):
+                for k in range(len(sets)):
+                    s = sets[(k + tid) % len(sets)]
+                    w = want[(k + tid) % len(sets)]
+                    r = handle.projectBatch(s)
+                    if not (np.array_equal(r.x.view(np.uint64), w["x"].view(np.uint64)) and np.array_equal(r.ok, w["ok"])):
+                        errors.append((tid, rep, k, "projectBatch"))
+                    f = handle.functionBatch(s[:50])
+                    if not np.array_equal(f.view(np.uint64), B.function(s[:50]).view(np.uint64)):
+                        errors.append((tid, rep, k, "functionBatch"))
+        except Exception as e:  # noqa: BLE001
+            errors.append((tid, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(t, c if t < 3 else c2)) for t in range(5)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:5]
