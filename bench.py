@@ -343,6 +343,30 @@ def aux_kernels(pkg, local, peak_flops):
                         "kernel": "ccp_ik_sample_kernel", "ms": ms, "targets_per_s": nt / ms * 1e3,
                         "success_fraction": float(r["ok"].float().mean()),
                         "mean_successful_restarts": float(r["n_success"].float().mean())}
+    # ---- goal sampling for the whole closed chain (sampleCalibGoal for a batch of object poses) ----
+    cs = pkg.KinematicChainConstraint.from_config("stefan", device=local)
+    cfg = cs.config
+    t_o7 = cs.graspFrames(cfg.t_wo_start, cfg.start)
+    ng = 100_000
+    To = np.tile(cfg.t_wo_start[None, :3, :], (ng, 1, 1))
+    To[:, :, 3] += rng.uniform(-0.06, 0.06, (ng, 3))
+    Td = torch.from_numpy(np.ascontiguousarray(To.reshape(ng, 12))).to(dev)
+    qref = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(cfg.start, (ng, 14)))).to(dev)
+    qo = torch.zeros((ng, 14), dtype=torch.float64, device=dev)
+    okg = torch.zeros(ng, dtype=torch.uint8, device=dev)
+    to7 = np.ascontiguousarray(t_o7.reshape(2, 12))
+    stg = torch.cuda.current_stream(dev).cuda_stream
+
+    def goal():
+        assert cs._lib.ccp_goal_sample_batch(cs._h, Td.data_ptr(), ng, to7.ctypes.data, qref.data_ptr(), 15, 5, 0.3, None,
+                                             qo.data_ptr(), okg.data_ptr(), stg) == 0
+        return okg
+
+    ms, r = best_ms(goal)
+    out["goal_sample"] = {"workload": "100 000 object poses around the stefan start pose: both arms' IK (15 restarts each, seeded with "
+                                      "the start configuration) -> closed-chain goal configurations (sampleCalibGoal, batched)",
+                          "kernels": "ccp_goal_targets_kernel + 2 x ccp_ik_sample_kernel + ccp_goal_combine_kernel", "ms": ms,
+                          "poses_per_s": ng / ms * 1e3, "success_fraction": float(r.float().mean())}
     return out
 
 

@@ -135,6 +135,8 @@ SYMBOLS = {
     "ccp_ik_default_options": (None, [C.POINTER(IkOptions)]),
     "ccp_ik_batch": (C.c_int, [_H, _I32, _P, _P, _I64, C.POINTER(IkOptions), _P, _P, _P, _P, _P]),
     "ccp_ik_sample_batch": (C.c_int, [_H, _I32, _P, _I64, _I32, C.c_uint64, C.c_double, _P, C.POINTER(IkOptions), _P, _P, _P, _P]),
+    "ccp_goal_sample_batch": (C.c_int, [_H, _P, _I64, _P, _P, _I32, C.c_uint64, C.c_double, C.POINTER(IkOptions), _P, _P, _P]),
+    "ccp_goal_sample_batch_host": (C.c_int, [_H, _P, _I64, _P, _P, _I32, C.c_uint64, C.c_double, C.POINTER(IkOptions), _P, _P]),
     "ccp_geodesic_batch": (C.c_int, [_H, _P, _P, _I64, C.c_double, C.c_double, _I32, _P, _P, _P, _P, _P]),
     "ccp_enforce_bounds_batch": (C.c_int, [_H, _P, _I64, _I32, _P]),
     "ccp_project_batch_host": (C.c_int, [_H, _P, _I64, _P, _P, _P, _P, _P]),

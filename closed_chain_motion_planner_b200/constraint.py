@@ -510,6 +510,45 @@ class KinematicChainConstraint:
         self._need()
         return self._flags(self._lib.ccp_joint_valid_batch, X, layout)
 
+    # -- goal sampling (jy_ValidStateSampler::sampleCalibGoal / sampleRandomGoal, batched) ---------
+    def graspFrames(self, t_wo_start, start_joint) -> np.ndarray:
+        """t_o7 of every arm as the reference derives it (ConstrainedPlanningCommon.cpp:105-111):
+        t_o7_a = t_wo_start^-1 * t_wb_a * getTransform(start segment of arm a).  Returns (K, 3, 4)."""
+        self._need()
+        q = np.ascontiguousarray(start_joint, dtype=np.float64).reshape(self.k_, 7)
+        Two_inv = np.linalg.inv(np.asarray(t_wo_start, dtype=np.float64).reshape(4, 4))
+        out = np.zeros((self.k_, 3, 4))
+        for a in range(self.k_):
+            T = np.zeros(12)
+            _check(self._lib, self._h, self._lib.ccp_arm_fk_batch_host(self._h, a, q[a].ctypes.data, 1, T.ctypes.data, None))
+            Tb = np.vstack([T.reshape(3, 4), [0, 0, 0, 1]])
+            out[a] = (Two_inv @ np.asarray(self._arms[a].t_wb, dtype=np.float64) @ Tb)[:3]
+        return out
+
+    def sampleGoalBatch(self, T_obj, t_o7, q_ref=None, restarts: int = 15, rng_seed: int = 0, sigma: float = 0.3, **ik_opts):
+        """Closed-chain goal configurations for a batch of object poses (ccp_goal_sample_batch): per arm the IK target is
+        t_wb^-1 * T_obj * t_o7 (ik_task.cpp:16-27), `restarts` solves side by side, the seeded one (q_ref's segment) wins,
+        else the nearest success.  T_obj: (n, 3, 4) or (n, 4, 4) world poses; t_o7: (K, 3, 4) (graspFrames); q_ref: (n, 7K)
+        or a single 7K-vector or None (sampleRandomGoal).  Returns dict(q=(n, 7K), ok=(n,)) as numpy arrays."""
+        self._need()
+        T = np.ascontiguousarray(np.asarray(T_obj, dtype=np.float64)[..., :3, :].reshape(-1, 12))
+        n = T.shape[0]
+        to7 = np.ascontiguousarray(np.asarray(t_o7, dtype=np.float64)[..., :3, :].reshape(self.k_, 12))
+        ref = None
+        if q_ref is not None:
+            ref = np.asarray(q_ref, dtype=np.float64)
+            ref = np.ascontiguousarray(np.broadcast_to(ref.reshape(-1, self.n_), (n, self.n_)))
+        o = _capi.IkOptions()
+        self._lib.ccp_ik_default_options(C.byref(o))
+        for k, v in ik_opts.items():
+            setattr(o, k, v)
+        q = np.zeros((n, self.n_))
+        ok = np.zeros(n, np.uint8)
+        _check(self._lib, self._h, self._lib.ccp_goal_sample_batch_host(
+            self._h, T.ctypes.data, n, to7.ctypes.data, ref.ctypes.data if ref is not None else None, restarts, rng_seed, sigma,
+            C.byref(o), q.ctypes.data, ok.ctypes.data))
+        return dict(q=q, ok=ok)
+
     # -- measurement helpers --------------------------------------------------------------------
     def fp64PeakProbe(self, repeats: int = 5):
         self._need()

@@ -1190,10 +1190,89 @@ int ccp_ik_sample_batch(ccp_handle* h, int32_t arm, const double* T_target_dev, 
   cudaError_t e = cudaMemsetAsync(counters, 0, cbytes, st);
   if (e == cudaSuccess)
     e = ccp_launch_ik_sample(h->sm_count, h->model, arm, T_target_dev, q_ref_dev, n_targets, restarts, rng_seed, sigma, O,
-                             q_best_dev, ok_dev, n_success_dev, scratch, counters, st);
+                             q_best_dev, ok_dev, n_success_dev, scratch, counters, CCPC_DOF, st);
   h->launches += (n_targets + CCP_IK_SAMPLE_CHUNK - 1) / CCP_IK_SAMPLE_CHUNK;
   cudaFreeAsync(scratch, st);
   if (e != cudaSuccess) return set_err(h, CCP_ERR_CUDA, "IK sample kernel launch: %s", cudaGetErrorString(e));
+  return CCP_OK;
+}
+
+int ccp_goal_sample_batch(ccp_handle* h, const double* T_obj_dev, int64_t n, const double* t_o7_host, const double* q_ref_dev,
+                          int32_t restarts, uint64_t rng_seed, double sigma, const ccp_ik_options* opt, double* q_out_dev,
+                          uint8_t* ok_dev, void* stream) {
+  if (!h) return CCP_ERR_INVALID;
+  if (n < 0) return set_err(h, CCP_ERR_INVALID, "%s", "negative count");
+  if (restarts < 1 || restarts > 32) return set_err(h, CCP_ERR_INVALID, "%s", "IK restarts must be 1..32");
+  if (!(sigma >= 0)) return set_err(h, CCP_ERR_INVALID, "%s", "IK sigma must be >= 0");
+  if (!t_o7_host || (n > 0 && (!T_obj_dev || !q_out_dev || !ok_dev))) return set_err(h, CCP_ERR_INVALID, "%s", "null goal-sampling buffer");
+  if (n > CCP_IK_SAMPLE_CHUNK * CCP_IK_SAMPLE_MAX_LAUNCHES)
+    return set_err(h, CCP_ERR_INVALID, "%s", "more than 16 M object poses in one call: split the batch");
+  ccp_ik_opt O;
+  int rc = ik_options(h, opt, &O);
+  if (rc) return rc;
+  if (n == 0) return CCP_OK;
+  device_guard g(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int K = h->model.n_arms, nq = CCPC_DOF * K;
+  // scratch: per-arm targets [K][n][12] | per-arm verdicts [K][n] | IK selection scratch | one work counter per chunk launch and arm
+  const size_t tb = (sizeof(double) * 12 * (size_t)K * (size_t)n + 255) & ~(size_t)255;
+  const size_t ob = ((size_t)K * (size_t)n + 255) & ~(size_t)255;
+  const size_t sb = (ccp_ik_sample_scratch_bytes(n, restarts) + 255) & ~(size_t)255;
+  const size_t cb = sizeof(unsigned long long) * CCP_IK_SAMPLE_MAX_LAUNCHES * CCPC_MAX_ARMS;
+  char* base = nullptr;
+  CCP_CUDA(cudaMallocFromPoolAsync((void**)&base, tb + ob + sb + cb, h->pool, st));
+  double* Tt = (double*)base;
+  uint8_t* ok_arm = (uint8_t*)(base + tb);
+  void* scratch = base + tb + ob;
+  unsigned long long* counters = (unsigned long long*)(base + tb + ob + sb);
+  cudaError_t e = cudaMemsetAsync(counters, 0, cb, st);
+  if (e == cudaSuccess) e = ccp_launch_goal_targets(h->sm_count, h->model, t_o7_host, T_obj_dev, n, Tt, st);
+  h->launches++;
+  for (int a = 0; a < K && e == cudaSuccess; ++a) {
+    // every arm draws its own restarts from the stream; its seven joints sit at column 7 a of the 7K-wide rows
+    e = ccp_launch_ik_sample(h->sm_count, h->model, a, Tt + (size_t)a * n * 12, q_ref_dev ? q_ref_dev + a * CCPC_DOF : nullptr, n,
+                             restarts, rng_seed + 0x9E3779B97F4A7C15ull * (uint64_t)a, sigma, O, q_out_dev + a * CCPC_DOF,
+                             ok_arm + (size_t)a * n, nullptr, scratch, counters + a * CCP_IK_SAMPLE_MAX_LAUNCHES, nq, st);
+    h->launches += (n + CCP_IK_SAMPLE_CHUNK - 1) / CCP_IK_SAMPLE_CHUNK;
+  }
+  if (e == cudaSuccess) e = ccp_launch_goal_combine(h->sm_count, ok_arm, n, K, ok_dev, st);
+  h->launches++;
+  cudaFreeAsync(base, st);
+  if (e != cudaSuccess) return set_err(h, CCP_ERR_CUDA, "goal sampling launch: %s", cudaGetErrorString(e));
+  return CCP_OK;
+}
+
+int ccp_goal_sample_batch_host(ccp_handle* h, const double* T_obj_host, int64_t n, const double* t_o7_host,
+                               const double* q_ref_host, int32_t restarts, uint64_t rng_seed, double sigma,
+                               const ccp_ik_options* opt, double* q_out_host, uint8_t* ok_host) {
+  if (!h) return CCP_ERR_INVALID;
+  if (n < 0) return set_err(h, CCP_ERR_INVALID, "%s", "negative count");
+  if (n > 0 && (!T_obj_host || !t_o7_host || !q_out_host || !ok_host)) return set_err(h, CCP_ERR_INVALID, "%s", "null goal-sampling buffer");
+  if (n == 0) return CCP_OK;
+  std::lock_guard<std::mutex> host_lock(h->host_mu);
+  device_guard g(h->device);
+  cudaStream_t st = h->hstream[1];
+  const int nq = CCPC_DOF * h->model.n_arms;
+  const size_t tb = sizeof(double) * 12 * (size_t)n, qb = sizeof(double) * nq * (size_t)n;
+  char* base = nullptr;
+  CCP_CUDA(cudaMallocFromPoolAsync((void**)&base, tb + 2 * qb + (size_t)n + 64, h->pool, st));
+  double* dT = (double*)base;
+  double* dref = (double*)(base + tb);
+  double* dq = (double*)(base + tb + qb);
+  uint8_t* dok = (uint8_t*)(base + tb + 2 * qb);
+  cudaError_t e = cudaMemcpyAsync(dT, T_obj_host, tb, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && q_ref_host) e = cudaMemcpyAsync(dref, q_ref_host, qb, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(dq, 0, qb, st);
+  int rc = CCP_OK;
+  if (e == cudaSuccess)
+    rc = ccp_goal_sample_batch(h, dT, n, t_o7_host, q_ref_host ? dref : nullptr, restarts, rng_seed, sigma, opt, dq, dok, st);
+  if (rc == CCP_OK && e == cudaSuccess) e = cudaMemcpyAsync(q_out_host, dq, qb, cudaMemcpyDeviceToHost, st);
+  if (rc == CCP_OK && e == cudaSuccess) e = cudaMemcpyAsync(ok_host, dok, (size_t)n, cudaMemcpyDeviceToHost, st);
+  cudaFreeAsync(base, st);
+  cudaError_t e2 = cudaStreamSynchronize(st);
+  if (rc) return rc;
+  if (e != cudaSuccess || e2 != cudaSuccess)
+    return set_err(h, CCP_ERR_CUDA, "ccp_goal_sample_batch_host: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
   return CCP_OK;
 }
 

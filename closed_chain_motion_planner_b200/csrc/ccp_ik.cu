@@ -75,8 +75,8 @@ struct ccp_ik_sample_scratch {
 
 __global__ void __launch_bounds__(128, CCP_IK_BLOCKS_PER_SM)
 ccp_ik_sample_kernel(const __grid_constant__ ccp_model M, int arm, const double* __restrict__ Tt,
-                     const double* __restrict__ qref, long long n_targets, int restarts, unsigned long long rng_seed,
-                     long long first_target, double sigma, const __grid_constant__ ccp_ik_opt O,
+                     const double* __restrict__ qref, int q_stride, long long n_targets, int restarts,
+                     unsigned long long rng_seed, long long first_target, double sigma, const __grid_constant__ ccp_ik_opt O,
                      const __grid_constant__ ccp_ik_sample_scratch W, double* __restrict__ qbest, uint8_t* __restrict__ ok,
                      int32_t* __restrict__ n_success, unsigned long long* __restrict__ counter) {
   double T[12], q[CCPC_DOF], ref[CCPC_DOF];
@@ -95,7 +95,7 @@ ccp_ik_sample_kernel(const __grid_constant__ ccp_model M, int arm, const double*
 #pragma unroll
       for (int k = 0; k < 12; ++k) T[k] = __ldg(Tt + t * 12 + k);
 #pragma unroll
-      for (int k = 0; k < CCPC_DOF; ++k) ref[k] = qref ? __ldg(qref + t * CCPC_DOF + k) : 0.5 * (M.lb[k] + M.ub[k]);
+      for (int k = 0; k < CCPC_DOF; ++k) ref[k] = qref ? __ldg(qref + t * q_stride + k) : 0.5 * (M.lb[k] + M.ub[k]);
       if (r == 0 && qref) {
 #pragma unroll
         for (int k = 0; k < CCPC_DOF; ++k) q[k] = ref[k];
@@ -141,7 +141,7 @@ ccp_ik_sample_kernel(const __grid_constant__ ccp_model M, int arm, const double*
         const bool any = best < 1e300;
         if (any) {
 #pragma unroll
-          for (int k = 0; k < CCPC_DOF; ++k) qbest[t * CCPC_DOF + k] = __ldcg(W.q + (t * restarts + who) * CCPC_DOF + k);
+          for (int k = 0; k < CCPC_DOF; ++k) qbest[t * q_stride + k] = __ldcg(W.q + (t * restarts + who) * CCPC_DOF + k);
         }
         ok[t] = any;
         if (n_success) n_success[t] = cnt;
@@ -170,7 +170,7 @@ size_t ccp_ik_sample_scratch_bytes(long long n_targets, int restarts) {
 cudaError_t ccp_launch_ik_sample(int sm_count, const ccp_model& M, int arm, const double* Tt, const double* qref,
                                  long long n_targets, int restarts, unsigned long long rng_seed, double sigma,
                                  const ccp_ik_opt& O, double* qbest, uint8_t* ok, int32_t* n_success, void* scratch,
-                                 unsigned long long* counters, cudaStream_t st) {
+                                 unsigned long long* counters, int q_stride, cudaStream_t st) {
   // targets go through in chunks so that the scratch stays bounded; every chunk has its own work counter
   int launch = 0;
   for (long long first = 0; first < n_targets; first += CCP_IK_SAMPLE_CHUNK, ++launch) {
@@ -188,11 +188,78 @@ cudaError_t ccp_launch_ik_sample(int sm_count, const ccp_model& M, int arm, cons
     const long long items = nt * restarts;
     long long need = (items + 31) / 32, cap = (long long)sm_count * CCP_IK_BLOCKS_PER_SM;
     const int grid = (int)(need < cap ? (need < 1 ? 1 : need) : cap);
-    ccp_ik_sample_kernel<<<grid, 128, 0, st>>>(M, arm, Tt + first * 12, qref ? qref + first * CCPC_DOF : nullptr, nt, restarts,
-                                                rng_seed, first, sigma, O, W, qbest + first * CCPC_DOF, ok + first,
+    ccp_ik_sample_kernel<<<grid, 128, 0, st>>>(M, arm, Tt + first * 12, qref ? qref + first * q_stride : nullptr, q_stride, nt,
+                                                restarts, rng_seed, first, sigma, O, W, qbest + first * q_stride, ok + first,
                                                 n_success ? n_success + first : nullptr, counters + launch);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
   return cudaSuccess;
+}
+
+// ---- goal sampling for the whole closed chain (jy_ConstrainedValidStateSampler.h:63-189) ----
+// IK target of arm a for object pose T_obj: t_b7 = t_wb_a^-1 * T_obj * t_o7_a (IKTask::solve, ik_task.cpp:16-27), 3x4 row-major
+struct ccp_goal_frames {
+  double to7[CCPC_MAX_ARMS][12];
+};
+__global__ void __launch_bounds__(128)
+ccp_goal_targets_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ ccp_goal_frames F, const double* __restrict__ Tobj,
+                        long long n, int n_arms, double* __restrict__ Tt /*[arms][n][12]*/) {
+  const long long total = n * n_arms;
+  for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < total; w += (long long)gridDim.x * blockDim.x) {
+    const int a = (int)(w / n);
+    const long long i = w - (long long)a * n;
+    double To[12], X[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) To[k] = __ldg(Tobj + i * 12 + k);
+    // X = T_obj * t_o7
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        double acc = (c == 3) ? To[4 * r + 3] : 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) acc = CCP_FMA(To[4 * r + k], F.to7[a][4 * k + c], acc);
+        X[4 * r + c] = acc;
+      }
+    }
+    // t_wb^-1 * X = [R^T | -R^T p] X
+    const ccp_arm& A = M.arm[a];
+    double* out = Tt + ((long long)a * n + i) * 12;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) acc = CCP_FMA(A.Rwb[3 * k + r], (c == 3) ? X[4 * k + 3] - A.pwb[k] : X[4 * k + c], acc);
+        out[4 * r + c] = acc;
+      }
+    }
+  }
+}
+__global__ void __launch_bounds__(256)
+ccp_goal_combine_kernel(const uint8_t* __restrict__ ok_arm /*[arms][n]*/, long long n, int n_arms, uint8_t* __restrict__ ok) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    uint8_t all = 1;
+    for (int a = 0; a < n_arms; ++a) all &= ok_arm[(long long)a * n + i];
+    ok[i] = all;
+  }
+}
+
+cudaError_t ccp_launch_goal_targets(int sm_count, const ccp_model& M, const double* to7 /*[arms][12] host*/, const double* Tobj,
+                                    long long n, double* Tt, cudaStream_t st) {
+  ccp_goal_frames F;
+  for (int a = 0; a < M.n_arms; ++a)
+    for (int k = 0; k < 12; ++k) F.to7[a][k] = to7[a * 12 + k];
+  long long need = (n * M.n_arms + 127) / 128, cap = (long long)sm_count * 8;
+  const int grid = (int)(need < cap ? (need < 1 ? 1 : need) : cap);
+  ccp_goal_targets_kernel<<<grid, 128, 0, st>>>(M, F, Tobj, n, M.n_arms, Tt);
+  return cudaGetLastError();
+}
+cudaError_t ccp_launch_goal_combine(int sm_count, const uint8_t* ok_arm, long long n, int n_arms, uint8_t* ok, cudaStream_t st) {
+  long long need = (n + 255) / 256, cap = (long long)sm_count * 8;
+  const int grid = (int)(need < cap ? (need < 1 ? 1 : need) : cap);
+  ccp_goal_combine_kernel<<<grid, 256, 0, st>>>(ok_arm, n, n_arms, ok);
+  return cudaGetLastError();
 }

@@ -30,4 +30,9 @@ size_t ccp_ik_sample_scratch_bytes(long long n_targets, int restarts);
 cudaError_t ccp_launch_ik_sample(int sm_count, const ccp_model& M, int arm, const double* Tt, const double* qref,
                                  long long n_targets, int restarts, unsigned long long rng_seed, double sigma,
                                  const ccp_ik_opt& O, double* qbest, uint8_t* ok, int32_t* n_success, void* scratch,
-                                 unsigned long long* counters, cudaStream_t st);
+                                 unsigned long long* counters, int q_stride /* doubles between rows of qref / qbest */,
+                                 cudaStream_t st);
+// goal sampling of the whole chain: per-arm IK targets from object poses, and the AND of the arms' verdicts
+cudaError_t ccp_launch_goal_targets(int sm_count, const ccp_model& M, const double* to7_host, const double* Tobj, long long n,
+                                    double* Tt, cudaStream_t st);
+cudaError_t ccp_launch_goal_combine(int sm_count, const uint8_t* ok_arm, long long n, int n_arms, uint8_t* ok, cudaStream_t st);

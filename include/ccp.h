@@ -319,6 +319,21 @@ int ccp_ik_sample_batch(ccp_handle* h, int32_t arm, const double* T_target_dev, 
                         uint64_t rng_seed, double sigma, const double* q_ref_dev, const ccp_ik_options* opt,
                         double* q_best_dev, uint8_t* ok_dev, int32_t* n_success_dev, void* stream);
 
+/* ≙ jy_ValidStateSampler::sampleCalibGoal / sampleRandomGoal (base/jy_ConstrainedValidStateSampler.h:63-189) for a BATCH of
+ * object poses: for every arm a of the handle the IK target is t_b7 = t_wb_a^-1 * T_obj * t_o7_a (IKTask::solve /
+ * random_solve, src/base/constraints/ik_task.cpp:16-49; t_wb_a is the handle's, t_o7_a the grasp frame the reference
+ * derives from the start configuration, ConstrainedPlanningCommon.cpp:105-111) and ccp_ik_sample_batch's restarts run on it
+ * — restart 0 from the arm's seven joints of q_ref (sampleCalibGoal's q0_ / start_state segment) when q_ref_dev is given,
+ * the others from N(mid-range, sigma); the seeded solution wins, else the successful restart nearest to the reference.
+ * A pose is ok when EVERY arm found a solution: q_out then holds the 7K-vector of a closed-chain goal configuration (its
+ * closure error is the IK tolerance, so project() accepts it as it is); arms that failed leave their columns untouched.
+ *   T_obj_dev double[n][12] row-major 3x4 object poses in the world; t_o7_host double[K][12] (host); q_ref_dev double[n][7K]
+ *   or NULL (sampleRandomGoal); q_out_dev double[n][7K]; ok_dev uint8[n].  The reference's IKValid collision check
+ *   (jy_ConstrainedValidStateSampler.h:190-197) is a host concern: validate the ok rows.                               */
+int ccp_goal_sample_batch(ccp_handle* h, const double* T_obj_dev, int64_t n, const double* t_o7_host,
+                          const double* q_ref_dev, int32_t restarts, uint64_t rng_seed, double sigma,
+                          const ccp_ik_options* opt, double* q_out_dev, uint8_t* ok_dev, void* stream);
+
 /* ---- host-buffer entry points (what a planner that owns host states calls) -------------- */
 /* Same as ccp_project_batch but all pointers are HOST memory, AOS double[count][n]
  * (the gathered OMPL states).  Copies in, projects, copies out; synchronous.                */
@@ -380,6 +395,9 @@ int ccp_geodesic_batch_host(ccp_handle* h, const double* from_host, const double
 int ccp_ik_sample_batch_host(ccp_handle* h, int32_t arm, const double* T_target_host, int64_t n_targets, int32_t restarts,
                              uint64_t rng_seed, double sigma, const double* q_ref_host, const ccp_ik_options* opt,
                              double* q_best_host, uint8_t* ok_host, int32_t* n_success_host);
+int ccp_goal_sample_batch_host(ccp_handle* h, const double* T_obj_host, int64_t n, const double* t_o7_host,
+                               const double* q_ref_host, int32_t restarts, uint64_t rng_seed, double sigma,
+                               const ccp_ik_options* opt, double* q_out_host, uint8_t* ok_host);
 int ccp_jacobian_batch_host(ccp_handle* h, const double* x_host, int64_t count, double* J_host);
 /* ≙ PandaModel::getTransform / getJacobianMatrix for host 7-vectors (AOS): T_host double[count][12],
  * J_host double[count][42]; either output may be NULL.                                          */

@@ -361,4 +361,15 @@ inline void ikSampleBatch(const KinematicChainConstraint& c, int arm, const doub
     throw Exception(std::string("ikSampleBatch: ") + ccp_last_error(c.handle()));
 }
 
+// jy_ValidStateSampler::sampleCalibGoal / sampleRandomGoal (jy_ConstrainedValidStateSampler.h:63-189) for a batch of object
+// poses: T_obj n x 12 (row-major 3x4, world), t_o7 K x 12 (the grasp frames, ConstrainedPlanningCommon.cpp:105-111),
+// q_ref n x 7K or nullptr; q_out n x 7K, ok n.  A pose is ok when every arm found an IK solution; the row is then a
+// closed-chain goal configuration.  The reference's IKValid collision check stays with the caller.
+inline void sampleGoalBatch(const KinematicChainConstraint& c, const double* T_obj, int64_t n, const double* t_o7,
+                            const double* q_ref, double* q_out, uint8_t* ok, int restarts = 15, uint64_t rng_seed = 0,
+                            double sigma = 0.3) {
+  if (ccp_goal_sample_batch_host(c.handle(), T_obj, n, t_o7, q_ref, restarts, rng_seed, sigma, nullptr, q_out, ok) != CCP_OK)
+    throw Exception(std::string("sampleGoalBatch: ") + ccp_last_error(c.handle()));
+}
+
 }  // namespace ccp

@@ -94,8 +94,32 @@ int main(int argc, char** argv) {
   std::vector<double> failed_too((size_t)SF * 14);
   for (int i = 0; i < SF; ++i) all_states->sampleUniform(&failed_too[(size_t)i * 14]);
 
+  // ---- goal sampling for the whole chain (sampleCalibGoal): the object frame is taken as the world frame, so
+  // t_o7_a = t_wb_a * FK_a(start_a) and the object pose "identity" asks both arms back to their start poses ----
+  double t_o7[2][12], T_obj[2][12] = {{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0}, {1, 0, 0, 0.01, 0, 1, 0, 0, 0, 0, 1, 0}};
+  const int arm_frames[2] = {0, 2};
+  for (int a = 0; a < 2; ++a) {
+    auto Tb = pm.getTransform(start + 7 * a);  // 3x4 in the arm's base frame
+    auto W = ccp::base_frame(arm_frames[a]);   // 3x4 base frame in the world
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 4; ++c) {
+        double acc = (c == 3) ? W[4 * r + 3] : 0.0;
+        for (int k = 0; k < 3; ++k) acc += W[4 * r + k] * Tb[4 * k + c];
+        t_o7[a][4 * r + c] = acc;
+      }
+  }
+  double goal_q[2][14];
+  uint8_t goal_ok[2];
+  double goal_ref[2][14];
+  for (int i = 0; i < 2; ++i) std::copy(start, start + 14, goal_ref[i]);
+  ccp::sampleGoalBatch(*constraint, &T_obj[0][0], 2, &t_o7[0][0], &goal_ref[0][0], &goal_q[0][0], goal_ok, 15, 3);
+  uint8_t goal_sat[2] = {(uint8_t)constraint->isSatisfied(goal_q[0]), (uint8_t)constraint->isSatisfied(goal_q[1])};
+
   FILE* o = fopen(argv[2], "wb");
   if (!o) return 7;
+  fwrite(goal_q, sizeof(double), 28, o);
+  fwrite(goal_ok, 1, 2, o);
+  fwrite(goal_sat, 1, 2, o);
   fwrite(ahead_samples.data(), sizeof(double), ahead_samples.size(), o);
   fwrite(&ahead_refills, sizeof ahead_refills, 1, o);
   fwrite(failed_too.data(), sizeof(double), failed_too.size(), o);

@@ -34,6 +34,12 @@ def test_cpp_state_space_program(tmp_path):
         return a
 
     S, E, MS, NT = 300, 64, 48, 32
+    goal_q, goal_ok, goal_sat = take(np.float64, 28).reshape(2, 14), take(np.uint8, 2), take(np.uint8, 2)
+    # goal sampling: "object at the world origin" sends both arms back to the start; 1 cm along x is another closed pose
+    assert goal_ok.all() and goal_sat.all()
+    assert np.max(np.abs(goal_q[0] - cfg.start)) < 1e-3
+    f_goal = A.function(goal_q)
+    assert f_goal[:, 0].max() < 1e-4 and f_goal[:, 1].max() < 1e-4
     ahead = take(np.float64, 700 * 14).reshape(700, 14)
     ahead_refills = int(take(np.int64, 1)[0])
     failed_too = take(np.float64, 120 * 14).reshape(120, 14)

@@ -103,3 +103,59 @@ def test_ik_unreachable_target_fails_cleanly(setup):
     assert np.all(r["ok"] == 0) and np.all(r["n_success"] == 0)
     r1 = pm.ikBatch(Tfar, q_true[:32])
     assert np.all(r1["ok"] == 0) and np.all(r1["iters"] == 200) and np.all(np.isfinite(r1["q"]))
+
+
+def test_goal_sample_batch_closes_the_chain():
+    """ccp_goal_sample_batch (≙ sampleCalibGoal / sampleRandomGoal for a batch of object poses): per-arm IK on
+    t_wb^-1 T_obj t_o7; every ok row is a closed-chain configuration — both arms hold the object at the pose asked for, by the
+    reference-faithful FK, so the constraint residual is at IK tolerance and project() accepts the row unchanged."""
+    import closed_chain_motion_planner_b200 as pkg
+    from oracle.oracle import OracleA
+
+    c = pkg.KinematicChainConstraint.from_config("stefan", device=0)
+    cfg = c.config
+    A = OracleA(cfg.arm_indices)
+    A.set_initial_position(cfg.start)
+    gp = pkg.grasping_point()
+    t_o7 = c.graspFrames(cfg.t_wo_start, cfg.start)
+    # the grasp frames reproduce the start: t_wb_a FK(start_a) t_o7_a^-1 == t_wo_start
+    for a, ix in enumerate(cfg.arm_indices):
+        Tb = np.vstack([A.arm_transform(a, cfg.start[7 * a:7 * a + 7])[0], [0, 0, 0, 1]])
+        Two = gp.t_wb[ix] @ Tb @ np.linalg.inv(np.vstack([t_o7[a], [0, 0, 0, 1]]))
+        assert np.max(np.abs(Two - cfg.t_wo_start)) < 1e-12
+    # object poses around the start pose: small translations and rotations
+    rng = np.random.default_rng(3)
+    n = 3000
+    from scipy.spatial.transform import Rotation
+
+    T_obj = np.tile(cfg.t_wo_start[None, :, :], (n, 1, 1))
+    T_obj[:, :3, 3] += rng.uniform(-0.06, 0.06, (n, 3))
+    dR = Rotation.from_rotvec(rng.uniform(-0.15, 0.15, (n, 3))).as_matrix()
+    T_obj[:, :3, :3] = np.einsum("nij,jk->nik", dR, cfg.t_wo_start[:3, :3])
+    for q_ref in (cfg.start, None):
+        r = c.sampleGoalBatch(T_obj, t_o7, q_ref=q_ref, restarts=15, rng_seed=11)
+        ok = r["ok"].astype(bool)
+        assert ok.mean() > (0.9 if q_ref is not None else 0.6), ok.mean()
+        q = r["q"][ok]
+        # each arm holds the object where it was asked to (reference-faithful FK)
+        for a, ix in enumerate(cfg.arm_indices):
+            Tq = A.arm_transform(a, q[:, 7 * a:7 * a + 7])
+            Tb = np.concatenate([Tq, np.tile(np.array([[[0.0, 0, 0, 1]]]), (len(q), 1, 1))], axis=1)
+            Two = gp.t_wb[ix][None] @ Tb @ np.linalg.inv(np.vstack([t_o7[a], [0, 0, 0, 1]]))[None]
+            assert np.abs(Two[:, :3, 3] - T_obj[ok][:, :3, 3]).max() < 3e-5
+            assert np.abs(Two[:, :3, :3] - T_obj[ok][:, :3, :3]).max() < 3e-5
+        # the closed-chain constraint is satisfied at IK tolerance; project() takes 0 iterations and keeps the row
+        f = A.function(q)
+        assert f[:, 0].max() < 1e-4 and f[:, 1].max() < 1e-4
+        assert np.all(q >= np.tile(LB, 2) + 1e-3 - 1e-12) and np.all(q <= np.tile(UB, 2) - 1e-3 + 1e-12)
+        p = c.projectBatch(q)
+        assert np.all(p.ok == 1) and np.all(p.iters == 0) and np.array_equal(p.x, q)
+        if q_ref is not None:  # seeded: the answers stay near the reference configuration
+            assert np.median(np.linalg.norm(q - cfg.start[None, :], axis=1)) < 1.0
+    # an unreachable object pose fails cleanly
+    far = T_obj[:16].copy()
+    far[:, :3, 3] += np.array([0.0, 0.0, 3.0])
+    r = c.sampleGoalBatch(far, t_o7, q_ref=cfg.start, restarts=8)
+    assert np.all(r["ok"] == 0)
+    with pytest.raises(pkg.CcpError):
+        c.sampleGoalBatch(T_obj[:4], t_o7, restarts=0)
