@@ -12,6 +12,7 @@ CCP_MAX_ARMS = 3
 CCP_DOF = 7
 CCP_LAYOUT_AOS = 0
 CCP_LAYOUT_SOA = 1
+CCP_MODEL_NO_STOCK = 1  # ccp_model_desc.flags
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CCP_LIB") or os.path.join(_HERE, "csrc", "libccp.so")  # CCP_LIB: a tuning build of the same ABI
@@ -32,7 +33,7 @@ class ArmDesc(C.Structure):
 class ModelDesc(C.Structure):
     _fields_ = [
         ("n_arms", C.c_int32),
-        ("reserved", C.c_int32),
+        ("flags", C.c_int32),  # 0 or CCP_MODEL_NO_STOCK
         ("arm", ArmDesc * CCP_MAX_ARMS),
         ("lb", C.c_double * CCP_DOF),
         ("ub", C.c_double * CCP_DOF),

@@ -155,7 +155,7 @@ static int set_err(ccp_handle* h, int code, const char* fmt, const char* a = "",
 // ------------------------------------------------------------------------------------------
 // small batched kernels (thread per state, grid-stride)
 // ------------------------------------------------------------------------------------------
-template <int K, bool PANDA, bool SOA>
+template <int K, int PANDA, bool SOA>
 __global__ void __launch_bounds__(128)
 ccp_function_kernel(const __grid_constant__ ccp_model M, const double* __restrict__ xin, long long count,
                     double* __restrict__ f, uint8_t* __restrict__ satisfied) {
@@ -178,7 +178,7 @@ ccp_function_kernel(const __grid_constant__ ccp_model M, const double* __restric
   }
 }
 
-template <int K, bool PANDA, bool SOA>
+template <int K, int PANDA, bool SOA>
 __global__ void __launch_bounds__(128)
 ccp_jacobian_kernel(const __grid_constant__ ccp_model M, const double* __restrict__ xin, long long count,
                     double* __restrict__ Jout) {
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(256) ccp_wrap_kernel(double* __restrict__ x, l
     x[i] = ccp_wrap_pi(x[i]);
 }
 
-template <int K, bool PANDA>
+template <int K, int PANDA>
 __global__ void ccp_reference_kernel(const __grid_constant__ ccp_model M, const double* __restrict__ q_start,
                                      ccp_pair_ref* __restrict__ out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -303,13 +303,13 @@ __global__ void ccp_publish_count_kernel(const long long* __restrict__ n_ok, con
   }
 }
 
-// dispatch helper: (arms, structured alpha) -> template arguments
+// dispatch helper: (arms, link-code mode 0 generic / 1 structured alpha / 2 stock) -> template arguments
 #define CCP_DISPATCH_KP(h, CALL)                                                  \
   do {                                                                            \
     if ((h)->model.n_arms == 2) {                                                 \
-      if ((h)->model.panda_alpha) { CALL(2, true); } else { CALL(2, false); }     \
+      if ((h)->model.stock) { CALL(2, 2); } else if ((h)->model.panda_alpha) { CALL(2, 1); } else { CALL(2, 0); } \
     } else {                                                                      \
-      if ((h)->model.panda_alpha) { CALL(3, true); } else { CALL(3, false); }     \
+      if ((h)->model.stock) { CALL(3, 2); } else if ((h)->model.panda_alpha) { CALL(3, 1); } else { CALL(3, 0); } \
     }                                                                             \
   } while (0)
 
@@ -353,12 +353,15 @@ static int ensure_pipeline(ccp_handle* h) {
 
 static int dispatch_project(ccp_handle* h, ccp_project_args& A, bool soa, cudaStream_t st) {
   cudaError_t e = cudaSuccess;
+  const int mode = h->model.stock ? 2 : (h->model.panda_alpha ? 1 : 0);
   if (h->model.n_arms == 2)
-    e = h->model.panda_alpha ? ccp_launch_project_K2_P1(h->sm_count, h->model, A, soa, st)
-                             : ccp_launch_project_K2_P0(h->sm_count, h->model, A, soa, st);
+    e = mode == 2 ? ccp_launch_project_K2_P2(h->sm_count, h->model, A, soa, st)
+        : mode == 1 ? ccp_launch_project_K2_P1(h->sm_count, h->model, A, soa, st)
+                    : ccp_launch_project_K2_P0(h->sm_count, h->model, A, soa, st);
   else
-    e = h->model.panda_alpha ? ccp_launch_project_K3_P1(h->sm_count, h->model, A, soa, st)
-                             : ccp_launch_project_K3_P0(h->sm_count, h->model, A, soa, st);
+    e = mode == 2 ? ccp_launch_project_K3_P2(h->sm_count, h->model, A, soa, st)
+        : mode == 1 ? ccp_launch_project_K3_P1(h->sm_count, h->model, A, soa, st)
+                    : ccp_launch_project_K3_P0(h->sm_count, h->model, A, soa, st);
   if (e != cudaSuccess) return set_err(h, CCP_ERR_CUDA, "project kernel launch: %s", cudaGetErrorString(e));
   return CCP_OK;
 }

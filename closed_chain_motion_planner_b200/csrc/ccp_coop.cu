@@ -24,7 +24,7 @@
 __device__ __forceinline__ double shfl_from(double v, int src) { return __shfl_sync(CCP_FULL, v, src); }
 __device__ __forceinline__ double shfl_xor1(double v) { return __shfl_xor_sync(CCP_FULL, v, 1); }
 
-template <bool PANDA, bool SOA>
+template <int PANDA, bool SOA>
 __global__ void __launch_bounds__(CCP_COOP_BLOCK, 2)
 ccp_project_coop_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ ccp_project_args A) {
   constexpr int n = 2 * CCPC_DOF, H = CCPC_DOF;
@@ -213,7 +213,7 @@ ccp_project_coop_kernel(const __grid_constant__ ccp_model M, const __grid_consta
   }
 }
 
-template <bool PANDA>
+template <int PANDA>
 static cudaError_t launch_coop(int sm_count, const ccp_model& M, const ccp_project_args& A, bool soa, cudaStream_t st) {
   // 16 samples per warp; spread one warp per block before any block gets a second one, at most 3 blocks per SM
   long long need = (A.count + 15) / 16;
@@ -227,5 +227,6 @@ static cudaError_t launch_coop(int sm_count, const ccp_model& M, const ccp_proje
 
 cudaError_t ccp_launch_project_coop(int sm_count, const ccp_model& M, const ccp_project_args& A, bool soa, cudaStream_t st) {
   if (M.n_arms != 2) return cudaErrorInvalidValue;
-  return M.panda_alpha ? launch_coop<true>(sm_count, M, A, soa, st) : launch_coop<false>(sm_count, M, A, soa, st);
+  if (M.stock) return launch_coop<2>(sm_count, M, A, soa, st);
+  return M.panda_alpha ? launch_coop<1>(sm_count, M, A, soa, st) : launch_coop<0>(sm_count, M, A, soa, st);
 }

@@ -24,7 +24,7 @@ __device__ __forceinline__ ccp_pair ccp_make_pair() {
 }
 
 // forward evaluation: the pair's residual (e2, sv2, d0 on BOTH lanes) and the own arm's gradient start vectors (w, m)
-template <bool PANDA>
+template <int PANDA>
 __device__ __forceinline__ void ccp_pair_forward(const ccp_model& M, const ccp_pair& P, const double* x, ccp_sc_local<1>& S,
                                                  double* w, double* m, double& e2, double& sv2, double& d0) {
   const int a = P.a;
@@ -74,7 +74,7 @@ __device__ __forceinline__ void ccp_pair_forward(const ccp_model& M, const ccp_p
 }
 
 // one Newton step of the pair (ccp_jacobian + ccp_newton_step + optional clamp); every lane of the pair calls it
-template <bool PANDA>
+template <int PANDA>
 __device__ __forceinline__ void ccp_pair_step(const ccp_model& M, const ccp_pair& P, const ccp_sc_local<1>& S, double* w, double* m,
                                               double e2, double sv2, double d0, double* x) {
   constexpr int H = CCPC_DOF;

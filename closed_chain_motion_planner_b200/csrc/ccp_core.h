@@ -85,7 +85,9 @@ struct ccp_model {
   int32_t max_iter;
   int32_t panda_alpha;  // 1: every arm has the stock Panda alpha pattern (0,-pi/2,pi/2,pi/2,-pi/2,pi/2,pi/2)
                         //    EXACTLY (no alpha calibration): the kernels use the structured link code
-  int32_t reserved;
+  int32_t stock;        // 1 (implies panda_alpha): additionally no theta calibration, exact zeros where the stock a / d
+                        //    tables have zeros, and every base-to-base rotation Rrel a diagonal of +-1 (the reference's
+                        //    grasping_point frames): the kernels skip those terms (template argument PANDA = 2)
   double tol_p, tol_r;  // tolerance1_, tolerance2_
   double tol_p2;        // tol_p^2
   double tan2_r;        // tan^2(tol_r / 2): f1 > tol_r  <=>  |vec d|^2 > tan2_r d_w^2   (0 < tol_r < pi)
@@ -308,6 +310,16 @@ CCP_HD void ccp_qrot_inv(const double* q, double* v) {
 // sqrt(2)^12 = 64 is removed from the chain quaternion with one exact scaling.
 // PANDA = false is the generic path (calibrated alpha offsets, panda_rbdl.cpp:92-95).
 // ------------------------------------------------------------------------------------------
+// PANDA = 2 ("stock"): on top of the structured alpha pattern the link table is the stock one where that one is ZERO —
+// a = (0, 0, 0, .0825, -.0825, 0, .088), d = (.333, 0, .316, 0, .384, 0, 0) (panda_rbdl.cpp:98-99), no theta calibration —
+// and the base-to-base rotation is a diagonal of +-1.  Terms that are exactly zero are not computed and their constants not
+// loaded (FP64 instructions take no constant-bank operand: every constant is a load).  x + 0 and x - 0 are x and
+// fma(a, b, 0) is a b rounded once, so the results equal the PANDA = 1 code's except for the sign of an exact zero.
+template <int I>
+struct ccp_stock_zero {
+  static constexpr bool a = (I == 0 || I == 1 || I == 2 || I == 5);  // a_I == 0: no x translation
+  static constexpr bool d = (I == 1 || I == 3 || I == 5 || I == 6);  // d_I == 0: no y / z translation
+};
 template <int I>
 struct ccp_panda_sgn {  // sign of alpha_I / (pi/2): link 0 has alpha = 0
   static constexpr int value = (I == 0) ? 0 : ((I == 1 || I == 4) ? -1 : 1);
@@ -315,7 +327,7 @@ struct ccp_panda_sgn {  // sign of alpha_I / (pi/2): link 0 has alpha = 0
 #define CCP_PANDA_QSCALE 0.015625  // 1/64 = (1/sqrt 2)^12: six quarter-turn links per arm, two arms
 
 // One link going DOWN the chain (frame i -> frame i-1): v <- Rx(alpha) Rz(theta) v (+ t)
-template <bool PANDA, int I>
+template <int PANDA, int I>
 CCP_HD void ccp_down_vec(const ccp_link& L, double s, double c, double* v) {
   ccp_rot2(c, s, v[0], v[1]);
   if (!PANDA) {
@@ -330,10 +342,10 @@ CCP_HD void ccp_down_vec(const ccp_link& L, double s, double c, double* v) {
     v[2] = -y;
   }
 }
-template <bool PANDA, int I>
+template <int PANDA, int I>
 CCP_HD void ccp_down_pt(const ccp_link& L, double s, double c, double* r) {
   // as ccp_down_vec, with the x translation folded into the rotation's FMA chain
-  const double nx = CCP_FMA(c, r[0], CCP_FMA(-s, r[1], L.tx));
+  const double nx = (PANDA == 2 && ccp_stock_zero<I>::a) ? CCP_FMA(c, r[0], -(s * r[1])) : CCP_FMA(c, r[0], CCP_FMA(-s, r[1], L.tx));
   const double ny = CCP_FMA(s, r[0], c * r[1]);
   r[0] = nx;
   r[1] = ny;
@@ -348,15 +360,18 @@ CCP_HD void ccp_down_pt(const ccp_link& L, double s, double c, double* r) {
     r[1] = r[2];
     r[2] = -y;
   }
+  if (PANDA == 2 && ccp_stock_zero<I>::d) return;
   if (!PANDA || ccp_panda_sgn<I>::value != 0) r[1] += L.ty;
   if (!PANDA || ccp_panda_sgn<I>::value == 0) r[2] += L.tz;
 }
 // One link going UP the chain (frame i-1 -> frame i): r <- Rz(theta)^T Rx(alpha)^T (r - t)
-template <bool PANDA, int I>
+template <int PANDA, int I>
 CCP_HD void ccp_up_pt(const ccp_link& L, double s, double c, double* r) {
-  r[0] -= L.tx;
-  if (!PANDA || ccp_panda_sgn<I>::value != 0) r[1] -= L.ty;
-  if (!PANDA || ccp_panda_sgn<I>::value == 0) r[2] -= L.tz;
+  if (!(PANDA == 2 && ccp_stock_zero<I>::a)) r[0] -= L.tx;
+  if (!(PANDA == 2 && ccp_stock_zero<I>::d)) {
+    if (!PANDA || ccp_panda_sgn<I>::value != 0) r[1] -= L.ty;
+    if (!PANDA || ccp_panda_sgn<I>::value == 0) r[2] -= L.tz;
+  }
   if (!PANDA) {
     ccp_rot2t(L.ca, L.sa, r[1], r[2]);
   } else if (ccp_panda_sgn<I>::value > 0) {
@@ -371,7 +386,7 @@ CCP_HD void ccp_up_pt(const ccp_link& L, double s, double c, double* r) {
   ccp_rot2t(c, s, r[0], r[1]);
 }
 // q <- q (x) q_Rx(alpha_I)   (unscaled in PANDA mode)
-template <bool PANDA, int I>
+template <int PANDA, int I>
 CCP_HD void ccp_qmul_link_rx(const ccp_link& L, double* q) {
   if (!PANDA) {
     ccp_qmul_rx(q, L.cha, L.sha);
@@ -431,10 +446,11 @@ CCP_HD void ccp_residual(const ccp_fwd<K>& F, double* f, double* sv_out) {
 // FROM_IDENTITY: the chain starts here from the identity quaternion (link 0 of an arm whose base rotation was folded
 // into the other arm's start): q = q_Rx(alpha_0) (x) q_Rz(theta/2) without a multiplication when alpha_0 = 0
 // `a` only indexes x and S (the cooperative kernel passes a lane's own 7 joints with a = 0); A is the arm's constants.
-template <bool PANDA, int I, bool FROM_IDENTITY = false, class SC, class XT>
+template <int PANDA, int I, bool FROM_IDENTITY = false, class SC, class XT>
 CCP_HD void ccp_fwd_link_quat(const ccp_arm& A, int a, const XT& x, double* q, SC& S) {
   const ccp_link& L = A.link[I];
-  double h = CCP_FMA(0.5, x[a * CCPC_DOF + I], (I == 6) ? A.hq7 : L.hqoff);  // joint 7 carries the EE yaw
+  // joint 7 carries the EE yaw; stock: no theta calibration on the others
+  double h = (PANDA == 2 && I != 6) ? 0.5 * x[a * CCPC_DOF + I] : CCP_FMA(0.5, x[a * CCPC_DOF + I], (I == 6) ? A.hq7 : L.hqoff);
   double sh, ch;
   ccp_sincos(h, &sh, &ch);
   if (FROM_IDENTITY && PANDA && I == 0) {
@@ -454,7 +470,7 @@ CCP_HD void ccp_fwd_link_quat(const ccp_arm& A, int a, const XT& x, double* q, S
 // ---- the pieces of the forward evaluation, one arm at a time (ccp_forward composes them; the cooperative kernel runs
 // them on the lane that owns the arm) ----
 // links 1..6 of an arm's quaternion chain (link 0 differs between the arms: see ccp_forward)
-template <bool PANDA, class SC, class XT>
+template <int PANDA, class SC, class XT>
 CCP_HD void ccp_fwd_quat_links_1_6(const ccp_arm& A, int a, const XT& x, double* q, SC& S) {
   ccp_fwd_link_quat<PANDA, 1>(A, a, x, q, S);
   ccp_fwd_link_quat<PANDA, 2>(A, a, x, q, S);
@@ -465,7 +481,7 @@ CCP_HD void ccp_fwd_quat_links_1_6(const ccp_arm& A, int a, const XT& x, double*
 }
 // EE-0 origin: (0, 0, fl) in frame 7' of arm 0 (on joint 7's axis: no lever arm there, and its image in frame 6
 // is the constant r6) -> base 0.  Leaves the lever arms (rx, ry) of joints 5..0.  a = index of arm 0 in S.
-template <bool PANDA, class SC>
+template <int PANDA, class SC>
 CCP_HD void ccp_fwd_down_arm0(const ccp_arm& A, int a, SC& S, double* r) {
   r[0] = A.r6[0]; r[1] = A.r6[1]; r[2] = A.r6[2];
   S.rx(a, 5) = r[0]; S.ry(a, 5) = r[1];
@@ -483,11 +499,17 @@ CCP_HD void ccp_fwd_down_arm0(const ccp_arm& A, int a, SC& S, double* r) {
 }
 // arm a >= 1: base 0 -> base a in one constant transform (t_wb_a^-1 t_wb_0, packed on the host), then up the arm to
 // frame 7' (= the EE frame up to the flange shift along z).  r: the EE-0 origin in base 0; v: tc = R_a^T (p_0 - p_a).
-template <bool PANDA, class SC>
+template <int PANDA, class SC>
 CCP_HD void ccp_fwd_up_arm(const ccp_arm& A, int a, SC& S, const double* r, double* v) {
-  v[0] = CCP_FMA(A.Rrel[0], r[0], CCP_FMA(A.Rrel[1], r[1], CCP_FMA(A.Rrel[2], r[2], A.prel[0])));
-  v[1] = CCP_FMA(A.Rrel[3], r[0], CCP_FMA(A.Rrel[4], r[1], CCP_FMA(A.Rrel[5], r[2], A.prel[1])));
-  v[2] = CCP_FMA(A.Rrel[6], r[0], CCP_FMA(A.Rrel[7], r[1], CCP_FMA(A.Rrel[8], r[2], A.prel[2])));
+  if (PANDA == 2) {  // a diagonal of +-1 (the reference's base frames: translations, and the top arm turned about z)
+    v[0] = CCP_FMA(A.Rrel[0], r[0], A.prel[0]);
+    v[1] = CCP_FMA(A.Rrel[4], r[1], A.prel[1]);
+    v[2] = CCP_FMA(A.Rrel[8], r[2], A.prel[2]);
+  } else {
+    v[0] = CCP_FMA(A.Rrel[0], r[0], CCP_FMA(A.Rrel[1], r[1], CCP_FMA(A.Rrel[2], r[2], A.prel[0])));
+    v[1] = CCP_FMA(A.Rrel[3], r[0], CCP_FMA(A.Rrel[4], r[1], CCP_FMA(A.Rrel[5], r[2], A.prel[1])));
+    v[2] = CCP_FMA(A.Rrel[6], r[0], CCP_FMA(A.Rrel[7], r[1], CCP_FMA(A.Rrel[8], r[2], A.prel[2])));
+  }
   ccp_up_pt<PANDA, 0>(A.link[0], S.s(a, 0), S.c(a, 0), v);
   S.rx(a, 0) = v[0]; S.ry(a, 0) = v[1];
   ccp_up_pt<PANDA, 1>(A.link[1], S.s(a, 1), S.c(a, 1), v);
@@ -505,7 +527,7 @@ CCP_HD void ccp_fwd_up_arm(const ccp_arm& A, int a, SC& S, const double* r, doub
   v[2] -= A.fl;  // frame 7' is the EE frame up to this shift along z
 }
 // residual of pair p (arm p + 1 against arm 0) from tc = v and the two chain quaternions
-template <int K, bool PANDA>
+template <int K, int PANDA>
 CCP_HD void ccp_fwd_pair(const ccp_pair_ref& ref, const double* v, const double* qa, const double* q0, double* tc, double* qc,
                          double* d, double* e, double& e2, double& sv2) {
   tc[0] = v[0]; tc[1] = v[1]; tc[2] = v[2];
@@ -521,7 +543,7 @@ CCP_HD void ccp_fwd_pair(const ccp_pair_ref& ref, const double* v, const double*
   sv2 = CCP_FMA(d[1], d[1], CCP_FMA(d[2], d[2], d[3] * d[3]));
 }
 
-template <int K, bool PANDA, class SC, class XT>
+template <int K, int PANDA, class SC, class XT>
 CCP_HD void ccp_forward(const ccp_model& M, const XT& x, SC& S, ccp_fwd<K>& F) {
   double q[K][4];
 #pragma unroll
@@ -615,7 +637,7 @@ struct ccp_jac {
   CCP_HD double z(int p, int r, int i) const { return J0[p][r][i]; }
 };
 
-template <bool PANDA, int I, bool ARM0, class SC, class JT>
+template <int PANDA, int I, bool ARM0, class SC, class JT>
 CCP_HD void ccp_jac_link(const ccp_arm& A, int a, int p, const SC& S, double* w, double* m, JT& J) {
   // joint I sees (r, w, m) in frame I:  d f0 / d q = +-(r x w)_z,  d f1 / d q = +-m_z  (+ on arm 0);
   // r = lever arm to the EE-0 origin, left behind by the forward pass
@@ -637,7 +659,7 @@ CCP_HD void ccp_jac_link(const ccp_arm& A, int a, int p, const SC& S, double* w,
     ccp_down_vec<PANDA, I>(A.link[I], s, c, m);
   }
 }
-template <bool PANDA, bool ARM0, class SC, class JT>
+template <int PANDA, bool ARM0, class SC, class JT>
 CCP_HD void ccp_jac_arm(const ccp_arm& A, int a, int p, const SC& S, double* w, double* m, JT& J) {
   ccp_jac_link<PANDA, 6, ARM0>(A, a, p, S, w, m, J);
   ccp_jac_link<PANDA, 5, ARM0>(A, a, p, S, w, m, J);
@@ -648,7 +670,7 @@ CCP_HD void ccp_jac_arm(const ccp_arm& A, int a, int p, const SC& S, double* w, 
   ccp_jac_link<PANDA, 0, ARM0>(A, a, p, S, w, m, J);
 }
 
-template <int K, bool PANDA, class SC, class JT>
+template <int K, int PANDA, class SC, class JT>
 CCP_HD void ccp_jacobian(const ccp_model& M, const SC& S, const ccp_fwd<K>& F, JT& J) {
 #pragma unroll
   for (int p = 0; p < K - 1; ++p) {
@@ -852,7 +874,7 @@ CCP_HD void ccp_jac_dense(const ccp_fwd<K>& F, const ccp_jac<K>& J, double* out)
 // Used as-is by the host build; the CUDA kernel runs the same three calls inside its
 // lane-refill loop.
 // ------------------------------------------------------------------------------------------
-template <int K, bool PANDA>
+template <int K, int PANDA>
 CCP_HD void ccp_project_one(const ccp_model& M, double* x, double* f_out, int32_t* iters, bool* converged,
                             bool* ok) {
   ccp_fwd<K> F;
@@ -876,7 +898,7 @@ CCP_HD void ccp_project_one(const ccp_model& M, double* x, double* f_out, int32_
 
 // setInitialPosition (ConstraintFunction.h:31-40): reference chain = chain at q_start with an
 // identity reference.
-template <int K, bool PANDA>
+template <int K, int PANDA>
 CCP_HD void ccp_reference_chain(ccp_model& M, const double* q_start) {
 #pragma unroll
   for (int p = 0; p < K - 1; ++p) {

@@ -28,7 +28,7 @@ struct ccp_geodesic_args {
 #ifndef CCP_GEO_BLOCKS_K2
 #define CCP_GEO_BLOCKS_K2 3
 #endif
-template <int K, bool PANDA>
+template <int K, int PANDA>
 __global__ void __launch_bounds__(128, K == 2 ? CCP_GEO_BLOCKS_K2 : CCP_GEO_BLOCKS_K3)
 ccp_geodesic_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ ccp_geodesic_args A) {
   constexpr int n = CCPC_DOF * K;
@@ -137,7 +137,7 @@ ccp_geodesic_kernel(const __grid_constant__ ccp_model M, const __grid_constant__
 // batch sizes (the k = 5 edges of a new vertex, stefanBiPRM.cpp:315; a few thousand at most) what matters is the time of
 // one Newton trip of a lone warp, which the cooperative mapping shortens.  Pairs run independently (pair-masked
 // shuffles); distances are accumulated across the pair in joint order, so every number equals the one-thread walk's.
-template <bool PANDA>
+template <int PANDA>
 __global__ void __launch_bounds__(128, 2)
 ccp_geodesic_coop_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ ccp_geodesic_args A) {
   constexpr int n = 2 * CCPC_DOF, H = CCPC_DOF;
@@ -271,8 +271,9 @@ cudaError_t ccp_launch_geodesic(int sm_count, const ccp_model& M, const double* 
     const long long capc = (long long)sm_count * 2;
     int gridc = (int)(needc < capc ? needc : capc);
     if (gridc < 1) gridc = 1;
-    if (M.panda_alpha) ccp_geodesic_coop_kernel<true><<<gridc, 128, 0, st>>>(M, A);
-    else ccp_geodesic_coop_kernel<false><<<gridc, 128, 0, st>>>(M, A);
+    if (M.stock) ccp_geodesic_coop_kernel<2><<<gridc, 128, 0, st>>>(M, A);
+    else if (M.panda_alpha) ccp_geodesic_coop_kernel<1><<<gridc, 128, 0, st>>>(M, A);
+    else ccp_geodesic_coop_kernel<0><<<gridc, 128, 0, st>>>(M, A);
     return cudaGetLastError();
   }
   long long need = (edges + 31) / 32;  // one warp's worth of edges per block before any block gets more
@@ -280,11 +281,13 @@ cudaError_t ccp_launch_geodesic(int sm_count, const ccp_model& M, const double* 
   int grid = (int)(need < cap ? need : cap);
   if (grid < 1) grid = 1;
   if (M.n_arms == 2) {
-    if (M.panda_alpha) ccp_geodesic_kernel<2, true><<<grid, 128, 0, st>>>(M, A);
-    else ccp_geodesic_kernel<2, false><<<grid, 128, 0, st>>>(M, A);
+    if (M.stock) ccp_geodesic_kernel<2, 2><<<grid, 128, 0, st>>>(M, A);
+    else if (M.panda_alpha) ccp_geodesic_kernel<2, 1><<<grid, 128, 0, st>>>(M, A);
+    else ccp_geodesic_kernel<2, 0><<<grid, 128, 0, st>>>(M, A);
   } else {
-    if (M.panda_alpha) ccp_geodesic_kernel<3, true><<<grid, 128, 0, st>>>(M, A);
-    else ccp_geodesic_kernel<3, false><<<grid, 128, 0, st>>>(M, A);
+    if (M.stock) ccp_geodesic_kernel<3, 2><<<grid, 128, 0, st>>>(M, A);
+    else if (M.panda_alpha) ccp_geodesic_kernel<3, 1><<<grid, 128, 0, st>>>(M, A);
+    else ccp_geodesic_kernel<3, 0><<<grid, 128, 0, st>>>(M, A);
   }
   return cudaGetLastError();
 }

@@ -9,6 +9,8 @@ cudaError_t ccp_launch_project_K2_P0(int sm_count, const ccp_model& M, const ccp
 cudaError_t ccp_launch_project_K2_P1(int sm_count, const ccp_model& M, const ccp_project_args& A, bool soa, cudaStream_t st);
 cudaError_t ccp_launch_project_K3_P0(int sm_count, const ccp_model& M, const ccp_project_args& A, bool soa, cudaStream_t st);
 cudaError_t ccp_launch_project_K3_P1(int sm_count, const ccp_model& M, const ccp_project_args& A, bool soa, cudaStream_t st);
+cudaError_t ccp_launch_project_K2_P2(int sm_count, const ccp_model& M, const ccp_project_args& A, bool soa, cudaStream_t st);
+cudaError_t ccp_launch_project_K3_P2(int sm_count, const ccp_model& M, const ccp_project_args& A, bool soa, cudaStream_t st);
 
 // cooperative kernel (two lanes per sample, K = 2, complete launches without pipelining / peers): ccp_coop.cu
 cudaError_t ccp_launch_project_coop(int sm_count, const ccp_model& M, const ccp_project_args& A, bool soa, cudaStream_t st);

@@ -115,6 +115,23 @@ static inline int ccp_pack_model(const ccp_model_desc* d, ccp_model* M) {
   for (int p = 0; p < CCPC_MAX_ARMS - 1; ++p) {
     M->ref[p].q0[0] = 1.0;
   }
+  // "stock" (ccp_core.h, PANDA = 2): the terms the specialised code skips must be exact zeros / unit diagonals
+  int stock = panda && !(d->flags & CCP_MODEL_NO_STOCK);
+  static const int kZeroA[7] = {1, 1, 1, 0, 0, 1, 0}, kZeroD[7] = {0, 1, 0, 1, 0, 1, 1};
+  for (int a = 0; a < d->n_arms && stock; ++a) {
+    for (int i = 0; i < CCP_DOF; ++i) {
+      if (d->arm[a].dh_theta_offset[i] != 0.0) stock = 0;
+      if (kZeroA[i] && d->arm[a].dh_a[i] != 0.0) stock = 0;
+      if (kZeroD[i] && d->arm[a].dh_d[i] != 0.0) stock = 0;
+    }
+    if (a >= 1)
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+          const double v = M->arm[a].Rrel[3 * r + c];
+          if (r == c ? (v != 1.0 && v != -1.0) : (v != 0.0)) stock = 0;
+        }
+  }
+  M->stock = stock;
   return 0;
 }
 

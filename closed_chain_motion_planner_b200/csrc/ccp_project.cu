@@ -1,5 +1,5 @@
 // ccp_project.cu — the persistent lane-refill projection kernel (the hot path) and its launchers.
-// Compiled once per (K arms, PANDA structured-alpha) pair: -DCCP_TU_K=2|3 -DCCP_TU_PANDA=0|1, so the four
+// Compiled once per (K arms, PANDA link-code mode) pair: -DCCP_TU_K=2|3 -DCCP_TU_PANDA=0|1|2, so the six
 // translation units build in parallel.  Each exports ccp_launch_project_K<k>_P<p>().
 //
 // Replaces KinematicChainConstraint::project (ConstraintFunction.h:57-82) for a whole batch.
@@ -346,7 +346,7 @@ __device__ __forceinline__ void write_result(const ccp_model& M, const ccp_proje
 //   * pipelined mode (A.park != nullptr): the warp writes its live samples to the park buffer and exits; the next
 //     launch adopts them as its first work items.  No lane ever idles on a straggler.
 // Which lane (or launch) ran a sample never affects its result.
-template <int K, bool PANDA, bool SOA, int BLOCK, int MINB, int SM>
+template <int K, int PANDA, bool SOA, int BLOCK, int MINB, int SM>
 __global__ void __launch_bounds__(BLOCK, MINB)
 ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ ccp_project_args A) {
   constexpr int n = CCPC_DOF * K, m = 2 * (K - 1);
@@ -588,7 +588,7 @@ ccp_project_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ 
 // projection launch configuration: BLOCK threads, MINB resident blocks per SM (persistent grid), and
 // which per-sample arrays live in shared memory.  CCP_PROJ_VARIANT (environment, read once) selects
 // among the compiled configurations for tuning; the default is the best one measured on B200.
-template <int K, bool PANDA, bool SOA, int BLOCK, int MINB, int SM>
+template <int K, int PANDA, bool SOA, int BLOCK, int MINB, int SM>
 static cudaError_t launch_project_v(int sm_count, const ccp_model& M, const ccp_project_args& A, cudaStream_t st) {
   // persistent grid: MINB blocks per SM; a small batch is spread one warp's worth (32 samples) per block so that
   // it runs at one-warp-per-scheduler latency on many SMs instead of crowding a few
@@ -629,7 +629,7 @@ static int proj_variant() {
   return v;
 }
 
-template <int K, bool PANDA, bool SOA>
+template <int K, int PANDA, bool SOA>
 static cudaError_t launch_project_g(int sm_count, const ccp_model& M, const ccp_project_args& A, cudaStream_t st) {
 #ifdef CCP_TUNE
   if constexpr (K == 2) {
@@ -674,7 +674,7 @@ cudaError_t CCP_CAT(ccp_launch_project_K, CCP_TU_K, _P, CCP_TU_PANDA)(int sm_cou
                                                                      const ccp_project_args& A, bool soa,
                                                                      cudaStream_t st) {
   constexpr int K = CCP_TU_K;
-  constexpr bool PANDA = CCP_TU_PANDA != 0;
+  constexpr int PANDA = CCP_TU_PANDA;  // 0 generic links, 1 structured alpha, 2 stock (ccp_core.h)
   if (soa) return launch_project_g<K, PANDA, true>(sm_count, M, A, st);
   return launch_project_g<K, PANDA, false>(sm_count, M, A, st);
 }

@@ -45,6 +45,8 @@ typedef enum ccp_status {
   CCP_ERR_NCCL = -4
 } ccp_status;
 
+#define CCP_MODEL_NO_STOCK 1
+
 typedef enum ccp_layout { CCP_LAYOUT_AOS = 0, CCP_LAYOUT_SOA = 1 } ccp_layout;
 
 /* One arm.  Replaces ArmModel{rbdl_model, t_wb} (kinematics/panda_model.h:7-23) and
@@ -64,7 +66,8 @@ typedef struct ccp_arm_desc {
  * arm[a>=1] closes the chain against arm[0] (ConstraintFunction.h:89-92).          */
 typedef struct ccp_model_desc {
   int32_t n_arms;                  /* 2 (reference) or 3 (21-DoF extension) */
-  int32_t reserved;
+  int32_t flags;                   /* 0, or CCP_MODEL_NO_STOCK: do not use the kernels specialised to the reference's stock
+                                      Panda table and base frames even when the model matches them (tests, tuning)       */
   ccp_arm_desc arm[CCP_MAX_ARMS];
   double lb[CCP_DOF];              /* ConstraintFunction.h:27 */
   double ub[CCP_DOF];              /* ConstraintFunction.h:28 */

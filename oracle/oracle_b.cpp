@@ -23,17 +23,17 @@
 #endif
 
 namespace {
-// dispatch on (arms, structured-alpha) exactly like the CUDA library does
+// dispatch on (arms, link-code mode: generic / structured alpha / stock) exactly like the CUDA library does
 #define OB_DISPATCH(M, CALL)                                  \
   do {                                                        \
     if ((M)->n_arms == 2) {                                   \
-      if ((M)->panda_alpha) { CALL(2, true); } else { CALL(2, false); } \
+      if ((M)->stock) { CALL(2, 2); } else if ((M)->panda_alpha) { CALL(2, 1); } else { CALL(2, 0); } \
     } else {                                                  \
-      if ((M)->panda_alpha) { CALL(3, true); } else { CALL(3, false); } \
+      if ((M)->stock) { CALL(3, 2); } else if ((M)->panda_alpha) { CALL(3, 1); } else { CALL(3, 0); } \
     }                                                         \
   } while (0)
 
-template <int K, bool P>
+template <int K, int P>
 static void function_batch(const ccp_model* M, const double* x, int64_t count, double* f, uint8_t* sat) {
   constexpr int n = 7 * K, m = 2 * (K - 1);
 #pragma omp parallel for schedule(static)
@@ -48,7 +48,7 @@ static void function_batch(const ccp_model* M, const double* x, int64_t count, d
   }
 }
 
-template <int K, bool P>
+template <int K, int P>
 static void jacobian_batch(const ccp_model* M, const double* x, int64_t count, double* Jout) {
   constexpr int n = 7 * K, m = 2 * (K - 1);
 #pragma omp parallel for schedule(static)
@@ -62,7 +62,7 @@ static void jacobian_batch(const ccp_model* M, const double* x, int64_t count, d
   }
 }
 
-template <int K, bool P>
+template <int K, int P>
 static void project_batch(const ccp_model* M, double* x, int64_t count, uint8_t* ok, uint8_t* conv,
                           int32_t* iters, double* resid, int nthreads) {
   constexpr int n = 7 * K, m = 2 * (K - 1);
@@ -81,7 +81,7 @@ static void project_batch(const ccp_model* M, double* x, int64_t count, uint8_t*
 }
 
 // host twin of ccp_geodesic_kernel (same calls, same order)
-template <int K, bool P>
+template <int K, int P>
 static void geodesic_batch(const ccp_model* M, const double* from, const double* to, int64_t edges, double delta,
                            double lambda, int max_states, double* states, int32_t* n_states, uint8_t* reached,
                            int32_t* total_iters) {

@@ -156,3 +156,52 @@ def test_coop_geodesic_equals_thread_per_edge(name):
         assert np.array_equal(r1.iters.cpu().numpy(), it_b)
         for e in range(E):
             assert np.array_equal(_bits(r1.states[e, :ns_b[e]]), st_b[e, :ns_b[e]].view(np.uint64))
+
+
+@pytest.mark.parametrize("name", ["dumbbell", "stefan_three_arm"])
+def test_stock_specialisation_changes_no_bit(name):
+    """The kernels specialised to the reference's stock Panda table and base frames (PANDA = 2: exact-zero link terms and the
+    diagonal base-to-base rotation are skipped, their constants not loaded) against the structured-alpha kernels
+    (CCP_MODEL_NO_STOCK) on the same model: states, flags, iteration counts, residuals, function and Jacobian values —
+    identical bits.  Both projection kernels and the geodesic walk."""
+    import closed_chain_motion_planner_b200 as pkg
+    from closed_chain_motion_planner_b200 import _capi
+
+    cfg = pkg.grasping_point().loadConfig(name)
+    arms = [pkg.ArmModel(name=nm, index=ix, t_wb=cfg.t_wb[ix]) for nm, ix in zip(cfg.arm_names, cfg.arm_indices)]
+    cs = pkg.KinematicChainConstraint(7 * len(arms))
+    cs.setArmModels(*arms)
+    cn = pkg.KinematicChainConstraint(7 * len(arms))
+    cn._arms = list(arms)
+    d = pkg.make_model_desc(arms)
+    d.flags = _capi.CCP_MODEL_NO_STOCK
+    import ctypes as C
+
+    h = C.c_void_p()
+    assert cn._lib.ccp_create(C.byref(d), 0, C.byref(h)) == 0
+    cn._h, cn._desc = h, d
+    for c in (cs, cn):
+        c.setInitialPosition(cfg.start)
+    n = cs.getAmbientDimension()
+    rng = np.random.default_rng(1)
+    lb = np.tile([-2.8973, -1.7628, -2.8973, -3.0718, -2.8973, -0.0175, -2.8973], n // 7)
+    ub = np.tile([2.8973, 1.7628, 2.8973, -0.0698, 2.8973, 3.7525, 2.8973], n // 7)
+    seeds = np.concatenate([rng.uniform(lb, ub, (20_000, n)), cfg.start[None, :] + 0.1 * rng.standard_normal((10_000, n))])
+    xs = torch.from_numpy(seeds).cuda()
+    for count in (300, len(seeds)):  # cooperative kernel (two arms) / thread-per-sample kernel
+        a, b = cs.projectBatch(xs[:count].contiguous()), cn.projectBatch(xs[:count].contiguous())
+        torch.cuda.synchronize()
+        assert np.array_equal(_bits(a.x), _bits(b.x)) and torch.equal(a.ok, b.ok) and torch.equal(a.iters, b.iters)
+        assert np.array_equal(_bits(a.resid), _bits(b.resid))
+    assert np.array_equal(_bits(cs.functionBatch(xs[:2000].contiguous())), _bits(cn.functionBatch(xs[:2000].contiguous())))
+    assert np.array_equal(_bits(cs.jacobianBatch(xs[:500].contiguous())), _bits(cn.jacobianBatch(xs[:500].contiguous())))
+    if n == 14:
+        ss = pkg.jy_ProjectedStateSpace(pkg.KinematicChainSpace(14), cs)
+        sn = pkg.jy_ProjectedStateSpace(pkg.KinematicChainSpace(14), cn)
+        V = a.x[a.ok.bool()][:400].contiguous()
+        frm = torch.from_numpy(cfg.start[None, :]).cuda().repeat(200, 1).contiguous()
+        ga, gb = ss.discreteGeodesicBatch(frm, V[:200].contiguous(), max_states=24), sn.discreteGeodesicBatch(frm, V[:200].contiguous(), max_states=24)
+        assert torch.equal(ga.reached, gb.reached) and torch.equal(ga.n_states, gb.n_states) and torch.equal(ga.iters, gb.iters)
+        for e in range(200):
+            k = int(ga.n_states[e])
+            assert np.array_equal(_bits(ga.states[e, :k]), _bits(gb.states[e, :k]))
