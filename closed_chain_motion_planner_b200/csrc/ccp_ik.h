@@ -100,8 +100,9 @@ CCP_HD bool ccp_ik_trip(const ccp_arm& A, const double* lb, const double* ub, co
     conv = (ep_inf <= O.eps_p) && (er_inf <= O.eps_r);
     if (conv || it >= O.max_iter) return true;
     ++it;
-    // G = J J^T + lambda^2 I (lower triangle), Cholesky G = L L^T, solve G y = e
-    double L[6][6], invd[6];
+    // G = J J^T + lambda^2 I (lower triangle), G = L D L^T with unit-diagonal L (no square roots: an FP64 sqrt is ~15
+    // instructions and a Cholesky needs six), solve G y = e
+    double L[6][6], dinv[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i)
 #pragma unroll
@@ -113,35 +114,36 @@ CCP_HD bool ccp_ik_trip(const ccp_arm& A, const double* lb, const double* ub, co
       }
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
+      // column j.  Below the diagonal L[i][k] (k < j) holds l_ik and, above it, L[k][i] (k < i) holds l_ik d_k
       double d = L[j][j];
 #pragma unroll
-      for (int k = 0; k < j; ++k) d = CCP_FMA(-L[j][k], L[j][k], d);
-      d = sqrt(fmax(d, 1e-300));
+      for (int k = 0; k < j; ++k) d = CCP_FMA(-L[j][k], L[k][j], d);
+      d = fmax(d, 1e-300);  // G is positive definite by construction (lambda^2 > 0); guards a zero Jacobian with lambda = 0
       const double inv = 1.0 / d;
-      invd[j] = inv;  // the triangular solves multiply by it instead of dividing by the pivot twelve more times
-      L[j][j] = d;
+      dinv[j] = inv;
 #pragma unroll
       for (int i = j + 1; i < 6; ++i) {
         double v = L[i][j];
 #pragma unroll
-        for (int k = 0; k < j; ++k) v = CCP_FMA(-L[i][k], L[j][k], v);
-        L[i][j] = v * inv;
+        for (int k = 0; k < j; ++k) v = CCP_FMA(-L[i][k], L[k][j], v);
+        L[j][i] = v;         // l_ij d_j
+        L[i][j] = v * inv;   // l_ij
       }
     }
     double y[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
+    for (int i = 0; i < 6; ++i) {  // L z = e
       double v = e[i];
 #pragma unroll
       for (int k = 0; k < i; ++k) v = CCP_FMA(-L[i][k], y[k], v);
-      y[i] = v * invd[i];
+      y[i] = v;
     }
 #pragma unroll
-    for (int i = 5; i >= 0; --i) {
-      double v = y[i];
+    for (int i = 5; i >= 0; --i) {  // L^T y = D^-1 z
+      double v = y[i] * dinv[i];
 #pragma unroll
       for (int k = i + 1; k < 6; ++k) v = CCP_FMA(-L[k][i], y[k], v);
-      y[i] = v * invd[i];
+      y[i] = v;
     }
     // q <- clamp(q + J^T y)      (KDL ChainIkSolverPos_NR_JL clamps to the limits after every step)
 #pragma unroll
