@@ -25,7 +25,7 @@
 
 // Batched pose IK (ccp_ik.h), per damped-Newton iteration of ONE arm, same conventions:
 //   FK with general 3x3 products 7 x (18 + 36) + 6 + 18 = 402 ; geometric Jacobian 7 x 12 = 84 ; rotation error 55 ;
-//   J J^T + lambda^2 I (21 entries x 7 FMA) 294 ; 6x6 Cholesky 85 ; two triangular solves 60 ; J^T y + update 91
+//   J J^T + lambda^2 I (21 entries x 7 FMA) 294 ; 6x6 factorisation (counted as the Cholesky it replaced; the LDL^T does 9 more multiplies and no square roots) 85 ; two triangular solves 60 ; J^T y + update 91
 //   => 1070 FLOP + 7 sincos + 7 sqrt + 19 div.   Tail (the final FK + error evaluation of every solve): 540.
 #define CCP_FLOPS_IK_ITER 1070.0
 #define CCP_FLOPS_IK_TAIL 540.0
