@@ -44,7 +44,10 @@
 #define CCP_ZERO_COPY_MAX 512   /* host batches up to this many states run in place in page-locked host memory */
 /* batch size up to which the two-lanes-per-sample kernel is the faster one: one cooperative warp (16 samples) per
  * scheduler, 3/4 full — measured crossover on B200 between 4 000 and 10 000 samples (tools/coop_probe.py) */
-#define CCP_COOP_MAX_PER_SM 48
+// complete launches up to this many samples per SM take the cooperative kernel: one cooperative warp per scheduler
+// (4 x 16 two-arm samples; the three-arm kernel holds 8 per warp and still wins with two warps per scheduler)
+#define CCP_COOP_MAX_PER_SM 64
+#define CCP_COOP3_MAX_PER_SM 64
 #define CCP_HOST_MAX_CHUNKS 24  /* < CCP_NUM_DESC / 2: every chunk launch of a host call stays pipelined */
 
 // per-launch device record (ring of CCP_NUM_COUNTERS): zeroed by ONE stream-ordered memset before the launch
@@ -133,7 +136,7 @@ struct ccp_handle {
   double* peer_mc;
   int peer_world, peer_rank;
   long long peer_cap;
-  long long coop_max;  // complete launches of at most this many samples take the cooperative kernel (K = 2)
+  long long coop_max;  // complete launches of at most this many samples take the cooperative kernel
   std::mutex mu;
   std::mutex host_mu;  // the *_host entry points share the stage buffer and the private streams: one at a time
   char err[512];
@@ -406,9 +409,10 @@ static int launch_project(ccp_handle* h, ccp_project_args& A, int layout, cudaSt
   // a small complete launch: latency, not throughput, is what it costs — two lanes per sample (ccp_coop.cu).  When every
   // sample has its static place in the grid (always, below the default threshold) the work counter is never touched and
   // its stream-ordered zeroing — one more operation on the path of a single project() call — is skipped.
-  const bool coop = !defer && !h->pipeline_open && h->model.n_arms == 2 && A.count <= h->coop_max && A.peer_world == 0 &&
-                    !A.own_n_ok;
-  const bool coop_static = coop && A.count <= 64LL * ((A.count + 15) / 16 < 3LL * h->sm_count ? (A.count + 15) / 16 : 3LL * h->sm_count);
+  const long long spw = h->model.n_arms == 2 ? 16 : 8;  // samples per warp of the cooperative kernels
+  const bool coop = !defer && !h->pipeline_open && A.count <= h->coop_max &&
+                    A.peer_world == 0 && !A.own_n_ok;
+  const bool coop_static = coop && A.count <= 4 * spw * (long long)ccp_coop_grid(h->sm_count, A.count, (int)spw);
   if (coop_static) A.counter = nullptr;
   else CCP_CUDA(cudaMemsetAsync(h->d_counters + slot, 0, sizeof(ccp_launch_rec), st));
   if (defer || h->pipeline_open) {
@@ -537,7 +541,8 @@ int ccp_create(const ccp_model_desc* model, int32_t device, ccp_handle** out) {
   device_guard g(device);
   cudaError_t e = g.ok ? cudaSuccess : cudaErrorInvalidDevice;
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&nh->sm_count, cudaDevAttrMultiProcessorCount, device);
-  if (e == cudaSuccess && nh->coop_max < 0) nh->coop_max = (long long)nh->sm_count * CCP_COOP_MAX_PER_SM;
+  if (e == cudaSuccess && nh->coop_max < 0)
+    nh->coop_max = (long long)nh->sm_count * (model->n_arms == 2 ? CCP_COOP_MAX_PER_SM : CCP_COOP3_MAX_PER_SM);
   if (e == cudaSuccess) e = cudaMalloc(&nh->d_counters, 2 * CCP_NUM_COUNTERS * sizeof(ccp_launch_rec));
   for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&nh->hstream[i], cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreate(&nh->ev0);
@@ -696,7 +701,7 @@ int ccp_set_options(ccp_handle* h, const ccp_options* opt) {
 
 int ccp_set_coop_threshold(ccp_handle* h, int64_t max_count) {
   if (!h) return CCP_ERR_INVALID;
-  h->coop_max = max_count < 0 ? (long long)h->sm_count * CCP_COOP_MAX_PER_SM : max_count;
+  h->coop_max = max_count < 0 ? (long long)h->sm_count * (h->model.n_arms == 2 ? CCP_COOP_MAX_PER_SM : CCP_COOP3_MAX_PER_SM) : max_count;
   return CCP_OK;
 }
 
@@ -1111,7 +1116,7 @@ int ccp_geodesic_batch(ccp_handle* h, const double* from_dev, const double* to_d
   CCP_CUDA(cudaMemsetAsync(h->d_counters + slot, 0, sizeof(ccp_launch_rec), st));
   cudaError_t e = ccp_launch_geodesic(h->sm_count, h->model, from_dev, to_dev, edges, delta, lambda, max_states, states_dev,
                                       n_states_dev, reached_dev, iters_dev, counter,
-                                      4 * h->coop_max /* a walk is long: two lanes per edge win up to ~4x the projection's threshold */, st);
+                                      3 * h->coop_max /* a walk is long: two lanes per edge win up to ~3x the projection's threshold (28 416 edges on B200) */, st);
   if (e != cudaSuccess) return set_err(h, CCP_ERR_CUDA, "geodesic kernel launch: %s", cudaGetErrorString(e));
   return CCP_OK;
 }

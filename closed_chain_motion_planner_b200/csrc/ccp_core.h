@@ -737,6 +737,47 @@ CCP_HD double ccp_row_dot7(const double* a, const double* b) {
   return acc;
 }
 
+// m x m (lower triangle of G): L D L^T with row dropping — a vanished or dependent row (pivot <= 0) is dropped, its
+// multiplier is 0.  Lm is unit lower triangular, D the pivots.
+template <int m>
+CCP_HD void ccp_solve_ldlt(const double (&G)[m][m], const double* rhs, double* y) {
+  double D[m], invD[m];
+  double Lm[m][m];
+#pragma unroll
+  for (int k = 0; k < m; ++k) {
+    double dk = G[k][k];
+#pragma unroll
+    for (int j = 0; j < k; ++j) dk = CCP_FMA(-(Lm[k][j] * D[j]), Lm[k][j], dk);
+    const bool keep = dk > 0.0;
+    D[k] = keep ? dk : 0.0;
+    invD[k] = keep ? 1.0 / dk : 0.0;
+#pragma unroll
+    for (int i = k + 1; i < m; ++i) {
+      double v = G[i][k];
+#pragma unroll
+      for (int j = 0; j < k; ++j) v = CCP_FMA(-(Lm[i][j] * D[j]), Lm[k][j], v);
+      Lm[i][k] = v * invD[k];
+    }
+  }
+  // forward substitution L z = f, scale by D^-1, back substitution L^T y = z
+#pragma unroll
+  for (int k = 0; k < m; ++k) {
+    double v = rhs[k];
+#pragma unroll
+    for (int j = 0; j < k; ++j) v = CCP_FMA(-Lm[k][j], y[j], v);
+    y[k] = v;
+  }
+#pragma unroll
+  for (int k = 0; k < m; ++k) y[k] = y[k] * invD[k];
+#pragma unroll
+  for (int k = m - 1; k >= 0; --k) {
+    double v = y[k];
+#pragma unroll
+    for (int j = k + 1; j < m; ++j) v = CCP_FMA(-Lm[j][k], y[j], v);
+    y[k] = (invD[k] != 0.0) ? v : 0.0;
+  }
+}
+
 template <int K, class JT, class XT>
 CCP_HD void ccp_newton_step(const ccp_model& M, const ccp_fwd<K>& F, const JT& J, XT& x) {
   constexpr int m = 2 * (K - 1);
@@ -774,42 +815,7 @@ CCP_HD void ccp_newton_step(const ccp_model& M, const ccp_fwd<K>& F, const JT& J
   if (m == 2) {
     ccp_solve_2x2(G[0][0], G[1][0], G[1][1], rhs, y);
   } else {
-  // L D L^T with row dropping.  Lm is unit lower triangular, D the pivots.
-  double D[m], invD[m];
-  double Lm[m][m];
-#pragma unroll
-  for (int k = 0; k < m; ++k) {
-    double dk = G[k][k];
-#pragma unroll
-    for (int j = 0; j < k; ++j) dk = CCP_FMA(-(Lm[k][j] * D[j]), Lm[k][j], dk);
-    const bool keep = dk > 0.0;
-    D[k] = keep ? dk : 0.0;
-    invD[k] = keep ? 1.0 / dk : 0.0;
-#pragma unroll
-    for (int i = k + 1; i < m; ++i) {
-      double v = G[i][k];
-#pragma unroll
-      for (int j = 0; j < k; ++j) v = CCP_FMA(-(Lm[i][j] * D[j]), Lm[k][j], v);
-      Lm[i][k] = v * invD[k];
-    }
-  }
-  // forward substitution L z = f, scale by D^-1, back substitution L^T y = z
-#pragma unroll
-  for (int k = 0; k < m; ++k) {
-    double v = rhs[k];
-#pragma unroll
-    for (int j = 0; j < k; ++j) v = CCP_FMA(-Lm[k][j], y[j], v);
-    y[k] = v;
-  }
-#pragma unroll
-  for (int k = 0; k < m; ++k) y[k] = y[k] * invD[k];
-#pragma unroll
-  for (int k = m - 1; k >= 0; --k) {
-    double v = y[k];
-#pragma unroll
-    for (int j = k + 1; j < m; ++j) v = CCP_FMA(-Lm[j][k], y[j], v);
-    y[k] = (invD[k] != 0.0) ? v : 0.0;
-  }
+    ccp_solve_ldlt<m>(G, rhs, y);
   }
   // x -= step * J^T y
 #pragma unroll

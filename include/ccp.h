@@ -111,10 +111,11 @@ int ccp_get_reference(const ccp_handle* h, int32_t pair, double* t0_host, double
 int ccp_set_tolerance(ccp_handle* h, double tol_position, double tol_rotation);
 int ccp_set_options(ccp_handle* h, const ccp_options* opt);
 int ccp_get_options(const ccp_handle* h, ccp_options* opt, double* tol_position, double* tol_rotation);
-/* Tuning knob, not semantics: complete (non-pipelined) two-arm launches of at most max_count samples run on the
- * cooperative kernel (two lanes per sample, one arm each: a third of the latency per Newton iteration at 1.4x the issue
- * slots), larger ones on the thread-per-sample kernel.  Results are bit-identical either way.  0 = never,
- * negative = the built-in default (also settable through the environment variable CCP_COOP_MAX).                  */
+/* Tuning knob, not semantics: complete (non-pipelined) launches of at most max_count samples run on the cooperative
+ * kernel (two lanes per sample, one arm each; three arms: four lanes per sample — a Newton iteration takes 1.2x / 1.7x
+ * fewer cycles at 1.4x - 2x the issue slots), larger ones on the thread-per-sample kernel.  Results are bit-identical
+ * either way.  0 = never, negative = the built-in default (64 samples per SM; also settable through the environment
+ * variable CCP_COOP_MAX).                                                                                           */
 int ccp_set_coop_threshold(ccp_handle* h, int64_t max_count);
 
 /* ---- batched constraint API, device pointers ------------------------------------------- */

@@ -96,6 +96,87 @@ def test_coop_edge_cases_options_and_calibrated_model():
     assert np.array_equal(_bits(r0.x), _bits(r1.x)) and torch.equal(r0.ok, r1.ok) and torch.equal(r0.iters, r1.iters)
 
 
+@pytest.mark.parametrize("layout", ["aos", "soa"])
+@pytest.mark.parametrize("calibrated", [False, True])
+def test_coop_three_arms_equals_thread_per_sample(layout, calibrated):
+    """21 DoF: four lanes per sample (ccp_project_coop3_kernel; lane 3 repeats arm 0 for the second residual pair) against the
+    thread-per-sample kernel and the host build of the engine arithmetic — bit for bit, stock and calibrated link code,
+    every output, the sampler's wrap + compaction, non-default options."""
+    import closed_chain_motion_planner_b200 as pkg
+    from oracle.oracle import OracleA, OracleB
+    from test_parity_full_gpu import Q3
+
+    gp = pkg.grasping_point()
+    dh = 1e-2 * np.random.default_rng(11).standard_normal((3, 7, 4)) if calibrated else [None] * 3
+    arms = [pkg.ArmModel(f"arm{i}", i, gp.t_wb[i], dh_offsets=dh[i]) for i in range(3)]
+    c = pkg.KinematicChainConstraint(21)
+    c.setArmModels(*arms)
+    c.setInitialPosition(Q3)
+    A = OracleA([0, 1, 2])
+    B = OracleB(pkg.make_model_desc(arms))
+    B.set_initial_position(Q3)
+    lay = pkg.CCP_LAYOUT_AOS if layout == "aos" else pkg.CCP_LAYOUT_SOA
+    rng = np.random.default_rng(5)
+    for count in (1, 7, 8, 9, 33, 1000, 6001):
+        d = rng.standard_normal((count, 21))
+        d *= 0.25 / np.linalg.norm(d, axis=1, keepdims=True)
+        seeds = np.concatenate([A.seeds_uniform(2, 0, count), Q3[None, :] + d])[:max(count, 1)]
+        if count == 33:
+            seeds[3, 5] = np.nan
+            seeds[4, :] = 1e300
+        xs = torch.from_numpy(seeds if layout == "aos" else np.ascontiguousarray(seeds.T)).cuda()
+
+        def run():
+            compact = torch.zeros((len(seeds), 21), dtype=torch.float64, device="cuda")
+            n_ok = torch.zeros(1, dtype=torch.int64, device="cuda")
+            r = c.projectBatch(xs, layout=lay, compact=compact, n_ok=n_ok)
+            return r, compact, n_ok
+
+        (r0, c0, n0), (r1, c1, n1) = _both(c, run)
+        assert np.array_equal(_bits(r0.x), _bits(r1.x)), (layout, calibrated, count)
+        assert torch.equal(r0.ok, r1.ok) and torch.equal(r0.converged, r1.converged) and torch.equal(r0.iters, r1.iters)
+        assert np.array_equal(_bits(r0.resid), _bits(r1.resid))
+        k = int(n0.item())
+        assert k == int(n1.item()) == int(r0.ok.sum())
+        srt = lambda m: m[np.lexsort(m.T[::-1])]
+        assert np.array_equal(srt(c0[:k].cpu().numpy()).view(np.uint64), srt(c1[:k].cpu().numpy()).view(np.uint64))
+        if count == 1000:
+            rb = B.project(seeds, nthreads=8)
+            x1 = r1.x.cpu().numpy() if layout == "aos" else r1.x.cpu().numpy().T
+            assert np.array_equal(x1.view(np.uint64), rb["x"].view(np.uint64)) and np.array_equal(r1.iters.cpu().numpy(), rb["iters"])
+            assert int(r1.ok.sum()) > 0
+    if layout == "aos":
+        xs = torch.from_numpy(A.seeds_uniform(3, 0, 400)).cuda()
+        for opts in (dict(max_iter=0), dict(max_iter=3), dict(damping=1e-4, clamp=True), dict(step=0.5, joint_margin=0.0)):
+            c.setOptions(**opts)
+            r0, r1 = _both(c, lambda: c.projectBatch(xs))
+            assert np.array_equal(_bits(r0.x), _bits(r1.x)), opts
+            assert torch.equal(r0.ok, r1.ok) and torch.equal(r0.iters, r1.iters) and np.array_equal(_bits(r0.resid), _bits(r1.resid))
+        c.setOptions()
+        # the sampler path: seed kernel -> projection with the enforceBounds wrap
+        from closed_chain_motion_planner_b200 import _capi
+
+        def sample():
+            a = _capi.SamplerArgs(rng_seed=3, first_index=5, mode=0, wrap_bounds=1, distance=0.0, near_host=None)
+            x = torch.empty((3000, 21), dtype=torch.float64, device="cuda")
+            ok = torch.empty(3000, dtype=torch.uint8, device="cuda")
+            it = torch.empty(3000, dtype=torch.int32, device="cuda")
+            st = torch.cuda.current_stream().cuda_stream
+            assert c._lib.ccp_sample_project_batch(c._h, C.byref(a), 3000, 0, x.data_ptr(), ok.data_ptr(), it.data_ptr(), None, None, st) == 0
+            return x, ok, it
+
+        (x0, ok0, it0), (x1, ok1, it1) = _both(c, sample)
+        assert np.array_equal(_bits(x0), _bits(x1)) and torch.equal(ok0, ok1) and torch.equal(it0, it1)
+        # host entry point (one launch, in place) takes the same kernel choice
+        assert c._lib.ccp_set_coop_threshold(c._h, FORCE) == 0
+        hs = A.seeds_uniform(4, 0, 50)
+        rh = c.projectBatch(hs)
+        assert c._lib.ccp_set_coop_threshold(c._h, NEVER) == 0
+        rt = c.projectBatch(hs)
+        assert c._lib.ccp_set_coop_threshold(c._h, -1) == 0
+        assert np.array_equal(rh.x.view(np.uint64), rt.x.view(np.uint64)) and np.array_equal(rh.ok, rt.ok)
+
+
 def test_coop_sampler_wrap_and_golden_rows():
     """the sampler path (seed kernel -> projection with the enforceBounds wrap and compaction) and the reference's dumped
     path rows through the cooperative kernel"""

@@ -16,7 +16,7 @@ cfgname = sys.argv[1] if len(sys.argv) > 1 else "dumbbell"
 c = pkg.KinematicChainConstraint.from_config(cfgname)
 A = OracleA(c.config.arm_indices)
 rows = []
-for count in (1, 16, 256, 1000, 4000, 10_000, 20_000, 40_000, 80_000, 160_000, 320_000):
+for count in [int(v) for v in os.environ.get("COOP_PROBE_COUNTS", "1,16,256,1000,4000,10000,20000,40000,80000,160000,320000").split(",")]:
     seeds = torch.from_numpy(A.seeds_uniform(0, 0, count)).cuda()
     out = torch.empty_like(seeds)
     row = {"count": count}
