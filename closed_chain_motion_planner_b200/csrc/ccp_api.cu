@@ -1116,7 +1116,7 @@ int ccp_geodesic_batch(ccp_handle* h, const double* from_dev, const double* to_d
   CCP_CUDA(cudaMemsetAsync(h->d_counters + slot, 0, sizeof(ccp_launch_rec), st));
   cudaError_t e = ccp_launch_geodesic(h->sm_count, h->model, from_dev, to_dev, edges, delta, lambda, max_states, states_dev,
                                       n_states_dev, reached_dev, iters_dev, counter,
-                                      3 * h->coop_max /* a walk is long: two lanes per edge win up to ~3x the projection's threshold (28 416 edges on B200) */, st);
+                                      (h->model.n_arms == 2 ? 7 : 8) * h->coop_max /* a walk is a serial chain of projections with frequent bookkeeping: several lanes per edge win up to ~66 000 (two arms) / ~76 000 (three arms) edges on B200 */, st);
   if (e != cudaSuccess) return set_err(h, CCP_ERR_CUDA, "geodesic kernel launch: %s", cudaGetErrorString(e));
   return CCP_OK;
 }

@@ -249,6 +249,119 @@ ccp_geodesic_coop_kernel(const __grid_constant__ ccp_model M, const __grid_const
   }
 }
 
+// ---- three arms: FOUR lanes per edge (ccp_coop.cuh, ccp_quad: lanes 0, 1, 2 carry arms 0, 1, 2; lane 3 repeats arm 0) ----
+template <int PANDA>
+__global__ void __launch_bounds__(128, 2)
+ccp_geodesic_coop3_kernel(const __grid_constant__ ccp_model M, const __grid_constant__ ccp_geodesic_args A) {
+  constexpr int n = 3 * CCPC_DOF, H = CCPC_DOF;
+  const ccp_quad Q = ccp_make_quad();
+  const int arm = Q.arm;
+  const bool writer = Q.g != 3;  // lane 3's copy of arm 0 is never stored
+  double x[H], prev[H], tov[H];
+  ccp_geo_state g;
+  g.dist = g.total = g.max = 0.0;
+  int it = 0, ns = 0, iters_sum = 0;
+  const long long static_edges = (long long)gridDim.x * (blockDim.x / 4);
+  long long e = ((long long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 8 + ((threadIdx.x & 31) >> 2);
+  bool need_edge = true, first = true;
+  for (;;) {
+    if (need_edge) {
+      if (!first) {
+        unsigned long long c = 0;
+        if (Q.g == 0) c = atomicAdd(A.counter, 1ULL);
+        const unsigned lo = __shfl_sync(Q.mask, (unsigned)c, Q.lane0), hi = __shfl_sync(Q.mask, (unsigned)(c >> 32), Q.lane0);
+        e = static_edges + (long long)(((unsigned long long)hi << 32) | lo);
+      }
+      first = false;
+      if (e >= A.edges) break;
+      const double* fr = A.from + e * n + arm * H;
+      const double* to = A.to + e * n + arm * H;
+      double* out = A.states + (e * A.max_states) * n + arm * H;
+#pragma unroll
+      for (int j = 0; j < H; ++j) {
+        prev[j] = __ldg(fr + j);
+        tov[j] = __ldg(to + j);
+        if (writer) out[j] = prev[j];
+        x[j] = prev[j];
+      }
+      g.dist = ccp_quad_distance(Q, prev, tov);
+      g.total = 0.0;
+      g.max = g.dist * A.lambda;
+      ns = 1;
+      iters_sum = 0;
+      if (g.dist <= A.delta) {  // already there
+        if (Q.g == 0) {
+          A.n_states[e] = 1;
+          A.reached[e] = 1;
+          if (A.total_iters) A.total_iters[e] = 0;
+        }
+        continue;
+      }
+      const double t = A.delta / g.dist;
+#pragma unroll
+      for (int j = 0; j < H; ++j) x[j] = ccp_interpolate_joint(x[j], tov[j], t);
+      it = 0;
+      need_edge = false;
+    }
+    ccp_sc_local<1> S;
+    double w[3], m[3], e2[2], sv2[2], d0[2];
+    ccp_quad_forward<PANDA>(M, Q, x, S, w, m, e2, sv2, d0);
+    const double dw2a = M.tan2_r * (d0[0] * d0[0]), dw2b = M.tan2_r * (d0[1] * d0[1]);
+    const bool cont = ((e2[0] > M.tol_p2) || (sv2[0] > dw2a) || (e2[1] > M.tol_p2) || (sv2[1] > dw2b)) && it < M.max_iter;
+    if (cont) {
+      ++it;
+      ccp_quad_step<PANDA>(M, Q, S, w, m, e2, sv2, d0, x);
+    } else {
+      // ---- the projection of this step finished: bookkeeping of the walk (ccp_geodesic_advance, term by term) ----
+      iters_sum += it;
+      const bool cv = (e2[0] <= M.tol_p2) && (sv2[0] < dw2a) && (e2[1] <= M.tol_p2) && (sv2[1] < dw2b);
+      const bool okk = ccp_quad_joint_valid(M, Q, x) && cv;
+      int code = 2;
+      if (okk) {
+        const double step = ccp_quad_distance(Q, prev, x);
+        if (!(step > A.lambda * A.delta)) {
+          g.total += step;
+          if (!(g.total > g.max)) {
+            const double newDist = ccp_quad_distance(Q, x, tov);
+            if (!(newDist >= g.dist)) {
+              g.dist = newDist;
+              code = (g.dist >= A.delta) ? 0 : 1;
+            }
+          }
+        }
+      }
+      bool overflow = false;
+      if (code != 2) {
+        if (ns < A.max_states) {
+          double* out = A.states + (e * A.max_states + ns) * n + arm * H;
+#pragma unroll
+          for (int j = 0; j < H; ++j) {
+            if (writer) out[j] = x[j];
+            prev[j] = x[j];
+          }
+          ++ns;
+        } else {
+          code = 2;  // out of room: report as not reached
+          overflow = true;
+        }
+      }
+      if (code == 0) {
+        const double t = A.delta / g.dist;
+#pragma unroll
+        for (int j = 0; j < H; ++j) x[j] = ccp_interpolate_joint(x[j], tov[j], t);
+        it = 0;
+      } else {
+        if (Q.g == 0) {
+          A.n_states[e] = ns;
+          A.reached[e] = (!overflow && g.dist <= A.delta) ? 1 : 0;
+          if (A.total_iters) A.total_iters[e] = iters_sum;
+        }
+        need_edge = true;
+      }
+    }
+  }
+}
+
 cudaError_t ccp_launch_geodesic(int sm_count, const ccp_model& M, const double* from, const double* to, long long edges,
                                 double delta, double lambda, int max_states, double* states, int32_t* n_states,
                                 uint8_t* reached, int32_t* total_iters, unsigned long long* counter, long long coop_max,
@@ -265,15 +378,20 @@ cudaError_t ccp_launch_geodesic(int sm_count, const ccp_model& M, const double* 
   A.max_states = max_states;
   A.delta = delta;
   A.lambda = lambda;
-  if (M.n_arms == 2 && edges <= coop_max) {
-    // few edges: two lanes per edge, one cooperative warp (16 edges) per block before any block gets a second one
-    long long needc = (edges + 15) / 16;
-    const long long capc = (long long)sm_count * 2;
-    int gridc = (int)(needc < capc ? needc : capc);
-    if (gridc < 1) gridc = 1;
-    if (M.stock) ccp_geodesic_coop_kernel<2><<<gridc, 128, 0, st>>>(M, A);
-    else if (M.panda_alpha) ccp_geodesic_coop_kernel<1><<<gridc, 128, 0, st>>>(M, A);
-    else ccp_geodesic_coop_kernel<0><<<gridc, 128, 0, st>>>(M, A);
+  if (edges <= coop_max) {
+    // few edges: several lanes per edge (two arms: 2 lanes, 16 edges per warp; three arms: 4 lanes, 8 edges per warp), one
+    // cooperative warp per scheduler before any SM gets a second block
+    if (M.n_arms == 2) {
+      const int gridc = ccp_coop_grid(sm_count, edges, 16, 2);
+      if (M.stock) ccp_geodesic_coop_kernel<2><<<gridc, 128, 0, st>>>(M, A);
+      else if (M.panda_alpha) ccp_geodesic_coop_kernel<1><<<gridc, 128, 0, st>>>(M, A);
+      else ccp_geodesic_coop_kernel<0><<<gridc, 128, 0, st>>>(M, A);
+    } else {
+      const int gridc = ccp_coop_grid(sm_count, edges, 8, 2);
+      if (M.stock) ccp_geodesic_coop3_kernel<2><<<gridc, 128, 0, st>>>(M, A);
+      else if (M.panda_alpha) ccp_geodesic_coop3_kernel<1><<<gridc, 128, 0, st>>>(M, A);
+      else ccp_geodesic_coop3_kernel<0><<<gridc, 128, 0, st>>>(M, A);
+    }
     return cudaGetLastError();
   }
   long long need = (edges + 31) / 32;  // one warp's worth of edges per block before any block gets more

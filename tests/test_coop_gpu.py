@@ -211,17 +211,21 @@ def test_coop_sampler_wrap_and_golden_rows():
     assert bool((r.ok == 1).all()) and int(r.iters.max()) <= 1 and float((r.x - rows).abs().max()) < 5e-4
 
 
-@pytest.mark.parametrize("name", ["stefan", "Wine_Bottle"])
+@pytest.mark.parametrize("name", ["stefan", "Wine_Bottle", "stefan_three_arm"])
 def test_coop_geodesic_equals_thread_per_edge(name):
-    """discreteGeodesic with two lanes per edge (ccp_geodesic_coop_kernel) against the one-thread walk and the host twin:
-    the same states, state counts, reached flags and iteration totals, bit for bit."""
+    """discreteGeodesic with two lanes per edge (ccp_geodesic_coop_kernel; three arms: four lanes, ccp_geodesic_coop3_kernel)
+    against the one-thread walk and the host twin: the same states, state counts, reached flags and iteration totals, bit
+    for bit."""
     import closed_chain_motion_planner_b200 as pkg
 
     cfg, A, B = make_oracles(name)
     c = pkg.KinematicChainConstraint.from_config(name, device=0)
-    space = pkg.jy_ProjectedStateSpace(pkg.KinematicChainSpace(14), c)
-    smp = space.allocStateSampler(pool_size=8192, rng_seed=5)
-    V = smp.sampleUniformBatch(8000)
+    space = pkg.jy_ProjectedStateSpace(pkg.KinematicChainSpace(c.getAmbientDimension()), c)
+    # (three arms: 4 % of uniform seeds end inside the limits)
+    two = c.getAmbientDimension() == 14
+    smp = space.allocStateSampler(pool_size=8192 if two else 1 << 16, rng_seed=5)
+    V = smp.sampleUniformBatch(8000 if two else 60_000)
+    assert V.shape[0] >= 1400
     for E in (1, 5, 17, 700):
         frm = torch.cat([torch.from_numpy(cfg.start[None, :]).cuda().repeat(E // 2 + 1, 1), V[:E]])[:E].contiguous()
         to = V[E:2 * E].contiguous()
