@@ -130,6 +130,7 @@ class jy_ProjectedStateSampler {
   bool return_failed_ = false, prefetch_ = false;
   double* next_pool_ = nullptr;  // page-locked (ccp_host_alloc): the pool being projected ahead
   int64_t next_ticket_ = 0;
+  bool next_failed_ = false;     // the batch in flight was submitted with return_failed_ set
 };
 typedef std::shared_ptr<jy_ProjectedStateSampler> jy_ProjectedStateSamplerPtr;
 
@@ -227,6 +228,7 @@ inline void jy_ProjectedStateSampler::submit_next() {
   std::memset(&b, 0, sizeof b);
   b.sampler = &a;
   b.count = pool_size_;
+  next_failed_ = return_failed_;
   if (return_failed_) b.x_out_host = next_pool_;
   else {
     b.compact_host = next_pool_;
@@ -238,17 +240,17 @@ inline void jy_ProjectedStateSampler::submit_next() {
 
 inline void jy_ProjectedStateSampler::refill() {
   ccp_handle* h = space_->getConstraint()->handle();
-  if (prefetch_) {
+  if (prefetch_ || next_ticket_) {  // (a pool still in flight after setPrefetch(false) is consumed first)
     if (!next_ticket_) submit_next();
     int64_t n_ok = -1;
     if (ccp_host_batch_wait(h, next_ticket_, &n_ok) != CCP_OK)
       throw Exception(std::string("jy_ProjectedStateSampler: ") + ccp_last_error(h));
     next_ticket_ = 0;
-    count_ = return_failed_ ? pool_size_ : n_ok;
+    count_ = next_failed_ ? pool_size_ : n_ok;  // as submitted, whatever setReturnFailed says by now
     std::memcpy(pool_.data(), next_pool_, sizeof(double) * (size_t)count_ * n_);
     pos_ = 0;
     ++refills_;
-    submit_next();  // the GPU works on the next pool while the planner consumes this one
+    if (prefetch_) submit_next();  // the GPU works on the next pool while the planner consumes this one
     return;
   }
   ccp_sampler_args a;

@@ -85,7 +85,10 @@ int main(int argc, char** argv) {
   std::vector<double> ahead_samples((size_t)SA * 14);
   for (int i = 0; i < SA; ++i) {
     ahead->sampleUniform(&ahead_samples[(size_t)i * 14]);
-    if (i == 100) constraint->isSatisfied(&ahead_samples[0]);  // other calls on the handle while a pool is in flight
+    if (i == 100) {
+      constraint->isSatisfied(&ahead_samples[0]);  // other calls on the handle while a pool is in flight
+      ahead->setPrefetch(false);                   // the pool in flight is still consumed next, nothing after it is prefetched
+    }
   }
   int64_t ahead_refills = ahead->refills();
   auto all_states = space->allocStateSampler(500, /*rng_seed*/ 11);
