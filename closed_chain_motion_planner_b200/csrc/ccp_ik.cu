@@ -8,14 +8,27 @@
 #define CCP_IK_BLOCKS_PER_SM 3  // 168 registers: measured 5 % / 12 % faster than 2 blocks at 212 / 226 registers
 #endif
 
-// `arm` is uniform; the switch keeps the model in the constant bank
+// `arm` is uniform.  The model is a __grid_constant__ parameter, so M.arm[arm] is an indexed read of the constant bank:
+// ONE copy of the trip's code (a switch over the arm made three: 102 KB of SASS, and ncu showed 28 % of the sampling
+// kernel's stall samples waiting for instructions).
 __device__ __forceinline__ bool ik_trip(const ccp_model& M, int arm, const double* T, double* q, const ccp_ik_opt& O, int32_t& it,
                                         bool& conv, double& ep, double& er) {
+  return ccp_ik_trip(M.arm[arm], M.lb, M.ub, T, q, O, it, conv, ep, er);
+}
+// The explicit-seed kernel's loop is short enough for three copies (one per arm, constants at fixed offsets): 2 % faster
+// there than the indexed read.
+__device__ __forceinline__ bool ik_trip_per_arm(const ccp_model& M, int arm, const double* T, double* q, const ccp_ik_opt& O,
+                                                int32_t& it, bool& conv, double& ep, double& er) {
   switch (arm) {
     case 0: return ccp_ik_trip(M.arm[0], M.lb, M.ub, T, q, O, it, conv, ep, er);
     case 1: return ccp_ik_trip(M.arm[1], M.lb, M.ub, T, q, O, it, conv, ep, er);
     default: return ccp_ik_trip(M.arm[2], M.lb, M.ub, T, q, O, it, conv, ep, er);
   }
+}
+
+// one out-of-line copy of the Box-Muller draw (log, sincos) instead of seven inlined ones in the refill path
+static __device__ __noinline__ double ik_gauss01(unsigned long long seed, unsigned long long sample, unsigned j) {
+  return gauss01(seed, sample, j);
 }
 
 // Explicit seeds: one lane owns one (target, seed) pair at a time.  Iteration counts spread 0 .. max_iter (a solve
@@ -44,7 +57,7 @@ ccp_ik_kernel(const __grid_constant__ ccp_model M, int arm, const double* __rest
     }
     bool conv;
     double ep, er;
-    if (ik_trip(M, arm, T, q, O, it, conv, ep, er)) {
+    if (ik_trip_per_arm(M, arm, T, q, O, it, conv, ep, er)) {
 #pragma unroll
       for (int k = 0; k < CCPC_DOF; ++k) qout[i * CCPC_DOF + k] = q[k];
       if (ok) ok[i] = ccp_ik_accept(M.lb, M.ub, q, O, conv);
@@ -103,7 +116,7 @@ ccp_ik_sample_kernel(const __grid_constant__ ccp_model M, int arm, const double*
 #pragma unroll
         for (int k = 0; k < CCPC_DOF; ++k)
           q[k] = ccp_ik_random_joint(M.lb[k], M.ub[k], sigma,
-                                     gauss01(rng_seed, (unsigned long long)(first_target + t) * 64ull + (unsigned)r, (unsigned)k));
+                                     ik_gauss01(rng_seed, (unsigned long long)(first_target + t) * 64ull + (unsigned)r, (unsigned)k));
       }
       it = 0;
       load = false;
