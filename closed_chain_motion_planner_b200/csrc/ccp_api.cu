@@ -44,10 +44,13 @@
 #define CCP_ZERO_COPY_MAX 512   /* host batches up to this many states run in place in page-locked host memory */
 /* batch size up to which the two-lanes-per-sample kernel is the faster one: one cooperative warp (16 samples) per
  * scheduler, 3/4 full — measured crossover on B200 between 4 000 and 10 000 samples (tools/coop_probe.py) */
-// complete launches up to this many samples per SM take the cooperative kernel: one cooperative warp per scheduler
-// (4 x 16 two-arm samples; the three-arm kernel holds 8 per warp and still wins with two warps per scheduler)
-#define CCP_COOP_MAX_PER_SM 64
-#define CCP_COOP3_MAX_PER_SM 64
+// Complete launches up to this many samples per SM take the cooperative kernel (measured crossovers on B200, DESIGN.md
+// 4.1b): two arms 128 (two resident blocks x 4 warps x 16 samples), three arms 72 (8 samples per warp; a little beyond
+// the 64 with a static place).  The geodesic walk switches much later (4.2): its thresholds are these times a ratio.
+#define CCP_COOP_MAX_PER_SM 128
+#define CCP_COOP3_MAX_PER_SM 72
+#define CCP_GEO_COOP_PER_SM 448    // two arms: ~66 000 edges on B200
+#define CCP_GEO_COOP3_PER_SM 512   // three arms: ~76 000 edges
 #define CCP_HOST_MAX_CHUNKS 24  /* < CCP_NUM_DESC / 2: every chunk launch of a host call stays pipelined */
 
 // per-launch device record (ring of CCP_NUM_COUNTERS): zeroed by ONE stream-ordered memset before the launch
@@ -1094,6 +1097,14 @@ int ccp_sample_project_batch(ccp_handle* h, const ccp_sampler_args* a, int64_t c
   return sample_project_impl(h, a, count, layout, x_out_dev, ok_dev, iters_dev, compact_dev, n_ok_dev, stream, false);
 }
 
+// the geodesic kernels' crossover, scaled with the handle's cooperative threshold (ccp_set_coop_threshold: 0 = never)
+static long long geo_coop_max(const ccp_handle* h) {
+  const bool two = h->model.n_arms == 2;
+  const double ratio = two ? (double)CCP_GEO_COOP_PER_SM / CCP_COOP_MAX_PER_SM : (double)CCP_GEO_COOP3_PER_SM / CCP_COOP3_MAX_PER_SM;
+  const double v = (double)h->coop_max * ratio;
+  return v > 4.0e18 ? (long long)4e18 : (long long)v;
+}
+
 int ccp_geodesic_batch(ccp_handle* h, const double* from_dev, const double* to_dev, int64_t edges, double delta,
                        double lambda, int32_t max_states, double* states_dev, int32_t* n_states_dev,
                        uint8_t* reached_dev, int32_t* iters_dev, void* stream) {
@@ -1116,7 +1127,7 @@ int ccp_geodesic_batch(ccp_handle* h, const double* from_dev, const double* to_d
   CCP_CUDA(cudaMemsetAsync(h->d_counters + slot, 0, sizeof(ccp_launch_rec), st));
   cudaError_t e = ccp_launch_geodesic(h->sm_count, h->model, from_dev, to_dev, edges, delta, lambda, max_states, states_dev,
                                       n_states_dev, reached_dev, iters_dev, counter,
-                                      (h->model.n_arms == 2 ? 7 : 8) * h->coop_max /* a walk is a serial chain of projections with frequent bookkeeping: several lanes per edge win up to ~66 000 (two arms) / ~76 000 (three arms) edges on B200 */, st);
+                                      geo_coop_max(h) /* a walk is a serial chain of projections with frequent bookkeeping: several lanes per edge win up to ~66 000 (two arms) / ~76 000 (three arms) edges on B200 */, st);
   if (e != cudaSuccess) return set_err(h, CCP_ERR_CUDA, "geodesic kernel launch: %s", cudaGetErrorString(e));
   return CCP_OK;
 }

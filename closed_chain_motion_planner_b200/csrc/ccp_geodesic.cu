@@ -382,12 +382,12 @@ cudaError_t ccp_launch_geodesic(int sm_count, const ccp_model& M, const double* 
     // few edges: several lanes per edge (two arms: 2 lanes, 16 edges per warp; three arms: 4 lanes, 8 edges per warp), one
     // cooperative warp per scheduler before any SM gets a second block
     if (M.n_arms == 2) {
-      const int gridc = ccp_coop_grid(sm_count, edges, 16, 2);
+      const int gridc = ccp_coop_grid(sm_count, edges, 16);
       if (M.stock) ccp_geodesic_coop_kernel<2><<<gridc, 128, 0, st>>>(M, A);
       else if (M.panda_alpha) ccp_geodesic_coop_kernel<1><<<gridc, 128, 0, st>>>(M, A);
       else ccp_geodesic_coop_kernel<0><<<gridc, 128, 0, st>>>(M, A);
     } else {
-      const int gridc = ccp_coop_grid(sm_count, edges, 8, 2);
+      const int gridc = ccp_coop_grid(sm_count, edges, 8);
       if (M.stock) ccp_geodesic_coop3_kernel<2><<<gridc, 128, 0, st>>>(M, A);
       else if (M.panda_alpha) ccp_geodesic_coop3_kernel<1><<<gridc, 128, 0, st>>>(M, A);
       else ccp_geodesic_coop3_kernel<0><<<gridc, 128, 0, st>>>(M, A);

@@ -16,7 +16,7 @@ cudaError_t ccp_launch_project_K3_P2(int sm_count, const ccp_model& M, const ccp
 // ccp_coop.cu.  Grid of a launch of `count` samples, `spw` samples per warp, 4 warps per block: one warp per SM first,
 // then the other three warps of those blocks (one per scheduler) before any SM gets a second block; at most blocks_per_sm
 // blocks per SM.  Every sample of a launch with count <= grid * 4 * spw has a static place (the work counter is not touched).
-static inline int ccp_coop_grid(int sm_count, long long count, int spw, int blocks_per_sm = 3) {
+static inline int ccp_coop_grid(int sm_count, long long count, int spw, int blocks_per_sm = 2) {
   const long long need = (count + spw - 1) / spw;
   long long grid = need <= 4LL * sm_count ? (need < sm_count ? need : sm_count) : (need + 3) / 4;
   if (grid > (long long)blocks_per_sm * sm_count) grid = (long long)blocks_per_sm * sm_count;

@@ -114,8 +114,8 @@ int ccp_get_options(const ccp_handle* h, ccp_options* opt, double* tol_position,
 /* Tuning knob, not semantics: complete (non-pipelined) launches of at most max_count samples run on the cooperative
  * kernel (two lanes per sample, one arm each; three arms: four lanes per sample — a Newton iteration takes 1.2x / 1.7x
  * fewer cycles at 1.4x - 2x the issue slots), larger ones on the thread-per-sample kernel.  Results are bit-identical
- * either way.  0 = never, negative = the built-in default (64 samples per SM; also settable through the environment
- * variable CCP_COOP_MAX).                                                                                           */
+ * either way.  0 = never, negative = the built-in default (128 / 72 samples per SM for two / three arms, the measured
+ * crossovers on B200; also settable through the environment variable CCP_COOP_MAX).                                                                                           */
 int ccp_set_coop_threshold(ccp_handle* h, int64_t max_count);
 
 /* ---- batched constraint API, device pointers ------------------------------------------- */
