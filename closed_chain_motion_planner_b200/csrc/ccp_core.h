@@ -928,34 +928,65 @@ CCP_HD void ccp_reference_chain(ccp_model& M, const double* q_start) {
 // Single-arm kinematics in the arm's BASE frame (RobotModel API, panda_rbdl.cpp:9-42).
 // T: row-major 3x4 [R|p].  Jac: 6x7 row-major, rows [linear; angular] (panda_rbdl.cpp:16-19).
 // ------------------------------------------------------------------------------------------
-CCP_HD void ccp_arm_fk(const ccp_arm& A, const double* q, double* T, double* Jac) {
+// One link of the matrix recursion: o += R t ; R <- R Rx(alpha) Rz(theta).  PANDA >= 1 compiles the stock alpha pattern
+// in (Rx is a signed permutation of columns, the structurally zero translation component is skipped), PANDA = 2 also the
+// stock table's zero a / d entries — the batched IK iteration (ccp_ik.h) is 8 % shorter with it.  PANDA = 0 is the
+// generic code, which the public FK / Jacobian entry points always use.
+template <int PANDA, int I>
+CCP_HD void ccp_arm_fk_link(const ccp_link& L, double s, double c, double* R, double* o) {
+  constexpr int sg = ccp_panda_sgn<I>::value;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    double acc = o[r];
+    if (!PANDA) {
+      acc = CCP_FMA(R[3 * r], L.tx, CCP_FMA(R[3 * r + 1], L.ty, CCP_FMA(R[3 * r + 2], L.tz, acc)));
+    } else {
+      if (!(PANDA == 2 && ccp_stock_zero<I>::d)) {
+        if (sg == 0) acc = CCP_FMA(R[3 * r + 2], L.tz, acc);  // alpha = 0: t = (a, 0, d)
+        else acc = CCP_FMA(R[3 * r + 1], L.ty, acc);         // alpha = +-pi/2: t = (a, -+d, 0)
+      }
+      if (!(PANDA == 2 && ccp_stock_zero<I>::a)) acc = CCP_FMA(R[3 * r], L.tx, acc);
+    }
+    o[r] = acc;
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const double c0 = R[3 * r], c1 = R[3 * r + 1], c2 = R[3 * r + 2];
+    double n1, n2;  // columns 1, 2 of R Rx(alpha)
+    if (!PANDA) {
+      n1 = CCP_FMA(c1, L.ca, c2 * L.sa);
+      n2 = CCP_FMA(c2, L.ca, -(c1 * L.sa));
+    } else if (sg > 0) {
+      n1 = c2; n2 = -c1;
+    } else if (sg < 0) {
+      n1 = -c2; n2 = c1;
+    } else {
+      n1 = c1; n2 = c2;
+    }
+    R[3 * r] = CCP_FMA(c0, c, n1 * s);
+    R[3 * r + 1] = CCP_FMA(n1, c, -(c0 * s));
+    R[3 * r + 2] = n2;
+  }
+}
+template <int PANDA, int I>
+CCP_HD void ccp_arm_fk_links(const ccp_arm& A, const double* q, double* R, double* o, double (*zs)[3], double (*os)[3]) {
+  const ccp_link& L = A.link[I];
+  double s, c;
+  ccp_sincos((PANDA == 2) ? q[I] : q[I] + L.qoff, &s, &c);  // stock: no theta calibration
+  ccp_arm_fk_link<PANDA, I>(L, s, c, R, o);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    zs[I][r] = R[3 * r + 2];
+    os[I][r] = o[r];
+  }
+  if (I + 1 < CCPC_DOF) ccp_arm_fk_links<PANDA, (I + 1 < CCPC_DOF ? I + 1 : I)>(A, q, R, o, zs, os);
+}
+template <int PANDA>
+CCP_HD void ccp_arm_fk_t(const ccp_arm& A, const double* q, double* T, double* Jac) {
   double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   double o[3] = {0, 0, 0};
   double zs[CCPC_DOF][3], os[CCPC_DOF][3];
-#pragma unroll
-  for (int i = 0; i < CCPC_DOF; ++i) {
-    const ccp_link& L = A.link[i];
-    double s, c;
-    ccp_sincos(q[i] + L.qoff, &s, &c);
-    // o += R t ;  R <- R Rx(alpha) Rz(theta)
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-      o[r] = CCP_FMA(R[3 * r], L.tx, CCP_FMA(R[3 * r + 1], L.ty, CCP_FMA(R[3 * r + 2], L.tz, o[r])));
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      double c0 = R[3 * r], c1 = R[3 * r + 1], c2 = R[3 * r + 2];
-      double n1 = CCP_FMA(c1, L.ca, c2 * L.sa);     // column 1 of R Rx
-      double n2 = CCP_FMA(c2, L.ca, -(c1 * L.sa));  // column 2 of R Rx
-      R[3 * r] = CCP_FMA(c0, c, n1 * s);
-      R[3 * r + 1] = CCP_FMA(n1, c, -(c0 * s));
-      R[3 * r + 2] = n2;
-    }
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      zs[i][r] = R[3 * r + 2];
-      os[i][r] = o[r];
-    }
-  }
+  ccp_arm_fk_links<PANDA, 0>(A, q, R, o, zs, os);
   double p[3];
 #pragma unroll
   for (int r = 0; r < 3; ++r) p[r] = CCP_FMA(R[3 * r + 2], A.fl, o[r]);
@@ -982,6 +1013,7 @@ CCP_HD void ccp_arm_fk(const ccp_arm& A, const double* q, double* T, double* Jac
     }
   }
 }
+CCP_HD void ccp_arm_fk(const ccp_arm& A, const double* q, double* T, double* Jac) { ccp_arm_fk_t<0>(A, q, T, Jac); }
 
 // KinematicChainSpace::enforceBounds (KinematicChain.h:118-130): fmod wrap into [-pi, pi).
 // fmod is exact in IEEE arithmetic, so host and device agree bit for bit.

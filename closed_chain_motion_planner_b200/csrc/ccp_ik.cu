@@ -11,18 +11,20 @@
 // `arm` is uniform.  The model is a __grid_constant__ parameter, so M.arm[arm] is an indexed read of the constant bank:
 // ONE copy of the trip's code (a switch over the arm made three: 102 KB of SASS, and ncu showed 28 % of the sampling
 // kernel's stall samples waiting for instructions).
+template <int PANDA>
 __device__ __forceinline__ bool ik_trip(const ccp_model& M, int arm, const double* T, double* q, const ccp_ik_opt& O, int32_t& it,
                                         bool& conv, double& ep, double& er) {
-  return ccp_ik_trip(M.arm[arm], M.lb, M.ub, T, q, O, it, conv, ep, er);
+  return ccp_ik_trip<PANDA>(M.arm[arm], M.lb, M.ub, T, q, O, it, conv, ep, er);
 }
 // The explicit-seed kernel's loop is short enough for three copies (one per arm, constants at fixed offsets): 2 % faster
 // there than the indexed read.
+template <int PANDA>
 __device__ __forceinline__ bool ik_trip_per_arm(const ccp_model& M, int arm, const double* T, double* q, const ccp_ik_opt& O,
                                                 int32_t& it, bool& conv, double& ep, double& er) {
   switch (arm) {
-    case 0: return ccp_ik_trip(M.arm[0], M.lb, M.ub, T, q, O, it, conv, ep, er);
-    case 1: return ccp_ik_trip(M.arm[1], M.lb, M.ub, T, q, O, it, conv, ep, er);
-    default: return ccp_ik_trip(M.arm[2], M.lb, M.ub, T, q, O, it, conv, ep, er);
+    case 0: return ccp_ik_trip<PANDA>(M.arm[0], M.lb, M.ub, T, q, O, it, conv, ep, er);
+    case 1: return ccp_ik_trip<PANDA>(M.arm[1], M.lb, M.ub, T, q, O, it, conv, ep, er);
+    default: return ccp_ik_trip<PANDA>(M.arm[2], M.lb, M.ub, T, q, O, it, conv, ep, er);
   }
 }
 
@@ -36,6 +38,7 @@ static __device__ __noinline__ double ik_gauss01(unsigned long long seed, unsign
 // projection kernel: one loop pass = one Newton trip of the lane's current solve, and a lane whose solve finished
 // writes it out and takes the next pair (first pair static and interleaved over the blocks, the rest from a global
 // counter, one warp-aggregated atomic per refill event).  Measured before: 4.8 of 32 lanes active per instruction.
+template <int PANDA>
 __global__ void __launch_bounds__(128, CCP_IK_BLOCKS_PER_SM)
 ccp_ik_kernel(const __grid_constant__ ccp_model M, int arm, const double* __restrict__ Tt, const double* __restrict__ qseed,
               long long count, const __grid_constant__ ccp_ik_opt O, double* __restrict__ qout, uint8_t* __restrict__ ok,
@@ -57,7 +60,7 @@ ccp_ik_kernel(const __grid_constant__ ccp_model M, int arm, const double* __rest
     }
     bool conv;
     double ep, er;
-    if (ik_trip_per_arm(M, arm, T, q, O, it, conv, ep, er)) {
+    if (ik_trip_per_arm<PANDA>(M, arm, T, q, O, it, conv, ep, er)) {
 #pragma unroll
       for (int k = 0; k < CCPC_DOF; ++k) qout[i * CCPC_DOF + k] = q[k];
       if (ok) ok[i] = ccp_ik_accept(M.lb, M.ub, q, O, conv);
@@ -86,6 +89,7 @@ struct ccp_ik_sample_scratch {
   unsigned* done;     // [n_targets] restarts finished (zeroed before the launch)
 };
 
+template <int PANDA>
 __global__ void __launch_bounds__(128, CCP_IK_BLOCKS_PER_SM)
 ccp_ik_sample_kernel(const __grid_constant__ ccp_model M, int arm, const double* __restrict__ Tt,
                      const double* __restrict__ qref, int q_stride, long long n_targets, int restarts,
@@ -123,7 +127,7 @@ ccp_ik_sample_kernel(const __grid_constant__ ccp_model M, int arm, const double*
     }
     bool conv;
     double ep, er;
-    if (ik_trip(M, arm, T, q, O, it, conv, ep, er)) {
+    if (ik_trip<PANDA>(M, arm, T, q, O, it, conv, ep, er)) {
       const bool okk = ccp_ik_accept(M.lb, M.ub, q, O, conv);
       double dist2 = 0.0;
 #pragma unroll
@@ -171,7 +175,9 @@ cudaError_t ccp_launch_ik(int sm_count, const ccp_model& M, int arm, const doubl
   // persistent grid: 2 blocks of 128 per SM at ~250 registers; a small batch is spread one warp's worth per block
   long long need = (count + 31) / 32, cap = (long long)sm_count * CCP_IK_BLOCKS_PER_SM;
   const int grid = (int)(need < cap ? (need < 1 ? 1 : need) : cap);
-  ccp_ik_kernel<<<grid, 128, 0, st>>>(M, arm, Tt, qseed, count, O, qout, ok, iters, err, counter);
+  if (M.stock) ccp_ik_kernel<2><<<grid, 128, 0, st>>>(M, arm, Tt, qseed, count, O, qout, ok, iters, err, counter);
+  else if (M.panda_alpha) ccp_ik_kernel<1><<<grid, 128, 0, st>>>(M, arm, Tt, qseed, count, O, qout, ok, iters, err, counter);
+  else ccp_ik_kernel<0><<<grid, 128, 0, st>>>(M, arm, Tt, qseed, count, O, qout, ok, iters, err, counter);
   return cudaGetLastError();
 }
 
@@ -201,9 +207,14 @@ cudaError_t ccp_launch_ik_sample(int sm_count, const ccp_model& M, int arm, cons
     const long long items = nt * restarts;
     long long need = (items + 31) / 32, cap = (long long)sm_count * CCP_IK_BLOCKS_PER_SM;
     const int grid = (int)(need < cap ? (need < 1 ? 1 : need) : cap);
-    ccp_ik_sample_kernel<<<grid, 128, 0, st>>>(M, arm, Tt + first * 12, qref ? qref + first * q_stride : nullptr, q_stride, nt,
-                                                restarts, rng_seed, first, sigma, O, W, qbest + first * q_stride, ok + first,
-                                                n_success ? n_success + first : nullptr, counters + launch);
+#define CCP_IK_SAMPLE_LAUNCH(P)                                                                                              \
+  ccp_ik_sample_kernel<P><<<grid, 128, 0, st>>>(M, arm, Tt + first * 12, qref ? qref + first * q_stride : nullptr, q_stride, nt, \
+                                                 restarts, rng_seed, first, sigma, O, W, qbest + first * q_stride, ok + first,     \
+                                                 n_success ? n_success + first : nullptr, counters + launch)
+    if (M.stock) CCP_IK_SAMPLE_LAUNCH(2);
+    else if (M.panda_alpha) CCP_IK_SAMPLE_LAUNCH(1);
+    else CCP_IK_SAMPLE_LAUNCH(0);
+#undef CCP_IK_SAMPLE_LAUNCH
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }

@@ -12,7 +12,8 @@
 // tests check with the reference-faithful FK of oracle A.  The iteration here is KDL's ChainIkSolverPos_NR_JL idea
 // (Newton step on the 6-D pose error, clamp to the limits) with a damped normal-equation solve:
 //     dq = J^T (J J^T + lambda^2 I)^-1 e,   e = (p_t - p, 2 sgn(w) vec(quat(R_t R^T))),   q <- clamp(q + dq).
-// FK and the geometric Jacobian are ccp_arm_fk (ccp_core.h), i.e. PandaModel::getTransform / getJacobianMatrix.
+// FK and the geometric Jacobian are ccp_arm_fk_t (ccp_core.h), i.e. PandaModel::getTransform / getJacobianMatrix, in the
+// model's link-code mode (the stock alpha pattern turns R Rx(alpha) into a column permutation).
 #pragma once
 
 #include "ccp_core.h"
@@ -77,6 +78,8 @@ CCP_HD void ccp_rot_error(const double* Rt, const double* R, double* er) {
 // solve is finished (returns true, q untouched); otherwise take one damped Newton step, clamp, count it, return false.
 // The kernels run one trip per loop pass (lane refill); ccp_ik_solve_one below is the same trips in a plain loop.
 // Tt: target EE pose in the arm's base frame, row-major 3x4 [R|p] (the frame getTransform returns).
+// PANDA: link-code mode of the FK (0 generic, 1 structured alpha, 2 stock table: ccp_arm_fk_t).
+template <int PANDA>
 CCP_HD bool ccp_ik_trip(const ccp_arm& A, const double* lb, const double* ub, const double* Tt, double* q,
                         const ccp_ik_opt& O, int32_t& it, bool& conv, double& ep_inf, double& er_inf) {
   double Rt[9];
@@ -86,7 +89,7 @@ CCP_HD bool ccp_ik_trip(const ccp_arm& A, const double* lb, const double* ub, co
     for (int c = 0; c < 3; ++c) Rt[3 * r + c] = Tt[4 * r + c];
   {
     double T[12], J[42];
-    ccp_arm_fk(A, q, T, J);
+    ccp_arm_fk_t<PANDA>(A, q, T, J);
     double R[9], e[6];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
@@ -169,12 +172,13 @@ CCP_HD bool ccp_ik_accept(const double* lb, const double* ub, const double* q, c
 }
 
 // One solve.  q: seed in, last iterate out.  err[0] = |p_t - p|_inf, err[1] = |e_rot|_inf at exit.
+template <int PANDA>
 CCP_HD void ccp_ik_solve_one(const ccp_arm& A, const double* lb, const double* ub, const double* Tt, double* q,
                              const ccp_ik_opt& O, int32_t* iters, bool* ok, double* err) {
   int32_t it = 0;
   bool conv = false;
   double ep_inf = 0.0, er_inf = 0.0;
-  while (!ccp_ik_trip(A, lb, ub, Tt, q, O, it, conv, ep_inf, er_inf)) {
+  while (!ccp_ik_trip<PANDA>(A, lb, ub, Tt, q, O, it, conv, ep_inf, er_inf)) {
   }
   *iters = it;
   *ok = ccp_ik_accept(lb, ub, q, O, conv);

@@ -215,7 +215,10 @@ void ob_ik_batch(const ccp_model* M, int arm, const double* Tt, const double* qs
     double q[7], e[2];
     for (int k = 0; k < 7; ++k) q[k] = qseed[7 * s + k];
     int32_t it; bool okk;
-    ccp_ik_solve_one(M->arm[arm], M->lb, M->ub, Tt + 12 * s, q, O, &it, &okk, e);
+    // the link-code mode the CUDA library picks for this model (ccp_launch_ik)
+    if (M->stock) ccp_ik_solve_one<2>(M->arm[arm], M->lb, M->ub, Tt + 12 * s, q, O, &it, &okk, e);
+    else if (M->panda_alpha) ccp_ik_solve_one<1>(M->arm[arm], M->lb, M->ub, Tt + 12 * s, q, O, &it, &okk, e);
+    else ccp_ik_solve_one<0>(M->arm[arm], M->lb, M->ub, Tt + 12 * s, q, O, &it, &okk, e);
     for (int k = 0; k < 7; ++k) qout[7 * s + k] = q[k];
     if (ok) ok[s] = okk;
     if (iters) iters[s] = it;
