@@ -82,17 +82,16 @@ ccp_ik_kernel(const __grid_constant__ ccp_model M, int arm, const double* __rest
 // (and, when it succeeded, its solution) in scratch memory and counts itself done; whichever lane finishes a target's
 // LAST restart picks the winner: the seeded solution if it succeeded, else the successful restart nearest to the
 // reference (sampleCalibGoal) — or, without a reference, the lowest-numbered successful restart.  Ties go to the lower
-// restart number, so the result does not depend on which lane ran what.  With a reference, restarts still running when
-// the seeded one succeeds are abandoned (the answer is decided): n_success then counts the restarts that got to finish.
+// restart number, so the result does not depend on which lane ran what.  Restarts that can no longer win are abandoned
+// (see the loop): n_success counts the successful restarts that got to finish.
 struct ccp_ik_sample_scratch {
   double* key;        // [n_targets][restarts] selection key, 1e300 = failed
   double* q;          // [n_targets][restarts][7] solutions of the successful restarts
   unsigned* done;     // [n_targets] restarts finished (zeroed before the launch)
-  unsigned* decided;  // [n_targets] 1 once the seeded restart has succeeded (zeroed with `done`)
+  unsigned* decided;  // [n_targets] restarts - r of the lowest-numbered restart that has decided the target (zeroed with `done`)
 };
 
-// SEEDED: a reference configuration is given (qref != nullptr)
-template <int PANDA, bool SEEDED>
+template <int PANDA>
 __global__ void __launch_bounds__(128, CCP_IK_BLOCKS_PER_SM)
 ccp_ik_sample_kernel(const __grid_constant__ ccp_model M, int arm, const double* __restrict__ Tt,
                      const double* __restrict__ qref, int q_stride, long long n_targets, int restarts,
@@ -110,16 +109,10 @@ ccp_ik_sample_kernel(const __grid_constant__ ccp_model M, int arm, const double*
   for (;;) {
     if (load) {
       if (w >= items) break;
-      // with a reference, restart-major: every target's seeded restart (r = 0) is handed out before any random restart, so that in a launch
-      // larger than the machine the random restarts of a target whose seeded solve succeeded find it decided at once
-      // (without a reference every restart runs whatever the order: target-major keeps a warp on one target's row)
-      if (SEEDED) {
-        r = (int)(w / n_targets);
-        t = w - (long long)r * n_targets;
-      } else {
-        t = w / restarts;
-        r = (int)(w - t * restarts);
-      }
+      // restart-major: every target's restart 0 is handed out before any restart 1, ...: in a launch larger than the
+      // machine a restart that can no longer win (below) finds its target decided at once
+      r = (int)(w / n_targets);
+      t = w - (long long)r * n_targets;
 #pragma unroll
       for (int k = 0; k < 12; ++k) T[k] = __ldg(Tt + t * 12 + k);
 #pragma unroll
@@ -138,17 +131,22 @@ ccp_ik_sample_kernel(const __grid_constant__ ccp_model M, int arm, const double*
     }
     bool conv;
     double ep, er;
-    // sampleCalibGoal only draws random restarts when the seeded solve failed: once the seeded restart of this target has
-    // succeeded the others are abandoned (the look is issued before the trip and read after it, off the critical path)
-    const unsigned decided = (SEEDED && r > 0) ? __ldcg(W.decided + t) : 0u;
+    // Restarts that can no longer win are abandoned.  sampleCalibGoal draws random restarts only when the seeded solve
+    // failed (jy_ConstrainedValidStateSampler.h:80-101), so with a reference a successful restart 0 decides the target.
+    // sampleRandomGoal (:126-136) runs all its draws and keeps the last success; the draws are i.i.d., so any successful
+    // one is distributed alike — here the lowest-numbered success is the answer and higher-numbered draws give up once a
+    // lower one has succeeded.  W.decided[t] holds restarts - r of the lowest-numbered restart that has decided target t;
+    // restart r gives up when that is above its own restarts - r.  (The look is issued before the trip and read after
+    // it, off the critical path.)
+    const unsigned decided = (r > 0) ? __ldcg(W.decided + t) : 0u;
     bool fin = ik_trip<PANDA>(M, arm, T, q, O, it, conv, ep, er);
-    if (decided) {
+    if (decided > (unsigned)(restarts - r)) {
       fin = true;
       conv = false;
     }
     if (fin) {
       const bool okk = ccp_ik_accept(M.lb, M.ub, q, O, conv);
-      if (SEEDED && okk && r == 0) W.decided[t] = 1u;
+      if (okk && (r == 0 || !qref)) atomicMax(W.decided + t, (unsigned)(restarts - r));
       double dist2 = 0.0;
 #pragma unroll
       for (int k = 0; k < CCPC_DOF; ++k) {
@@ -228,19 +226,13 @@ cudaError_t ccp_launch_ik_sample(int sm_count, const ccp_model& M, int arm, cons
     const long long items = nt * restarts;
     long long need = (items + 31) / 32, cap = (long long)sm_count * CCP_IK_BLOCKS_PER_SM;
     const int grid = (int)(need < cap ? (need < 1 ? 1 : need) : cap);
-#define CCP_IK_SAMPLE_LAUNCH(P, S)                                                                                             \
-  ccp_ik_sample_kernel<P, S><<<grid, 128, 0, st>>>(M, arm, Tt + first * 12, qref ? qref + first * q_stride : nullptr, q_stride, nt, \
+#define CCP_IK_SAMPLE_LAUNCH(P)                                                                                                \
+  ccp_ik_sample_kernel<P><<<grid, 128, 0, st>>>(M, arm, Tt + first * 12, qref ? qref + first * q_stride : nullptr, q_stride, nt, \
                                                  restarts, rng_seed, first, sigma, O, W, qbest + first * q_stride, ok + first,     \
                                                  n_success ? n_success + first : nullptr, counters + launch)
-    if (qref) {
-      if (M.stock) CCP_IK_SAMPLE_LAUNCH(2, true);
-      else if (M.panda_alpha) CCP_IK_SAMPLE_LAUNCH(1, true);
-      else CCP_IK_SAMPLE_LAUNCH(0, true);
-    } else {
-      if (M.stock) CCP_IK_SAMPLE_LAUNCH(2, false);
-      else if (M.panda_alpha) CCP_IK_SAMPLE_LAUNCH(1, false);
-      else CCP_IK_SAMPLE_LAUNCH(0, false);
-    }
+    if (M.stock) CCP_IK_SAMPLE_LAUNCH(2);
+    else if (M.panda_alpha) CCP_IK_SAMPLE_LAUNCH(1);
+    else CCP_IK_SAMPLE_LAUNCH(0);
 #undef CCP_IK_SAMPLE_LAUNCH
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;

@@ -318,8 +318,10 @@ int ccp_ik_batch(ccp_handle* h, int32_t arm, const double* T_target_dev, const d
  * clipped to the limits (TrackIKAdaptor::getRandomConfig, sigma = 0.3 there) — and keep the seeded solution if it
  * succeeded, else the successful one nearest to q_ref (without q_ref: the lowest-numbered successful restart).
  * q_best_dev double[n_targets][7] (untouched where ok == 0), ok_dev uint8[n_targets], n_success_dev int32[n_targets]
- * (how many restarts converged) or NULL.  With q_ref, restarts still running when the seeded one succeeds are abandoned,
- * as the reference only draws them after a failed seeded solve: n_success then counts the restarts that got to finish. */
+ * (how many restarts converged) or NULL.  Restarts that can no longer win are abandoned — with q_ref once the seeded one
+ * has succeeded (the reference only draws the others after a failed seeded solve), without q_ref once a lower-numbered
+ * one has succeeded (the draws are i.i.d.: any success is distributed alike) — so n_success counts the successful
+ * restarts that got to finish; ok and q_best do not depend on it.                                                   */
 int ccp_ik_sample_batch(ccp_handle* h, int32_t arm, const double* T_target_dev, int64_t n_targets, int32_t restarts,
                         uint64_t rng_seed, double sigma, const double* q_ref_dev, const ccp_ik_options* opt,
                         double* q_best_dev, uint8_t* ok_dev, int32_t* n_success_dev, void* stream);
