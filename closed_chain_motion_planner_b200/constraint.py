@@ -673,7 +673,9 @@ class PandaModel:
     def ikSampleBatch(self, targets, restarts: int = 15, rng_seed: int = 0, sigma: float = 0.3, q_ref=None, **opts):
         """The goal sampler's per-arm loop for a batch of targets (jy_ConstrainedValidStateSampler.h:63-189): `restarts`
         solves per target side by side (restart 0 from q_ref if given, the rest from N(mid-range, sigma) clipped to the
-        limits); the seeded solution wins, else the successful one nearest to q_ref.  Returns dict(q, ok, n_success)."""
+        limits); the seeded solution wins, else the successful one nearest to q_ref (without q_ref: the lowest-numbered
+        success).  Restarts that can no longer win are abandoned, so n_success counts the successful restarts that got to
+        finish.  Returns dict(q, ok, n_success)."""
         import torch
 
         c = self._c

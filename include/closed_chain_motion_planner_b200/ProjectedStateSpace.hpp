@@ -353,8 +353,9 @@ class MultiGpuProjectedSampler {
 
 // The goal sampler's per-arm IK loop (jy_ConstrainedValidStateSampler.h:63-189) for a batch of targets: `restarts`
 // solves per target (restart 0 from q_ref if given, the rest from N(mid-range, 0.3) clipped to the limits); the seeded
-// solution wins, else the successful restart nearest to q_ref.  targets: n_targets x 12 (row-major 3x4 EE pose in the
-// arm's base frame); q_best: n_targets x 7.
+// solution wins, else the successful restart nearest to q_ref (without q_ref: the lowest-numbered success; restarts that
+// can no longer win are abandoned, n_success counts those that finished).  targets: n_targets x 12 (row-major 3x4 EE pose
+// in the arm's base frame); q_best: n_targets x 7.
 inline void ikSampleBatch(const KinematicChainConstraint& c, int arm, const double* targets, int64_t n_targets, int restarts,
                           uint64_t rng_seed, const double* q_ref, double* q_best, uint8_t* ok, int32_t* n_success = nullptr,
                           double sigma = 0.3) {
